@@ -1,0 +1,161 @@
+/*
+ * protpore_b200.h -- C ABI of the B200-native profile-HMM scoring/decoding engine.
+ *
+ * This is the drop-in boundary for ONE hot path of mitenjain/protpore: scoring and decoding many
+ * segmented nanopore events against a baked yahmm `Model`.  The reference has no stable native
+ * interface for this path (its sweeps are Cython `cdef` methods on private memoryviews,
+ * yahmm/yahmm.pyx:2029-2040), so every entry point below names the reference routine it replaces;
+ * INTEGRATION.md shows the ctypes binding a maintainer adds to yahmm.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.  Nothing throws across the ABI.
+ *   - Every call returns PP_OK (0) or a negative pp_status; pp_last_error() gives the message of
+ *     the last failure on the calling thread.
+ *   - The caller owns every input/output buffer.  `mem` says where ALL data buffers of that call
+ *     live: PP_MEM_HOST (library stages H2D/D2H itself; pinned memory recommended) or
+ *     PP_MEM_DEVICE (device pointers on the model's GPU; work is enqueued on the model's stream and
+ *     the call returns after that stream is synchronised).
+ *   - The library owns only the opaque model handle and its device workspace.  A handle is not
+ *     thread-safe; distinct handles are.  One handle per GPU (one process per GPU under torchrun).
+ *   - Events are passed CSR-style: `obs` holds the segment means of all events back to back
+ *     (float32 or float64, see pp_dtype), `offsets[n_events + 1]` (int64) delimits them.  Every
+ *     event must have at least one observation (the reference raises on empty sequences,
+ *     yahmm.pyx:2836).
+ *   - Impossible events (log-probability -inf) are reported in-band: logp = -inf, path_len = -1;
+ *     the Python layer maps them to the reference's (-inf, None) / (None, None).
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     PP_ERR_CUDA.
+ */
+#ifndef PROTPORE_B200_H
+#define PROTPORE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pp_status {
+    PP_OK = 0,
+    PP_ERR_ARG = -1,         /* bad argument (null pointer, empty event, inconsistent CSR ...) */
+    PP_ERR_CUDA = -2,        /* CUDA runtime failure or no device */
+    PP_ERR_NOMEM = -3,       /* batch needs more device workspace than the handle's limit */
+    PP_ERR_UNSUPPORTED = -4, /* model shape outside what the kernels lower */
+    PP_ERR_CAPACITY = -5     /* caller's path buffer too small; *path_total holds the needed size */
+} pp_status;
+
+typedef enum pp_mem { PP_MEM_HOST = 0, PP_MEM_DEVICE = 1 } pp_mem;
+typedef enum pp_dtype { PP_F32 = 0, PP_F64 = 1 } pp_dtype;
+typedef enum pp_emission_kind { PP_EMIT_NORMAL = 0, PP_EMIT_UNIFORM = 1 } pp_emission_kind;
+
+/*
+ * Baked model, exactly the arrays Model.bake produces (yahmm.pyx:2280-2655):
+ * states [0, silent_start) emit, [silent_start, n_states) are silent in topological order.
+ *   in_ptr/in_src/in_logp    = in_edge_count / in_transitions / in_transition_log_probabilities
+ *   out_ptr/out_dst/out_logp = out_edge_count / out_transitions / out_transition_log_probabilities
+ *   emit_kind/p0/p1          = distribution family and parameters of each emitting state
+ *                              (Normal: mean, std -- std == 0 selects the point-mass branch,
+ *                              yahmm.pyx:383-387; Uniform: start, end, yahmm.pyx:257-262)
+ *   emit_logw                = state_weights = log(state.weight) (yahmm.pyx:2515-2517)
+ */
+typedef struct pp_model_desc {
+    int32_t n_states, silent_start, start_index, end_index, finite, n_edges;
+    const int32_t *in_ptr, *in_src;
+    const double *in_logp;
+    const int32_t *out_ptr, *out_dst;
+    const double *out_logp;
+    const int32_t *emit_kind;
+    const double *emit_p0, *emit_p1, *emit_logw;
+} pp_model_desc;
+
+typedef struct pp_model pp_model;
+
+/* Build a device-resident, kernel-lowered copy of a baked model on CUDA device `device`.
+ * Replaces the implicit "self." state every reference sweep reads (yahmm.pyx:2029-2040). */
+int pp_model_create(const pp_model_desc *desc, int device, pp_model **out);
+void pp_model_destroy(pp_model *model);
+
+/* New parameters, same topology (after a Baum-Welch M-step, yahmm.pyx:4277-4327). */
+int pp_model_update_params(pp_model *model, const pp_model_desc *desc);
+
+/* Upper limit for the handle's device workspace in bytes (default: 70% of free memory at creation). */
+int pp_model_set_workspace_limit(pp_model *model, int64_t bytes);
+
+/* Device workspace pp_viterbi_batch needs for these events (offsets on the HOST). Lets a host
+ * caller split a job into chunks that fit. */
+int64_t pp_viterbi_workspace_bytes(const pp_model *model, const int64_t *offsets_host, int64_t n_events);
+
+/*
+ * Batched Model.log_probability (yahmm.pyx:3366-3396 over Model._forward, 2810-2930):
+ * logp_out[e] = log P(event e | model), float64, -inf if impossible.
+ * Computed by the scaled linear-space fp32 column kernel with exact power-of-two rescaling
+ * (DESIGN.md "forward"); |error| <= 1e-3 nats abs or 1e-6 rel against the float64 reference.
+ */
+int pp_forward_batch(pp_model *model, const void *obs, int32_t obs_dtype, const int64_t *offsets,
+                     int64_t n_events, int32_t mem, double *logp_out);
+
+/*
+ * Batched Model.viterbi (yahmm.pyx:3444-3652): float64 max-plus sweep with the reference's exact
+ * operation order and tie-breaking, packed traceback pointers in HBM, traceback on the GPU.
+ *   logp_out[e]     : Viterbi score (bit-identical to the reference), -inf if impossible
+ *   path_len_out[e] : number of states on the path (start ... end, silent states included),
+ *                     -1 if impossible (reference returns (-inf, None), 3621-3623)
+ *   path_out        : state indices of all paths back to back in event order, uint16
+ *                     (n_states <= 65535); event e occupies [sum_{j<e} max(len_j,0), +len_e)
+ *   path_capacity   : number of uint16 elements path_out can hold
+ *   path_total      : receives the total number of elements (written or needed)
+ * path_out may be NULL (scores and lengths only; path_total still reported).
+ */
+int pp_viterbi_batch(pp_model *model, const void *obs, int32_t obs_dtype, const int64_t *offsets,
+                     int64_t n_events, int32_t mem, double *logp_out, int64_t *path_len_out,
+                     uint16_t *path_out, int64_t path_capacity, int64_t *path_total);
+
+/*
+ * Full DP tables of ONE event in float64 log space, the reference's return values:
+ *   pp_forward_table  -> Model.forward  (yahmm.pyx:2780-2930), table_out[(n+1) x n_states]
+ *   pp_backward_table -> Model.backward (yahmm.pyx:2932-3156), table_out[(n+1) x n_states]
+ * obs is float64[n]; buffers follow `mem`.
+ */
+int pp_forward_table(pp_model *model, const double *obs, int64_t n, int32_t mem, double *table_out);
+int pp_backward_table(pp_model *model, const double *obs, int64_t n, int32_t mem, double *table_out);
+
+/*
+ * Model.forward_backward for a batch (yahmm.pyx:3158-3364, tie == False) and the E-step of
+ * Model._train_once_baum_welch (4107-4236) in sufficient-statistic form:
+ *   logp_out[e]            : sequence log-probability (-inf => event skipped, contributes nothing)
+ *   edge_counts[n_edges]   : += expected transition counts, indexed like the OUT-edge CSR
+ *   emit_moments[3 * silent_start] : += (sum w, sum w x, sum w x^2) per emitting state
+ *   emit_minmax[2 * silent_start]  : min / max over whole events that gave the state non-zero weight
+ *   posteriors_out         : optional (may be NULL): log emission weights, float64, event e row i
+ *                            state k at [(offsets[e] + i) * silent_start + k]  (3304-3321)
+ * Accumulators are read-modify-write so a caller can sum shards before an allreduce.
+ */
+int pp_forward_backward_batch(pp_model *model, const void *obs, int32_t obs_dtype, const int64_t *offsets,
+                              int64_t n_events, int32_t mem, double *logp_out, double *edge_counts,
+                              double *emit_moments, double *emit_minmax, double *posteriors_out);
+
+/*
+ * Length-conditioned ancestral sampler used to make synthetic events:
+ * event e gets exactly lengths[e] observations; edges into `end` are masked (and the remaining
+ * out-probabilities renormalised) until the last emission.  Deterministic in (seed, e).
+ * obs_out is float32 on the device or host per `mem`; offsets = exclusive scan of lengths.
+ */
+int pp_sample_events(pp_model *model, const int64_t *offsets, int64_t n_events, uint64_t seed, int32_t mem,
+                     float *obs_out);
+
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+int64_t pp_launch_count(const pp_model *model);
+
+/* CUDA stream the handle enqueues on (a cudaStream_t as an integer), for timing with CUDA events. */
+uint64_t pp_model_stream(const pp_model *model);
+
+/* Message of the last failure on this thread ("" if none). */
+const char *pp_last_error(void);
+
+/* ABI version, bumped on any incompatible change. */
+int pp_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROTPORE_B200_H */

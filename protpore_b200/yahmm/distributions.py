@@ -1,0 +1,217 @@
+"""Emission distributions of the drop-in `yahmm` API.
+
+Mirrors the reference interface (yahmm.pyx:101-231 `Distribution`, 233-348 `UniformDistribution`,
+350-523 `NormalDistribution`): same constructor arguments, `parameters` / `summaries` / `name` /
+`frozen` attributes, and method names.  These Python methods are the *host-side* definition (used
+for single-symbol queries, sampling and the Baum-Welch M-step); the per-observation evaluation on
+the hot path happens inside the CUDA column kernels from the lowered (kind, p0, p1) table.
+
+Only the two families the pro_001 peptide model uses are device-lowerable this round.  Any other
+`Distribution` subclass can still be put in a `State` and baked; asking the GPU path to score it
+raises `NotImplementedError`, never a CPU fallback.
+"""
+import math
+import random
+
+import numpy
+
+NEGINF = float("-inf")
+SQRT_2_PI = 2.50662827463   # the reference's truncated constant (yahmm.pyx:33) -- kept bit-for-bit
+
+KIND_NORMAL = 0
+KIND_UNIFORM = 1
+
+
+def _log(x):
+    """log(x) for x > 0, else -inf (yahmm.pyx:36-42)."""
+    return math.log(x) if x > 0 else NEGINF
+
+
+class Distribution(object):
+    """Base class (yahmm.pyx:101-231)."""
+
+    name = "Distribution"
+
+    def __init__(self):
+        self.name = "Distribution"
+        self.frozen = False
+        self.parameters = []
+        self.summaries = []
+
+    def __str__(self):
+        parameters = [list(p) if isinstance(p, numpy.ndarray) else p for p in self.parameters]
+        return "{}({})".format(self.name, ", ".join(map(str, parameters)))
+
+    __repr__ = __str__
+
+    def copy(self):
+        return self.__class__(*self.parameters)
+
+    def freeze(self):
+        self.frozen = True
+
+    def thaw(self):
+        self.frozen = False
+
+    def log_probability(self, symbol):
+        raise NotImplementedError
+
+    def sample(self):
+        raise NotImplementedError
+
+    def from_sample(self, items, weights=None):
+        if self.frozen:
+            return
+        raise NotImplementedError
+
+    def summarize(self, items, weights=None):
+        # default: keep the raw sample (yahmm.pyx:198-218)
+        if len(self.summaries) == 0:
+            self.summaries = [items, weights]
+        else:
+            prior_items, prior_weights = self.summaries
+            items = numpy.concatenate([prior_items, items])
+            if weights is not None:
+                weights = numpy.concatenate([prior_weights, weights])
+            self.summaries = [items, weights]
+
+    def from_summaries(self):
+        if self.frozen:
+            return
+        self.from_sample(*self.summaries)
+        self.summaries = []
+
+    # ---- device lowering hook (new) -----------------------------------
+    def device_params(self):
+        """(kind, p0, p1) for the CUDA emission table, or raise if this family is host-only."""
+        raise NotImplementedError(
+            "{} has no sm_100a emission kernel yet (only Normal/Uniform are lowered)".format(self.name))
+
+
+class UniformDistribution(Distribution):
+    """Uniform on [start, end] (yahmm.pyx:233-348)."""
+
+    def __init__(self, start, end, frozen=False):
+        self.parameters = [start, end]
+        self.summaries = []
+        self.name = "UniformDistribution"
+        self.frozen = frozen
+
+    def log_probability(self, symbol):
+        a, b = float(self.parameters[0]), float(self.parameters[1])
+        symbol = float(symbol)
+        if symbol == a and symbol == b:
+            return 0.0
+        if a <= symbol <= b:
+            return _log(1.0 / (b - a))
+        return NEGINF
+
+    def sample(self):
+        return random.uniform(self.parameters[0], self.parameters[1])
+
+    def from_sample(self, items, weights=None, inertia=0.0):
+        if self.frozen:
+            return
+        weights = numpy.ones_like(items) if weights is None else numpy.asarray(weights)
+        if weights.sum() == 0 or len(items) == 0:
+            return
+        lo, hi = self.parameters
+        self.parameters[0] = lo * inertia + numpy.min(items) * (1 - inertia)
+        self.parameters[1] = hi * inertia + numpy.max(items) * (1 - inertia)
+
+    def summarize(self, items, weights=None):
+        # the summary is [min, max] of the WHOLE sample whenever the total weight is non-zero (304-326)
+        weights = numpy.ones_like(items) if weights is None else numpy.asarray(weights)
+        if weights.sum() == 0 or len(items) == 0:
+            return
+        items = numpy.asarray(items)
+        self.summaries.append([items.min(), items.max()])
+
+    def from_summaries(self, inertia=0.0):
+        if self.frozen:
+            return
+        s = numpy.asarray(self.summaries)
+        lo, hi = self.parameters
+        # NB the reference indexes s[:, 0] unguarded (338-348): with no summaries it raises IndexError.
+        self.parameters = [lo * inertia + s[:, 0].min() * (1 - inertia),
+                           hi * inertia + s[:, 1].max() * (1 - inertia)]
+        self.summaries = []
+
+    def device_params(self):
+        return KIND_UNIFORM, float(self.parameters[0]), float(self.parameters[1])
+
+
+class NormalDistribution(Distribution):
+    """Normal(mean, std) with the sigma == 0 point-mass branch (yahmm.pyx:350-523)."""
+
+    def __init__(self, mean, std, frozen=False):
+        self.parameters = [mean, std]
+        self.summaries = []
+        self.name = "NormalDistribution"
+        self.frozen = frozen
+
+    def log_probability(self, symbol, epsilon=1E-4):
+        mu, sigma = float(self.parameters[0]), float(self.parameters[1])
+        symbol = float(symbol)
+        if sigma == 0.0:
+            return 0.0 if abs(symbol - mu) < epsilon else NEGINF
+        d = symbol - mu
+        # C evaluates pow(d, 2) as d*d and 2*sigma**2 as 2*(sigma*sigma) (yahmm.pyx:389-390)
+        return _log(1.0 / (sigma * SQRT_2_PI)) - (d * d) / (2 * (sigma * sigma))
+
+    def sample(self):
+        return random.normalvariate(*self.parameters)
+
+    def from_sample(self, items, weights=None, inertia=0.0, min_std=0.01):
+        if len(items) == 0 or self.frozen:
+            return
+        items = numpy.asarray(items)
+        weights = numpy.ones_like(items) if weights is None else numpy.asarray(weights)
+        if weights.sum() == 0:
+            return
+        mean = numpy.average(items, weights=weights)
+        if len(weights[weights != 0]) > 1:
+            variance = numpy.dot(items ** 2 - mean ** 2, weights) / weights.sum()
+            std = math.sqrt(variance) if variance >= 0 else 0
+        else:
+            std = self.parameters[1]
+        std = max(numpy.array([std, min_std]))
+        prior_mean, prior_std = self.parameters
+        self.parameters = [prior_mean * inertia + mean * (1 - inertia),
+                           prior_std * inertia + std * (1 - inertia)]
+
+    def summarize(self, items, weights=None):
+        items = numpy.asarray(items)
+        weights = numpy.ones_like(items) if weights is None else numpy.asarray(weights)
+        if weights.sum() == 0:
+            return
+        mean = numpy.average(items, weights=weights)
+        variance = numpy.dot(items ** 2 - mean ** 2, weights) / weights.sum()
+        self.summaries.append([mean, variance, weights.sum()])
+
+    def summarize_moments(self, w_sum, wx_sum, wxx_sum):
+        """Batched-path entry (new): push one summary from global moments (sum w, sum w x, sum w x^2).
+
+        Algebraically the same triple `summarize` stores ([mean, var, sum w], 462-486); lets the GPU
+        E-step hand over allreduced sufficient statistics instead of per-sequence weight vectors.
+        """
+        if w_sum == 0:
+            return
+        mean = wx_sum / w_sum
+        self.summaries.append([mean, wxx_sum / w_sum - mean * mean, w_sum])
+
+    def from_summaries(self, inertia=0.0, min_std=0.01):
+        if len(self.summaries) == 0 or self.frozen:
+            return
+        s = numpy.asarray(self.summaries)
+        mean = numpy.average(s[:, 0], weights=s[:, 2])
+        variance = numpy.sum([(v + m ** 2) * w for m, v, w in s]) / s[:, 2].sum() - mean ** 2
+        std = math.sqrt(variance) if variance >= 0 else 0
+        std = max(min_std, std)
+        prior_mean, prior_std = self.parameters
+        self.parameters = [prior_mean * inertia + mean * (1 - inertia),
+                           prior_std * inertia + std * (1 - inertia)]
+        self.summaries = []
+
+    def device_params(self):
+        return KIND_NORMAL, float(self.parameters[0]), float(self.parameters[1])
