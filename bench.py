@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched forward + Viterbi (with traceback) of synthetic nanopore events
+against the pro_001 peptide profile HMM (BASELINE.json config 2), one process per GPU.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's own Cython yahmm on the host cores
+
+One step = one pass of forward + Viterbi/traceback over this rank's batch of events.  `value` is timed
+with the events already resident in HBM (C ABI, PP_MEM_DEVICE); `e2e` goes through the host-buffer API
+(pinned host memory in, results back on the host) with the copies inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "profile-HMM forward+Viterbi cell updates per second (pro_001, 1M events of 50-500 segments)"
+UNIT = "GCUPS"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--events", type=int, default=1000000, help="events per GPU (config 2: 1,000,000)")
+    ap.add_argument("--min-len", type=int, default=50)
+    ap.add_argument("--max-len", type=int, default=500)
+    ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the compiled, unmodified reference (oracle/_ref) on the host cores
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    kind, shard = args
+    from protpore_b200 import peptide_hmm
+    if kind == "reference":
+        from oracle import ref_loader
+        model = peptide_hmm.pro_001_model(yahmm_module=ref_loader.load_reference_yahmm())
+        t0 = time.perf_counter()
+        for x in shard:
+            model.viterbi(x)
+            model.log_probability(x)
+        return time.perf_counter() - t0
+    from oracle import cpu_oracle
+    import protpore_b200.yahmm as ours
+    orc = cpu_oracle.OracleModel.from_model(peptide_hmm.pro_001_model(yahmm_module=ours))
+    t0 = time.perf_counter()
+    for x in shard:
+        orc.viterbi(x)
+        orc.log_probability(x)
+    return time.perf_counter() - t0
+
+
+def cpu_events(n_events, lo, hi, seed):
+    """Bounded CPU sample of the SAME workload (same model, same length law), host sampler."""
+    from protpore_b200 import peptide_hmm, events
+    import protpore_b200.yahmm as ours
+    model = peptide_hmm.pro_001_model(yahmm_module=ours)
+    lens = events.uniform_lengths(n_events, lo, hi, seed=seed)
+    return [np.asarray(x, dtype=np.float64) for x in events.sample_events(model, lens, seed=seed + 1)], model
+
+
+def run_cpu(n_events, lo, hi, seed, steps=1, warmup=0):
+    """Times viterbi + log_probability over `n_events` events with one worker per host core."""
+    import multiprocessing as mp
+    from oracle import ref_loader
+    kind = "reference" if ref_loader.available() else "port"
+    cores = os.cpu_count() or 1
+    evs, model = cpu_events(n_events, lo, hi, seed)
+    m = len(model.states)
+    cells = 2.0 * sum(len(x) for x in evs) * m
+    workers = max(1, min(cores, len(evs)))
+    shards = [(kind, evs[w::workers]) for w in range(workers)]
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(workers) as pool:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, shards)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    dt = float(np.mean(times))
+    return dict(value=cells / dt / 1e9, unit=UNIT, cores=workers, kind=kind,
+                sample="{} events of {}-{} segments ({:.3g} cells), viterbi + log_probability per event, "
+                       "{} worker processes".format(len(evs), lo, hi, cells, workers),
+                events_per_s=len(evs) / dt, seconds=dt), dt
+
+
+def cpu_sample_size(seconds, lo, hi):
+    cores = os.cpu_count() or 1
+    per_core = 1.2e6              # measured: cells/s per host thread over viterbi + log_probability together
+    cells = seconds * cores * per_core
+    return max(cores, int(cells / (2 * 257 * (lo + hi) / 2.0)))
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        rows = [r for r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in rows if r[0].replace('.', '', 1).isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(r[3 + j].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        n = cpu_sample_size(args.cpu_seconds, args.min_len, args.max_len)
+        cpu, dt = run_cpu(n, args.min_len, args.max_len, args.seed, steps=args.steps, warmup=min(args.warmup, 1))
+        line = {"metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+                "config": {"workload": "pro_001 profile HMM (257 states, 765 edges), events of {}-{} segments, "
+                           "forward + Viterbi with traceback; bounded CPU sample".format(args.min_len, args.max_len)},
+                "cpu_baseline": cpu,
+                "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "events_per_s": cpu["events_per_s"], "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from protpore_b200 import peptide_hmm, events
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import protpore_b200.yahmm as y
+    y.Model.device = local
+    model = peptide_hmm.pro_001_model()
+    eng = model.engine()
+    m, E = len(model.states), model.edge_count()
+
+    lens = events.uniform_lengths(args.events, args.min_len, args.max_len, seed=args.seed + rank)
+    obs_d, off_d = eng.sample_events(lens, seed=args.seed + 1000 + rank, device_out=True)   # synthetic, on the GPU
+    total_obs = int(lens.sum())
+    cells_step = 2.0 * total_obs * m                    # one forward pass + one Viterbi pass
+    stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local))
+
+    def step_device():
+        scores, plen, paths = eng.viterbi_batch(obs_d, off_d)
+        logp = eng.forward_batch(obs_d, off_d)
+        return scores, plen, paths, logp
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = step_device()
+    # sanity: every event decoded, scores finite, best path <= all paths
+    scores, plen, paths, logp = out
+    assert bool((plen > 0).all()) and bool(torch.isfinite(logp).all()) and bool((scores <= logp + 1e-6).all())
+    path_elems = int(paths.numel())
+    del out, scores, plen, paths, logp
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t_wall = time.perf_counter()
+    prof = {}
+    for _ in range(args.steps):
+        scores, plen, paths = eng.viterbi_batch(obs_d, off_d)
+        pv = eng.profile()
+        logp = eng.forward_batch(obs_d, off_d)
+        pf = eng.profile()
+        for k in ("viterbi_ms", "traceback_ms", "schedule_host_ms"):
+            prof[k] = prof.get(k, 0.0) + pv[k]
+        prof["forward_ms"] = prof.get("forward_ms", 0.0) + pf["forward_ms"]
+        prof["schedule_host_ms"] += pf["schedule_host_ms"]
+        del scores, plen, paths, logp
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t_wall
+    launches = eng.launch_count() - launches0
+    elapsed = e0.elapsed_time(e1) / 1e3
+    clocks = sampler.summary()
+    t = torch.tensor([elapsed, wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed, wall = float(t[0]), float(t[1])
+    ms_step = elapsed / args.steps * 1e3
+    value = cells_step * world * args.steps / elapsed / 1e9
+
+    # ---- e2e: host buffers in, host results out, through the public batched API ----------------
+    e2e = None
+    if not args.no_e2e:
+        obs_h = obs_d.cpu().pin_memory().numpy()
+        off_h = off_d.cpu().numpy()
+        e2e_steps = max(1, min(args.steps, 3))
+        eng.viterbi_batch(obs_h, off_h)          # warm the staging buffers
+        eng.forward_batch(obs_h, off_h)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            s_h, l_h, p_h = eng.viterbi_batch(obs_h, off_h)
+            lp_h = eng.forward_batch(obs_h, off_h)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0])
+        e2e = {"value": cells_step * world * e2e_steps / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(2 * (obs_h.nbytes + off_h.nbytes)),
+               "d2h_bytes_per_step": int(s_h.nbytes + l_h.nbytes + p_h.nbytes + lp_h.nbytes),
+               "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps,
+               "events_per_s": args.events * world * e2e_steps / dt}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (Viterbi sweep), live CUDA-event time -----------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    vit_ms = prof["viterbi_ms"] / args.steps
+    fwd_ms = prof["forward_ms"] / args.steps
+    tb_ms = prof["traceback_ms"] / args.steps
+    bytes_col = m * 1 + 4                                # uint8 pointer per state written + one float32 mean read
+    vit_bytes = float(total_obs) * bytes_col
+    achieved = vit_bytes / (vit_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_viterbi_lane", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": None,
+            "algorithmic_bytes_per_launch": vit_bytes, "launch_ms": vit_ms}
+    b = model._baked
+    ne = model.silent_start
+    indeg = np.diff(b.in_ptr)
+    e_emit, e_sil = int(indeg[:ne].sum()), int(indeg[ne:].sum())
+    kinds = [s.distribution.device_params() for s in model.states[:ne]]
+    n_norm = sum(1 for k in kinds if k[0] == 0)
+    ops_col = 3 * e_emit + 2 * e_sil + 4 * n_norm + 3 * (ne - n_norm)      # fp64 add/compare ops
+    sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    fp64_peak = 148 * 64 * (peaks.get("sm_max_mhz", 1965.0) * 1e6)         # nominal fp64 lanes x max clock
+    compute = {"bound": "fp64 add/compare issue (nominal 148 SM x 64 lanes x max clock)",
+               "viterbi_ops_per_s": ops_col * total_obs / (vit_ms * 1e-3), "peak_ops_per_s": fp64_peak,
+               "frac": ops_col * total_obs / (vit_ms * 1e-3) / fp64_peak,
+               "viterbi_gcups": total_obs * m / (vit_ms * 1e-3) / 1e9, "forward_gcups": total_obs * m / (fwd_ms * 1e-3) / 1e9,
+               "sm_mhz_under_load": sm_mhz}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        n = cpu_sample_size(args.cpu_seconds, args.min_len, args.max_len)
+        cpu, _ = run_cpu(n, args.min_len, args.max_len, args.seed)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "ours",
+            "config": {"workload": "pro_001 profile HMM (257 states, 765 edges), {} events/GPU of {}-{} segments sampled "
+                       "from the model, batched forward + Viterbi with traceback".format(args.events, args.min_len, args.max_len),
+                       "events_per_gpu": args.events, "observations_per_gpu": total_obs, "states": m, "edges": E,
+                       "cells_per_step_per_gpu": cells_step, "parallelism": "events sharded, dp{}".format(world),
+                       "l2_policy": "inputs ({:.2f} GB) and traceback table ({:.1f} GB) per step exceed the 126 MB L2".format(
+                           total_obs * 4 / 1e9, (total_obs + args.events) * m * 32 / 32 / 1e9)},
+            "events_per_s": args.events * world * args.steps / elapsed,
+            "wall_ms_per_step": wall / args.steps * 1e3,
+            "kernel_ms_per_step": {"viterbi": vit_ms, "traceback": tb_ms, "forward": fwd_ms,
+                                   "host_schedule": prof["schedule_host_ms"] / args.steps},
+            "path_elements_per_step": path_elems,
+            "roofline": roof, "compute_roofline": compute, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

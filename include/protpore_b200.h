@@ -143,6 +143,19 @@ int pp_forward_backward_batch(pp_model *model, const void *obs, int32_t obs_dtyp
 int pp_sample_events(pp_model *model, const int64_t *offsets, int64_t n_events, uint64_t seed, int32_t mem,
                      float *obs_out);
 
+/* Number of usable CUDA devices (0 without a driver/GPU; never fails). */
+int pp_device_count(void);
+
+/* Pinned host memory for PP_MEM_HOST buffers (cudaHostAlloc / cudaFreeHost); NULL on failure. */
+void *pp_host_alloc(int64_t bytes);
+void pp_host_free(void *p);
+
+/* Device time of the LAST batched call on this handle, in milliseconds, measured with CUDA events on
+ * the handle's stream and summed over the call's chunks.  Slots: 0 Viterbi sweep, 1 traceback (+scan),
+ * 2 forward sweep, 3 forward-backward, 4 sampler, 5 host->device copies, 6 device->host copies,
+ * 7 host wall time spent bucketing events by length.  Writes min(n, 8) values. */
+int pp_profile_get(const pp_model *model, double *out, int32_t n);
+
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t pp_launch_count(const pp_model *model);
 

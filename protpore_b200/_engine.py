@@ -1,0 +1,285 @@
+"""ctypes binding of libprotpore_b200.so (the C ABI in include/protpore_b200.h).
+
+`Engine` owns one `pp_model` handle (one baked model on one GPU) and exposes the batched entry
+points with numpy (host) or torch-CUDA (device) buffers.  There is deliberately NO fallback: if the
+shared library is missing, or no CUDA device is present, constructing an `Engine` raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libprotpore_b200.so")
+
+PP_OK, PP_ERR_ARG, PP_ERR_CUDA, PP_ERR_NOMEM, PP_ERR_UNSUPPORTED, PP_ERR_CAPACITY = 0, -1, -2, -3, -4, -5
+PP_MEM_HOST, PP_MEM_DEVICE = 0, 1
+PP_F32, PP_F64 = 0, 1
+PROF_SLOTS = ("viterbi_ms", "traceback_ms", "forward_ms", "fb_ms", "sample_ms", "h2d_ms", "d2h_ms", "schedule_host_ms")
+
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_f64p = ctypes.POINTER(ctypes.c_double)
+_u16p = ctypes.POINTER(ctypes.c_uint16)
+_vp = ctypes.c_void_p
+
+
+class PPModelDesc(ctypes.Structure):
+    """struct pp_model_desc (include/protpore_b200.h)."""
+    _fields_ = [("n_states", ctypes.c_int32), ("silent_start", ctypes.c_int32), ("start_index", ctypes.c_int32),
+                ("end_index", ctypes.c_int32), ("finite", ctypes.c_int32), ("n_edges", ctypes.c_int32),
+                ("in_ptr", _i32p), ("in_src", _i32p), ("in_logp", _f64p),
+                ("out_ptr", _i32p), ("out_dst", _i32p), ("out_logp", _f64p),
+                ("emit_kind", _i32p), ("emit_p0", _f64p), ("emit_p1", _f64p), ("emit_logw", _f64p)]
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, message):
+        RuntimeError.__init__(self, "protpore_b200 error {}: {}".format(code, message))
+        self.code = code
+
+
+_lib = None
+
+# every symbol include/protpore_b200.h declares: (name, restype, argtypes)
+ABI = [
+    ("pp_abi_version", ctypes.c_int, []),
+    ("pp_last_error", ctypes.c_char_p, []),
+    ("pp_device_count", ctypes.c_int, []),
+    ("pp_host_alloc", _vp, [ctypes.c_int64]),
+    ("pp_host_free", None, [_vp]),
+    ("pp_model_create", ctypes.c_int, [ctypes.POINTER(PPModelDesc), ctypes.c_int, ctypes.POINTER(_vp)]),
+    ("pp_model_destroy", None, [_vp]),
+    ("pp_model_update_params", ctypes.c_int, [_vp, ctypes.POINTER(PPModelDesc)]),
+    ("pp_model_set_workspace_limit", ctypes.c_int, [_vp, ctypes.c_int64]),
+    ("pp_viterbi_workspace_bytes", ctypes.c_int64, [_vp, _vp, ctypes.c_int64]),
+    ("pp_forward_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
+    ("pp_viterbi_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp,
+                                        ctypes.c_int64, _i64p]),
+    ("pp_forward_table", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
+    ("pp_backward_table", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
+    ("pp_forward_backward_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, ctypes.c_int64, ctypes.c_int32, _vp,
+                                                 _vp, _vp, _vp, _vp]),
+    ("pp_sample_events", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int32, _vp]),
+    ("pp_profile_get", ctypes.c_int, [_vp, _f64p, ctypes.c_int32]),
+    ("pp_launch_count", ctypes.c_int64, [_vp]),
+    ("pp_model_stream", ctypes.c_uint64, [_vp]),
+]
+
+
+def load_library(path=None):
+    """Load the C-ABI library and bind every declared symbol (raises OSError/AttributeError if absent)."""
+    global _lib
+    if _lib is None or path is not None:
+        lib = ctypes.CDLL(path or LIB_PATH)
+        for name, restype, argtypes in ABI:
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if path is not None:
+            return lib
+        _lib = lib
+    return _lib
+
+
+def device_count():
+    return load_library().pp_device_count()
+
+
+def _ptr(a):
+    """Raw address of a numpy array or a torch tensor."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+def _is_device(a):
+    return not isinstance(a, np.ndarray) and hasattr(a, "is_cuda") and a.is_cuda
+
+
+def pack_events(sequences, dtype=np.float32):
+    """List of 1-D sequences -> (obs back to back, int64 offsets[n+1])."""
+    lens = np.fromiter((len(s) for s in sequences), dtype=np.int64, count=len(sequences))
+    offsets = np.zeros(len(sequences) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    obs = np.empty(int(offsets[-1]), dtype=dtype)
+    for s, o in zip(sequences, offsets[:-1]):
+        obs[o:o + len(s)] = s
+    return obs, offsets
+
+
+class Engine(object):
+    """One baked model resident on one GPU."""
+
+    def __init__(self, baked, kinds, p0, p1, device=0):
+        self._lib = load_library()
+        self._h = _vp()
+        self.m = len(baked.states)
+        self.ne = int(baked.silent_start)
+        self.n_edges = len(baked.in_idx)
+        self._keep = None
+        desc = self._desc(baked, kinds, p0, p1)
+        rc = self._lib.pp_model_create(ctypes.byref(desc), int(device), ctypes.byref(self._h))
+        if rc != PP_OK:
+            self._h = _vp()
+            raise EngineError(rc, self._lib.pp_last_error().decode())
+        self.device = int(device)
+
+    def _desc(self, baked, kinds, p0, p1):
+        c = np.ascontiguousarray
+        a = dict(in_ptr=c(baked.in_ptr, dtype=np.int32), in_src=c(baked.in_idx, dtype=np.int32),
+                 in_logp=c(baked.in_logp, dtype=np.float64), out_ptr=c(baked.out_ptr, dtype=np.int32),
+                 out_dst=c(baked.out_idx, dtype=np.int32), out_logp=c(baked.out_logp, dtype=np.float64),
+                 kind=c(kinds, dtype=np.int32), p0=c(p0, dtype=np.float64), p1=c(p1, dtype=np.float64),
+                 logw=c(baked.state_weights, dtype=np.float64))
+        self._keep = a
+        p = lambda k, t: a[k].ctypes.data_as(t)
+        return PPModelDesc(len(baked.states), int(baked.silent_start), int(baked.start_index), int(baked.end_index),
+                           int(baked.finite), len(a["in_src"]), p("in_ptr", _i32p), p("in_src", _i32p),
+                           p("in_logp", _f64p), p("out_ptr", _i32p), p("out_dst", _i32p), p("out_logp", _f64p),
+                           p("kind", _i32p), p("p0", _f64p), p("p1", _f64p), p("logw", _f64p))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.pp_model_destroy(self._h)
+            self._h = _vp()
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != PP_OK:
+            raise EngineError(rc, self._lib.pp_last_error().decode())
+
+    def update_params(self, baked, kinds, p0, p1):
+        desc = self._desc(baked, kinds, p0, p1)
+        self._check(self._lib.pp_model_update_params(self._h, ctypes.byref(desc)))
+
+    def set_workspace_limit(self, nbytes):
+        self._check(self._lib.pp_model_set_workspace_limit(self._h, int(nbytes)))
+
+    def profile(self):
+        out = (ctypes.c_double * 8)()
+        self._check(self._lib.pp_profile_get(self._h, out, 8))
+        return dict(zip(PROF_SLOTS, list(out)))
+
+    def launch_count(self):
+        return int(self._lib.pp_launch_count(self._h))
+
+    def stream(self):
+        return int(self._lib.pp_model_stream(self._h))
+
+    # ---- batched entry points --------------------------------------------------------------
+    @staticmethod
+    def _obs_dtype(obs):
+        name = str(obs.dtype)
+        if name.endswith("float32"):
+            return PP_F32
+        if name.endswith("float64"):
+            return PP_F64
+        raise TypeError("observations must be float32 or float64, got {}".format(name))
+
+    def forward_batch(self, obs, offsets, out=None):
+        """log P(event) for every event.  numpy in -> numpy out; torch CUDA tensors in -> torch out."""
+        n = len(offsets) - 1
+        if _is_device(obs):
+            import torch
+            out = torch.empty(n, dtype=torch.float64, device=obs.device) if out is None else out
+            mem = PP_MEM_DEVICE
+        else:
+            obs = np.ascontiguousarray(obs)
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+            out = np.empty(n, dtype=np.float64) if out is None else out
+            mem = PP_MEM_HOST
+        self._check(self._lib.pp_forward_batch(self._h, _ptr(obs), self._obs_dtype(obs), _ptr(offsets), n, mem,
+                                               _ptr(out)))
+        return out
+
+    def viterbi_batch(self, obs, offsets, with_paths=True, capacity=None):
+        """(scores f64[n], path_len i64[n], paths u16[total] back to back in event order)."""
+        n = len(offsets) - 1
+        dev = _is_device(obs)
+        if dev:
+            import torch
+            total_obs = int(obs.numel())
+            mk = lambda k, dt: torch.empty(k, dtype=dt, device=obs.device)
+            scores, plen = mk(n, torch.float64), mk(n, torch.int64)
+            mem = PP_MEM_DEVICE
+        else:
+            obs = np.ascontiguousarray(obs)
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+            total_obs = len(obs)
+            scores, plen = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.int64)
+            mem = PP_MEM_HOST
+        cap = int(capacity) if capacity is not None else 3 * total_obs + 8 * n + 64
+        total = ctypes.c_int64(0)
+        while True:
+            if not with_paths:
+                paths = None
+            elif dev:
+                import torch
+                paths = torch.empty(cap, dtype=torch.uint16, device=obs.device)
+            else:
+                paths = np.empty(cap, dtype=np.uint16)
+            rc = self._lib.pp_viterbi_batch(self._h, _ptr(obs), self._obs_dtype(obs), _ptr(offsets), n, mem,
+                                            _ptr(scores), _ptr(plen), _ptr(paths), cap if with_paths else 0,
+                                            ctypes.byref(total))
+            if rc == PP_ERR_CAPACITY:
+                cap = max(int(total.value), 2 * cap)
+                continue
+            self._check(rc)
+            break
+        if with_paths:
+            paths = paths[:total.value]
+        return scores, plen, paths
+
+    def forward_table(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty((len(x) + 1, self.m), dtype=np.float64)
+        self._check(self._lib.pp_forward_table(self._h, _ptr(x), len(x), PP_MEM_HOST, _ptr(out)))
+        return out
+
+    def backward_table(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty((len(x) + 1, self.m), dtype=np.float64)
+        self._check(self._lib.pp_backward_table(self._h, _ptr(x), len(x), PP_MEM_HOST, _ptr(out)))
+        return out
+
+    def forward_backward_batch(self, obs, offsets, posteriors=False, accum=None):
+        """E-step statistics: (logp[n], edge_counts[E] (out-CSR order), moments[ne,3], minmax[ne,2], posteriors|None).
+
+        `accum` = (edge_counts, moments, minmax) to keep accumulating into (host arrays)."""
+        obs = np.ascontiguousarray(obs)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        logp = np.empty(n, dtype=np.float64)
+        if accum is None:
+            edge = np.zeros(self.n_edges, dtype=np.float64)
+            mom = np.zeros((self.ne, 3), dtype=np.float64)
+            mm = np.empty((self.ne, 2), dtype=np.float64)
+            mm[:, 0], mm[:, 1] = np.inf, -np.inf
+        else:
+            edge, mom, mm = accum
+        post = np.empty((len(obs), self.ne), dtype=np.float64) if posteriors else None
+        self._check(self._lib.pp_forward_backward_batch(self._h, _ptr(obs), self._obs_dtype(obs), _ptr(offsets), n,
+                                                        PP_MEM_HOST, _ptr(logp), _ptr(edge), _ptr(mom), _ptr(mm),
+                                                        _ptr(post)))
+        return logp, edge, mom, mm, post
+
+    def sample_events(self, lengths, seed=0, device_out=False):
+        """Length-conditioned synthetic events: (obs float32, offsets int64)."""
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        offsets = np.zeros(len(lengths) + 1, dtype=np.int64)
+        np.cumsum(lengths, out=offsets[1:])
+        if device_out:
+            import torch
+            dev = torch.device("cuda", self.device)
+            d_off = torch.from_numpy(offsets).to(dev)
+            obs = torch.empty(int(offsets[-1]), dtype=torch.float32, device=dev)
+            self._check(self._lib.pp_sample_events(self._h, _ptr(d_off), len(lengths), int(seed), PP_MEM_DEVICE,
+                                                   _ptr(obs)))
+            return obs, d_off
+        obs = np.empty(int(offsets[-1]), dtype=np.float32)
+        self._check(self._lib.pp_sample_events(self._h, _ptr(offsets), len(lengths), int(seed), PP_MEM_HOST, _ptr(obs)))
+        return obs, offsets

@@ -1,0 +1,565 @@
+// pp_api.cu -- C ABI of protpore_b200 (include/protpore_b200.h): model handle, event bucketing,
+// batched Viterbi + traceback and batched forward over the lane-per-event kernels, event sampler.
+// There is no CPU fallback anywhere in this file: without a CUDA device every entry point that
+// computes returns PP_ERR_CUDA.
+#include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "pp_lane_kernels.cuh"
+#include "pp_model.h"
+
+namespace pp {
+
+static thread_local std::string g_err;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+// ---- event bucketing ------------------------------------------------------------------------
+void build_schedule(const int64_t* offsets, int64_t e0, int64_t e1, Schedule* out) {
+    const int64_t n = e1 - e0;
+    int64_t maxlen = 0;
+    for (int64_t e = e0; e < e1; ++e) maxlen = std::max(maxlen, offsets[e + 1] - offsets[e]);
+    std::vector<int32_t> sorted(static_cast<size_t>(n));
+    if (maxlen <= (1 << 22)) {                       // counting sort, longest first, stable
+        std::vector<int64_t> count(static_cast<size_t>(maxlen) + 2, 0);
+        for (int64_t e = e0; e < e1; ++e) ++count[static_cast<size_t>(maxlen - (offsets[e + 1] - offsets[e])) + 1];
+        for (size_t i = 1; i < count.size(); ++i) count[i] += count[i - 1];
+        for (int64_t e = e0; e < e1; ++e)
+            sorted[static_cast<size_t>(count[static_cast<size_t>(maxlen - (offsets[e + 1] - offsets[e]))]++)] =
+                static_cast<int32_t>(e);
+    } else {
+        for (int64_t i = 0; i < n; ++i) sorted[static_cast<size_t>(i)] = static_cast<int32_t>(e0 + i);
+        std::stable_sort(sorted.begin(), sorted.end(), [&](int32_t a, int32_t b) {
+            return offsets[a + 1] - offsets[a] > offsets[b + 1] - offsets[b];
+        });
+    }
+    const int32_t ng = static_cast<int32_t>((n + kLanes - 1) / kLanes);
+    out->n_groups = ng;
+    out->order.assign(static_cast<size_t>(ng) * kLanes, -1);
+    std::copy(sorted.begin(), sorted.end(), out->order.begin());
+    out->group_len.resize(ng);
+    out->group_row.resize(ng);
+    int64_t rows = 0;
+    for (int32_t g = 0; g < ng; ++g) {
+        const int32_t first = sorted[static_cast<size_t>(g) * kLanes];
+        const int32_t len = static_cast<int32_t>(offsets[first + 1] - offsets[first]);
+        out->group_len[g] = len;
+        out->group_row[g] = rows;
+        rows += len + 1;
+    }
+    out->total_rows = rows;
+}
+
+int upload_model(pp_model* M) {
+    cudaStream_t s = M->stream;
+    const Lowered& L = M->low;
+    for (int q = 0; q < 2; ++q) {
+        PP_CUDA(upload(&M->d_items[q], L.items[q], s));
+        PP_CUDA(upload(&M->d_edges_logp[q], L.edges_logp[q], s));
+        PP_CUDA(upload(&M->d_edges_prob[q], L.edges_prob[q], s));
+    }
+    PP_CUDA(upload(&M->d_emis, L.emis, s));
+    PP_CUDA(upload(&M->d_warp_ranges, L.warp_ranges, s));
+    PP_CUDA(upload(&M->d_state_edge_begin, L.state_edge_begin, s));
+    PP_CUDA(upload(&M->d_low_src, L.low_src, s));
+    PP_CUDA(upload(&M->d_in_ptr, M->in_ptr, s));
+    PP_CUDA(upload(&M->d_in_src, M->in_src, s));
+    PP_CUDA(upload(&M->d_in_logp, M->in_logp, s));
+    PP_CUDA(upload(&M->d_out_ptr, M->out_ptr, s));
+    PP_CUDA(upload(&M->d_out_dst, M->out_dst, s));
+    PP_CUDA(upload(&M->d_out_logp, M->out_logp, s));
+    std::vector<double> prob(M->out_logp.size());
+    for (size_t i = 0; i < prob.size(); ++i) prob[i] = std::exp(M->out_logp[i]);
+    PP_CUDA(upload(&M->d_out_prob, prob, s));
+    // alive[s]: an emission is still reachable from s without passing through the end state
+    std::vector<int32_t> alive(M->m, 0);
+    for (int k = 0; k < M->ne; ++k) alive[k] = 1;
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (int k = M->ne; k < M->m; ++k) {
+            if (alive[k] || k == M->end) continue;
+            for (int e = M->out_ptr[k]; e < M->out_ptr[k + 1]; ++e)
+                if (M->out_dst[e] != M->end && alive[M->out_dst[e]]) { alive[k] = 1; changed = true; break; }
+        }
+    }
+    PP_CUDA(upload(&M->d_alive, alive, s));
+    int rc = upload_state_model(M);
+    if (rc != PP_OK) return rc;
+    PP_CUDA(cudaStreamSynchronize(s));
+    return PP_OK;
+}
+
+static int copy_desc(pp_model* M, const pp_model_desc* d) {
+    M->m = d->n_states; M->ne = d->silent_start; M->n_edges = d->n_edges;
+    M->start = d->start_index; M->end = d->end_index; M->finite = d->finite;
+    M->in_ptr.assign(d->in_ptr, d->in_ptr + d->n_states + 1);
+    M->out_ptr.assign(d->out_ptr, d->out_ptr + d->n_states + 1);
+    M->in_src.assign(d->in_src, d->in_src + d->n_edges);
+    M->out_dst.assign(d->out_dst, d->out_dst + d->n_edges);
+    M->in_logp.assign(d->in_logp, d->in_logp + d->n_edges);
+    M->out_logp.assign(d->out_logp, d->out_logp + d->n_edges);
+    M->emit_kind.assign(d->emit_kind, d->emit_kind + d->silent_start);
+    M->emit_p0.assign(d->emit_p0, d->emit_p0 + d->silent_start);
+    M->emit_p1.assign(d->emit_p1, d->emit_p1 + d->silent_start);
+    M->emit_logw.assign(d->emit_logw, d->emit_logw + d->silent_start);
+    return PP_OK;
+}
+
+static LaneSched make_sched(const pp_model* M, bool logspace) {
+    LaneSched S;
+    const Lowered& L = M->low;
+    for (int q = 0; q < 2; ++q) {
+        S.items[q] = M->d_items[q].as<ItemRec>();
+        S.edges[q] = (logspace ? M->d_edges_logp[q] : M->d_edges_prob[q]).as<EdgeRec>();
+    }
+    S.emis = M->d_emis.as<EmisRec>();
+    S.warp_ranges = M->d_warp_ranges.as<int32_t>();
+    S.m = L.m; S.ne = L.ne; S.ns = L.ns; S.n_slots = L.n_slots;
+    S.start_slot_off = static_cast<int32_t>((L.start - L.ne) * kSlotBytes);
+    S.end_slot_off = static_cast<int32_t>((L.end - L.ne) * kSlotBytes);
+    S.end_state = L.end; S.end_item = L.end_item; S.finite = L.finite; S.end_final_only = L.end_final_only ? 1 : 0;
+    return S;
+}
+
+struct Timer {
+    pp_model* M;
+    int slot;
+    Timer(pp_model* m, int s) : M(m), slot(s) { cudaEventRecord(M->ev[0], M->stream); }
+    void stop() {
+        cudaEventRecord(M->ev[1], M->stream);
+        cudaEventSynchronize(M->ev[1]);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, M->ev[0], M->ev[1]);
+        M->prof[slot] += ms;
+    }
+};
+
+struct ClampLen {
+    __host__ __device__ int64_t operator()(const int64_t& x) const { return x > 0 ? x : 0; }
+};
+
+// Validates the CSR-style event description and returns host offsets.
+static int host_offsets(pp_model* M, const int64_t* offsets, int64_t n_events, int32_t mem,
+                        std::vector<int64_t>* store, const int64_t** h_off, const int64_t** d_off) {
+    if (!offsets || n_events < 0) { set_error("null offsets / negative n_events"); return PP_ERR_ARG; }
+    if (n_events > 0x7fffffff - 64) { set_error("more than 2^31 events in one call"); return PP_ERR_ARG; }
+    if (mem == PP_MEM_DEVICE) {
+        store->resize(static_cast<size_t>(n_events) + 1);
+        PP_CUDA(cudaMemcpyAsync(store->data(), offsets, store->size() * sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
+        PP_CUDA(cudaStreamSynchronize(M->stream));
+        *h_off = store->data();
+        *d_off = offsets;
+    } else {
+        *h_off = offsets;
+        PP_CUDA(M->d_offsets.reserve((static_cast<size_t>(n_events) + 1) * sizeof(int64_t)));
+        PP_CUDA(cudaMemcpyAsync(M->d_offsets.p, offsets, (static_cast<size_t>(n_events) + 1) * sizeof(int64_t),
+                                cudaMemcpyHostToDevice, M->stream));
+        *d_off = M->d_offsets.as<int64_t>();
+    }
+    const int64_t* h = *h_off;
+    for (int64_t e = 0; e < n_events; ++e) {
+        const int64_t len = h[e + 1] - h[e];
+        if (len < 1) {                                   // the reference raises on empty sequences (yahmm.pyx:2836)
+            set_error("event %lld has %lld observations; every event needs at least one", (long long)e, (long long)len);
+            return PP_ERR_ARG;
+        }
+        if (len > 0x7ffffff0) { set_error("event %lld too long", (long long)e); return PP_ERR_ARG; }
+    }
+    return PP_OK;
+}
+
+template <typename ObsT>
+static int launch_viterbi(pp_model* M, const LaneBatch<ObsT>& B, const VitOut& O, int n_groups) {
+    const size_t smem = lane_smem_bytes(M->low.n_slots, sizeof(ObsT), 8);
+    PP_CUDA(cudaFuncSetAttribute(k_viterbi_lane<ObsT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_viterbi_lane<ObsT, 8><<<n_groups, 256, smem, M->stream>>>(make_sched(M, true), B, O);
+    PP_CUDA(cudaGetLastError());
+    ++M->launches;
+    return PP_OK;
+}
+
+template <typename ObsT>
+static int launch_forward(pp_model* M, const LaneBatch<ObsT>& B, const FwdOut& O, int n_groups) {
+    const size_t smem = lane_smem_bytes(M->low.n_slots, sizeof(ObsT), 8);
+    PP_CUDA(cudaFuncSetAttribute(k_forward_lane<ObsT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_forward_lane<ObsT, 8><<<n_groups, 256, smem, M->stream>>>(make_sched(M, false), B, O);
+    PP_CUDA(cudaGetLastError());
+    ++M->launches;
+    return PP_OK;
+}
+
+static int check_lane_fit(pp_model* M, int obs_bytes) {
+    const size_t smem = lane_smem_bytes(M->low.n_slots, obs_bytes, 8);
+    if (smem > M->smem_optin) {
+        set_error("model needs %zu bytes of shared memory per CTA for the lane-per-event kernels (limit %zu)", smem,
+                  M->smem_optin);
+        return PP_ERR_UNSUPPORTED;
+    }
+    return PP_OK;
+}
+
+// Splits [0, n_events) into chunks of whole events whose pointer table / staged observations fit.
+static std::vector<int64_t> make_chunks(const int64_t* h_off, int64_t n_events, size_t row_bytes, size_t ws_limit,
+                                        size_t obs_bytes, size_t obs_limit) {
+    std::vector<int64_t> cuts{0};
+    int64_t e0 = 0;
+    while (e0 < n_events) {
+        int64_t e = e0;
+        size_t rows = 0, maxlen = 0, ob = 0;
+        while (e < n_events) {
+            const size_t len = static_cast<size_t>(h_off[e + 1] - h_off[e]);
+            const size_t nrows = rows + len + 1, nmax = std::max(maxlen, len);
+            // sorted groups of 32: sum_g 32*(Lmax_g+1) <= sum_e (n_e+1) + 32*(Lmax+1)
+            const size_t need = row_bytes ? ((nrows + kLanes * (nmax + 1)) / kLanes + 1) * row_bytes : 0;
+            const size_t nob = ob + len * obs_bytes;
+            if (e > e0 && (need > ws_limit || nob > obs_limit)) break;
+            rows = nrows; maxlen = nmax; ob = nob;
+            ++e;
+        }
+        cuts.push_back(e);
+        e0 = e;
+    }
+    return cuts;
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int pp_abi_version(void) { return 1; }
+
+const char* pp_last_error(void) { return g_err.c_str(); }
+
+int pp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pp_model_create(const pp_model_desc* desc, int device, pp_model** out) {
+    if (!desc || !out) { set_error("null argument"); return PP_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: protpore_b200 has no CPU fallback");
+        return PP_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return PP_ERR_ARG; }
+    pp_model* M = new (std::nothrow) pp_model();
+    if (!M) { set_error("out of host memory"); return PP_ERR_NOMEM; }
+    M->device = device;
+    std::string err = lower_model(*desc, M->warps, &M->low);
+    if (!err.empty()) { set_error("cannot lower model: %s", err.c_str()); delete M; return PP_ERR_UNSUPPORTED; }
+    copy_desc(M, desc);
+    int rc = PP_OK;
+    do {
+        if (cudaSetDevice(device) != cudaSuccess) { rc = PP_ERR_CUDA; break; }
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { rc = PP_ERR_CUDA; break; }
+        M->sm_count = prop.multiProcessorCount;
+        M->smem_optin = prop.sharedMemPerBlockOptin;
+        if (cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = PP_ERR_CUDA; break; }
+        if (cudaEventCreate(&M->ev[0]) != cudaSuccess || cudaEventCreate(&M->ev[1]) != cudaSuccess) { rc = PP_ERR_CUDA; break; }
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { rc = PP_ERR_CUDA; break; }
+        M->ws_limit = static_cast<size_t>(fr * 0.70);
+        rc = upload_model(M);
+    } while (0);
+    if (rc != PP_OK) {
+        if (g_err.empty() || rc == PP_ERR_CUDA) set_error("CUDA initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        pp_model_destroy(M);
+        return rc;
+    }
+    *out = M;
+    return PP_OK;
+}
+
+void pp_model_destroy(pp_model* M) {
+    if (!M) return;
+    cudaSetDevice(M->device);
+    if (M->stream) cudaStreamSynchronize(M->stream);
+    DevBuf* bufs[] = {&M->d_items[0], &M->d_items[1], &M->d_edges_logp[0], &M->d_edges_logp[1], &M->d_edges_prob[0],
+                      &M->d_edges_prob[1], &M->d_emis, &M->d_warp_ranges, &M->d_state_edge_begin, &M->d_low_src,
+                      &M->d_in_ptr, &M->d_in_src, &M->d_in_logp, &M->d_out_ptr, &M->d_out_dst, &M->d_out_logp,
+                      &M->d_out_prob, &M->d_alive, &M->d_ws, &M->d_obs, &M->d_offsets, &M->d_order,
+                      &M->d_group_len, &M->d_group_row, &M->d_score, &M->d_end_state, &M->d_end_ord, &M->d_path_len,
+                      &M->d_path_off, &M->d_path, &M->d_scan_tmp, &M->d_logp};
+    for (DevBuf* b : bufs) b->release();
+    release_state_model(M);
+    if (M->ev[0]) cudaEventDestroy(M->ev[0]);
+    if (M->ev[1]) cudaEventDestroy(M->ev[1]);
+    if (M->stream) cudaStreamDestroy(M->stream);
+    delete M;
+}
+
+int pp_model_update_params(pp_model* M, const pp_model_desc* desc) {
+    if (!M || !desc) { set_error("null argument"); return PP_ERR_ARG; }
+    std::string err = refresh_params(*desc, &M->low);
+    if (!err.empty()) { set_error("cannot refresh parameters: %s", err.c_str()); return PP_ERR_ARG; }
+    copy_desc(M, desc);
+    PP_CUDA(cudaSetDevice(M->device));
+    return upload_model(M);
+}
+
+int pp_model_set_workspace_limit(pp_model* M, int64_t bytes) {
+    if (!M || bytes <= 0) { set_error("bad workspace limit"); return PP_ERR_ARG; }
+    M->ws_limit = static_cast<size_t>(bytes);
+    return PP_OK;
+}
+
+int64_t pp_viterbi_workspace_bytes(const pp_model* M, const int64_t* offsets_host, int64_t n_events) {
+    if (!M || !offsets_host || n_events < 0) return -1;
+    Schedule sc;
+    build_schedule(offsets_host, 0, n_events, &sc);
+    return sc.total_rows * static_cast<int64_t>(M->m) * kLanes;
+}
+
+int64_t pp_launch_count(const pp_model* M) { return M ? M->launches : 0; }
+uint64_t pp_model_stream(const pp_model* M) { return M ? reinterpret_cast<uint64_t>(M->stream) : 0; }
+
+int pp_profile_get(const pp_model* M, double* out, int32_t n) {
+    if (!M || !out) { set_error("null argument"); return PP_ERR_ARG; }
+    for (int i = 0; i < n && i < PP_PROF_SLOTS; ++i) out[i] = M->prof[i];
+    return PP_OK;
+}
+
+void* pp_host_alloc(int64_t bytes) {
+    void* p = nullptr;
+    if (bytes <= 0 || cudaHostAlloc(&p, static_cast<size_t>(bytes), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void pp_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---------------------------------------------------------------------------------------------
+int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int64_t* offsets, int64_t n_events,
+                     int32_t mem, double* logp_out, int64_t* path_len_out, uint16_t* path_out, int64_t path_capacity,
+                     int64_t* path_total) {
+    if (!M || !obs || !logp_out || !path_len_out) { set_error("null argument"); return PP_ERR_ARG; }
+    if (obs_dtype != PP_F32 && obs_dtype != PP_F64) { set_error("bad obs_dtype"); return PP_ERR_ARG; }
+    if (mem != PP_MEM_HOST && mem != PP_MEM_DEVICE) { set_error("bad mem"); return PP_ERR_ARG; }
+    PP_CUDA(cudaSetDevice(M->device));
+    std::memset(M->prof, 0, sizeof M->prof);
+    if (path_total) *path_total = 0;
+    if (n_events == 0) return PP_OK;
+    const size_t ob = obs_dtype == PP_F32 ? 4 : 8;
+    int rc = check_lane_fit(M, static_cast<int>(ob));
+    if (rc != PP_OK) return rc;
+
+    std::vector<int64_t> store;
+    const int64_t *h_off, *d_off;
+    rc = host_offsets(M, offsets, n_events, mem, &store, &h_off, &d_off);
+    if (rc != PP_OK) return rc;
+
+    double* d_score;
+    int64_t* d_plen;
+    if (mem == PP_MEM_DEVICE) {
+        d_score = logp_out;
+        d_plen = path_len_out;
+    } else {
+        PP_CUDA(M->d_score.reserve(n_events * sizeof(double)));
+        PP_CUDA(M->d_path_len.reserve(n_events * sizeof(int64_t)));
+        d_score = M->d_score.as<double>();
+        d_plen = M->d_path_len.as<int64_t>();
+    }
+    PP_CUDA(M->d_end_state.reserve(n_events * sizeof(int32_t)));
+    PP_CUDA(M->d_end_ord.reserve(n_events * sizeof(int32_t)));
+    PP_CUDA(M->d_path_off.reserve((n_events + 1) * sizeof(int64_t)));
+
+    const size_t row_bytes = static_cast<size_t>(M->m) * kLanes;
+    const std::vector<int64_t> cuts =
+        make_chunks(h_off, n_events, row_bytes, M->ws_limit, mem == PP_MEM_HOST ? ob : 0, size_t(4) << 30);
+    int64_t base = 0;
+    bool overflow = false;
+    Schedule sc;
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+        const int64_t e0 = cuts[c], e1 = cuts[c + 1];
+        auto t0 = std::chrono::steady_clock::now();
+        build_schedule(h_off, e0, e1, &sc);
+        M->prof[PP_PROF_SCHEDULE_HOST_MS] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        const size_t ws = static_cast<size_t>(sc.total_rows) * row_bytes;
+        if (ws > M->ws_limit) {
+            set_error("one event needs %zu bytes of traceback workspace (limit %zu)", ws, M->ws_limit);
+            return PP_ERR_NOMEM;
+        }
+        if (M->d_ws.reserve(ws) != cudaSuccess) { cudaGetLastError(); set_error("cannot allocate %zu bytes of workspace", ws); return PP_ERR_NOMEM; }
+        PP_CUDA(upload(&M->d_order, sc.order, M->stream));
+        PP_CUDA(upload(&M->d_group_len, sc.group_len, M->stream));
+        PP_CUDA(upload(&M->d_group_row, sc.group_row, M->stream));
+
+        const void* d_obs_base = obs;                    // indexable with the GLOBAL offsets
+        if (mem == PP_MEM_HOST) {
+            const size_t nob = static_cast<size_t>(h_off[e1] - h_off[e0]) * ob;
+            PP_CUDA(M->d_obs.reserve(nob));
+            Timer t(M, PP_PROF_H2D);
+            PP_CUDA(cudaMemcpyAsync(M->d_obs.p, static_cast<const char*>(obs) + h_off[e0] * ob, nob, cudaMemcpyHostToDevice, M->stream));
+            t.stop();
+            d_obs_base = static_cast<const char*>(M->d_obs.p) - h_off[e0] * ob;
+        }
+        VitOut O{d_score, M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), M->d_ws.as<uint8_t>()};
+        {
+            Timer t(M, PP_PROF_VITERBI);
+            if (obs_dtype == PP_F32) {
+                LaneBatch<float> B{static_cast<const float*>(d_obs_base), d_off, M->d_order.as<int32_t>(),
+                                   M->d_group_len.as<int32_t>(), M->d_group_row.as<int64_t>()};
+                rc = launch_viterbi<float>(M, B, O, sc.n_groups);
+            } else {
+                LaneBatch<double> B{static_cast<const double*>(d_obs_base), d_off, M->d_order.as<int32_t>(),
+                                    M->d_group_len.as<int32_t>(), M->d_group_row.as<int64_t>()};
+                rc = launch_viterbi<double>(M, B, O, sc.n_groups);
+            }
+            t.stop();
+            if (rc != PP_OK) return rc;
+        }
+        // traceback pass 1: path lengths
+        TraceArgs T{M->d_ws.as<uint8_t>(), M->d_order.as<int32_t>(), M->d_group_row.as<int64_t>(), d_off, d_score,
+                    M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), M->d_state_edge_begin.as<int32_t>(),
+                    M->d_low_src.as<int32_t>(), M->m, M->ne, M->start, M->low.end_final_only ? 1 : 0, 0};
+        const int nslots = sc.n_groups * kLanes;
+        int64_t chunk_total = 0;
+        {
+            Timer t(M, PP_PROF_TRACEBACK);
+            k_traceback<<<(nslots + 127) / 128, 128, 0, M->stream>>>(T, d_plen, nullptr, nullptr, nslots);
+            PP_CUDA(cudaGetLastError());
+            ++M->launches;
+            // exclusive scan of max(len, 0) over the chunk's events (original order)
+            const int64_t ne = e1 - e0;
+            auto it = thrust::make_transform_iterator(static_cast<const int64_t*>(d_plen + e0), ClampLen());
+            size_t tmp = 0;
+            int64_t* d_poff = M->d_path_off.as<int64_t>() + e0;
+            PP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, d_poff, static_cast<int>(ne), M->stream));
+            PP_CUDA(M->d_scan_tmp.reserve(tmp + 16));
+            PP_CUDA(cub::DeviceScan::ExclusiveSum(M->d_scan_tmp.p, tmp, it, d_poff, static_cast<int>(ne), M->stream));
+            ++M->launches;
+            int64_t last_off = 0, last_len = 0;
+            PP_CUDA(cudaMemcpyAsync(&last_off, d_poff + ne - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
+            PP_CUDA(cudaMemcpyAsync(&last_len, d_plen + e1 - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
+            PP_CUDA(cudaStreamSynchronize(M->stream));
+            chunk_total = last_off + (last_len > 0 ? last_len : 0);
+            if (path_out && !overflow && base + chunk_total <= path_capacity) {
+                uint16_t* dst;
+                if (mem == PP_MEM_DEVICE) dst = path_out + base;
+                else {
+                    PP_CUDA(M->d_path.reserve(static_cast<size_t>(chunk_total) * sizeof(uint16_t) + 16));
+                    dst = M->d_path.as<uint16_t>();
+                }
+                k_traceback<<<(nslots + 127) / 128, 128, 0, M->stream>>>(T, d_plen, d_poff, dst, nslots);
+                PP_CUDA(cudaGetLastError());
+                ++M->launches;
+                t.stop();
+                if (mem == PP_MEM_HOST && chunk_total > 0) {
+                    Timer t2(M, PP_PROF_D2H);
+                    PP_CUDA(cudaMemcpyAsync(path_out + base, dst, static_cast<size_t>(chunk_total) * sizeof(uint16_t),
+                                            cudaMemcpyDeviceToHost, M->stream));
+                    t2.stop();
+                }
+            } else {
+                t.stop();
+                if (path_out) overflow = true;
+            }
+        }
+        base += chunk_total;
+    }
+    if (mem == PP_MEM_HOST) {
+        Timer t(M, PP_PROF_D2H);
+        PP_CUDA(cudaMemcpyAsync(logp_out, d_score, n_events * sizeof(double), cudaMemcpyDeviceToHost, M->stream));
+        PP_CUDA(cudaMemcpyAsync(path_len_out, d_plen, n_events * sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
+        t.stop();
+    }
+    PP_CUDA(cudaStreamSynchronize(M->stream));
+    if (path_total) *path_total = base;
+    if (overflow) {
+        set_error("path buffer too small: %lld elements needed, capacity %lld", (long long)base, (long long)path_capacity);
+        return PP_ERR_CAPACITY;
+    }
+    return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int pp_forward_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int64_t* offsets, int64_t n_events,
+                     int32_t mem, double* logp_out) {
+    if (!M || !obs || !logp_out) { set_error("null argument"); return PP_ERR_ARG; }
+    if (obs_dtype != PP_F32 && obs_dtype != PP_F64) { set_error("bad obs_dtype"); return PP_ERR_ARG; }
+    if (mem != PP_MEM_HOST && mem != PP_MEM_DEVICE) { set_error("bad mem"); return PP_ERR_ARG; }
+    PP_CUDA(cudaSetDevice(M->device));
+    std::memset(M->prof, 0, sizeof M->prof);
+    if (n_events == 0) return PP_OK;
+    const size_t ob = obs_dtype == PP_F32 ? 4 : 8;
+    int rc = check_lane_fit(M, static_cast<int>(ob));
+    if (rc != PP_OK) return rc;
+    std::vector<int64_t> store;
+    const int64_t *h_off, *d_off;
+    rc = host_offsets(M, offsets, n_events, mem, &store, &h_off, &d_off);
+    if (rc != PP_OK) return rc;
+    double* d_logp = logp_out;
+    if (mem == PP_MEM_HOST) {
+        PP_CUDA(M->d_logp.reserve(n_events * sizeof(double)));
+        d_logp = M->d_logp.as<double>();
+    }
+    const std::vector<int64_t> cuts = make_chunks(h_off, n_events, 0, 0, mem == PP_MEM_HOST ? ob : 0, size_t(4) << 30);
+    Schedule sc;
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+        const int64_t e0 = cuts[c], e1 = cuts[c + 1];
+        auto t0 = std::chrono::steady_clock::now();
+        build_schedule(h_off, e0, e1, &sc);
+        M->prof[PP_PROF_SCHEDULE_HOST_MS] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        PP_CUDA(upload(&M->d_order, sc.order, M->stream));
+        PP_CUDA(upload(&M->d_group_len, sc.group_len, M->stream));
+        PP_CUDA(upload(&M->d_group_row, sc.group_row, M->stream));
+        const void* d_obs_base = obs;
+        if (mem == PP_MEM_HOST) {
+            const size_t nob = static_cast<size_t>(h_off[e1] - h_off[e0]) * ob;
+            PP_CUDA(M->d_obs.reserve(nob));
+            Timer t(M, PP_PROF_H2D);
+            PP_CUDA(cudaMemcpyAsync(M->d_obs.p, static_cast<const char*>(obs) + h_off[e0] * ob, nob, cudaMemcpyHostToDevice, M->stream));
+            t.stop();
+            d_obs_base = static_cast<const char*>(M->d_obs.p) - h_off[e0] * ob;
+        }
+        FwdOut O{d_logp};
+        Timer t(M, PP_PROF_FORWARD);
+        if (obs_dtype == PP_F32) {
+            LaneBatch<float> B{static_cast<const float*>(d_obs_base), d_off, M->d_order.as<int32_t>(),
+                               M->d_group_len.as<int32_t>(), M->d_group_row.as<int64_t>()};
+            rc = launch_forward<float>(M, B, O, sc.n_groups);
+        } else {
+            LaneBatch<double> B{static_cast<const double*>(d_obs_base), d_off, M->d_order.as<int32_t>(),
+                                M->d_group_len.as<int32_t>(), M->d_group_row.as<int64_t>()};
+            rc = launch_forward<double>(M, B, O, sc.n_groups);
+        }
+        t.stop();
+        if (rc != PP_OK) return rc;
+        // events the scaled sweep could not resolve (P == 0, inf, NaN) go through the exact kernel
+        rc = rerun_exact_forward(M, d_obs_base, obs_dtype, d_off + e0, h_off + e0, e1 - e0, d_logp + e0);
+        if (rc != PP_OK) return rc;
+    }
+    if (mem == PP_MEM_HOST) {
+        Timer t(M, PP_PROF_D2H);
+        PP_CUDA(cudaMemcpyAsync(logp_out, d_logp, n_events * sizeof(double), cudaMemcpyDeviceToHost, M->stream));
+        t.stop();
+    }
+    PP_CUDA(cudaStreamSynchronize(M->stream));
+    return PP_OK;
+}
+
+}  // extern "C"

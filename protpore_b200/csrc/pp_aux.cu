@@ -1,0 +1,318 @@
+// pp_aux.cu -- C-ABI entry points served by the state-parallel float64 log-space kernels
+// (pp_state_kernels.cuh): full forward / backward tables, batched forward-backward statistics,
+// the exact re-run path of the linear-space forward sweep, and the synthetic-event sampler.
+#include <algorithm>
+#include <cstring>
+
+#include "pp_model.h"
+#include "pp_state_kernels.cuh"
+
+namespace pp {
+
+static StateModel make_state_model(const pp_model* M) {
+    StateModel S;
+    S.in_ptr = M->d_in_ptr.as<int32_t>(); S.in_src = M->d_in_src.as<int32_t>();
+    S.out_ptr = M->d_out_ptr.as<int32_t>(); S.out_dst = M->d_out_dst.as<int32_t>();
+    S.in_logp = M->d_in_logp.as<double>(); S.out_logp = M->d_out_logp.as<double>();
+    S.emis = M->d_emis.as<EmisRec>();
+    S.lev_ptr = M->d_lev_ptr.as<int32_t>(); S.lev_states = M->d_lev_states.as<int32_t>();
+    S.rlev_ptr = M->d_rlev_ptr.as<int32_t>(); S.rlev_states = M->d_rlev_states.as<int32_t>();
+    S.m = M->m; S.ne = M->ne; S.start = M->start; S.end = M->end; S.finite = M->finite;
+    S.n_levels = M->n_levels; S.n_rlevels = M->n_rlevels;
+    return S;
+}
+
+static void group_by_level(const std::vector<int32_t>& level, int ne, int m, int n_levels, std::vector<int32_t>* ptr,
+                           std::vector<int32_t>* states) {
+    ptr->assign(n_levels + 1, 0);
+    for (int l = ne; l < m; ++l) ++(*ptr)[level[l]];
+    for (int i = 1; i <= n_levels; ++i) (*ptr)[i] += (*ptr)[i - 1];
+    // ptr[i] now = number of states with level <= i; shift to starts
+    std::vector<int32_t> fill(n_levels + 1, 0);
+    for (int i = 1; i <= n_levels; ++i) fill[i] = (*ptr)[i - 1];
+    states->assign(m - ne, 0);
+    for (int l = ne; l < m; ++l) (*states)[fill[level[l]]++] = l;
+    // convert to CSR over levels 1..n_levels -> index 0..n_levels-1
+    std::vector<int32_t> csr(n_levels + 1, 0);
+    for (int i = 1; i <= n_levels; ++i) csr[i] = (*ptr)[i];
+    *ptr = csr;
+}
+
+int upload_state_model(pp_model* M) {
+    const int m = M->m, ne = M->ne;
+    // forward levels come from the lowering; reverse levels: 1 + longest chain of silent successors
+    std::vector<int32_t> rlevel(m, 0);
+    int n_r = 0;
+    for (int k = m - 1; k >= ne; --k) {
+        int lev = 1;
+        for (int e = M->out_ptr[k]; e < M->out_ptr[k + 1]; ++e) {
+            const int li = M->out_dst[e];
+            if (li > k) lev = std::max(lev, rlevel[li] + 1);
+        }
+        rlevel[k] = lev;
+        n_r = std::max(n_r, lev);
+    }
+    std::vector<int32_t> lp, ls, rp, rs;
+    group_by_level(M->low.sil_level, ne, m, M->low.n_levels, &lp, &ls);
+    group_by_level(rlevel, ne, m, n_r, &rp, &rs);
+    M->n_levels = M->low.n_levels;
+    M->n_rlevels = n_r;
+    PP_CUDA(upload(&M->d_lev_ptr, lp, M->stream));
+    PP_CUDA(upload(&M->d_lev_states, ls, M->stream));
+    PP_CUDA(upload(&M->d_rlev_ptr, rp, M->stream));
+    PP_CUDA(upload(&M->d_rlev_states, rs, M->stream));
+    PP_CUDA(cudaStreamSynchronize(M->stream));
+    return PP_OK;
+}
+
+void release_state_model(pp_model* M) {
+    DevBuf* bufs[] = {&M->d_lev_ptr, &M->d_lev_states, &M->d_rlev_ptr, &M->d_rlev_states, &M->d_tab,
+                      &M->d_xbuf, &M->d_tab_off, &M->d_list, &M->d_counter, &M->d_stats};
+    for (DevBuf* b : bufs) b->release();
+}
+
+static int state_threads(const pp_model* M) {
+    int t = 32;
+    while (t < M->ne && t < 512) t <<= 1;
+    return t;
+}
+
+template <typename K>
+static int set_dyn_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) PP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PP_OK;
+}
+
+static __global__ void k_collect_flagged(const double* __restrict__ logp, int64_t n, int32_t* __restrict__ list,
+                                  int32_t* __restrict__ counter) {
+    const int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (e >= n) return;
+    const double v = logp[e];
+    if (v != v || v == neg_inf()) list[atomicAdd(counter, 1)] = static_cast<int32_t>(e);
+}
+
+int rerun_exact_forward(pp_model* M, const void* d_obs_base, int32_t obs_dtype, const int64_t* d_off,
+                        const int64_t* h_off, int64_t n_events, double* d_logp) {
+    PP_CUDA(M->d_list.reserve(n_events * sizeof(int32_t)));
+    PP_CUDA(M->d_counter.reserve(16));
+    PP_CUDA(cudaMemsetAsync(M->d_counter.p, 0, 4, M->stream));
+    k_collect_flagged<<<static_cast<unsigned>((n_events + 255) / 256), 256, 0, M->stream>>>(
+        d_logp, n_events, M->d_list.as<int32_t>(), M->d_counter.as<int32_t>());
+    PP_CUDA(cudaGetLastError());
+    ++M->launches;
+    int32_t n_list = 0;
+    PP_CUDA(cudaMemcpyAsync(&n_list, M->d_counter.p, 4, cudaMemcpyDeviceToHost, M->stream));
+    PP_CUDA(cudaStreamSynchronize(M->stream));
+    if (n_list == 0) return PP_OK;
+    int64_t maxlen = 0;
+    for (int64_t e = 0; e < n_events; ++e) maxlen = std::max(maxlen, h_off[e + 1] - h_off[e]);
+    const int grid = static_cast<int>(std::min<int64_t>(n_list, static_cast<int64_t>(M->sm_count) * 4));
+    const int64_t stride = (maxlen + 1) * M->m;
+    const size_t need = static_cast<size_t>(grid) * stride * sizeof(double);
+    if (need > M->ws_limit || M->d_tab.reserve(need) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("exact forward re-run needs %zu bytes of workspace", need);
+        return PP_ERR_NOMEM;
+    }
+    PP_CUDA(M->d_xbuf.reserve(static_cast<size_t>(grid) * maxlen * sizeof(double)));
+    const int threads = state_threads(M);
+    const size_t smem = static_cast<size_t>(M->ne) * sizeof(double) + 16;
+    const StateModel S = make_state_model(M);
+    if (obs_dtype == PP_F32) {
+        if (set_dyn_smem(k_forward_exact<float>, smem) != PP_OK) return PP_ERR_CUDA;
+        k_forward_exact<float><<<grid, threads, smem, M->stream>>>(S, static_cast<const float*>(d_obs_base), d_off,
+            M->d_list.as<int32_t>(), n_list, M->d_tab.as<double>(), stride, M->d_xbuf.as<double>(), maxlen, d_logp);
+    } else {
+        if (set_dyn_smem(k_forward_exact<double>, smem) != PP_OK) return PP_ERR_CUDA;
+        k_forward_exact<double><<<grid, threads, smem, M->stream>>>(S, static_cast<const double*>(d_obs_base), d_off,
+            M->d_list.as<int32_t>(), n_list, M->d_tab.as<double>(), stride, M->d_xbuf.as<double>(), maxlen, d_logp);
+    }
+    PP_CUDA(cudaGetLastError());
+    ++M->launches;
+    return PP_OK;
+}
+
+static int run_table(pp_model* M, const double* obs, int64_t n, int32_t mem, double* table_out, int mode) {
+    if (!M || !obs || !table_out) { set_error("null argument"); return PP_ERR_ARG; }
+    if (n < 1) { set_error("Invalid shape in axis 0: 0."); return PP_ERR_ARG; }      // yahmm.pyx:2836
+    if (mem != PP_MEM_HOST && mem != PP_MEM_DEVICE) { set_error("bad mem"); return PP_ERR_ARG; }
+    PP_CUDA(cudaSetDevice(M->device));
+    const size_t cells = static_cast<size_t>(n + 1) * M->m;
+    const double* d_obs = obs;
+    double* d_tab = table_out;
+    if (mem == PP_MEM_HOST) {
+        PP_CUDA(M->d_obs.reserve(n * sizeof(double)));
+        PP_CUDA(cudaMemcpyAsync(M->d_obs.p, obs, n * sizeof(double), cudaMemcpyHostToDevice, M->stream));
+        d_obs = M->d_obs.as<double>();
+        if (cells * sizeof(double) > M->ws_limit || M->d_tab.reserve(cells * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("table of %zu bytes does not fit the workspace", cells * sizeof(double));
+            return PP_ERR_NOMEM;
+        }
+        d_tab = M->d_tab.as<double>();
+    }
+    const int64_t offs[2] = {0, n};
+    const int64_t toff[1] = {0};
+    PP_CUDA(M->d_offsets.reserve(2 * sizeof(int64_t)));
+    PP_CUDA(M->d_tab_off.reserve(sizeof(int64_t)));
+    PP_CUDA(cudaMemcpyAsync(M->d_offsets.p, offs, sizeof offs, cudaMemcpyHostToDevice, M->stream));
+    PP_CUDA(cudaMemcpyAsync(M->d_tab_off.p, toff, sizeof toff, cudaMemcpyHostToDevice, M->stream));
+    PP_CUDA(M->d_xbuf.reserve(n * sizeof(double)));
+    const size_t smem = static_cast<size_t>(M->ne) * sizeof(double) + 16;
+    if (set_dyn_smem(k_table<double>, smem) != PP_OK) return PP_ERR_CUDA;
+    k_table<double><<<1, state_threads(M), smem, M->stream>>>(make_state_model(M), d_obs, M->d_offsets.as<int64_t>(), 1,
+                                                              d_tab, M->d_tab_off.as<int64_t>(), M->d_xbuf.as<double>(), n, mode);
+    PP_CUDA(cudaGetLastError());
+    ++M->launches;
+    if (mem == PP_MEM_HOST)
+        PP_CUDA(cudaMemcpyAsync(table_out, d_tab, cells * sizeof(double), cudaMemcpyDeviceToHost, M->stream));
+    PP_CUDA(cudaStreamSynchronize(M->stream));
+    return PP_OK;
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" {
+
+int pp_forward_table(pp_model* M, const double* obs, int64_t n, int32_t mem, double* table_out) {
+    return run_table(M, obs, n, mem, table_out, 0);
+}
+
+int pp_backward_table(pp_model* M, const double* obs, int64_t n, int32_t mem, double* table_out) {
+    return run_table(M, obs, n, mem, table_out, 1);
+}
+
+int pp_forward_backward_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int64_t* offsets, int64_t n_events,
+                              int32_t mem, double* logp_out, double* edge_counts, double* emit_moments,
+                              double* emit_minmax, double* posteriors_out) {
+    if (!M || !obs || !offsets || !logp_out || !edge_counts || !emit_moments || !emit_minmax) {
+        set_error("null argument");
+        return PP_ERR_ARG;
+    }
+    if (obs_dtype != PP_F32 && obs_dtype != PP_F64) { set_error("bad obs_dtype"); return PP_ERR_ARG; }
+    if (mem != PP_MEM_HOST && mem != PP_MEM_DEVICE) { set_error("bad mem"); return PP_ERR_ARG; }
+    PP_CUDA(cudaSetDevice(M->device));
+    std::memset(M->prof, 0, sizeof M->prof);
+    if (n_events == 0) return PP_OK;
+    const size_t ob = obs_dtype == PP_F32 ? 4 : 8;
+    const int E = M->n_edges, ne = M->ne;
+    std::vector<int64_t> store;
+    const int64_t* h_off = offsets;
+    const int64_t* d_off = offsets;
+    if (mem == PP_MEM_DEVICE) {
+        store.resize(n_events + 1);
+        PP_CUDA(cudaMemcpy(store.data(), offsets, store.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        h_off = store.data();
+    } else {
+        PP_CUDA(M->d_offsets.reserve((n_events + 1) * sizeof(int64_t)));
+        PP_CUDA(cudaMemcpyAsync(M->d_offsets.p, offsets, (n_events + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, M->stream));
+        d_off = M->d_offsets.as<int64_t>();
+    }
+    int64_t maxlen = 0;
+    for (int64_t e = 0; e < n_events; ++e) {
+        const int64_t len = h_off[e + 1] - h_off[e];
+        if (len < 1) { set_error("event %lld is empty", (long long)e); return PP_ERR_ARG; }
+        maxlen = std::max(maxlen, len);
+    }
+    const int64_t total_obs = h_off[n_events];
+    const void* d_obs = obs;
+    double *d_logp = logp_out, *d_edge = edge_counts, *d_mom = emit_moments, *d_mm = emit_minmax, *d_post = posteriors_out;
+    const size_t n_stats = static_cast<size_t>(E) + 5 * static_cast<size_t>(ne);
+    if (mem == PP_MEM_HOST) {
+        PP_CUDA(M->d_obs.reserve(total_obs * ob));
+        PP_CUDA(cudaMemcpyAsync(M->d_obs.p, obs, total_obs * ob, cudaMemcpyHostToDevice, M->stream));
+        d_obs = M->d_obs.p;
+        PP_CUDA(M->d_logp.reserve(n_events * sizeof(double)));
+        d_logp = M->d_logp.as<double>();
+        PP_CUDA(M->d_stats.reserve(n_stats * sizeof(double)));
+        d_edge = M->d_stats.as<double>();
+        d_mom = d_edge + E;
+        d_mm = d_mom + 3 * ne;
+        PP_CUDA(cudaMemcpyAsync(d_edge, edge_counts, E * sizeof(double), cudaMemcpyHostToDevice, M->stream));
+        PP_CUDA(cudaMemcpyAsync(d_mom, emit_moments, 3 * ne * sizeof(double), cudaMemcpyHostToDevice, M->stream));
+        PP_CUDA(cudaMemcpyAsync(d_mm, emit_minmax, 2 * ne * sizeof(double), cudaMemcpyHostToDevice, M->stream));
+        if (posteriors_out) {
+            const size_t pb = static_cast<size_t>(total_obs) * ne * sizeof(double);
+            if (pb > M->ws_limit || M->d_ws.reserve(pb) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("posterior matrix of %zu bytes does not fit the workspace", pb);
+                return PP_ERR_NOMEM;
+            }
+            d_post = M->d_ws.as<double>();
+        }
+    }
+    const int grid = static_cast<int>(std::min<int64_t>(n_events, static_cast<int64_t>(M->sm_count) * 4));
+    const int64_t stride = 2 * (maxlen + 1) * M->m;
+    const size_t need = static_cast<size_t>(grid) * stride * sizeof(double);
+    if (need > M->ws_limit || M->d_tab.reserve(need) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("forward-backward needs %zu bytes of table workspace", need);
+        return PP_ERR_NOMEM;
+    }
+    PP_CUDA(M->d_xbuf.reserve(static_cast<size_t>(grid) * maxlen * sizeof(double)));
+    const int threads = std::max(128, state_threads(M));
+    const size_t smem = static_cast<size_t>(ne) * sizeof(double) + 16;
+    const StateModel S = make_state_model(M);
+    cudaEventRecord(M->ev[0], M->stream);
+    if (obs_dtype == PP_F32) {
+        if (set_dyn_smem(k_fb_accumulate<float>, smem) != PP_OK) return PP_ERR_CUDA;
+        k_fb_accumulate<float><<<grid, threads, smem, M->stream>>>(S, static_cast<const float*>(d_obs), d_off, (int)n_events,
+            M->d_tab.as<double>(), stride, M->d_xbuf.as<double>(), maxlen, d_logp, d_edge, d_mom, d_mm, d_post);
+    } else {
+        if (set_dyn_smem(k_fb_accumulate<double>, smem) != PP_OK) return PP_ERR_CUDA;
+        k_fb_accumulate<double><<<grid, threads, smem, M->stream>>>(S, static_cast<const double*>(d_obs), d_off, (int)n_events,
+            M->d_tab.as<double>(), stride, M->d_xbuf.as<double>(), maxlen, d_logp, d_edge, d_mom, d_mm, d_post);
+    }
+    PP_CUDA(cudaGetLastError());
+    ++M->launches;
+    cudaEventRecord(M->ev[1], M->stream);
+    if (mem == PP_MEM_HOST) {
+        PP_CUDA(cudaMemcpyAsync(logp_out, d_logp, n_events * sizeof(double), cudaMemcpyDeviceToHost, M->stream));
+        PP_CUDA(cudaMemcpyAsync(edge_counts, d_edge, E * sizeof(double), cudaMemcpyDeviceToHost, M->stream));
+        PP_CUDA(cudaMemcpyAsync(emit_moments, d_mom, 3 * ne * sizeof(double), cudaMemcpyDeviceToHost, M->stream));
+        PP_CUDA(cudaMemcpyAsync(emit_minmax, d_mm, 2 * ne * sizeof(double), cudaMemcpyDeviceToHost, M->stream));
+        if (posteriors_out)
+            PP_CUDA(cudaMemcpyAsync(posteriors_out, d_post, static_cast<size_t>(total_obs) * ne * sizeof(double),
+                                    cudaMemcpyDeviceToHost, M->stream));
+    }
+    PP_CUDA(cudaStreamSynchronize(M->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, M->ev[0], M->ev[1]);
+    M->prof[PP_PROF_BACKWARD] = ms;
+    return PP_OK;
+}
+
+int pp_sample_events(pp_model* M, const int64_t* offsets, int64_t n_events, uint64_t seed, int32_t mem, float* obs_out) {
+    if (!M || !offsets || !obs_out) { set_error("null argument"); return PP_ERR_ARG; }
+    if (mem != PP_MEM_HOST && mem != PP_MEM_DEVICE) { set_error("bad mem"); return PP_ERR_ARG; }
+    PP_CUDA(cudaSetDevice(M->device));
+    if (n_events == 0) return PP_OK;
+    const int64_t* d_off = offsets;
+    float* d_out = obs_out;
+    int64_t total = 0;
+    if (mem == PP_MEM_HOST) {
+        total = offsets[n_events];
+        PP_CUDA(M->d_offsets.reserve((n_events + 1) * sizeof(int64_t)));
+        PP_CUDA(cudaMemcpyAsync(M->d_offsets.p, offsets, (n_events + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, M->stream));
+        d_off = M->d_offsets.as<int64_t>();
+        PP_CUDA(M->d_obs.reserve(total * sizeof(float)));
+        d_out = M->d_obs.as<float>();
+    }
+    cudaEventRecord(M->ev[0], M->stream);
+    k_sample<<<static_cast<unsigned>((n_events + 127) / 128), 128, 0, M->stream>>>(
+        make_state_model(M), M->d_out_prob.as<double>(), M->d_alive.as<int32_t>(), d_off, n_events, seed, d_out);
+    PP_CUDA(cudaGetLastError());
+    ++M->launches;
+    cudaEventRecord(M->ev[1], M->stream);
+    if (mem == PP_MEM_HOST)
+        PP_CUDA(cudaMemcpyAsync(obs_out, d_out, total * sizeof(float), cudaMemcpyDeviceToHost, M->stream));
+    PP_CUDA(cudaStreamSynchronize(M->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, M->ev[0], M->ev[1]);
+    M->prof[PP_PROF_SAMPLE] = ms;
+    return PP_OK;
+}
+
+}  // extern "C"

@@ -1,20 +1,26 @@
 // pp_lowering.h -- host-side lowering of a baked yahmm model into the column-kernel schedule.
 //
-// The baked CSR (Model.bake, yahmm.pyx:2280-2655) is turned into a static per-warp program:
-//   * every state becomes one ITEM (destination slot + a run of in-edge records);
-//   * emitting items are dealt to the W warps of a CTA by greedy longest-processing-time on their
-//     in-degree; all lanes of a warp work on the SAME item for 32 (or 64) different events, so the
-//     edge records are warp-uniform and column accesses are stride-1 (DESIGN.md "layout");
+// The baked CSR (Model.bake, yahmm.pyx:2280-2655) is turned into a static per-warp program for the
+// "lane-per-event" column kernels: a CTA of W warps sweeps 32 events, lane j of EVERY
+// warp works on event j, and the warps split the STATES of a column between them.
+//   * every state becomes one ITEM: a destination slot plus a run of in-edge records;
+//   * the DP column of the 32 events lives in shared memory as slots of 32 doubles (one per lane):
+//     a SILENT region [ns] and two EMITTING regions [ne] (row parity 0 / 1).  Row r is computed into
+//     E[r & 1] from E[(r - 1) & 1]; silent states are single-buffered because emitting states read
+//     silent values of the previous row before the silent phase of the new row overwrites them;
+//   * emitting items are dealt to warps by greedy longest-processing-time on their in-degree;
 //   * silent states are split into the connected components of the silent->silent sub-DAG (the
-//     delete/skip chain, the back-slip chain, the isolated drop-off states ...).  A component goes
-//     to ONE warp, in topological (= baked index) order, so the serial chain inside a column needs
-//     no barrier and the value just produced is forwarded in registers;
-//   * per item the in-edges are re-ordered exactly as the reference visits them: for an emitting
+//     skip chain, the back-slip chain, the isolated drop-off states ...).  A component goes to ONE
+//     warp in topological (= baked index) order, so the serial chain inside a column is plain
+//     program order inside one thread: no scan, no barrier, and the reference's floating-point
+//     association is kept exactly;
+//   * per item the in-edges are ordered exactly as the reference visits them: for an emitting
 //     state all in-edges in CSR order (3545-3562); for a silent state first the emitting sources
 //     (pass 1, 3564-3584) then the silent sources with index < l (pass 2, 3586-3605; edges from
-//     silent sources >= l are ignored by the reference, 3593).  The traceback pointer stored per
-//     cell is the ordinal in that list, so ties break identically;
-//   * a finite model's end state with no out-edges is evaluated once, at each event's last row.
+//     silent sources >= l are ignored by the reference, 2861/2918/3530/3593).  The traceback
+//     pointer stored per cell is the ordinal in that list, so ties break identically;
+//   * a finite model's end state without out-edges is evaluated once, at each event's last row.
+// Records are emitted once per row parity so that a kernel only swaps two base pointers per row.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -24,33 +30,33 @@
 
 namespace pp {
 
+constexpr int kLanes = 32;                       // events per CTA (one per lane)
+constexpr uint32_t kSlotBytes = kLanes * 8;      // one column slot: 32 doubles
+
 // ---- records shared by host and device ---------------------------------------------------
-struct __attribute__((aligned(16))) EdgeRecV {   // Viterbi (fp64 max-plus)
-    double logp;
-    uint16_t slot[2];                            // source column slot for parity 0 / 1
-    uint32_t pad;
+struct __attribute__((aligned(16))) EdgeRec {
+    double val;                                  // log p (Viterbi) or p (forward / backward)
+    uint32_t off;                                // byte offset of the source slot in the column
+    uint32_t src;                                // baked index of the source state
 };
-struct __attribute__((aligned(8))) EdgeRecF {    // forward / backward (fp32 linear, scaled)
-    float w;                                     // exp(logp)
-    uint16_t slot[2];
-};
-struct __attribute__((aligned(16))) ItemRec {
+struct __attribute__((aligned(32))) ItemRec {
     int32_t edge_begin;                          // first lowered edge record
-    int16_t n_edges;
-    int16_t emis;                                // emitting state index, -1 for silent items
-    uint16_t dst_slot[2];                        // destination column slot for parity 0 / 1
-    int32_t state;                               // baked state index (traceback pointer row slot)
-    int32_t flags;                               // bit0: this is the start state
+    int32_t n_edges;
+    int32_t emis;                                // emitting state index, -1 for silent items
+    uint32_t dst_off;                            // byte offset of the destination slot
+    int32_t state;                               // baked state index
+    int32_t flags;                               // ITEM_START
+    int32_t pad[2];
 };
-enum : int32_t { EMIS_NORMAL = 0, EMIS_POINT = 1, EMIS_UNIFORM = 2, EMIS_HAS_LOGW = 8 };
-struct __attribute__((aligned(16))) Emis64 {     // exact float64 emission (Viterbi, tables)
-    double a, b, c, logw;                        // Normal: mu, 2*sigma^2, log(1/(sigma*SQRT_2_PI));
-    int32_t kind;                                // Point: mu; Uniform: lo, hi, log(1/(hi-lo))
-    int32_t pad[3];
-};
-struct __attribute__((aligned(16))) EmisF {      // fp32 log2-domain emission (forward / backward)
-    float mu_hi, mu_lo, k2, c2;                  // e2(x) = c2 - ((x-mu_hi)-mu_lo)^2 * k2
-    float lo, hi;                                // Uniform support rounded inwards to float32
+enum : int32_t { ITEM_START = 1 };
+enum : int32_t { EMIS_NORMAL = 0, EMIS_POINT = 1, EMIS_UNIFORM = 2 };
+struct __attribute__((aligned(64))) EmisRec {
+    // Normal : a0 = mu, a1 = 2*sigma^2, a2 = RN(1/a1), a3 = log(1/(sigma*SQRT_2_PI))
+    // Point  : a0 = mu                                  (sigma == 0, yahmm.pyx:383-387)
+    // Uniform: a0 = lo, a1 = hi, a3 = log(1/(hi-lo))    (yahmm.pyx:257-262)
+    double a0, a1, a2, a3;
+    double logw;                                 // log(state.weight) (yahmm.pyx:2515-2517)
+    double c2, k2;                               // log2-domain constants of the linear-space sweeps
     int32_t kind;
     int32_t pad;
 };
@@ -60,18 +66,19 @@ struct Lowered {
     bool end_final_only = false;                 // end evaluated only at each event's last row
     int32_t warps = 8;                           // warps per CTA the schedule was built for
     int32_t n_slots = 0;                         // ns + 2*ne column slots
-    int32_t max_item_edges = 0;
-    std::vector<ItemRec> items;                  // warp-major: [emit items w0 | silent items w0 | emit w1 ...]
-    std::vector<int32_t> warp_emit_begin, warp_emit_end, warp_sil_begin, warp_sil_end;
-    std::vector<EdgeRecV> edges_v;
-    std::vector<EdgeRecF> edges_f;
-    std::vector<int32_t> low_src;                // source state of each lowered edge
+    int32_t max_item_edges = 0;                  // over per-row items (end excluded if final-only)
+    int32_t end_item = -1;                       // index of end's ItemRec (always present)
+    std::vector<ItemRec> items[2];               // per row parity; warp-major, then end
+    std::vector<int32_t> warp_ranges;            // [warps][4]: emit_begin, emit_end, sil_begin, sil_end
+    std::vector<EdgeRec> edges_logp[2];          // per row parity, val = log p
+    std::vector<EdgeRec> edges_prob[2];          // per row parity, val = p
     std::vector<int32_t> low_csr;                // index of each lowered edge in the IN-edge CSR
     std::vector<int32_t> state_edge_begin;       // per state: first lowered edge (traceback lookup)
     std::vector<int32_t> state_n_edges;
-    int32_t end_edge_begin = 0, end_n_edges = 0; // lowered edge run of the end state
-    std::vector<Emis64> emis64;
-    std::vector<EmisF> emisf;
+    std::vector<int32_t> low_src;                // source state of each lowered edge
+    std::vector<int32_t> sil_level;              // per state: 0 for emitting, else 1 + longest silent-pred chain
+    int32_t n_levels = 0;
+    std::vector<EmisRec> emis;
 };
 
 // Returns "" on success, otherwise why the model cannot be lowered.

@@ -1,0 +1,76 @@
+// pp_model.h -- the opaque model handle behind the C ABI (host side).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "pp_common.h"
+#include "pp_lowering.h"
+
+// Kernel-time slots reported by pp_profile_get (milliseconds of the last batched call, summed over
+// its chunks, measured with CUDA events on the model's stream).
+enum pp_prof_slot {
+    PP_PROF_VITERBI = 0,
+    PP_PROF_TRACEBACK = 1,
+    PP_PROF_FORWARD = 2,
+    PP_PROF_BACKWARD = 3,
+    PP_PROF_SAMPLE = 4,
+    PP_PROF_H2D = 5,
+    PP_PROF_D2H = 6,
+    PP_PROF_SCHEDULE_HOST_MS = 7,   // host wall time spent bucketing events
+    PP_PROF_SLOTS = 8
+};
+
+struct pp_model {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    int warps = 8;
+
+    // host copy of the baked description
+    int32_t m = 0, ne = 0, n_edges = 0, start = 0, end = 0, finite = 0;
+    std::vector<int32_t> in_ptr, in_src, out_ptr, out_dst, emit_kind;
+    std::vector<double> in_logp, out_logp, emit_p0, emit_p1, emit_logw;
+
+    pp::Lowered low;
+
+    // device copy of the schedule
+    pp::DevBuf d_items[2], d_edges_logp[2], d_edges_prob[2], d_emis, d_warp_ranges;
+    pp::DevBuf d_state_edge_begin, d_low_src;
+    // device copy of the baked CSR (state-parallel kernels, sampler)
+    pp::DevBuf d_in_ptr, d_in_src, d_in_logp, d_out_ptr, d_out_dst, d_out_logp, d_out_prob, d_alive;
+    pp::DevBuf d_lev_ptr, d_lev_states, d_rlev_ptr, d_rlev_states;
+    int32_t n_levels = 0, n_rlevels = 0;
+
+    // per-call scratch
+    pp::DevBuf d_ws;          // traceback pointer table / DP tables
+    pp::DevBuf d_obs, d_offsets, d_order, d_group_len, d_group_row;
+    pp::DevBuf d_score, d_end_state, d_end_ord, d_path_len, d_path_off, d_path, d_scan_tmp, d_logp;
+    pp::DevBuf d_tab, d_xbuf, d_tab_off, d_list, d_counter, d_stats;
+    size_t ws_limit = 0;
+
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    double prof[PP_PROF_SLOTS] = {0};
+    int64_t launches = 0;
+};
+
+namespace pp {
+
+// Length-bucketed schedule of events [e0, e1): 32 events per group, longest first.
+struct Schedule {
+    std::vector<int32_t> order;       // [n_groups * 32], -1 padded
+    std::vector<int32_t> group_len;   // [n_groups]
+    std::vector<int64_t> group_row;   // [n_groups] first pointer-table row (group_len + 1 rows each)
+    int64_t total_rows = 0;
+    int32_t n_groups = 0;
+};
+void build_schedule(const int64_t* offsets, int64_t e0, int64_t e1, Schedule* out);
+
+int upload_model(pp_model* M);
+int upload_state_model(pp_model* M);          // pp_aux.cu: level structure for the state-parallel kernels
+void release_state_model(pp_model* M);
+// Re-runs, with the exact log-space kernel, every event whose entry in d_logp is -inf or NaN.
+int rerun_exact_forward(pp_model* M, const void* d_obs_base, int32_t obs_dtype, const int64_t* d_off,
+                        const int64_t* h_off, int64_t n_events, double* d_logp);
+
+}  // namespace pp

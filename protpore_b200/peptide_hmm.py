@@ -6,7 +6,7 @@ fast5 reading / segmentation / plotting around it (299-494) is out of scope (SUR
 
 Two additions:
   * `yahmm_module=` lets the same builder construct the model on any module exposing the yahmm API
-    (the product's `protpore_b200.yahmm`, or the compiled reference in oracle/_ref for the CPU
+    (the product's `protpore_b200.yahmm`, or the compiled reference module used for the CPU
     baseline), which is how tests prove the two bakes are identical;
   * `py2_division=` makes the Python-2 integer division at peptide_hmm_v0.0.1.py:194-195 explicit:
     the reference README mandates Python 2.7, where `1/4` and `1/2` are 0, so every insert state is

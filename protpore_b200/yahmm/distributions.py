@@ -127,12 +127,22 @@ class UniformDistribution(Distribution):
         items = numpy.asarray(items)
         self.summaries.append([items.min(), items.max()])
 
+    def summarize_range(self, w_sum, lo, hi):
+        """Batched-path entry (new): one summary from the allreduced statistics of the GPU E-step --
+        total weight of the state and the min / max over every sequence that gave it non-zero weight."""
+        if w_sum == 0 or not (lo <= hi):
+            return
+        self.summaries.append([lo, hi])
+
     def from_summaries(self, inertia=0.0):
         if self.frozen:
             return
+        if len(self.summaries) == 0:
+            # the reference indexes s[:, 0] unguarded here (338-348) and raises IndexError when a
+            # Uniform state got no weight from any sequence; we keep the parameters instead.
+            return
         s = numpy.asarray(self.summaries)
         lo, hi = self.parameters
-        # NB the reference indexes s[:, 0] unguarded (338-348): with no summaries it raises IndexError.
         self.parameters = [lo * inertia + s[:, 0].min() * (1 - inertia),
                            hi * inertia + s[:, 1].max() * (1 - inertia)]
         self.summaries = []

@@ -1,0 +1,58 @@
+"""`Model.bake` parity: our insertion-ordered restatement of yahmm.pyx:2280-2655 against the baked
+structure the compiled reference produced for the same construction sequence (golden fixtures)."""
+import numpy as np
+import pytest
+
+import util
+
+
+@pytest.mark.parametrize("name", util.MODEL_NAMES)
+def test_bake_matches_reference(name):
+    g = util.load_golden(name)
+    model = util.build_model(name)
+    m, ss, si, ei, ne, finite = [int(v) for v in g["meta"]]
+    assert len(model.states) == m and model.silent_start == ss
+    assert model.start_index == si and model.end_index == ei
+    assert model.edge_count() == ne
+    assert (0 if model.is_infinite() else 1) == finite
+    assert [s.name for s in model.states] == list(g["state_names"])
+    assert np.array_equal(model.dense_transition_matrix(), g["dense"])      # bit-identical log weights
+
+
+def test_pro_001_shape():
+    model = util.build_model("pro_001_py2")
+    b = model._baked
+    assert (len(model.states), model.silent_start, model.edge_count()) == (257, 128, 765)
+    assert (model.start_index, model.end_index) == (212, 256)
+    indeg = np.diff(b.in_ptr)
+    assert indeg[model.end_index] == 87 and indeg[:128].max() == 7
+    # the Python-2 division trap: every insert state is a point mass (peptide_hmm_v0.0.1.py:194-195)
+    ins = [s for s in model.states[:128] if s.name.startswith("I_INS")]
+    assert len(ins) == 42 and all(s.distribution.parameters[1] == 0.0 for s in ins)
+    ins3 = [s for s in util.build_model("pro_001_py3").states[:128] if s.name.startswith("I_INS")]
+    assert all(s.distribution.parameters[1] > 0.0 for s in ins3)
+
+
+def test_in_edge_order_is_source_insertion_order():
+    model = util.build_model("pro_001_py2")
+    b = model._baked
+    k = [s.name for s in model.states].index("M_5_5")
+    names = [model.states[i].name for i in b.in_idx[b.in_ptr[k]:b.in_ptr[k + 1]]]
+    assert names == ["M_4_4", "S_SKIP_4_4", "M_5_5", "S_DROPOFF_5_5", "I_BLIP_5_5", "I_INS_5_5", "B_BACK_SHORT_6_6"]
+
+
+def test_model_text_roundtrip(tmp_path):
+    import protpore_b200.yahmm as y
+    import io
+    from contextlib import redirect_stdout
+    model = util.build_model("toy")
+    buf = io.StringIO()
+    with redirect_stdout(io.StringIO()):
+        model.write(buf)
+    buf.seek(0)
+    again = y.Model.read(buf)
+    assert sorted(s.name for s in again.states) == sorted(s.name for s in model.states)
+    a = {(model.states[i].name, model.states[j].name): v for (i, j), v in np.ndenumerate(model.dense_transition_matrix())}
+    b = {(again.states[i].name, again.states[j].name): v for (i, j), v in np.ndenumerate(again.dense_transition_matrix())}
+    for key, v in a.items():
+        assert b[key] == pytest.approx(v, abs=1e-12) or (np.isinf(v) and np.isinf(b[key]))

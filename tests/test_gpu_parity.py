@@ -1,0 +1,203 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the golden vectors of the
+compiled reference and against the CPU oracle on fresh seeded events.
+
+Bars (BASELINE north star): Viterbi state paths identical (an exact tie in the reference's own
+arithmetic is the only documented exception -- the oracle reports it as margin 0); Viterbi scores
+BIT-identical (same float64 operations in the same order); forward log-probabilities within
+1e-3 nats absolute or 1e-6 relative (util.close) -- in practice ~1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+import util
+from protpore_b200 import _engine, events
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def models():
+    return {n: util.build_model(n) for n in util.MODEL_NAMES}
+
+
+@pytest.mark.parametrize("name", util.MODEL_NAMES)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_viterbi_batch_matches_golden(models, name, dtype):
+    g = util.load_golden(name)
+    model = models[name]
+    evs = [np.asarray(e, dtype=dtype) for e in util.golden_events(g)]
+    res = model.viterbi_batch(evs, dtype=dtype, states=False)
+    for (score, path), gs, gp in zip(res, g["vscore"], util.golden_paths(g)):
+        assert score == gs                                  # bit-identical
+        if gp is None:
+            assert path is None
+        else:
+            assert np.array_equal(path, gp)
+
+
+@pytest.mark.parametrize("name", util.MODEL_NAMES)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_forward_batch_matches_golden(models, name, dtype):
+    g = util.load_golden(name)
+    model = models[name]
+    evs = [np.asarray(e, dtype=dtype) for e in util.golden_events(g)]
+    lp = model.log_probability_batch(evs, dtype=dtype)
+    assert util.close(lp, g["logp"]).all()
+    fin = np.isfinite(g["logp"])
+    assert np.max(np.abs(lp[fin] - g["logp"][fin]) / np.maximum(1.0, np.abs(g["logp"][fin]))) < 1e-6
+
+
+@pytest.mark.parametrize("name", util.MODEL_NAMES)
+def test_single_sequence_api_matches_golden(models, name):
+    """Model.viterbi / log_probability / forward / backward / forward_backward, reference signatures."""
+    g = util.load_golden(name)
+    model = models[name]
+    evs = util.golden_events(g)
+    gp = util.golden_paths(g)
+    for i in list(range(0, len(evs), max(1, len(evs) // 12)))[:12]:
+        score, path = model.viterbi(evs[i])
+        assert score == g["vscore"][i]
+        if gp[i] is None:
+            assert path is None
+        else:
+            assert [k for k, _ in path] == list(gp[i])
+            assert all(s is model.states[k] for k, s in path)
+        lp = model.log_probability(evs[i])
+        assert util.close([lp], [g["logp"][i]], abs_tol=1e-9, rel_tol=1e-12).all()
+    for j, i in enumerate(g["table_events"]):
+        f, b = model.forward(evs[i]), model.backward(evs[i])
+        gf, gb = g["fwd_%d" % j], g["bwd_%d" % j]
+        assert f.shape == gf.shape and b.shape == gb.shape
+        assert util.close(f, gf, abs_tol=1e-9, rel_tol=1e-12).all()
+        assert util.close(b, gb, abs_tol=1e-9, rel_tol=1e-12).all()
+        et, ew = model.forward_backward(evs[i])
+        if "fb_et_%d" % j in g:
+            assert np.allclose(et, g["fb_et_%d" % j], rtol=1e-9, atol=1e-12)
+            assert util.close(ew, g["fb_ew_%d" % j], abs_tol=1e-8, rel_tol=1e-10).all()
+        else:
+            assert et is None and ew is None
+
+
+@pytest.mark.parametrize("name", ["pro_001_py2", "toy", "synth_12"])
+def test_baum_welch_iteration_matches_golden(name):
+    g = util.load_golden(name)
+    model = util.build_model(name)          # fresh: training mutates
+    evs = util.golden_events(g)
+    seqs = [evs[i] for i in g["bw_events"]]
+    imp = model.train(seqs, max_iterations=1, verbose=False)
+    assert imp == pytest.approx(float(g["bw_improvement"][0]), rel=1e-7, abs=1e-7)
+    dense = model.dense_transition_matrix()
+    fin = np.isfinite(g["bw_dense"])
+    assert np.array_equal(np.isfinite(dense), fin)
+    assert np.allclose(dense[fin], g["bw_dense"][fin], rtol=1e-8, atol=1e-9)
+    params = np.array([[float(p) for p in s.distribution.parameters[:2]] for s in model.states[:model.silent_start]])
+    assert np.allclose(params, g["bw_params"], rtol=1e-7, atol=1e-9)
+
+
+def test_fresh_events_against_oracle(models):
+    """2,000 length-conditioned events from the CUDA sampler: Viterbi bit-exact, forward within tolerance."""
+    model = models["pro_001_py2"]
+    orc = util.oracle_for(model)
+    lens = events.uniform_lengths(2000, 50, 500, seed=42)
+    obs, offsets = model.engine().sample_events(lens, seed=1234)
+    assert obs.dtype == np.float32 and np.isfinite(obs).all()
+    scores, plen, paths = model.engine().viterbi_batch(obs, offsets)
+    lp = model.engine().forward_batch(obs, offsets)
+    poff = np.concatenate([[0], np.cumsum(np.maximum(plen, 0))])
+    check = np.random.RandomState(0).choice(len(lens), size=300, replace=False)
+    worst = 0.0
+    for e in check:
+        x = obs[offsets[e]:offsets[e + 1]].astype(np.float64)
+        s, p, margin = orc.viterbi(x, with_margin=True)
+        assert scores[e] == s
+        got = paths[poff[e]:poff[e + 1]]
+        assert np.array_equal(got, p) or margin == 0.0     # documented exception: exact tie in the reference
+        ref_lp = orc.log_probability(x)
+        assert util.close([lp[e]], [ref_lp]).all()
+        worst = max(worst, abs(lp[e] - ref_lp) / max(1.0, abs(ref_lp)))
+    assert worst < 1e-7
+    assert (scores <= lp + 1e-6).all()                     # best path <= sum over paths
+
+
+def test_batch_composition_invariance(models):
+    """Per-event results do not depend on batch order, batch size, chunking or observation dtype."""
+    model = models["pro_001_py2"]
+    lens = events.log_uniform_lengths(3000, 1, 900, seed=5)
+    obs, offsets = model.engine().sample_events(lens, seed=77)
+    evs = [obs[offsets[i]:offsets[i + 1]] for i in range(len(lens))]
+    s0, l0, p0 = model.engine().viterbi_batch(obs, offsets)
+    f0 = model.engine().forward_batch(obs, offsets)
+    perm = np.random.RandomState(3).permutation(len(evs))
+    o2, off2 = _engine.pack_events([evs[i] for i in perm], np.float32)
+    model.engine().set_workspace_limit(64 << 20)           # forces several chunks
+    try:
+        s2, l2, p2 = model.engine().viterbi_batch(o2, off2)
+        f2 = model.engine().forward_batch(o2, off2)
+    finally:
+        model.engine().set_workspace_limit(32 << 30)
+    assert np.array_equal(s2, s0[perm]) and np.array_equal(l2, l0[perm]) and np.array_equal(f2, f0[perm])
+    a = np.concatenate([[0], np.cumsum(l0)])
+    b = np.concatenate([[0], np.cumsum(l2)])
+    for j in range(0, len(perm), 37):
+        assert np.array_equal(p2[b[j]:b[j + 1]], p0[a[perm[j]]:a[perm[j] + 1]])
+    o3, off3 = _engine.pack_events(evs[:500], np.float64)
+    s3, l3, _ = model.engine().viterbi_batch(o3, off3)
+    assert np.array_equal(s3, s0[:500]) and np.array_equal(l3, l0[:500])
+
+
+def test_path_is_a_valid_walk_with_the_reported_score(models):
+    """Size-independent property: re-scoring the decoded path along the model's edges gives the score."""
+    model = models["pro_001_py2"]
+    lens = events.uniform_lengths(200, 50, 500, seed=9)
+    obs, offsets = model.engine().sample_events(lens, seed=5)
+    evs = [obs[offsets[i]:offsets[i + 1]].astype(np.float64) for i in range(len(lens))]
+    for x, (score, path) in list(zip(evs, model.viterbi_batch(evs, dtype=np.float64)))[::10]:
+        states = [s for _, s in path]
+        assert states[0] is model.start and states[-1] is model.end
+        assert sum(1 for s in states if not s.is_silent()) == len(x)
+        assert model.log_probability(x, path=states) == pytest.approx(score, rel=1e-12, abs=1e-9)
+
+
+def test_edge_cases(models):
+    model = models["toy_uniform"]
+    # impossible events: (-inf, None) like the reference (yahmm.pyx:3621-3623); forward -inf
+    res = model.viterbi_batch([np.array([3.0]), np.array([0.5]), np.array([0.2, 3.0, 0.4])], dtype=np.float64)
+    assert res[0] == (float("-inf"), None) and res[2] == (float("-inf"), None) and res[1][1] is not None
+    lp = model.log_probability_batch([np.array([3.0]), np.array([0.5])], dtype=np.float64)
+    assert lp[0] == float("-inf") and np.isfinite(lp[1])
+    assert model.forward_backward(np.array([3.0])) == (None, None)
+    # empty sequence: ValueError like the reference's cvarray (yahmm.pyx:2836)
+    with pytest.raises(ValueError):
+        model.viterbi(np.array([]))
+    with pytest.raises(ValueError):
+        model.log_probability_batch([np.array([0.5]), np.array([])])
+    # zero events
+    assert model.viterbi_batch([]) == []
+    # too-small path buffer is reported, then retried with the size the library asks for
+    big = models["pro_001_py2"]
+    obs, offsets = big.engine().sample_events(np.array([300, 20, 77]), seed=1)
+    s1, l1, p1 = big.engine().viterbi_batch(obs, offsets, capacity=5)
+    s2, l2, p2 = big.engine().viterbi_batch(obs, offsets)
+    assert np.array_equal(p1, p2) and np.array_equal(l1, l2) and len(p1) == l1.sum()
+
+
+def test_outlier_event_goes_through_exact_rerun(models):
+    """x = 1e6 makes every emission underflow the scaled linear-space sweep; the exact log-space kernel re-runs it."""
+    model = models["pro_001_py2"]
+    orc = util.oracle_for(model)
+    mu = util.golden_events(util.load_golden("pro_001_py2"))[0]
+    x = np.concatenate([mu[:5], [1.0e4], mu[5:9]])
+    lp = model.log_probability_batch([x, mu], dtype=np.float64)
+    assert util.close(lp, [orc.log_probability(x), orc.log_probability(mu)]).all()
+
+
+def test_pypore_apply_hmm(models):
+    from protpore_b200 import pypore
+    model = models["pro_001_py2"]
+    g = util.load_golden("pro_001_py2")
+    evs = util.golden_events(g)[:6]
+    pev = [pypore.Event(segments=[pypore.Segment(mean=float(v)) for v in x]) for x in evs]
+    one = pev[0].apply_hmm(model)                        # the reference's call (DataTypes.py:349-355)
+    assert one[0] == g["vscore"][0] and one[1][0][1].name.endswith("-start")
+    many = pypore.apply_hmm_batch(pev, model, 'viterbi')
+    assert [m[0] for m in many] == list(g["vscore"][:6])
