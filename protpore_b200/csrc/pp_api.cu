@@ -75,6 +75,8 @@ int upload_model(pp_model* M) {
     PP_CUDA(upload(&M->d_warp_ranges, L.warp_ranges, s));
     PP_CUDA(upload(&M->d_state_edge_begin, L.state_edge_begin, s));
     PP_CUDA(upload(&M->d_low_src, L.low_src, s));
+    PP_CUDA(upload(&M->d_state_pword, L.state_pword, s));
+    PP_CUDA(upload(&M->d_state_pshift, L.state_pshift, s));
     PP_CUDA(upload(&M->d_in_ptr, M->in_ptr, s));
     PP_CUDA(upload(&M->d_in_src, M->in_src, s));
     PP_CUDA(upload(&M->d_in_logp, M->in_logp, s));
@@ -131,6 +133,7 @@ static LaneSched make_sched(const pp_model* M, bool logspace) {
     S.start_slot_off = static_cast<int32_t>((L.start - L.ne) * kSlotBytes);
     S.end_slot_off = static_cast<int32_t>((L.end - L.ne) * kSlotBytes);
     S.end_state = L.end; S.end_item = L.end_item; S.finite = L.finite; S.end_final_only = L.end_final_only ? 1 : 0;
+    S.n_ptr_words = L.n_ptr_words;
     return S;
 }
 
@@ -183,6 +186,13 @@ static int host_offsets(pp_model* M, const int64_t* offsets, int64_t n_events, i
 
 template <typename ObsT>
 static int launch_viterbi(pp_model* M, const LaneBatch<ObsT>& B, const VitOut& O, int n_groups) {
+    if (M->spec.loaded() && M->use_spec) {
+        const int e = M->spec.viterbi(sizeof(ObsT) == 8, B.obs, B.offsets, B.order, B.group_len, B.group_row, O.score,
+                                      O.end_state, O.end_ord, O.ptr, n_groups, M->stream);
+        if (e != 0) { set_error("specialised Viterbi launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
+        ++M->launches;
+        return PP_OK;
+    }
     const size_t smem = lane_smem_bytes(M->low.n_slots, sizeof(ObsT), 8);
     PP_CUDA(cudaFuncSetAttribute(k_viterbi_lane<ObsT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_viterbi_lane<ObsT, 8><<<n_groups, 256, smem, M->stream>>>(make_sched(M, true), B, O);
@@ -193,6 +203,13 @@ static int launch_viterbi(pp_model* M, const LaneBatch<ObsT>& B, const VitOut& O
 
 template <typename ObsT>
 static int launch_forward(pp_model* M, const LaneBatch<ObsT>& B, const FwdOut& O, int n_groups) {
+    if (M->spec.loaded() && M->use_spec) {
+        const int e = M->spec.forward(sizeof(ObsT) == 8, B.obs, B.offsets, B.order, B.group_len, B.group_row, O.logp,
+                                      n_groups, M->stream);
+        if (e != 0) { set_error("specialised forward launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
+        ++M->launches;
+        return PP_OK;
+    }
     const size_t smem = lane_smem_bytes(M->low.n_slots, sizeof(ObsT), 8);
     PP_CUDA(cudaFuncSetAttribute(k_forward_lane<ObsT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_forward_lane<ObsT, 8><<<n_groups, 256, smem, M->stream>>>(make_sched(M, false), B, O);
@@ -298,7 +315,7 @@ void pp_model_destroy(pp_model* M) {
     cudaSetDevice(M->device);
     if (M->stream) cudaStreamSynchronize(M->stream);
     DevBuf* bufs[] = {&M->d_items[0], &M->d_items[1], &M->d_edges_logp[0], &M->d_edges_logp[1], &M->d_edges_prob[0],
-                      &M->d_edges_prob[1], &M->d_emis, &M->d_warp_ranges, &M->d_state_edge_begin, &M->d_low_src,
+                      &M->d_edges_prob[1], &M->d_emis, &M->d_warp_ranges, &M->d_state_edge_begin, &M->d_low_src, &M->d_state_pword, &M->d_state_pshift,
                       &M->d_in_ptr, &M->d_in_src, &M->d_in_logp, &M->d_out_ptr, &M->d_out_dst, &M->d_out_logp,
                       &M->d_out_prob, &M->d_alive, &M->d_ws, &M->d_obs, &M->d_offsets, &M->d_order,
                       &M->d_group_len, &M->d_group_row, &M->d_score, &M->d_end_state, &M->d_end_ord, &M->d_path_len,
@@ -317,7 +334,64 @@ int pp_model_update_params(pp_model* M, const pp_model_desc* desc) {
     if (!err.empty()) { set_error("cannot refresh parameters: %s", err.c_str()); return PP_ERR_ARG; }
     copy_desc(M, desc);
     PP_CUDA(cudaSetDevice(M->device));
-    return upload_model(M);
+    int rc = upload_model(M);
+    if (rc != PP_OK) return rc;
+    if (M->spec.loaded()) {
+        // emission KINDS are part of the specialised code (a point mass that became a Normal after an
+        // M-step changes the schedule header): rebuild when the header changed, else just refresh the table
+        if (generate_spec_header(M->low) != M->spec_header) {
+            spec_unload(&M->spec);
+            return pp_model_specialize(M, M->spec_src_dir.c_str(), M->spec_cache_dir.c_str());
+        }
+        const std::vector<double> w = spec_param_table(M->low);
+        const int e = M->spec.set_params(w.data(), static_cast<int>(w.size()), M->stream);
+        if (e != 0) { set_error("specialised parameter upload failed (%d)", e); return PP_ERR_CUDA; }
+        PP_CUDA(cudaStreamSynchronize(M->stream));
+    }
+    return PP_OK;
+}
+
+int pp_spec_build(const pp_model_desc* desc, const char* src_dir, const char* cache_dir, char* so_path_out, int64_t cap) {
+    if (!desc || !src_dir || !cache_dir) { set_error("null argument"); return PP_ERR_ARG; }
+    Lowered low;
+    std::string err = lower_model(*desc, 8, &low);
+    if (!err.empty()) { set_error("cannot lower model: %s", err.c_str()); return PP_ERR_UNSUPPORTED; }
+    std::string so, hash;
+    err = spec_build(low, src_dir, cache_dir, &so, &hash);
+    if (!err.empty()) { set_error("specialisation failed: %s", err.c_str()); return PP_ERR_UNSUPPORTED; }
+    if (so_path_out && cap > 0) std::snprintf(so_path_out, static_cast<size_t>(cap), "%s", so.c_str());
+    return PP_OK;
+}
+
+int pp_model_specialize(pp_model* M, const char* src_dir, const char* cache_dir) {
+    if (!M || !src_dir || !cache_dir) { set_error("null argument"); return PP_ERR_ARG; }
+    PP_CUDA(cudaSetDevice(M->device));
+    if (lane_smem_bytes(M->low.n_slots, 8, 8) > M->smem_optin) {
+        set_error("model too large for the lane-per-event kernels; nothing to specialise");
+        return PP_ERR_UNSUPPORTED;
+    }
+    std::string so, hash;
+    std::string err = spec_build(M->low, src_dir, cache_dir, &so, &hash);
+    if (!err.empty()) { set_error("specialisation failed: %s", err.c_str()); return PP_ERR_UNSUPPORTED; }
+    SpecModule mod;
+    err = spec_load(so, M->low, &mod);
+    if (!err.empty()) { set_error("specialisation failed: %s", err.c_str()); return PP_ERR_UNSUPPORTED; }
+    mod.hash = hash;
+    const std::vector<double> w = spec_param_table(M->low);
+    const int e = mod.set_params(w.data(), static_cast<int>(w.size()), M->stream);
+    if (e != 0) { set_error("specialised parameter upload failed (%d)", e); return PP_ERR_CUDA; }
+    PP_CUDA(cudaStreamSynchronize(M->stream));
+    M->spec = mod;
+    M->spec_header = generate_spec_header(M->low);
+    M->spec_src_dir = src_dir;
+    M->spec_cache_dir = cache_dir;
+    return PP_OK;
+}
+
+int pp_model_use_specialized(pp_model* M, int on) {
+    if (!M) { set_error("null argument"); return PP_ERR_ARG; }
+    M->use_spec = on != 0;
+    return (M->spec.loaded() && M->use_spec) ? 1 : 0;
 }
 
 int pp_model_set_workspace_limit(pp_model* M, int64_t bytes) {
@@ -330,7 +404,7 @@ int64_t pp_viterbi_workspace_bytes(const pp_model* M, const int64_t* offsets_hos
     if (!M || !offsets_host || n_events < 0) return -1;
     Schedule sc;
     build_schedule(offsets_host, 0, n_events, &sc);
-    return sc.total_rows * static_cast<int64_t>(M->m) * kLanes;
+    return sc.total_rows * static_cast<int64_t>(M->low.n_ptr_words) * kLanes * 4;
 }
 
 int64_t pp_launch_count(const pp_model* M) { return M ? M->launches : 0; }
@@ -387,7 +461,7 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     PP_CUDA(M->d_end_ord.reserve(n_events * sizeof(int32_t)));
     PP_CUDA(M->d_path_off.reserve((n_events + 1) * sizeof(int64_t)));
 
-    const size_t row_bytes = static_cast<size_t>(M->m) * kLanes;
+    const size_t row_bytes = static_cast<size_t>(M->low.n_ptr_words) * kLanes * sizeof(uint32_t);
     const std::vector<int64_t> cuts =
         make_chunks(h_off, n_events, row_bytes, M->ws_limit, mem == PP_MEM_HOST ? ob : 0, size_t(4) << 30);
     int64_t base = 0;
@@ -417,7 +491,7 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
             t.stop();
             d_obs_base = static_cast<const char*>(M->d_obs.p) - h_off[e0] * ob;
         }
-        VitOut O{d_score, M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), M->d_ws.as<uint8_t>()};
+        VitOut O{d_score, M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), M->d_ws.as<uint32_t>()};
         {
             Timer t(M, PP_PROF_VITERBI);
             if (obs_dtype == PP_F32) {
@@ -433,9 +507,11 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
             if (rc != PP_OK) return rc;
         }
         // traceback pass 1: path lengths
-        TraceArgs T{M->d_ws.as<uint8_t>(), M->d_order.as<int32_t>(), M->d_group_row.as<int64_t>(), d_off, d_score,
+        TraceArgs T{M->d_ws.as<uint32_t>(), M->d_order.as<int32_t>(), M->d_group_row.as<int64_t>(), d_off, d_score,
                     M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), M->d_state_edge_begin.as<int32_t>(),
-                    M->d_low_src.as<int32_t>(), M->m, M->ne, M->start, M->low.end_final_only ? 1 : 0, 0};
+                    M->d_low_src.as<int32_t>(), M->d_state_pword.as<int32_t>(), M->d_state_pshift.as<int32_t>(),
+                    M->m, M->ne, M->start, M->low.end_final_only ? 1 : 0, M->low.n_ptr_words,
+                    (1 << M->low.ptr_bits) - 1};
         const int nslots = sc.n_groups * kLanes;
         int64_t chunk_total = 0;
         {
@@ -464,7 +540,7 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
                     PP_CUDA(M->d_path.reserve(static_cast<size_t>(chunk_total) * sizeof(uint16_t) + 16));
                     dst = M->d_path.as<uint16_t>();
                 }
-                k_traceback<<<(nslots + 127) / 128, 128, 0, M->stream>>>(T, d_plen, d_poff, dst, nslots);
+                k_traceback<<<(nslots + 127) / 128, 128, 0, M->stream>>>(T, d_plen, M->d_path_off.as<int64_t>(), dst, nslots);
                 PP_CUDA(cudaGetLastError());
                 ++M->launches;
                 t.stop();

@@ -36,6 +36,7 @@ struct LaneSched {
     int32_t start_slot_off;          // byte offset of the start state's slot
     int32_t end_slot_off;            // byte offset of the end state's slot
     int32_t end_state, end_item, finite, end_final_only;
+    int32_t n_ptr_words;             // 32-bit traceback pointer words per lane per row
 };
 
 template <typename ObsT>
@@ -51,7 +52,7 @@ struct VitOut {
     double* score;                   // [n_events]
     int32_t* end_state;              // [n_events] state the traceback starts from
     int32_t* end_ord;                // [n_events] winning in-edge ordinal of a final-only end state
-    uint8_t* ptr;                    // [rows][m][32] winning in-edge ordinal per cell
+    uint32_t* ptr;                   // [rows][n_ptr_words][32] packed winning in-edge ordinals
 };
 
 struct FwdOut {
@@ -174,8 +175,9 @@ k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
     const int n = ev >= 0 ? static_cast<int>(B.offsets[ev + 1] - off) : 0;
     const int nmax = B.group_len[g];
     unsigned char* colb = smem + lane * 8;                       // this lane's column slice
-    uint8_t* prow = O.ptr + (static_cast<size_t>(B.group_row[g]) * S.m) * kLanes + lane;
-    const size_t row_stride = static_cast<size_t>(S.m) * kLanes;
+    uint32_t* prow = O.ptr + (static_cast<size_t>(B.group_row[g]) * S.n_ptr_words) * kLanes + lane;
+    const size_t row_stride = static_cast<size_t>(S.n_ptr_words) * kLanes;
+    uint32_t pw = 0;                                             // pointer word being assembled
 
     const int eb = S.warp_ranges[warp * 4 + 0], ee = S.warp_ranges[warp * 4 + 1];
     const int sb = S.warp_ranges[warp * 4 + 2], se = S.warp_ranges[warp * 4 + 3];
@@ -189,11 +191,21 @@ k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
         const ItemRec* items = S.items[0];
         for (int it = sb; it < se; ++it) {
             const ItemRec I = ldg_rec(items + it);
-            if (I.flags & ITEM_START) continue;
+            if (I.flags & ITEM_START) {
+                if (I.flags & ITEM_PFLUSH) {
+                    if (ev >= 0) prow[static_cast<size_t>(I.pword) * kLanes] = pw;
+                    pw = 0;
+                }
+                continue;
+            }
             double best; int arg;
             vit_item(I, S.edges[0], colb, 0.0, false, best, arg);
             *reinterpret_cast<double*>(colb + I.dst_off) = best;
-            if (ev >= 0) prow[static_cast<size_t>(I.state) * kLanes] = static_cast<uint8_t>(arg);
+            pw |= static_cast<uint32_t>(arg) << I.pshift;
+            if (I.flags & ITEM_PFLUSH) {
+                if (ev >= 0) prow[static_cast<size_t>(I.pword) * kLanes] = pw;
+                pw = 0;
+            }
         }
     }
     __syncthreads();
@@ -208,7 +220,7 @@ k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
         const bool active = r <= n;
         const ItemRec* items = q ? S.items[1] : S.items[0];
         const EdgeRec* edges = q ? S.edges[1] : S.edges[0];
-        uint8_t* pr = prow + static_cast<size_t>(r) * row_stride;
+        uint32_t* pr = prow + static_cast<size_t>(r) * row_stride;
 
         for (int it = eb; it < ee; ++it) {                           // emitting states (3545-3562)
             const ItemRec I = ldg_rec(items + it);
@@ -217,7 +229,11 @@ k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
             double best; int arg;
             vit_item(I, edges, colb, e, true, best, arg);
             *reinterpret_cast<double*>(colb + I.dst_off) = best;
-            if (active) pr[static_cast<size_t>(I.state) * kLanes] = static_cast<uint8_t>(arg);
+            pw |= static_cast<uint32_t>(arg) << I.pshift;
+            if (I.flags & ITEM_PFLUSH) {
+                if (active) pr[static_cast<size_t>(I.pword) * kLanes] = pw;
+                pw = 0;
+            }
         }
         __syncthreads();
         for (int it = sb; it < se; ++it) {                           // silent states (3564-3605)
@@ -225,7 +241,11 @@ k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
             double best; int arg;
             vit_item(I, edges, colb, 0.0, false, best, arg);
             *reinterpret_cast<double*>(colb + I.dst_off) = best;
-            if (active) pr[static_cast<size_t>(I.state) * kLanes] = static_cast<uint8_t>(arg);
+            pw |= static_cast<uint32_t>(arg) << I.pshift;
+            if (I.flags & ITEM_PFLUSH) {
+                if (active) pr[static_cast<size_t>(I.pword) * kLanes] = pw;
+                pw = 0;
+            }
         }
         __syncthreads();
 
@@ -261,7 +281,7 @@ k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
 // Pass 1 (path == nullptr) counts, pass 2 writes the path front-to-back at path_off[ev].
 // ------------------------------------------------------------------------------------------
 struct TraceArgs {
-    const uint8_t* ptr;
+    const uint32_t* ptr;
     const int32_t* order;
     const int64_t* group_row;
     const int64_t* offsets;
@@ -270,7 +290,9 @@ struct TraceArgs {
     const int32_t* end_ord;
     const int32_t* state_edge_begin;   // [m]
     const int32_t* low_src;            // [lowered edges]
-    int32_t m, ne, start, end_final_only, n_slots_total;
+    const int32_t* state_pword;        // [m] pointer word of a state's ordinal
+    const int32_t* state_pshift;       // [m] bit position inside the word
+    int32_t m, ne, start, end_final_only, n_ptr_words, ptr_mask;
 };
 
 static __global__ void k_traceback(const TraceArgs T, int64_t* __restrict__ path_len, const int64_t* __restrict__ path_off,
@@ -285,8 +307,8 @@ static __global__ void k_traceback(const TraceArgs T, int64_t* __restrict__ path
         return;
     }
     const int n = static_cast<int>(T.offsets[ev + 1] - T.offsets[ev]);
-    const uint8_t* base = T.ptr + (static_cast<size_t>(T.group_row[g]) * T.m) * kLanes + lane;
-    const size_t row_stride = static_cast<size_t>(T.m) * kLanes;
+    const uint32_t* base = T.ptr + (static_cast<size_t>(T.group_row[g]) * T.n_ptr_words) * kLanes + lane;
+    const size_t row_stride = static_cast<size_t>(T.n_ptr_words) * kLanes;
     int64_t len = 1;
     int px = n, py = T.end_state[ev];
     int64_t pos = 0;
@@ -300,7 +322,8 @@ static __global__ void k_traceback(const TraceArgs T, int64_t* __restrict__ path
         if (out) out[pos--] = static_cast<uint16_t>(py);
         int ord;
         if (first && T.end_final_only) ord = T.end_ord[ev];
-        else ord = base[static_cast<size_t>(px) * row_stride + static_cast<size_t>(py) * kLanes];
+        else ord = (base[static_cast<size_t>(px) * row_stride + static_cast<size_t>(T.state_pword[py]) * kLanes] >>
+                    T.state_pshift[py]) & T.ptr_mask;
         first = false;
         const int src = T.low_src[T.state_edge_begin[py] + ord];
         if (py < T.ne) --px;                             // emitting states point into the previous row

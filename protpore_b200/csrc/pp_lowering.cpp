@@ -195,20 +195,49 @@ std::string lower_model(const pp_model_desc& d, int warps, Lowered* low) {
             load[w] += cost(c);
         }
     }
+    // traceback pointer packing: ordinals of consecutive items of one (warp, phase) share 32-bit words
+    low->ptr_bits = low->max_item_edges <= 16 ? 4 : 8;
+    const int per_word = 32 / low->ptr_bits;
+    low->state_pword.assign(m, -1);
+    low->state_pshift.assign(m, 0);
+    int next_word = 0;
+    auto assign_slots = [&](const std::vector<int>& states) {
+        for (size_t i = 0; i < states.size(); ++i) {
+            low->state_pword[states[i]] = next_word + static_cast<int>(i) / per_word;
+            low->state_pshift[states[i]] = (static_cast<int>(i) % per_word) * low->ptr_bits;
+        }
+        next_word += (static_cast<int>(states.size()) + per_word - 1) / per_word;
+    };
+    for (int w = 0; w < warps; ++w) { assign_slots(emit_of[w]); assign_slots(sil_of[w]); }
+    low->n_ptr_words = next_word;
+    auto finish = [&](std::vector<ItemRec>& v, size_t first) {     // flag the last ordinal of every word
+        for (size_t i = first; i < v.size(); ++i) {
+            v[i].pword = low->state_pword[v[i].state];
+            v[i].pshift = low->state_pshift[v[i].state];
+            const bool last = (i + 1 == v.size()) || low->state_pword[v[i + 1].state] != v[i].pword;
+            if (last) v[i].flags |= ITEM_PFLUSH;
+        }
+    };
     low->warp_ranges.assign(static_cast<size_t>(warps) * 4, 0);
     for (int q = 0; q < 2; ++q) {
         low->items[q].clear();
         for (int w = 0; w < warps; ++w) {
-            low->warp_ranges[w * 4 + 0] = static_cast<int32_t>(low->items[q].size());
+            size_t first = low->items[q].size();
+            low->warp_ranges[w * 4 + 0] = static_cast<int32_t>(first);
             for (int l : emit_of[w]) low->items[q].push_back(make_item(l, q));
-            low->warp_ranges[w * 4 + 1] = static_cast<int32_t>(low->items[q].size());
-            low->warp_ranges[w * 4 + 2] = static_cast<int32_t>(low->items[q].size());
+            finish(low->items[q], first);
+            first = low->items[q].size();
+            low->warp_ranges[w * 4 + 1] = static_cast<int32_t>(first);
+            low->warp_ranges[w * 4 + 2] = static_cast<int32_t>(first);
             for (int l : sil_of[w]) low->items[q].push_back(make_item(l, q));
+            finish(low->items[q], first);
             low->warp_ranges[w * 4 + 3] = static_cast<int32_t>(low->items[q].size());
         }
         low->end_item = static_cast<int32_t>(low->items[q].size());
         low->items[q].push_back(make_item(d.end_index, q));
     }
+    low->emit_of = emit_of;
+    low->sil_of = sil_of;
     return "";
 }
 

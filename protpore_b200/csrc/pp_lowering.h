@@ -45,10 +45,11 @@ struct __attribute__((aligned(32))) ItemRec {
     int32_t emis;                                // emitting state index, -1 for silent items
     uint32_t dst_off;                            // byte offset of the destination slot
     int32_t state;                               // baked state index
-    int32_t flags;                               // ITEM_START
-    int32_t pad[2];
+    int32_t flags;                               // ITEM_START | ITEM_PFLUSH
+    int32_t pword;                               // traceback pointer word of this item (per lane, per row)
+    int32_t pshift;                              // bit position of this item's ordinal inside the word
 };
-enum : int32_t { ITEM_START = 1 };
+enum : int32_t { ITEM_START = 1, ITEM_PFLUSH = 2 };   // PFLUSH: last ordinal of its word -> store the word
 enum : int32_t { EMIS_NORMAL = 0, EMIS_POINT = 1, EMIS_UNIFORM = 2 };
 struct __attribute__((aligned(64))) EmisRec {
     // Normal : a0 = mu, a1 = 2*sigma^2, a2 = RN(1/a1), a3 = log(1/(sigma*SQRT_2_PI))
@@ -67,9 +68,13 @@ struct Lowered {
     int32_t warps = 8;                           // warps per CTA the schedule was built for
     int32_t n_slots = 0;                         // ns + 2*ne column slots
     int32_t max_item_edges = 0;                  // over per-row items (end excluded if final-only)
+    int32_t ptr_bits = 8;                        // traceback ordinal width: 4 if every item has <= 16 edges, else 8
+    int32_t n_ptr_words = 0;                     // 32-bit pointer words per lane per row
+    std::vector<int32_t> state_pword, state_pshift;   // per state (traceback lookup); -1 for a final-only end
     int32_t end_item = -1;                       // index of end's ItemRec (always present)
     std::vector<ItemRec> items[2];               // per row parity; warp-major, then end
     std::vector<int32_t> warp_ranges;            // [warps][4]: emit_begin, emit_end, sil_begin, sil_end
+    std::vector<std::vector<int>> emit_of, sil_of;   // states per warp, in execution order
     std::vector<EdgeRec> edges_logp[2];          // per row parity, val = log p
     std::vector<EdgeRec> edges_prob[2];          // per row parity, val = p
     std::vector<int32_t> low_csr;                // index of each lowered edge in the IN-edge CSR

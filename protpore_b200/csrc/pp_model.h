@@ -5,6 +5,7 @@
 
 #include "pp_common.h"
 #include "pp_lowering.h"
+#include "pp_spec.h"
 
 // Kernel-time slots reported by pp_profile_get (milliseconds of the last batched call, summed over
 // its chunks, measured with CUDA events on the model's stream).
@@ -36,7 +37,7 @@ struct pp_model {
 
     // device copy of the schedule
     pp::DevBuf d_items[2], d_edges_logp[2], d_edges_prob[2], d_emis, d_warp_ranges;
-    pp::DevBuf d_state_edge_begin, d_low_src;
+    pp::DevBuf d_state_edge_begin, d_low_src, d_state_pword, d_state_pshift;
     // device copy of the baked CSR (state-parallel kernels, sampler)
     pp::DevBuf d_in_ptr, d_in_src, d_in_logp, d_out_ptr, d_out_dst, d_out_logp, d_out_prob, d_alive;
     pp::DevBuf d_lev_ptr, d_lev_states, d_rlev_ptr, d_rlev_states;
@@ -48,6 +49,11 @@ struct pp_model {
     pp::DevBuf d_score, d_end_state, d_end_ord, d_path_len, d_path_off, d_path, d_scan_tmp, d_logp;
     pp::DevBuf d_tab, d_xbuf, d_tab_off, d_list, d_counter, d_stats;
     size_t ws_limit = 0;
+
+    // model-specialised kernel module (pp_spec.h); used instead of the runtime-schedule kernels when loaded
+    pp::SpecModule spec;
+    bool use_spec = true;
+    std::string spec_header, spec_src_dir, spec_cache_dir;
 
     cudaEvent_t ev[2] = {nullptr, nullptr};
     double prof[PP_PROF_SLOTS] = {0};
