@@ -95,6 +95,10 @@ int pp_spec_build(const pp_model_desc *desc, const char *src_dir, const char *ca
 int pp_model_specialize(pp_model *model, const char *src_dir, const char *cache_dir);
 int pp_model_use_specialized(pp_model *model, int on);
 
+/* Text dump of the run schedule the kernels execute for this model (one line per warp and phase); needs no
+ * GPU.  Returns the length of the full text (buf may be NULL to query it), < 0 on error. */
+int64_t pp_schedule_describe(const pp_model_desc *desc, char *buf, int64_t cap);
+
 /* Upper limit for the handle's device workspace in bytes (default: 70% of free memory at creation). */
 int pp_model_set_workspace_limit(pp_model *model, int64_t bytes);
 

@@ -57,6 +57,7 @@ ABI = [
     ("pp_spec_build", ctypes.c_int, [ctypes.POINTER(PPModelDesc), ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p,
                                      ctypes.c_int64]),
     ("pp_model_specialize", ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_char_p]),
+    ("pp_schedule_describe", ctypes.c_int64, [ctypes.POINTER(PPModelDesc), ctypes.c_char_p, ctypes.c_int64]),
     ("pp_model_use_specialized", ctypes.c_int, [_vp, ctypes.c_int]),
     ("pp_viterbi_workspace_bytes", ctypes.c_int64, [_vp, _vp, ctypes.c_int64]),
     ("pp_forward_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
@@ -112,6 +113,18 @@ def build_specialized(model, cache_dir=None):
     buf = ctypes.create_string_buffer(4096)
     rc = lib.pp_spec_build(ctypes.byref(desc), SRC_DIR.encode(), (cache_dir or SPEC_CACHE).encode(), buf, 4096)
     if rc != PP_OK:
+        raise EngineError(rc, lib.pp_last_error().decode())
+    return buf.value.decode()
+
+
+def describe_schedule(model):
+    """Text dump of the per-warp run schedule of a baked `Model` (no GPU needed)."""
+    lib = load_library()
+    kinds, p0, p1 = model._device_params()
+    desc, keep = make_desc(model._baked, kinds, p0, p1)
+    buf = ctypes.create_string_buffer(1 << 16)
+    rc = lib.pp_schedule_describe(ctypes.byref(desc), buf, 1 << 16)
+    if rc < 0:
         raise EngineError(rc, lib.pp_last_error().decode())
     return buf.value.decode()
 

@@ -27,6 +27,26 @@ void set_error(const char* fmt, ...) {
     g_err = buf;
 }
 
+// The run kernels read their schedule from the __constant__ arena of this translation unit, which all
+// handles of the process share: it is (re)uploaded, stream-ordered, whenever the handle about to launch
+// is not the one whose image is resident.  Batched calls are synchronous, so a mutex around
+// upload + launch + synchronise is all the coordination two handles need.
+static const pp_model* g_arena_owner = nullptr;
+
+static int bind_arena(pp_model* M) {
+    if (!M->low.lane_ok) { set_error("model cannot run on the lane-per-event kernels: %s", M->low.lane_why.c_str()); return PP_ERR_UNSUPPORTED; }
+    if (M->arena.size() > static_cast<size_t>(kArenaDoubles)) {
+        set_error("model schedule needs %zu bytes of constant memory (limit %d)", M->arena.size() * 8, kArenaDoubles * 8);
+        return PP_ERR_UNSUPPORTED;
+    }
+    if (g_arena_owner != M) {
+        PP_CUDA(cudaMemcpyToSymbolAsync(c_arena, M->arena.data(), M->arena.size() * sizeof(double), 0,
+                                        cudaMemcpyHostToDevice, M->stream));
+        g_arena_owner = M;
+    }
+    return PP_OK;
+}
+
 // ---- event bucketing ------------------------------------------------------------------------
 void build_schedule(const int64_t* offsets, int64_t e0, int64_t e1, Schedule* out) {
     const int64_t n = e1 - e0;
@@ -67,12 +87,35 @@ int upload_model(pp_model* M) {
     cudaStream_t s = M->stream;
     const Lowered& L = M->low;
     for (int q = 0; q < 2; ++q) {
-        PP_CUDA(upload(&M->d_items[q], L.items[q], s));
         PP_CUDA(upload(&M->d_edges_logp[q], L.edges_logp[q], s));
         PP_CUDA(upload(&M->d_edges_prob[q], L.edges_prob[q], s));
     }
     PP_CUDA(upload(&M->d_emis, L.emis, s));
-    PP_CUDA(upload(&M->d_warp_ranges, L.warp_ranges, s));
+    PP_CUDA(upload(&M->d_warp_run_ranges, L.warp_run_ranges, s));
+    {   // host image of the constant arena (uploaded to c_arena right before a launch, see bind_arena)
+        static_assert(sizeof(RunRec) % 8 == 0, "RunRec size");
+        const size_t run_d = L.runs.size() * sizeof(RunRec) / 8, n_low = L.low_src.size();
+        M->arena_emis = static_cast<int32_t>(run_d);                 // log(state.weight) per emitting state
+        M->arena.assign(run_d + static_cast<size_t>(L.ne), 0.0);
+        if (!L.runs.empty()) std::memcpy(M->arena.data(), L.runs.data(), L.runs.size() * sizeof(RunRec));
+        for (int k = 0; k < L.ne; ++k) M->arena[run_d + k] = L.emis[k].logw;
+        g_arena_owner = nullptr;                                     // force a re-upload
+        // global copies the kernels stage into shared memory: weights in lowered-edge order and
+        // 4-double emission records per kernel family
+        std::vector<double> wl(n_low), wp(n_low), ev(4 * static_cast<size_t>(L.ne)), ef(4 * static_cast<size_t>(L.ne));
+        for (size_t i = 0; i < n_low; ++i) { wl[i] = L.edges_logp[0][i].val; wp[i] = L.edges_prob[0][i].val; }
+        for (int k = 0; k < L.ne; ++k) {
+            const EmisRec& R = L.emis[k];
+            double* a = &ev[4 * static_cast<size_t>(k)];
+            double* b = &ef[4 * static_cast<size_t>(k)];
+            a[0] = R.a0; a[1] = R.a1; a[2] = R.a2; a[3] = R.a3;
+            b[0] = R.a0; b[1] = R.kind == EMIS_NORMAL ? R.k2 : R.a1; b[2] = R.c2; b[3] = R.logw * 1.4426950408889634074;
+        }
+        PP_CUDA(upload(&M->d_wtab_logp, wl, s));
+        PP_CUDA(upload(&M->d_wtab_prob, wp, s));
+        PP_CUDA(upload(&M->d_etab_vit, ev, s));
+        PP_CUDA(upload(&M->d_etab_fwd, ef, s));
+    }
     PP_CUDA(upload(&M->d_state_edge_begin, L.state_edge_begin, s));
     PP_CUDA(upload(&M->d_low_src, L.low_src, s));
     PP_CUDA(upload(&M->d_state_pword, L.state_pword, s));
@@ -123,16 +166,19 @@ static int copy_desc(pp_model* M, const pp_model_desc* d) {
 static LaneSched make_sched(const pp_model* M, bool logspace) {
     LaneSched S;
     const Lowered& L = M->low;
-    for (int q = 0; q < 2; ++q) {
-        S.items[q] = M->d_items[q].as<ItemRec>();
-        S.edges[q] = (logspace ? M->d_edges_logp[q] : M->d_edges_prob[q]).as<EdgeRec>();
-    }
-    S.emis = M->d_emis.as<EmisRec>();
-    S.warp_ranges = M->d_warp_ranges.as<int32_t>();
+    for (int q = 0; q < 2; ++q) S.end_edges[q] = (logspace ? M->d_edges_logp[q] : M->d_edges_prob[q]).as<EdgeRec>();
+    S.warp_run_ranges = M->d_warp_run_ranges.as<int32_t>();
+    S.wtab = (logspace ? M->d_wtab_logp : M->d_wtab_prob).as<double>();
+    S.etab = (logspace ? M->d_etab_vit : M->d_etab_fwd).as<double>();
+    S.n_low = static_cast<int32_t>(L.low_src.size());
+    S.logw_off = M->arena_emis;
+    S.end_edge_begin = L.state_edge_begin[L.end];
+    S.end_n_edges = L.state_n_edges[L.end];
+    S.ptr_bits = L.ptr_bits;
     S.m = L.m; S.ne = L.ne; S.ns = L.ns; S.n_slots = L.n_slots;
     S.start_slot_off = static_cast<int32_t>((L.start - L.ne) * kSlotBytes);
     S.end_slot_off = static_cast<int32_t>((L.end - L.ne) * kSlotBytes);
-    S.end_state = L.end; S.end_item = L.end_item; S.finite = L.finite; S.end_final_only = L.end_final_only ? 1 : 0;
+    S.end_state = L.end; S.finite = L.finite; S.end_final_only = L.end_final_only ? 1 : 0;
     S.n_ptr_words = L.n_ptr_words;
     return S;
 }
@@ -193,7 +239,9 @@ static int launch_viterbi(pp_model* M, const LaneBatch<ObsT>& B, const VitOut& O
         ++M->launches;
         return PP_OK;
     }
-    const size_t smem = lane_smem_bytes(M->low.n_slots, sizeof(ObsT), 8);
+    int brc = bind_arena(M);
+    if (brc != PP_OK) return brc;
+    const size_t smem = lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, 8);
     PP_CUDA(cudaFuncSetAttribute(k_viterbi_lane<ObsT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_viterbi_lane<ObsT, 8><<<n_groups, 256, smem, M->stream>>>(make_sched(M, true), B, O);
     PP_CUDA(cudaGetLastError());
@@ -210,7 +258,9 @@ static int launch_forward(pp_model* M, const LaneBatch<ObsT>& B, const FwdOut& O
         ++M->launches;
         return PP_OK;
     }
-    const size_t smem = lane_smem_bytes(M->low.n_slots, sizeof(ObsT), 8);
+    int brc = bind_arena(M);
+    if (brc != PP_OK) return brc;
+    const size_t smem = lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, 8);
     PP_CUDA(cudaFuncSetAttribute(k_forward_lane<ObsT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_forward_lane<ObsT, 8><<<n_groups, 256, smem, M->stream>>>(make_sched(M, false), B, O);
     PP_CUDA(cudaGetLastError());
@@ -219,7 +269,8 @@ static int launch_forward(pp_model* M, const LaneBatch<ObsT>& B, const FwdOut& O
 }
 
 static int check_lane_fit(pp_model* M, int obs_bytes) {
-    const size_t smem = lane_smem_bytes(M->low.n_slots, obs_bytes, 8);
+    const size_t smem = lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, 8);
+    (void)obs_bytes;
     if (smem > M->smem_optin) {
         set_error("model needs %zu bytes of shared memory per CTA for the lane-per-event kernels (limit %zu)", smem,
                   M->smem_optin);
@@ -314,8 +365,9 @@ void pp_model_destroy(pp_model* M) {
     if (!M) return;
     cudaSetDevice(M->device);
     if (M->stream) cudaStreamSynchronize(M->stream);
-    DevBuf* bufs[] = {&M->d_items[0], &M->d_items[1], &M->d_edges_logp[0], &M->d_edges_logp[1], &M->d_edges_prob[0],
-                      &M->d_edges_prob[1], &M->d_emis, &M->d_warp_ranges, &M->d_state_edge_begin, &M->d_low_src, &M->d_state_pword, &M->d_state_pshift,
+    if (g_arena_owner == M) g_arena_owner = nullptr;
+    DevBuf* bufs[] = {&M->d_edges_logp[0], &M->d_edges_logp[1], &M->d_edges_prob[0],
+                      &M->d_edges_prob[1], &M->d_emis, &M->d_warp_run_ranges, &M->d_wtab_logp, &M->d_wtab_prob, &M->d_etab_vit, &M->d_etab_fwd, &M->d_state_edge_begin, &M->d_low_src, &M->d_state_pword, &M->d_state_pshift,
                       &M->d_in_ptr, &M->d_in_src, &M->d_in_logp, &M->d_out_ptr, &M->d_out_dst, &M->d_out_logp,
                       &M->d_out_prob, &M->d_alive, &M->d_ws, &M->d_obs, &M->d_offsets, &M->d_order,
                       &M->d_group_len, &M->d_group_row, &M->d_score, &M->d_end_state, &M->d_end_ord, &M->d_path_len,
@@ -361,6 +413,16 @@ int pp_spec_build(const pp_model_desc* desc, const char* src_dir, const char* ca
     if (!err.empty()) { set_error("specialisation failed: %s", err.c_str()); return PP_ERR_UNSUPPORTED; }
     if (so_path_out && cap > 0) std::snprintf(so_path_out, static_cast<size_t>(cap), "%s", so.c_str());
     return PP_OK;
+}
+
+int64_t pp_schedule_describe(const pp_model_desc* desc, char* buf, int64_t cap) {
+    if (!desc) { set_error("null argument"); return PP_ERR_ARG; }
+    Lowered low;
+    std::string err = lower_model(*desc, 8, &low);
+    if (!err.empty()) { set_error("cannot lower model: %s", err.c_str()); return PP_ERR_UNSUPPORTED; }
+    const std::string text = describe_schedule(low);
+    if (buf && cap > 0) std::snprintf(buf, static_cast<size_t>(cap), "%s", text.c_str());
+    return static_cast<int64_t>(text.size());
 }
 
 int pp_model_specialize(pp_model* M, const char* src_dir, const char* cache_dir) {

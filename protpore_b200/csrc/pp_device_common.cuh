@@ -1,0 +1,175 @@
+// pp_device_common.cuh -- device helpers shared by every kernel family: batch / output descriptors, the
+// exact float64 emission log-density, the log2-domain emission of the linear-space sweeps, observation
+// tile staging, and the traceback kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pp_lowering.h"
+
+namespace pp {
+
+template <typename ObsT>
+struct LaneBatch {
+    const ObsT* obs;                 // all observations back to back
+    const int64_t* offsets;          // [n_events + 1]
+    const int32_t* order;            // [n_groups * 32] event id per (group, lane), -1 = padding
+    const int32_t* group_len;        // [n_groups] longest event of the group
+    const int64_t* group_row;        // [n_groups] first pointer-table row of the group
+};
+
+struct VitOut {
+    double* score;                   // [n_events]
+    int32_t* end_state;              // [n_events] state the traceback starts from
+    int32_t* end_ord;                // [n_events] winning in-edge ordinal of a final-only end state
+    uint32_t* ptr;                   // [rows][n_ptr_words][32] packed winning in-edge ordinals
+};
+
+struct FwdOut {
+    double* logp;                    // [n_events]
+};
+
+constexpr int kTileCols = 32;
+constexpr int kTileStride = 33;      // +1 pad: conflict-free transposed fill
+
+__host__ __device__ inline size_t lane_smem_bytes(int n_slots, int obs_bytes, int warps) {
+    return static_cast<size_t>(n_slots) * kSlotBytes + static_cast<size_t>(kTileCols) * kTileStride * obs_bytes +
+           static_cast<size_t>(warps) * kLanes * sizeof(int32_t);
+}
+
+__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xFFF0000000000000LL); }
+
+template <typename T>
+__device__ __forceinline__ T ldg_rec(const T* p) {
+    // 16-byte vector loads of a warp-uniform record through the read-only path
+    static_assert(sizeof(T) % 16 == 0, "record size");
+    T out;
+    const int4* s = reinterpret_cast<const int4*>(p);
+    int4* dst = reinterpret_cast<int4*>(&out);
+#pragma unroll
+    for (int i = 0; i < static_cast<int>(sizeof(T) / 16); ++i) dst[i] = __ldg(s + i);
+    return out;
+}
+
+// NormalDistribution._log_probability (yahmm.pyx:377-390), UniformDistribution._log_probability
+// (257-262), plus log(state.weight) (2839-2840).  Every operation is an explicitly rounded IEEE
+// float64 op (no FMA contraction).  The division (x-mu)^2 / (2 sigma^2) is evaluated as a
+// Markstein sequence q0 = a*y, r = fma(-q0, b, a), q = fma(r, y, q0) with y = RN(1/b): it returns
+// the correctly rounded quotient (checked against IEEE division on 2e8 random operands and on
+// every model constant in tests/test_emission.py) at 3 flops instead of a ~30-instruction divide.
+__device__ __forceinline__ double emission_log(const EmisRec& R, double x) {
+    double r;
+    if (R.kind == EMIS_NORMAL) {
+        const double d = __dsub_rn(x, R.a0);
+        const double d2 = __dmul_rn(d, d);
+        const double q0 = __dmul_rn(d2, R.a2);
+        const double rem = __fma_rn(-q0, R.a1, d2);
+        const double q = __fma_rn(rem, R.a2, q0);
+        r = __dsub_rn(R.a3, q);
+    } else if (R.kind == EMIS_POINT) {
+        r = (fabs(__dsub_rn(x, R.a0)) < 1E-4) ? 0.0 : neg_inf();
+    } else {
+        r = (x == R.a0 && x == R.a1) ? 0.0 : ((x >= R.a0 && x <= R.a1) ? R.a3 : neg_inf());
+    }
+    return __dadd_rn(r, R.logw);
+}
+
+// 2^(t + shift) as a double, t in the log2 domain.  The fraction goes through MUFU.EX2 (fp32,
+// rel. error ~2^-22); the integer part is written straight into the exponent field.  Below 2^-1000
+// the factor is flushed to zero, above 2^1000 it becomes +inf (caught by the caller's status).
+__device__ __forceinline__ double exp2_scaled(double t) {
+    if (!(t > -1000.0)) return 0.0;                  // also catches -inf and NaN
+    if (t > 1000.0) return __longlong_as_double(0x7FF0000000000000LL);
+    const double n = rint(t);
+    const float f = static_cast<float>(t - n);
+    float p;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(f));
+    const int hi = (static_cast<int>(n) + 1023) << 20;
+    return static_cast<double>(p) * __hiloint2double(hi, 0);
+}
+
+__device__ __forceinline__ double emission_log2(const EmisRec& R, double x) {
+    if (R.kind == EMIS_NORMAL) {
+        const double d = x - R.a0;
+        return fma(-(d * d), R.k2, R.c2);
+    }
+    if (R.kind == EMIS_POINT) return (fabs(x - R.a0) < 1E-4) ? R.c2 : neg_inf();
+    if (x == R.a0 && x == R.a1) return R.logw * 1.4426950408889634074;
+    return (x >= R.a0 && x <= R.a1) ? R.c2 : neg_inf();
+}
+
+// Stage the next 32 observations of the CTA's 32 events: warp w loads events w, w+W, ... with one
+// fully coalesced 32-wide load each and stores them transposed ([column][event]).
+template <typename ObsT, int W>
+__device__ __forceinline__ void fill_tile(ObsT* xt, const ObsT* __restrict__ obs, int64_t off, int n, int i0,
+                                          int warp, int lane) {
+#pragma unroll
+    for (int j = warp; j < kLanes; j += W) {
+        const int64_t oj = __shfl_sync(0xffffffffu, off, j);
+        const int nj = __shfl_sync(0xffffffffu, n, j);
+        const int c = i0 + lane;
+        xt[lane * kTileStride + j] = (c < nj) ? __ldg(obs + oj + c) : ObsT(0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Traceback (yahmm.pyx:3632-3646): one thread per event walks the ordinals back from (n, end).
+// Pass 1 (path == nullptr) counts, pass 2 writes the path front-to-back at path_off[ev].
+// ------------------------------------------------------------------------------------------
+struct TraceArgs {
+    const uint32_t* ptr;
+    const int32_t* order;
+    const int64_t* group_row;
+    const int64_t* offsets;
+    const double* score;
+    const int32_t* end_state;
+    const int32_t* end_ord;
+    const int32_t* state_edge_begin;   // [m]
+    const int32_t* low_src;            // [lowered edges]
+    const int32_t* state_pword;        // [m] pointer word of a state's ordinal
+    const int32_t* state_pshift;       // [m] bit position inside the word
+    int32_t m, ne, start, end_final_only, n_ptr_words, ptr_mask;
+};
+
+static __global__ void k_traceback(const TraceArgs T, int64_t* __restrict__ path_len, const int64_t* __restrict__ path_off,
+                            uint16_t* __restrict__ path, int n_slots) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const int ev = T.order[slot];
+    if (ev < 0) return;
+    const int g = slot >> 5, lane = slot & 31;
+    if (T.score[ev] == neg_inf()) {                      // impossible: (-inf, None) (3621-3623)
+        if (!path) path_len[ev] = -1;
+        return;
+    }
+    const int n = static_cast<int>(T.offsets[ev + 1] - T.offsets[ev]);
+    const uint32_t* base = T.ptr + (static_cast<size_t>(T.group_row[g]) * T.n_ptr_words) * kLanes + lane;
+    const size_t row_stride = static_cast<size_t>(T.n_ptr_words) * kLanes;
+    int64_t len = 1;
+    int px = n, py = T.end_state[ev];
+    int64_t pos = 0;
+    uint16_t* out = nullptr;
+    if (path) {
+        pos = path_len[ev] - 1;
+        out = path + path_off[ev];
+    }
+    bool first = true;
+    while (px != 0 || py != T.start) {
+        if (out) out[pos--] = static_cast<uint16_t>(py);
+        int ord;
+        if (first && T.end_final_only) ord = T.end_ord[ev];
+        else ord = (base[static_cast<size_t>(px) * row_stride + static_cast<size_t>(T.state_pword[py]) * kLanes] >>
+                    T.state_pshift[py]) & T.ptr_mask;
+        first = false;
+        const int src = T.low_src[T.state_edge_begin[py] + ord];
+        if (py < T.ne) --px;                             // emitting states point into the previous row
+        py = src;
+        ++len;
+    }
+    if (out) out[pos] = static_cast<uint16_t>(py);
+    else path_len[ev] = len;
+}
+
+constexpr int kFwdTargetExp = 900;   // a row's largest value is steered to ~2^900
+
+}  // namespace pp

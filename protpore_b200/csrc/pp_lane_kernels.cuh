@@ -1,163 +1,324 @@
-// pp_lane_kernels.cuh -- "lane-per-event" column kernels for sm_100a (runtime-schedule variant).
+// pp_lane_kernels.cuh -- "lane-per-event" column kernels for sm_100a, run-based.
 //
 // One CTA = W warps x 32 lanes sweeps 32 events.  Lane j of every warp works on event j; the warps
 // split the states of a column (pp_lowering.h).  Consequences:
-//   * the per-warp program (items, edges, emission records) is warp-uniform: record loads are
-//     broadcast loads, there is no divergence and no per-lane CSR walk;
+//   * a warp's program is warp-uniform: no divergence, no per-lane CSR walk;
 //   * column accesses are [slot][lane]: stride-1 across lanes, bank-conflict free;
 //   * a lane only ever touches ITS event's column, so the serial silent chain of a column is plain
 //     program order in one thread -- exact reference arithmetic, no scan;
 //   * two __syncthreads per row: after the emitting phase (silent states read the new emitting
 //     values) and after the silent phase (next row's emitting states read the silent values).
 //
+// The program of a warp is a short list of RUNS (pp_lowering.h): `count` items of one shape whose
+// slots, weights and emission records advance by constant strides.  A run is executed by a body
+// templated on the in-degree and on the number of items it handles at once (G = 2 or 4): all loads of
+// the group are issued first, then G independent compare chains, then the stores -- with only 4 warps
+// per scheduler (the float64 column of 32 events fills half an SM's shared memory) instruction-level
+// parallelism inside the warp is what hides LDS and FP64 latency.  A silent chain (skip / back-slip)
+// is a run whose last edge is forwarded in a register: per link the dependent sequence is
+// DADD -> DSETP -> FSEL.  Because the bodies are shared by all runs of a shape, the code a CTA touches
+// per row is a few KB however many states the model has (the first, fully unrolled specialisation of
+// these kernels spent 41 % of its time waiting for instructions; profiles/).
+//
+// Shared memory per CTA: [column: n_slots x 32 doubles][transition weights][emission records]
+// [observation tile][per-warp row maxima (forward)].  Run records live in a __constant__ arena.
+//
 // Viterbi (k_viterbi_lane): float64 max-plus sweep that follows Model._viterbi
 // (yahmm.pyx:3471-3652) operation for operation -- candidate (v + t) + e for emitting states,
 // v + t for silent ones, strict '>' in the reference's visiting order -- and writes the ordinal of
-// the winning in-edge (uint8) per cell to HBM for the traceback kernel.
+// the winning in-edge, packed 8 (or 4) to a 32-bit word, to HBM for the traceback kernel.
 //
 // Forward (k_forward_lane): Model._forward / _log_probability (yahmm.pyx:2810-2930, 3378-3396) in
 // scaled LINEAR space, float64: one DFMA per edge instead of the reference's exp + log per edge.
 // Each event carries a power-of-two scale that is re-derived every row from the previous row's
 // maximum, so the mantissas are untouched by rescaling (DESIGN.md "forward").
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
-
-#include "pp_lowering.h"
+#include "pp_device_common.cuh"
 
 namespace pp {
 
+constexpr int kArenaDoubles = 7680;                       // 60 KB of the 64 KB constant bank
+static __constant__ double c_arena[kArenaDoubles];        // run records (+ log state weights)
+
 struct LaneSched {
-    const ItemRec* items[2];
-    const EdgeRec* edges[2];
-    const EmisRec* emis;
-    const int32_t* warp_ranges;      // [W][4]
+    const EdgeRec* end_edges[2];     // lowered in-edges of the end state, per row parity (final score)
+    const int32_t* warp_run_ranges;  // [W][6]
+    const double* wtab;              // [n_low] transition weights in lowered-edge order: log p (Viterbi) or p (forward)
+    const double* etab;              // [ne][4] emission records of this kernel family
+    int32_t n_low;
+    int32_t logw_off;                // arena index of log(state.weight) per emitting state (Viterbi, rarely used)
     int32_t m, ne, ns, n_slots;
     int32_t start_slot_off;          // byte offset of the start state's slot
     int32_t end_slot_off;            // byte offset of the end state's slot
-    int32_t end_state, end_item, finite, end_final_only;
-    int32_t n_ptr_words;             // 32-bit traceback pointer words per lane per row
+    int32_t end_state, end_edge_begin, end_n_edges, finite, end_final_only;
+    int32_t n_ptr_words, ptr_bits;
 };
 
-template <typename ObsT>
-struct LaneBatch {
-    const ObsT* obs;                 // all observations back to back
-    const int64_t* offsets;          // [n_events + 1]
-    const int32_t* order;            // [n_groups * 32] event id per (group, lane), -1 = padding
-    const int32_t* group_len;        // [n_groups] longest event of the group
-    const int64_t* group_row;        // [n_groups] first pointer-table row of the group
-};
+// tile of staged observations: 32 columns for float32, 16 for float64 (same bytes)
+template <typename ObsT> struct TileCols { static constexpr int value = 128 / sizeof(ObsT); };
 
-struct VitOut {
-    double* score;                   // [n_events]
-    int32_t* end_state;              // [n_events] state the traceback starts from
-    int32_t* end_ord;                // [n_events] winning in-edge ordinal of a final-only end state
-    uint32_t* ptr;                   // [rows][n_ptr_words][32] packed winning in-edge ordinals
-};
-
-struct FwdOut {
-    double* logp;                    // [n_events]
-};
-
-constexpr int kTileCols = 32;
-constexpr int kTileStride = 33;      // +1 pad: conflict-free transposed fill
-
-__host__ __device__ inline size_t lane_smem_bytes(int n_slots, int obs_bytes, int warps) {
-    return static_cast<size_t>(n_slots) * kSlotBytes + static_cast<size_t>(kTileCols) * kTileStride * obs_bytes +
-           static_cast<size_t>(warps) * kLanes * sizeof(int32_t);
+__host__ __device__ inline size_t lane_smem_bytes2(int n_slots, int n_low, int ne, int warps) {
+    return static_cast<size_t>(n_slots) * kSlotBytes + static_cast<size_t>(n_low) * 8 + static_cast<size_t>(ne) * 32 +
+           static_cast<size_t>(32) * 33 * 4 + static_cast<size_t>(warps) * kLanes * sizeof(int32_t) + 64;
 }
 
-__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xFFF0000000000000LL); }
+__device__ __forceinline__ const RunRec& run_rec(int i) { return reinterpret_cast<const RunRec*>(c_arena)[i]; }
 
-template <typename T>
-__device__ __forceinline__ T ldg_rec(const T* p) {
-    // 16-byte vector loads of a warp-uniform record through the read-only path
-    static_assert(sizeof(T) % 16 == 0, "record size");
-    T out;
-    const int4* s = reinterpret_cast<const int4*>(p);
-    int4* dst = reinterpret_cast<int4*>(&out);
+// 32-bit shared-memory addressing: one register per pointer, LDS.64 / STS.64 with register + immediate
+__device__ __forceinline__ double lds64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
+// traceback ordinals of consecutive items are packed into 32-bit words, one STG per full word
+struct PtrPack {
+    uint32_t* base;      // this lane's pointer row
+    int word;
+    uint32_t pw;
+    int sh, bits;
+    bool active;
+    __device__ __forceinline__ void flush() {
+        if (sh != 0 && active) base[static_cast<size_t>(word) * kLanes] = pw;
+        pw = 0;
+        sh = 0;
+    }
+    __device__ __forceinline__ void seat(int pword, int pshift) {
+        if (word != pword) {
+            flush();
+            word = pword;
+        }
+        sh = pshift;
+    }
+    __device__ __forceinline__ void push(uint32_t packed, int nbits) {       // never straddles a word (lowering)
+        pw |= packed << sh;
+        sh += nbits;
+        if (sh == 32) {
+            if (active) base[static_cast<size_t>(word) * kLanes] = pw;
+            ++word;
+            pw = 0;
+            sh = 0;
+        }
+    }
+};
+
+// induction state of one run: shared-memory addresses and byte strides
+template <int NE>
+struct RunPtrs {
+    uint32_t sp[NE > 0 ? NE : 1];
+    int ss[NE > 0 ? NE : 1];
+    uint32_t dp, wp, ep;
+    int ds, ws, es;
+    int kind, logw_i, logw_s;        // logw_i < 0: every log(state.weight) of the run is 0
+    __device__ __forceinline__ void init(const RunRec& R, int par, uint32_t colb, uint32_t wtab, uint32_t etab,
+                                         int logw_off) {
 #pragma unroll
-    for (int i = 0; i < static_cast<int>(sizeof(T) / 16); ++i) dst[i] = __ldg(s + i);
-    return out;
-}
+        for (int j = 0; j < NE; ++j) {
+            ss[j] = R.src_stride[j];
+            sp[j] = colb + R.src_off[par][j];
+        }
+        ds = R.dst_stride;
+        dp = colb + R.dst_off[par];
+        ws = R.w_stride * 8;
+        wp = wtab + R.w_base * 8;
+        es = R.e_stride * 32;
+        ep = etab + R.e_base * 32;
+        kind = R.kind;
+        logw_i = R.has_logw ? logw_off + R.e_base : -1;
+        logw_s = R.e_stride;
+    }
+    __device__ __forceinline__ void advance(int g) {
+#pragma unroll
+        for (int j = 0; j < NE; ++j) sp[j] += g * ss[j];
+        dp += g * ds;
+        wp += g * ws;
+        ep += g * es;
+        if (logw_i >= 0) logw_i += g * logw_s;
+    }
+};
 
-// NormalDistribution._log_probability (yahmm.pyx:377-390), UniformDistribution._log_probability
-// (257-262), plus log(state.weight) (2839-2840).  Every operation is an explicitly rounded IEEE
-// float64 op (no FMA contraction).  The division (x-mu)^2 / (2 sigma^2) is evaluated as a
-// Markstein sequence q0 = a*y, r = fma(-q0, b, a), q = fma(r, y, q0) with y = RN(1/b): it returns
-// the correctly rounded quotient (checked against IEEE division on 2e8 random operands and on
-// every model constant in tests/test_emission.py) at 3 flops instead of a ~30-instruction divide.
-__device__ __forceinline__ double emission_log(const EmisRec& R, double x) {
+// exact float64 emission log-density from the shared-memory record {a0, a1, a2, a3} (see emission_log)
+__device__ __forceinline__ double smem_emission_log(int kind, uint32_t ep, double x) {
     double r;
-    if (R.kind == EMIS_NORMAL) {
-        const double d = __dsub_rn(x, R.a0);
+    if (kind == EMIS_NORMAL) {
+        const double mu = lds64(ep), b = lds64(ep + 8), rinv = lds64(ep + 16), c = lds64(ep + 24);
+        const double d = __dsub_rn(x, mu);
         const double d2 = __dmul_rn(d, d);
-        const double q0 = __dmul_rn(d2, R.a2);
-        const double rem = __fma_rn(-q0, R.a1, d2);
-        const double q = __fma_rn(rem, R.a2, q0);
-        r = __dsub_rn(R.a3, q);
-    } else if (R.kind == EMIS_POINT) {
-        r = (fabs(__dsub_rn(x, R.a0)) < 1E-4) ? 0.0 : neg_inf();
+        const double q0 = __dmul_rn(d2, rinv);
+        const double rem = __fma_rn(-q0, b, d2);
+        const double q = __fma_rn(rem, rinv, q0);
+        r = __dsub_rn(c, q);
+    } else if (kind == EMIS_POINT) {
+        r = (fabs(__dsub_rn(x, lds64(ep))) < 1E-4) ? 0.0 : neg_inf();
     } else {
-        r = (x == R.a0 && x == R.a1) ? 0.0 : ((x >= R.a0 && x <= R.a1) ? R.a3 : neg_inf());
+        const double a = lds64(ep), b = lds64(ep + 8);
+        r = (x == a && x == b) ? 0.0 : ((x >= a && x <= b) ? lds64(ep + 24) : neg_inf());
     }
-    return __dadd_rn(r, R.logw);
+    return r;
 }
 
-// 2^(t + shift) as a double, t in the log2 domain.  The fraction goes through MUFU.EX2 (fp32,
-// rel. error ~2^-22); the integer part is written straight into the exponent field.  Below 2^-1000
-// the factor is flushed to zero, above 2^1000 it becomes +inf (caught by the caller's status).
-__device__ __forceinline__ double exp2_scaled(double t) {
-    if (!(t > -1000.0)) return 0.0;                  // also catches -inf and NaN
-    if (t > 1000.0) return __longlong_as_double(0x7FF0000000000000LL);
-    const double n = rint(t);
-    const float f = static_cast<float>(t - n);
-    float p;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(f));
-    const int hi = (static_cast<int>(n) + 1023) << 20;
-    return static_cast<double>(p) * __hiloint2double(hi, 0);
+// forward record {a0, a1 | k2, c2, cu}: log2-domain emission of the linear-space sweep
+__device__ __forceinline__ double smem_emission_log2(int kind, uint32_t ep, double x) {
+    if (kind == EMIS_NORMAL) {
+        const double d = x - lds64(ep);
+        return fma(-(d * d), lds64(ep + 8), lds64(ep + 16));
+    }
+    if (kind == EMIS_POINT) return (fabs(x - lds64(ep)) < 1E-4) ? lds64(ep + 16) : neg_inf();
+    const double a = lds64(ep), b = lds64(ep + 8);
+    if (x == a && x == b) return lds64(ep + 24);
+    return (x >= a && x <= b) ? lds64(ep + 16) : neg_inf();
 }
 
-__device__ __forceinline__ double emission_log2(const EmisRec& R, double x) {
-    if (R.kind == EMIS_NORMAL) {
-        const double d = x - R.a0;
-        return fma(-(d * d), R.k2, R.c2);
-    }
-    if (R.kind == EMIS_POINT) return (fabs(x - R.a0) < 1E-4) ? R.c2 : neg_inf();
-    if (x == R.a0 && x == R.a1) return R.logw * 1.4426950408889634074;
-    return (x >= R.a0 && x <= R.a1) ? R.c2 : neg_inf();
-}
-
-// Stage the next 32 observations of the CTA's 32 events: warp w loads events w, w+W, ... with one
-// fully coalesced 32-wide load each and stores them transposed ([column][event]).
-template <typename ObsT, int W>
-__device__ __forceinline__ void fill_tile(ObsT* xt, const ObsT* __restrict__ obs, int64_t off, int n, int i0,
-                                          int warp, int lane) {
-#pragma unroll
-    for (int j = warp; j < kLanes; j += W) {
-        const int64_t oj = __shfl_sync(0xffffffffu, off, j);
-        const int nj = __shfl_sync(0xffffffffu, n, j);
-        const int c = i0 + lane;
-        xt[lane * kTileStride + j] = (c < nj) ? __ldg(obs + oj + c) : ObsT(0);
-    }
-}
+enum : int { MODE_EMIT = 0, MODE_SILENT = 1, MODE_CHAIN = 2 };
 
 // ------------------------------------------------------------------------------------------
 // Viterbi
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void vit_item(const ItemRec& I, const EdgeRec* __restrict__ edges,
-                                         const unsigned char* colb, double e, bool emitting, double& best,
-                                         int& arg) {
+// G consecutive items of a run.  MODE_CHAIN: the last edge of every item reads `prev`, the value of the
+// item before it.  The first candidate initialises (best, arg) directly: `s0 > -inf` can only be false
+// for s0 = -inf, which leaves the same (best, arg) = (-inf, 0) the reference ends up with.
+template <int NE, int MODE, int G>
+__device__ __forceinline__ void vit_group(RunPtrs<NE>& P, double x, bool start_row0, double& prev, PtrPack& pk) {
+    constexpr int NL = (MODE == MODE_CHAIN) ? NE - 1 : NE;          // edges read from the column
+    double v[G][NL > 0 ? NL : 1], w[G][NE > 0 ? NE : 1], e[G], best[G];
+    uint32_t arg[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+        for (int j = 0; j < NL; ++j) v[g][j] = lds64(P.sp[j] + g * P.ss[j]);
+#pragma unroll
+        for (int j = 0; j < NE; ++j) w[g][j] = lds64(P.wp + g * P.ws + j * 8);
+    }
+    if (MODE == MODE_EMIT) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            e[g] = smem_emission_log(P.kind, P.ep + g * P.es, x);
+            e[g] = __dadd_rn(e[g], P.logw_i >= 0 ? c_arena[P.logw_i + g * P.logw_s] : 0.0);   // + log(state.weight)
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        best[g] = neg_inf();
+        arg[g] = 0;
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+            double s = __dadd_rn(v[g][j], w[g][j]);
+            if (MODE == MODE_EMIT) s = __dadd_rn(s, e[g]);
+            if (j == 0) {
+                best[g] = s;
+            } else if (s > best[g]) {
+                best[g] = s;
+                arg[g] = j;
+            }
+        }
+    }
+    if (MODE == MODE_CHAIN) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const double t = __dadd_rn(prev, w[g][NE - 1]);
+            if (NE == 1 || t > best[g]) {
+                best[g] = t;
+                arg[g] = NE - 1;
+            }
+            prev = best[g];
+        }
+    }
+    uint32_t packed = 0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (start_row0) best[g] = 0.0;                // v[0, start] = 0 (3513-3514)
+        sts64(P.dp + g * P.ds, best[g]);
+        packed |= arg[g] << (g * pk.bits);
+    }
+    if (MODE != MODE_CHAIN) prev = best[G - 1];
+    pk.push(packed, G * pk.bits);
+    P.advance(G);
+}
+
+template <int NE, int MODE>
+__device__ __forceinline__ void vit_items(RunPtrs<NE>& P, int count, double x, bool start_row0, double& prev,
+                                          PtrPack& pk) {
+    constexpr int G = (NE >= 3) ? 2 : 4;
+    int i = 0;
+    for (; i + G <= count; i += G) vit_group<NE, MODE, G>(P, x, start_row0, prev, pk);
+    for (; i < count; ++i) vit_group<NE, MODE, 1>(P, x, start_row0, prev, pk);
+}
+
+template <int NE>
+__device__ __forceinline__ void vit_run_ne(const RunRec& R, int par, bool row0, uint32_t colb, uint32_t wtab,
+                                           uint32_t etab, double x, const LaneSched& S, PtrPack& pk) {
+    RunPtrs<NE> P;
+    P.init(R, par, colb, wtab, etab, S.logw_off);
+    pk.seat(R.pword, R.pshift);
+    double prev = 0.0;
+    const int count = R.count;
+    if (R.kind <= EMIS_UNIFORM) {
+        vit_items<NE, MODE_EMIT>(P, count, x, false, prev, pk);
+    } else if (NE > 0 && R.fwd) {
+        vit_group<NE, MODE_SILENT, 1>(P, x, false, prev, pk);       // chain head reads the column
+        vit_items<NE, MODE_CHAIN>(P, count - 1, x, false, prev, pk);
+    } else {
+        vit_items<NE, MODE_SILENT>(P, count, x, row0 && R.kind == RUN_START, prev, pk);
+    }
+}
+
+__device__ __forceinline__ void vit_run(int r, int par, bool row0, uint32_t colb, uint32_t wtab, uint32_t etab,
+                                        double x, const LaneSched& S, PtrPack& pk) {
+    const RunRec& R = run_rec(r);
+    switch (R.n_edges) {
+        case 0: vit_run_ne<0>(R, par, row0, colb, wtab, etab, x, S, pk); break;
+        case 1: vit_run_ne<1>(R, par, row0, colb, wtab, etab, x, S, pk); break;
+        case 2: vit_run_ne<2>(R, par, row0, colb, wtab, etab, x, S, pk); break;
+        case 3: vit_run_ne<3>(R, par, row0, colb, wtab, etab, x, S, pk); break;
+        case 4: vit_run_ne<4>(R, par, row0, colb, wtab, etab, x, S, pk); break;
+        case 5: vit_run_ne<5>(R, par, row0, colb, wtab, etab, x, S, pk); break;
+        case 6: vit_run_ne<6>(R, par, row0, colb, wtab, etab, x, S, pk); break;
+        case 7: vit_run_ne<7>(R, par, row0, colb, wtab, etab, x, S, pk); break;
+        default: vit_run_ne<8>(R, par, row0, colb, wtab, etab, x, S, pk); break;
+    }
+}
+
+// in-edges of the end state (any in-degree), evaluated once per event at its last row
+__device__ __forceinline__ void vit_end_item(const EdgeRec* __restrict__ ep, int n_edges, const unsigned char* colp,
+                                             double& best, int& arg) {
     best = neg_inf();
     arg = 0;
-    const EdgeRec* ep = edges + I.edge_begin;
 #pragma unroll 4
-    for (int k = 0; k < I.n_edges; ++k) {
+    for (int k = 0; k < n_edges; ++k) {
         const EdgeRec E = ldg_rec(ep + k);
-        const double v = *reinterpret_cast<const double*>(colb + E.off);
-        double s = __dadd_rn(v, E.val);
-        if (emitting) s = __dadd_rn(s, e);
+        const double s = __dadd_rn(*reinterpret_cast<const double*>(colp + E.off), E.val);
         if (s > best) { best = s; arg = k; }
+    }
+}
+
+// shared-memory carve-up shared by both kernels
+struct LaneSmem {
+    unsigned char* col;
+    double* wtab;
+    double* etab;
+    unsigned char* xt;
+    int32_t* wmax;
+    __device__ __forceinline__ LaneSmem(unsigned char* smem, const LaneSched& S) {
+        col = smem;
+        wtab = reinterpret_cast<double*>(smem + static_cast<size_t>(S.n_slots) * kSlotBytes);
+        etab = wtab + S.n_low;
+        xt = reinterpret_cast<unsigned char*>(etab + static_cast<size_t>(S.ne) * 4);
+        wmax = reinterpret_cast<int32_t*>(xt + 32 * 33 * 4);
+    }
+};
+
+template <typename ObsT, int W>
+__device__ __forceinline__ void fill_tile2(ObsT* xt, const ObsT* __restrict__ obs, int64_t off, int n, int i0, int warp,
+                                           int lane) {
+    constexpr int TC = TileCols<ObsT>::value;                 // columns per tile; row stride TC + 1 elements
+    for (int j = warp * (32 / TC) + lane / TC; j < kLanes; j += W * (32 / TC)) {
+        const int64_t oj = __shfl_sync(0xffffffffu, off, j);
+        const int nj = __shfl_sync(0xffffffffu, n, j);
+        const int c = i0 + (lane % TC);
+        xt[(lane % TC) * (kLanes + 1) + j] = (c < nj) ? __ldg(obs + oj + c) : ObsT(0);
     }
 }
 
@@ -165,8 +326,9 @@ template <typename ObsT, int W>
 __global__ void __launch_bounds__(W * 32, 2)
 k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
     extern __shared__ __align__(16) unsigned char smem[];
-    double* col = reinterpret_cast<double*>(smem);
-    ObsT* xt = reinterpret_cast<ObsT*>(smem + static_cast<size_t>(S.n_slots) * kSlotBytes);
+    const LaneSmem M(smem, S);
+    constexpr int TC = TileCols<ObsT>::value;
+    ObsT* xt = reinterpret_cast<ObsT*>(M.xt);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x;
@@ -174,78 +336,48 @@ k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
     const int64_t off = ev >= 0 ? B.offsets[ev] : 0;
     const int n = ev >= 0 ? static_cast<int>(B.offsets[ev + 1] - off) : 0;
     const int nmax = B.group_len[g];
-    unsigned char* colb = smem + lane * 8;                       // this lane's column slice
+    unsigned char* colp = smem + lane * 8;                       // this lane's column slice
+    const uint32_t colb = static_cast<uint32_t>(__cvta_generic_to_shared(colp));
+    const uint32_t wtab = static_cast<uint32_t>(__cvta_generic_to_shared(M.wtab));
+    const uint32_t etab = static_cast<uint32_t>(__cvta_generic_to_shared(M.etab));
     uint32_t* prow = O.ptr + (static_cast<size_t>(B.group_row[g]) * S.n_ptr_words) * kLanes + lane;
     const size_t row_stride = static_cast<size_t>(S.n_ptr_words) * kLanes;
-    uint32_t pw = 0;                                             // pointer word being assembled
 
-    const int eb = S.warp_ranges[warp * 4 + 0], ee = S.warp_ranges[warp * 4 + 1];
-    const int sb = S.warp_ranges[warp * 4 + 2], se = S.warp_ranges[warp * 4 + 3];
+    const int eb = S.warp_run_ranges[warp * 6 + 0], ee = S.warp_run_ranges[warp * 6 + 1];
+    const int sb = S.warp_run_ranges[warp * 6 + 3], se = S.warp_run_ranges[warp * 6 + 4];
 
-    // row 0: v[0, :] = -inf, v[0, start] = 0 (3513-3514), then the silent closure (3515-3542)
+    // stage the model: weights and emission records; row 0: v[0, :] = -inf, v[0, start] = 0 (3513-3514)
+    for (int i = threadIdx.x; i < S.n_low; i += W * 32) M.wtab[i] = __ldg(S.wtab + i);
+    for (int i = threadIdx.x; i < S.ne * 4; i += W * 32) M.etab[i] = __ldg(S.etab + i);
+    double* col = reinterpret_cast<double*>(smem);
     for (int s = threadIdx.x; s < S.n_slots * kLanes; s += W * 32) col[s] = neg_inf();
     __syncthreads();
-    if (warp == 0) *reinterpret_cast<double*>(colb + S.start_slot_off) = 0.0;
-    __syncthreads();
-    {
-        const ItemRec* items = S.items[0];
-        for (int it = sb; it < se; ++it) {
-            const ItemRec I = ldg_rec(items + it);
-            if (I.flags & ITEM_START) {
-                if (I.flags & ITEM_PFLUSH) {
-                    if (ev >= 0) prow[static_cast<size_t>(I.pword) * kLanes] = pw;
-                    pw = 0;
-                }
-                continue;
-            }
-            double best; int arg;
-            vit_item(I, S.edges[0], colb, 0.0, false, best, arg);
-            *reinterpret_cast<double*>(colb + I.dst_off) = best;
-            pw |= static_cast<uint32_t>(arg) << I.pshift;
-            if (I.flags & ITEM_PFLUSH) {
-                if (ev >= 0) prow[static_cast<size_t>(I.pword) * kLanes] = pw;
-                pw = 0;
-            }
-        }
+    {   // silent closure of row 0 (3515-3542)
+        PtrPack pk{prow, -1, 0u, 0, S.ptr_bits, ev >= 0};
+        for (int u = sb; u < se; ++u) vit_run(u, 0, true, colb, wtab, etab, 0.0, S, pk);
+        pk.flush();
     }
     __syncthreads();
 
     for (int r = 1; r <= nmax; ++r) {
         const int q = r & 1;
-        if (((r - 1) & (kTileCols - 1)) == 0) {
-            fill_tile<ObsT, W>(xt, B.obs, off, n, r - 1, warp, lane);
+        if (((r - 1) & (TC - 1)) == 0) {
+            fill_tile2<ObsT, W>(xt, B.obs, off, n, r - 1, warp, lane);
             __syncthreads();
         }
-        const double x = static_cast<double>(xt[((r - 1) & (kTileCols - 1)) * kTileStride + lane]);
+        const double x = static_cast<double>(xt[((r - 1) & (TC - 1)) * (kLanes + 1) + lane]);
         const bool active = r <= n;
-        const ItemRec* items = q ? S.items[1] : S.items[0];
-        const EdgeRec* edges = q ? S.edges[1] : S.edges[0];
         uint32_t* pr = prow + static_cast<size_t>(r) * row_stride;
-
-        for (int it = eb; it < ee; ++it) {                           // emitting states (3545-3562)
-            const ItemRec I = ldg_rec(items + it);
-            const EmisRec R = ldg_rec(S.emis + I.emis);
-            const double e = emission_log(R, x);
-            double best; int arg;
-            vit_item(I, edges, colb, e, true, best, arg);
-            *reinterpret_cast<double*>(colb + I.dst_off) = best;
-            pw |= static_cast<uint32_t>(arg) << I.pshift;
-            if (I.flags & ITEM_PFLUSH) {
-                if (active) pr[static_cast<size_t>(I.pword) * kLanes] = pw;
-                pw = 0;
-            }
+        {
+            PtrPack pk{pr, -1, 0u, 0, S.ptr_bits, active};
+            for (int u = eb; u < ee; ++u) vit_run(u, q, false, colb, wtab, etab, x, S, pk);      // emitting (3545-3562)
+            pk.flush();
         }
         __syncthreads();
-        for (int it = sb; it < se; ++it) {                           // silent states (3564-3605)
-            const ItemRec I = ldg_rec(items + it);
-            double best; int arg;
-            vit_item(I, edges, colb, 0.0, false, best, arg);
-            *reinterpret_cast<double*>(colb + I.dst_off) = best;
-            pw |= static_cast<uint32_t>(arg) << I.pshift;
-            if (I.flags & ITEM_PFLUSH) {
-                if (active) pr[static_cast<size_t>(I.pword) * kLanes] = pw;
-                pw = 0;
-            }
+        {
+            PtrPack pk{pr, -1, 0u, 0, S.ptr_bits, active};
+            for (int u = sb; u < se; ++u) vit_run(u, q, false, colb, wtab, etab, x, S, pk);      // silent (3564-3605)
+            pk.flush();
         }
         __syncthreads();
 
@@ -254,16 +386,15 @@ k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
         if (warp == 0 && __any_sync(0xffffffffu, r == n)) {
             double score; int est = S.end_state, eord = 0;
             if (S.finite && S.end_final_only) {
-                const ItemRec I = ldg_rec(items + S.end_item);
-                vit_item(I, edges, colb, 0.0, false, score, eord);
+                vit_end_item((q ? S.end_edges[1] : S.end_edges[0]) + S.end_edge_begin, S.end_n_edges, colp, score, eord);
             } else if (S.finite) {
-                score = *reinterpret_cast<const double*>(colb + S.end_slot_off);
+                score = *reinterpret_cast<const double*>(colp + S.end_slot_off);
             } else {                                                 // numpy.argmax(v[n]) : first maximum
-                score = *reinterpret_cast<const double*>(colb + static_cast<size_t>(S.ns + q * S.ne) * kSlotBytes);
+                score = *reinterpret_cast<const double*>(colp + static_cast<size_t>(S.ns + q * S.ne) * kSlotBytes);
                 est = 0;
                 for (int k = 1; k < S.m; ++k) {
                     const size_t slot = k < S.ne ? static_cast<size_t>(S.ns + q * S.ne + k) : static_cast<size_t>(k - S.ne);
-                    const double v = *reinterpret_cast<const double*>(colb + slot * kSlotBytes);
+                    const double v = *reinterpret_cast<const double*>(colp + slot * kSlotBytes);
                     if (v > score) { score = v; est = k; }
                 }
             }
@@ -277,88 +408,97 @@ k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Traceback (yahmm.pyx:3632-3646): one thread per event walks the ordinals back from (n, end).
-// Pass 1 (path == nullptr) counts, pass 2 writes the path front-to-back at path_off[ev].
-// ------------------------------------------------------------------------------------------
-struct TraceArgs {
-    const uint32_t* ptr;
-    const int32_t* order;
-    const int64_t* group_row;
-    const int64_t* offsets;
-    const double* score;
-    const int32_t* end_state;
-    const int32_t* end_ord;
-    const int32_t* state_edge_begin;   // [m]
-    const int32_t* low_src;            // [lowered edges]
-    const int32_t* state_pword;        // [m] pointer word of a state's ordinal
-    const int32_t* state_pshift;       // [m] bit position inside the word
-    int32_t m, ne, start, end_final_only, n_ptr_words, ptr_mask;
-};
-
-static __global__ void k_traceback(const TraceArgs T, int64_t* __restrict__ path_len, const int64_t* __restrict__ path_off,
-                            uint16_t* __restrict__ path, int n_slots) {
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= n_slots) return;
-    const int ev = T.order[slot];
-    if (ev < 0) return;
-    const int g = slot >> 5, lane = slot & 31;
-    if (T.score[ev] == neg_inf()) {                      // impossible: (-inf, None) (3621-3623)
-        if (!path) path_len[ev] = -1;
-        return;
-    }
-    const int n = static_cast<int>(T.offsets[ev + 1] - T.offsets[ev]);
-    const uint32_t* base = T.ptr + (static_cast<size_t>(T.group_row[g]) * T.n_ptr_words) * kLanes + lane;
-    const size_t row_stride = static_cast<size_t>(T.n_ptr_words) * kLanes;
-    int64_t len = 1;
-    int px = n, py = T.end_state[ev];
-    int64_t pos = 0;
-    uint16_t* out = nullptr;
-    if (path) {
-        pos = path_len[ev] - 1;
-        out = path + path_off[ev];
-    }
-    bool first = true;
-    while (px != 0 || py != T.start) {
-        if (out) out[pos--] = static_cast<uint16_t>(py);
-        int ord;
-        if (first && T.end_final_only) ord = T.end_ord[ev];
-        else ord = (base[static_cast<size_t>(px) * row_stride + static_cast<size_t>(T.state_pword[py]) * kLanes] >>
-                    T.state_pshift[py]) & T.ptr_mask;
-        first = false;
-        const int src = T.low_src[T.state_edge_begin[py] + ord];
-        if (py < T.ne) --px;                             // emitting states point into the previous row
-        py = src;
-        ++len;
-    }
-    if (out) out[pos] = static_cast<uint16_t>(py);
-    else path_len[ev] = len;
-}
-
-// ------------------------------------------------------------------------------------------
 // Forward (scaled linear space)
 // ------------------------------------------------------------------------------------------
-constexpr int kFwdTargetExp = 900;   // a row's largest value is steered to ~2^900
-
-__device__ __forceinline__ double fwd_item(const ItemRec& I, const EdgeRec* __restrict__ edges,
-                                           const unsigned char* colb) {
-    double acc = 0.0;
-    const EdgeRec* ep = edges + I.edge_begin;
-#pragma unroll 4
-    for (int k = 0; k < I.n_edges; ++k) {
-        const EdgeRec E = ldg_rec(ep + k);
-        acc = fma(*reinterpret_cast<const double*>(colb + E.off), E.val, acc);
+template <int NE, int MODE, int G>
+__device__ __forceinline__ void fwd_group(RunPtrs<NE>& P, double x, double shiftd, bool start_row0, double& prev,
+                                          int& mx) {
+    constexpr int NL = (MODE == MODE_CHAIN) ? NE - 1 : NE;
+    double v[G][NL > 0 ? NL : 1], w[G][NE > 0 ? NE : 1], acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+        for (int j = 0; j < NL; ++j) v[g][j] = lds64(P.sp[j] + g * P.ss[j]);
+#pragma unroll
+        for (int j = 0; j < NE; ++j) w[g][j] = lds64(P.wp + g * P.ws + j * 8);
     }
-    return acc;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        acc[g] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NL; ++j) acc[g] = fma(v[g][j], w[g][j], acc[g]);
+    }
+    if (MODE == MODE_EMIT) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc[g] *= exp2_scaled(smem_emission_log2(P.kind, P.ep + g * P.es, x) + shiftd);
+    }
+    if (MODE == MODE_CHAIN) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            acc[g] = fma(prev, w[g][NE - 1], acc[g]);
+            prev = acc[g];
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (start_row0) acc[g] = 1.0;
+        sts64(P.dp + g * P.ds, acc[g]);
+        mx = max(mx, __double2hiint(acc[g]));
+    }
+    if (MODE != MODE_CHAIN) prev = acc[G - 1];
+    P.advance(G);
+}
+
+template <int NE, int MODE>
+__device__ __forceinline__ void fwd_items(RunPtrs<NE>& P, int count, double x, double shiftd, bool start_row0,
+                                          double& prev, int& mx) {
+    constexpr int G = (NE >= 3) ? 2 : 4;
+    int i = 0;
+    for (; i + G <= count; i += G) fwd_group<NE, MODE, G>(P, x, shiftd, start_row0, prev, mx);
+    for (; i < count; ++i) fwd_group<NE, MODE, 1>(P, x, shiftd, start_row0, prev, mx);
+}
+
+template <int NE>
+__device__ __forceinline__ void fwd_run_ne(const RunRec& R, int par, bool row0, uint32_t colb, uint32_t wtab,
+                                           uint32_t etab, double x, double shiftd, int& mx) {
+    RunPtrs<NE> P;
+    P.init(R, par, colb, wtab, etab, 0);
+    double prev = 0.0;
+    const int count = R.count;
+    if (R.kind <= EMIS_UNIFORM) {
+        fwd_items<NE, MODE_EMIT>(P, count, x, shiftd, false, prev, mx);
+    } else if (NE > 0 && R.fwd) {
+        fwd_group<NE, MODE_SILENT, 1>(P, x, shiftd, false, prev, mx);
+        fwd_items<NE, MODE_CHAIN>(P, count - 1, x, shiftd, false, prev, mx);
+    } else {
+        fwd_items<NE, MODE_SILENT>(P, count, x, shiftd, row0 && R.kind == RUN_START, prev, mx);
+    }
+}
+
+__device__ __forceinline__ void fwd_run(int r, int par, bool row0, uint32_t colb, uint32_t wtab, uint32_t etab,
+                                        double x, double shiftd, int& mx) {
+    const RunRec& R = run_rec(r);
+    switch (R.n_edges) {
+        case 0: fwd_run_ne<0>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
+        case 1: fwd_run_ne<1>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
+        case 2: fwd_run_ne<2>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
+        case 3: fwd_run_ne<3>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
+        case 4: fwd_run_ne<4>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
+        case 5: fwd_run_ne<5>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
+        case 6: fwd_run_ne<6>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
+        case 7: fwd_run_ne<7>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
+        default: fwd_run_ne<8>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
+    }
 }
 
 template <typename ObsT, int W>
 __global__ void __launch_bounds__(W * 32, 2)
 k_forward_lane(const LaneSched S, const LaneBatch<ObsT> B, const FwdOut O) {
     extern __shared__ __align__(16) unsigned char smem[];
-    double* col = reinterpret_cast<double*>(smem);
-    ObsT* xt = reinterpret_cast<ObsT*>(smem + static_cast<size_t>(S.n_slots) * kSlotBytes);
-    int32_t* wmax = reinterpret_cast<int32_t*>(smem + static_cast<size_t>(S.n_slots) * kSlotBytes +
-                                               static_cast<size_t>(kTileCols) * kTileStride * sizeof(ObsT));
+    const LaneSmem M(smem, S);
+    constexpr int TC = TileCols<ObsT>::value;
+    ObsT* xt = reinterpret_cast<ObsT*>(M.xt);
+    int32_t* wmax = M.wmax;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x;
@@ -366,26 +506,21 @@ k_forward_lane(const LaneSched S, const LaneBatch<ObsT> B, const FwdOut O) {
     const int64_t off = ev >= 0 ? B.offsets[ev] : 0;
     const int n = ev >= 0 ? static_cast<int>(B.offsets[ev + 1] - off) : 0;
     const int nmax = B.group_len[g];
-    unsigned char* colb = smem + lane * 8;
+    unsigned char* colp = smem + lane * 8;
+    const uint32_t colb = static_cast<uint32_t>(__cvta_generic_to_shared(colp));
+    const uint32_t wtab = static_cast<uint32_t>(__cvta_generic_to_shared(M.wtab));
+    const uint32_t etab = static_cast<uint32_t>(__cvta_generic_to_shared(M.etab));
 
-    const int eb = S.warp_ranges[warp * 4 + 0], ee = S.warp_ranges[warp * 4 + 1];
-    const int sb = S.warp_ranges[warp * 4 + 2], se = S.warp_ranges[warp * 4 + 3];
+    const int eb = S.warp_run_ranges[warp * 6 + 0], ee = S.warp_run_ranges[warp * 6 + 1];
+    const int sb = S.warp_run_ranges[warp * 6 + 3], se = S.warp_run_ranges[warp * 6 + 4];
 
+    for (int i = threadIdx.x; i < S.n_low; i += W * 32) M.wtab[i] = __ldg(S.wtab + i);
+    for (int i = threadIdx.x; i < S.ne * 4; i += W * 32) M.etab[i] = __ldg(S.etab + i);
+    double* col = reinterpret_cast<double*>(smem);
     for (int s = threadIdx.x; s < S.n_slots * kLanes; s += W * 32) col[s] = 0.0;
     __syncthreads();
-    if (warp == 0) *reinterpret_cast<double*>(colb + S.start_slot_off) = 1.0;
-    __syncthreads();
     int mx = 0;                                   // max of the high words of this warp's new values
-    {
-        const ItemRec* items = S.items[0];
-        for (int it = sb; it < se; ++it) {
-            const ItemRec I = ldg_rec(items + it);
-            if (I.flags & ITEM_START) { mx = max(mx, __double2hiint(1.0)); continue; }
-            const double v = fwd_item(I, S.edges[0], colb);
-            *reinterpret_cast<double*>(colb + I.dst_off) = v;
-            mx = max(mx, __double2hiint(v));
-        }
-    }
+    for (int u = sb; u < se; ++u) fwd_run(u, 0, true, colb, wtab, etab, 0.0, 0.0, mx);
     wmax[warp * kLanes + lane] = mx;
     __syncthreads();
 
@@ -393,49 +528,42 @@ k_forward_lane(const LaneSched S, const LaneBatch<ObsT> B, const FwdOut O) {
     for (int r = 1; r <= nmax; ++r) {
         const int q = r & 1;
         // shift for this row from the previous row's maximum (exact power of two)
-        int M = 0;
+        int Mx = 0;
 #pragma unroll
-        for (int w = 0; w < W; ++w) M = max(M, wmax[w * kLanes + lane]);
-        const int ex = (M >> 20) & 0x7ff;
-        const int shift = (ex == 0 || ex == 0x7ff) ? 0 : (kFwdTargetExp + 1023 - ex);
+        for (int w = 0; w < W; ++w) Mx = max(Mx, wmax[w * kLanes + lane]);
+        const int ex = (Mx >> 20) & 0x7ff;
+        int shift = (ex == 0 || ex == 0x7ff) ? 0 : (kFwdTargetExp + 1023 - ex);
+        shift = max(-900, min(900, shift));
         scale_total += shift;
-        if (((r - 1) & (kTileCols - 1)) == 0) {
-            fill_tile<ObsT, W>(xt, B.obs, off, n, r - 1, warp, lane);
+        const double shiftd = static_cast<double>(shift);
+        if (((r - 1) & (TC - 1)) == 0) {
+            fill_tile2<ObsT, W>(xt, B.obs, off, n, r - 1, warp, lane);
+            __syncthreads();
         }
-        __syncthreads();                          // tile visible; everyone has read wmax
-        const double x = static_cast<double>(xt[((r - 1) & (kTileCols - 1)) * kTileStride + lane]);
-        const ItemRec* items = q ? S.items[1] : S.items[0];
-        const EdgeRec* edges = q ? S.edges[1] : S.edges[0];
+        const double x = static_cast<double>(xt[((r - 1) & (TC - 1)) * (kLanes + 1) + lane]);
         mx = 0;
-        for (int it = eb; it < ee; ++it) {                           // emitting states (2874-2889)
-            const ItemRec I = ldg_rec(items + it);
-            const EmisRec R = ldg_rec(S.emis + I.emis);
-            const double p = exp2_scaled(emission_log2(R, x) + static_cast<double>(shift));
-            const double v = fwd_item(I, edges, colb) * p;
-            *reinterpret_cast<double*>(colb + I.dst_off) = v;
-            mx = max(mx, __double2hiint(v));
-        }
+        for (int u = eb; u < ee; ++u) fwd_run(u, q, false, colb, wtab, etab, x, shiftd, mx);      // emitting (2874-2889)
         __syncthreads();
-        for (int it = sb; it < se; ++it) {                           // silent states (2891-2926)
-            const ItemRec I = ldg_rec(items + it);
-            const double v = fwd_item(I, edges, colb);
-            *reinterpret_cast<double*>(colb + I.dst_off) = v;
-            mx = max(mx, __double2hiint(v));
-        }
+        for (int u = sb; u < se; ++u) fwd_run(u, q, false, colb, wtab, etab, x, shiftd, mx);      // silent (2891-2926)
         wmax[warp * kLanes + lane] = mx;
         __syncthreads();
 
         if (warp == 0 && __any_sync(0xffffffffu, r == n)) {          // log_probability (3378-3396)
             double P;
             if (S.finite && S.end_final_only) {
-                const ItemRec I = ldg_rec(items + S.end_item);
-                P = fwd_item(I, edges, colb);
+                const EdgeRec* ep = (q ? S.end_edges[1] : S.end_edges[0]) + S.end_edge_begin;
+                P = 0.0;
+#pragma unroll 4
+                for (int k = 0; k < S.end_n_edges; ++k) {
+                    const EdgeRec E = ldg_rec(ep + k);
+                    P = fma(*reinterpret_cast<const double*>(colp + E.off), E.val, P);
+                }
             } else if (S.finite) {
-                P = *reinterpret_cast<const double*>(colb + S.end_slot_off);
+                P = *reinterpret_cast<const double*>(colp + S.end_slot_off);
             } else {
                 P = 0.0;
                 for (int k = 0; k < S.ne; ++k)
-                    P += *reinterpret_cast<const double*>(colb + static_cast<size_t>(S.ns + q * S.ne + k) * kSlotBytes);
+                    P += *reinterpret_cast<const double*>(colp + static_cast<size_t>(S.ns + q * S.ne + k) * kSlotBytes);
             }
             if (r == n) {
                 // P == 0 -> -inf (impossible, or every path underflowed: the host re-runs such events

@@ -131,36 +131,119 @@ std::string lower_model(const pp_model_desc& d, int warps, Lowered* low) {
         low->n_levels = std::max(low->n_levels, lev);
     }
 
-    // ---- deal items to warps ---------------------------------------------------------------
-    auto make_item = [&](int l, int q) {
-        ItemRec it{};
-        it.edge_begin = low->state_edge_begin[l];
-        it.n_edges = low->state_n_edges[l];
-        it.state = l;
-        it.flags = (l == d.start_index) ? ITEM_START : 0;
-        if (l < ne) {
-            it.emis = l;
-            it.dst_off = static_cast<uint32_t>(ns + q * ne + l) * kSlotBytes;
-        } else {
-            it.emis = -1;
-            it.dst_off = static_cast<uint32_t>(l - ne) * kSlotBytes;
+    // ---- deal states to warps, as RUNS -------------------------------------------------------
+    // A run is a sequence of items of one shape (emission kind, in-degree) whose destination slot,
+    // source slots, weight index and emission index all advance by constant strides -- position
+    // k, k+1, k+2 ... of a profile HMM.  The kernels execute a run with one shape-templated body and
+    // a handful of induction registers, so the code a CTA touches per row is a few KB however many
+    // states the model has.  A model without any regularity degrades to runs of length 1.
+    struct Desc { int dst; int src[kMaxRunEdges]; int wbase; int ne; int kind; };
+    auto slot_of_dst = [&](int l) { return l < ne ? ns + l : l - ne; };          // parity-0 slot; parity 1 adds ne for emitting
+    auto describe = [&](int l, Desc* o) -> bool {
+        o->ne = low->state_n_edges[l];
+        if (o->ne > kMaxRunEdges) return false;
+        o->dst = slot_of_dst(l);
+        o->wbase = low->state_edge_begin[l];
+        o->kind = l < ne ? low->emis[l].kind : (l == d.start_index ? RUN_START : RUN_SILENT);
+        for (int k = 0; k < o->ne; ++k) {
+            const int s = low->low_src[o->wbase + k];
+            // encode region in the slot number of parity 0: silent -> s-ne ; emitting, previous row (emitting dst) ->
+            // ns + ne + s ; emitting, this row (silent dst) -> ns + s.  (parity 1 swaps the two emitting regions)
+            o->src[k] = s >= ne ? s - ne : (l < ne ? ns + ne + s : ns + s);
         }
-        return it;
+        return true;
     };
+    auto same_region = [&](int a, int b) {        // both slots in the same column region?
+        auto reg = [&](int s) { return s < ns ? 0 : (s < ns + ne ? 1 : 2); };
+        return reg(a) == reg(b);
+    };
+    // can `nxt` extend a run whose last two items are prev2 (may be null) and prev?
+    auto extends = [&](const Desc* prev2, const Desc& prev, const Desc& nxt) {
+        if (nxt.kind != prev.kind || nxt.ne != prev.ne) return false;
+        if (!same_region(nxt.dst, prev.dst)) return false;
+        for (int k = 0; k < nxt.ne; ++k) if (!same_region(nxt.src[k], prev.src[k])) return false;
+        if (!prev2) return true;
+        if (nxt.dst - prev.dst != prev.dst - prev2->dst) return false;
+        if (nxt.wbase - prev.wbase != prev.wbase - prev2->wbase) return false;
+        for (int k = 0; k < nxt.ne; ++k) if (nxt.src[k] - prev.src[k] != prev.src[k] - prev2->src[k]) return false;
+        return true;
+    };
+    auto slot_bytes = [&](int slot0, int q) -> int32_t {       // parity-0 slot number -> byte offset for row parity q
+        int s = slot0;
+        if (q == 1 && s >= ns) s = (s < ns + ne) ? s + ne : s - ne;
+        return static_cast<int32_t>(s) * static_cast<int32_t>(kSlotBytes);
+    };
+    low->lane_ok = true;
+    for (int l = 0; l < m; ++l) {
+        if (low->end_final_only && l == d.end_index) continue;
+        if (low->state_n_edges[l] > kMaxRunEdges) { low->lane_ok = false; low->lane_why = "state " + std::to_string(l) + " has more than 8 usable in-edges"; }
+    }
+    if (!low->lane_ok) return "";                 // only the state-parallel kernels can take this model
+    auto make_runs = [&](const std::vector<int>& states, bool silent, std::vector<RunRec>* out) {
+        size_t i = 0;
+        while (i < states.size()) {
+            Desc a;
+            if (!describe(states[i], &a)) { ++i; continue; }
+            std::vector<Desc> seq{a};
+            size_t j = i + 1;
+            while (j < states.size()) {
+                Desc nx;
+                if (!describe(states[j], &nx)) break;
+                // emission indices must advance with a constant stride as well
+                if (!silent && seq.size() >= 2 &&
+                    states[j] - states[j - 1] != states[j - 1] - states[j - 2]) break;
+                if (!extends(seq.size() >= 2 ? &seq[seq.size() - 2] : nullptr, seq.back(), nx)) break;
+                seq.push_back(nx);
+                ++j;
+            }
+            RunRec r{};
+            r.kind = a.kind; r.n_edges = a.ne; r.count = static_cast<int32_t>(seq.size());
+            const Desc& b = seq.size() > 1 ? seq[1] : seq[0];
+            for (int q = 0; q < 2; ++q) {
+                r.dst_off[q] = slot_bytes(a.dst, q);
+                for (int k = 0; k < a.ne; ++k) r.src_off[q][k] = slot_bytes(a.src[k], q);
+            }
+            r.dst_stride = (b.dst - a.dst) * static_cast<int32_t>(kSlotBytes);
+            for (int k = 0; k < a.ne; ++k) r.src_stride[k] = (b.src[k] - a.src[k]) * static_cast<int32_t>(kSlotBytes);
+            r.w_base = a.wbase; r.w_stride = b.wbase - a.wbase;
+            r.e_base = silent ? 0 : states[i];
+            r.e_stride = (silent || seq.size() < 2) ? 0 : states[i + 1] - states[i];
+            r.has_logw = 0;
+            if (!silent)
+                for (size_t t = i; t < j; ++t)
+                    if (low->emis[states[t]].logw != 0.0) r.has_logw = 1;
+            // register forward: the LAST edge of every item but the first reads the previous item
+            r.fwd = 0;
+            if (silent && a.ne > 0 && seq.size() > 1) {
+                bool all = true;
+                for (size_t t = 1; t < seq.size(); ++t)
+                    if (low->low_src[seq[t].wbase + a.ne - 1] != states[i + t - 1]) { all = false; break; }
+                r.fwd = all ? 1 : 0;
+            }
+            out->push_back(r);
+            i = j;
+        }
+    };
+
     std::vector<std::vector<int>> emit_of(warps), sil_of(warps);
-    {   // emitting: greedy LPT on (in-degree + fixed per-item cost)
+    {   // emitting: sort by shape, then cut the sequence into W contiguous slices of equal cost
         std::vector<int> order(ne);
         std::iota(order.begin(), order.end(), 0);
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-            return low->state_n_edges[a] > low->state_n_edges[b];
+            if (low->state_n_edges[a] != low->state_n_edges[b]) return low->state_n_edges[a] > low->state_n_edges[b];
+            return low->emis[a].kind < low->emis[b].kind;
         });
-        std::vector<long> load(warps, 0);
+        auto cost = [&](int l) { return 9L * low->state_n_edges[l] + (low->emis[l].kind == EMIS_NORMAL ? 22 : 14); };
+        long total = 0;
+        for (int l : order) total += cost(l);
+        long acc = 0;
+        int w = 0;
         for (int l : order) {
-            int w = static_cast<int>(std::min_element(load.begin(), load.end()) - load.begin());
+            // move on when this warp has its share (keep at least the remaining warps non-empty-able)
+            if (w + 1 < warps && acc >= (total * (w + 1)) / warps) ++w;
             emit_of[w].push_back(l);
-            load[w] += low->state_n_edges[l] + 3;
+            acc += cost(l);
         }
-        for (auto& v : emit_of) std::sort(v.begin(), v.end());
     }
     {   // silent: connected components of the silent sub-DAG, whole components per warp
         UnionFind uf(m);
@@ -183,59 +266,64 @@ std::string lower_model(const pp_model_desc& d, int warps, Lowered* low) {
         std::iota(order.begin(), order.end(), 0);
         auto cost = [&](int c) {
             long s = 0;
-            for (int l : comps[c]) s += low->state_n_edges[l] + 2;
-            // a chain is latency-bound: weigh long components more than their edge count
-            return s + 4L * static_cast<long>(comps[c].size() > 1 ? comps[c].size() : 0);
+            for (int l : comps[c]) s += 9L * low->state_n_edges[l] + 8;
+            // a chain is latency-bound: weigh long components far above their instruction count
+            return s + (comps[c].size() > 1 ? 30L * static_cast<long>(comps[c].size()) : 0L);
         };
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
         std::vector<long> load(warps, 0);
+        std::vector<std::vector<int>> chains(warps), singles(warps);
         for (int c : order) {
             int w = static_cast<int>(std::min_element(load.begin(), load.end()) - load.begin());
-            for (int l : comps[c]) sil_of[w].push_back(l);
+            auto& dstv = comps[c].size() > 1 ? chains[w] : singles[w];
+            for (int l : comps[c]) dstv.push_back(l);
             load[w] += cost(c);
         }
+        for (int w = 0; w < warps; ++w) {
+            // independent single states first, sorted by (shape, index) so that they form runs; chains after
+            std::stable_sort(singles[w].begin(), singles[w].end(), [&](int a, int b) {
+                if (low->state_n_edges[a] != low->state_n_edges[b]) return low->state_n_edges[a] > low->state_n_edges[b];
+                return a < b;
+            });
+            sil_of[w] = chains[w];
+            sil_of[w].insert(sil_of[w].end(), singles[w].begin(), singles[w].end());
+        }
     }
+
     // traceback pointer packing: ordinals of consecutive items of one (warp, phase) share 32-bit words
     low->ptr_bits = low->max_item_edges <= 16 ? 4 : 8;
     const int per_word = 32 / low->ptr_bits;
     low->state_pword.assign(m, -1);
     low->state_pshift.assign(m, 0);
     int next_word = 0;
-    auto assign_slots = [&](const std::vector<int>& states) {
-        for (size_t i = 0; i < states.size(); ++i) {
-            low->state_pword[states[i]] = next_word + static_cast<int>(i) / per_word;
-            low->state_pshift[states[i]] = (static_cast<int>(i) % per_word) * low->ptr_bits;
+    low->runs.clear();
+    low->warp_run_ranges.assign(static_cast<size_t>(warps) * 6, 0);
+    for (int w = 0; w < warps; ++w) {
+        for (int phase = 0; phase < 2; ++phase) {
+            const std::vector<int>& states = phase == 0 ? emit_of[w] : sil_of[w];
+            low->warp_run_ranges[w * 6 + phase * 3 + 0] = static_cast<int32_t>(low->runs.size());
+            make_runs(states, phase == 1, &low->runs);
+            low->warp_run_ranges[w * 6 + phase * 3 + 1] = static_cast<int32_t>(low->runs.size());
+            low->warp_run_ranges[w * 6 + phase * 3 + 2] = next_word;         // first pointer word of this (warp, phase)
+            // ordinal slots: consecutive within a run; every run starts on a multiple of 4 slots so that the
+            // kernels can pack the ordinals of 2 or 4 items with one shift (a group never straddles a word)
+            int slot = 0;
+            size_t si = 0;
+            for (int r = low->warp_run_ranges[w * 6 + phase * 3]; r < low->warp_run_ranges[w * 6 + phase * 3 + 1]; ++r) {
+                RunRec& R = low->runs[r];
+                // a chain run handles its head alone and then groups of 4: seat the head on slot = 3 (mod 4)
+                slot = R.fwd ? (((slot + 4) & ~3) - 1) : ((slot + 3) & ~3);
+                R.pword = next_word + slot / per_word;
+                R.pshift = (slot % per_word) * low->ptr_bits;
+                for (int i = 0; i < R.count; ++i, ++si, ++slot) {
+                    low->state_pword[states[si]] = next_word + slot / per_word;
+                    low->state_pshift[states[si]] = (slot % per_word) * low->ptr_bits;
+                }
+            }
+            next_word += (slot + per_word - 1) / per_word;
         }
-        next_word += (static_cast<int>(states.size()) + per_word - 1) / per_word;
-    };
-    for (int w = 0; w < warps; ++w) { assign_slots(emit_of[w]); assign_slots(sil_of[w]); }
-    low->n_ptr_words = next_word;
-    auto finish = [&](std::vector<ItemRec>& v, size_t first) {     // flag the last ordinal of every word
-        for (size_t i = first; i < v.size(); ++i) {
-            v[i].pword = low->state_pword[v[i].state];
-            v[i].pshift = low->state_pshift[v[i].state];
-            const bool last = (i + 1 == v.size()) || low->state_pword[v[i + 1].state] != v[i].pword;
-            if (last) v[i].flags |= ITEM_PFLUSH;
-        }
-    };
-    low->warp_ranges.assign(static_cast<size_t>(warps) * 4, 0);
-    for (int q = 0; q < 2; ++q) {
-        low->items[q].clear();
-        for (int w = 0; w < warps; ++w) {
-            size_t first = low->items[q].size();
-            low->warp_ranges[w * 4 + 0] = static_cast<int32_t>(first);
-            for (int l : emit_of[w]) low->items[q].push_back(make_item(l, q));
-            finish(low->items[q], first);
-            first = low->items[q].size();
-            low->warp_ranges[w * 4 + 1] = static_cast<int32_t>(first);
-            low->warp_ranges[w * 4 + 2] = static_cast<int32_t>(first);
-            for (int l : sil_of[w]) low->items[q].push_back(make_item(l, q));
-            finish(low->items[q], first);
-            low->warp_ranges[w * 4 + 3] = static_cast<int32_t>(low->items[q].size());
-        }
-        low->end_item = static_cast<int32_t>(low->items[q].size());
-        low->items[q].push_back(make_item(d.end_index, q));
     }
+    low->n_ptr_words = next_word;
     low->emit_of = emit_of;
     low->sil_of = sil_of;
     return "";

@@ -39,18 +39,25 @@ struct __attribute__((aligned(16))) EdgeRec {
     uint32_t off;                                // byte offset of the source slot in the column
     uint32_t src;                                // baked index of the source state
 };
-struct __attribute__((aligned(32))) ItemRec {
-    int32_t edge_begin;                          // first lowered edge record
-    int32_t n_edges;
-    int32_t emis;                                // emitting state index, -1 for silent items
-    uint32_t dst_off;                            // byte offset of the destination slot
-    int32_t state;                               // baked state index
-    int32_t flags;                               // ITEM_START | ITEM_PFLUSH
-    int32_t pword;                               // traceback pointer word of this item (per lane, per row)
-    int32_t pshift;                              // bit position of this item's ordinal inside the word
+// A RUN: `count` items of one shape whose slots / weights / emission records advance by constant strides
+// (position k, k+1, ... of a profile).  Executed by one shape-templated loop body (pp_lane_kernels.cuh).
+constexpr int kMaxRunEdges = 8;
+enum : int32_t { EMIS_NORMAL = 0, EMIS_POINT = 1, EMIS_UNIFORM = 2, RUN_SILENT = 3, RUN_START = 4 };
+struct __attribute__((aligned(16))) RunRec {
+    int32_t kind;                                // EMIS_* for emitting items, RUN_SILENT, RUN_START (the start state)
+    int32_t n_edges;                             // in-edges per item (<= kMaxRunEdges), reference visiting order
+    int32_t count;                               // items in the run
+    int32_t fwd;                                 // 1: the last edge reads the previous item of the run (a chain link)
+    int32_t dst_off[2];                          // byte offset of the first destination slot, per row parity
+    int32_t dst_stride;                          // bytes per item
+    int32_t w_base, w_stride;                    // weight-table index of the first item's first edge; per item
+    int32_t e_base, e_stride;                    // emission-record index of the first item; per item
+    int32_t pword, pshift;                       // traceback ordinal of the first item: pointer word, bit position
+    int32_t has_logw;                            // some item of the run has log(state.weight) != 0
+    int32_t pad[2];
+    int32_t src_off[2][kMaxRunEdges];            // byte offset of each edge's first source slot, per row parity
+    int32_t src_stride[kMaxRunEdges];            // bytes per item
 };
-enum : int32_t { ITEM_START = 1, ITEM_PFLUSH = 2 };   // PFLUSH: last ordinal of its word -> store the word
-enum : int32_t { EMIS_NORMAL = 0, EMIS_POINT = 1, EMIS_UNIFORM = 2 };
 struct __attribute__((aligned(64))) EmisRec {
     // Normal : a0 = mu, a1 = 2*sigma^2, a2 = RN(1/a1), a3 = log(1/(sigma*SQRT_2_PI))
     // Point  : a0 = mu                                  (sigma == 0, yahmm.pyx:383-387)
@@ -71,9 +78,10 @@ struct Lowered {
     int32_t ptr_bits = 8;                        // traceback ordinal width: 4 if every item has <= 16 edges, else 8
     int32_t n_ptr_words = 0;                     // 32-bit pointer words per lane per row
     std::vector<int32_t> state_pword, state_pshift;   // per state (traceback lookup); -1 for a final-only end
-    int32_t end_item = -1;                       // index of end's ItemRec (always present)
-    std::vector<ItemRec> items[2];               // per row parity; warp-major, then end
-    std::vector<int32_t> warp_ranges;            // [warps][4]: emit_begin, emit_end, sil_begin, sil_end
+    std::vector<RunRec> runs;                    // warp-major: emitting runs then silent runs of each warp
+    std::vector<int32_t> warp_run_ranges;        // [warps][6]: {run_begin, run_end, first pointer word} x {emit, silent}
+    bool lane_ok = true;                         // false: some state has too many in-edges for the run kernels
+    std::string lane_why;
     std::vector<std::vector<int>> emit_of, sil_of;   // states per warp, in execution order
     std::vector<EdgeRec> edges_logp[2];          // per row parity, val = log p
     std::vector<EdgeRec> edges_prob[2];          // per row parity, val = p

@@ -36,7 +36,10 @@ struct pp_model {
     pp::Lowered low;
 
     // device copy of the schedule
-    pp::DevBuf d_items[2], d_edges_logp[2], d_edges_prob[2], d_emis, d_warp_ranges;
+    pp::DevBuf d_edges_logp[2], d_edges_prob[2], d_emis, d_warp_run_ranges;
+    std::vector<double> arena;            // host image of the constant arena: [runs | log p | p | emission records]
+    int32_t arena_emis = 0;
+    pp::DevBuf d_wtab_logp, d_wtab_prob, d_etab_vit, d_etab_fwd;
     pp::DevBuf d_state_edge_begin, d_low_src, d_state_pword, d_state_pshift;
     // device copy of the baked CSR (state-parallel kernels, sampler)
     pp::DevBuf d_in_ptr, d_in_src, d_in_logp, d_out_ptr, d_out_dst, d_out_logp, d_out_prob, d_alive;

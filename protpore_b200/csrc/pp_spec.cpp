@@ -35,7 +35,7 @@ std::string spec_build(const Lowered& L, const std::string& src_dir, const std::
     if (!file_exists(kernels)) return "kernel source not found: " + kernels;
     uint64_t h = fnv1a64(header, 0xCBF29CE484222325ULL);
     h = fnv1a64(read_file(kernels), h);
-    h = fnv1a64(read_file(src_dir + "/pp_lane_kernels.cuh"), h);
+    h = fnv1a64(read_file(src_dir + "/pp_device_common.cuh"), h);
     h = fnv1a64(read_file(src_dir + "/pp_lowering.h"), h);
     const char* extra = std::getenv("PP_SPEC_NVCC_FLAGS");
     h = fnv1a64(std::string("sm_100a;v1;") + (extra ? extra : ""), h);

@@ -27,6 +27,7 @@ struct SpecModule {
 std::string generate_spec_header(const Lowered& L);
 std::vector<double> spec_param_table(const Lowered& L);
 uint64_t fnv1a64(const std::string& s, uint64_t h);
+std::string describe_schedule(const Lowered& L);
 
 // Finds or builds <cache_dir>/pp_spec_<hash>.so for this schedule.  Returns "" or an error message.
 std::string spec_build(const Lowered& L, const std::string& src_dir, const std::string& cache_dir, std::string* so_path,

@@ -12,7 +12,7 @@
 //                           -DPP_SPEC_HEADER='"<cache>/pp_spec_<hash>.h"' pp_spec_kernels.cu
 #include PP_SPEC_HEADER
 
-#include "pp_lane_kernels.cuh"
+#include "pp_device_common.cuh"
 
 #ifndef PP_CTAS_PER_SM
 #define PP_CTAS_PER_SM 2
@@ -25,7 +25,7 @@ __constant__ double PP_WTAB[PP_N_WCONST];
 #define PP_LD(base, idx) (*reinterpret_cast<const double*>((base) + (idx) * 256))
 #define PP_WE(k, j) PP_WTAB[PP_EMIS_BASE + 8 * (k) + (j)]
 
-// ---- exact float64 emission log-density (see emission_log in pp_lane_kernels.cuh) ------------
+// ---- exact float64 emission log-density (see emission_log in pp_device_common.cuh) ------------
 #define PP_EMIS_N(k)                                                                             \
     __dadd_rn(__dsub_rn(PP_WE(k, 3), pp_quot(__dsub_rn(x, PP_WE(k, 0)), PP_WE(k, 1), PP_WE(k, 2))), PP_WE(k, 4))
 #define PP_EMIS_P(k) __dadd_rn((fabs(__dsub_rn(x, PP_WE(k, 0))) < 1E-4) ? 0.0 : neg_inf(), PP_WE(k, 4))

@@ -14,7 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "pp_lane_kernels.cuh"
+#include "pp_device_common.cuh"
 
 namespace pp {
 
