@@ -41,7 +41,6 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--generic-kernels", action="store_true", help="runtime-schedule kernels instead of the specialised build")
     return ap.parse_args()
 
 
@@ -176,8 +175,6 @@ def main():
     y.Model.device = local
     model = peptide_hmm.pro_001_model()
     eng = model.engine()
-    if not args.generic_kernels:
-        eng.specialize()                  # column kernels compiled against this model's schedule (cached .so)
     m, E = len(model.states), model.edge_count()
 
     lens = events.uniform_lengths(args.events, args.min_len, args.max_len, seed=args.seed + rank)
@@ -279,7 +276,7 @@ def main():
     bytes_col = m * 1 + 4                                # uint8 pointer per state written + one float32 mean read
     vit_bytes = float(total_obs) * bytes_col
     achieved = vit_bytes / (vit_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_viterbi_lane" if args.generic_kernels else "k_viterbi_spec", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+    roof = {"bound": "hbm", "kernel": "k_viterbi_lane", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
             "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": None,
             "algorithmic_bytes_per_launch": vit_bytes, "launch_ms": vit_ms}
     b = model._baked
@@ -309,7 +306,6 @@ def main():
                        "from the model, batched forward + Viterbi with traceback".format(args.events, args.min_len, args.max_len),
                        "events_per_gpu": args.events, "observations_per_gpu": total_obs, "states": m, "edges": E,
                        "cells_per_step_per_gpu": cells_step, "parallelism": "events sharded, dp{}".format(world),
-                       "kernels": "runtime-schedule" if args.generic_kernels else "model-specialised",
                        "l2_policy": "inputs ({:.2f} GB) and traceback table ({:.1f} GB) per step exceed the 126 MB L2".format(
                            total_obs * 4 / 1e9, (total_obs + args.events) * m * 32 / 32 / 1e9)},
             "events_per_s": args.events * world * args.steps / elapsed,

@@ -78,23 +78,6 @@ void pp_model_destroy(pp_model *model);
 /* New parameters, same topology (after a Baum-Welch M-step, yahmm.pyx:4277-4327). */
 int pp_model_update_params(pp_model *model, const pp_model_desc *desc);
 
-/*
- * Model-specialised kernels.  The column kernels exist in two builds of the same hand-written source:
- * a runtime-schedule build inside this library (any model, no compiler needed) and a build compiled
- * against ONE model's schedule (csrc/pp_spec_kernels.cu + a generated schedule header), where column
- * slots are immediate offsets and weights are constant-bank operands.  Only the topology is baked in;
- * parameters live in a __constant__ table that pp_model_update_params refreshes.
- *   pp_spec_build            finds or builds <cache_dir>/pp_spec_<hash>.so with nvcc (no GPU needed);
- *                            so_path_out (may be NULL) receives its path.
- *   pp_model_specialize      pp_spec_build + load; later batched Viterbi / forward calls use it.
- *   pp_model_use_specialized switches between the two builds (A/B tests); returns 1 if the specialised
- *                            build will be used by the next call, 0 if not, < 0 on error.
- */
-int pp_spec_build(const pp_model_desc *desc, const char *src_dir, const char *cache_dir, char *so_path_out,
-                  int64_t cap);
-int pp_model_specialize(pp_model *model, const char *src_dir, const char *cache_dir);
-int pp_model_use_specialized(pp_model *model, int on);
-
 /* Text dump of the run schedule the kernels execute for this model (one line per warp and phase); needs no
  * GPU.  Returns the length of the full text (buf may be NULL to query it), < 0 on error. */
 int64_t pp_schedule_describe(const pp_model_desc *desc, char *buf, int64_t cap);

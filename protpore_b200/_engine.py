@@ -11,8 +11,6 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libprotpore_b200.so")
-SRC_DIR = os.path.join(_HERE, "csrc")
-SPEC_CACHE = os.environ.get("PP_SPEC_CACHE", os.path.join(_HERE, "_speccache"))
 
 PP_OK, PP_ERR_ARG, PP_ERR_CUDA, PP_ERR_NOMEM, PP_ERR_UNSUPPORTED, PP_ERR_CAPACITY = 0, -1, -2, -3, -4, -5
 PP_MEM_HOST, PP_MEM_DEVICE = 0, 1
@@ -54,11 +52,7 @@ ABI = [
     ("pp_model_destroy", None, [_vp]),
     ("pp_model_update_params", ctypes.c_int, [_vp, ctypes.POINTER(PPModelDesc)]),
     ("pp_model_set_workspace_limit", ctypes.c_int, [_vp, ctypes.c_int64]),
-    ("pp_spec_build", ctypes.c_int, [ctypes.POINTER(PPModelDesc), ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p,
-                                     ctypes.c_int64]),
-    ("pp_model_specialize", ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_char_p]),
     ("pp_schedule_describe", ctypes.c_int64, [ctypes.POINTER(PPModelDesc), ctypes.c_char_p, ctypes.c_int64]),
-    ("pp_model_use_specialized", ctypes.c_int, [_vp, ctypes.c_int]),
     ("pp_viterbi_workspace_bytes", ctypes.c_int64, [_vp, _vp, ctypes.c_int64]),
     ("pp_forward_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
     ("pp_viterbi_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp,
@@ -103,18 +97,6 @@ def make_desc(baked, kinds, p0, p1):
                        p("in_logp", _f64p), p("out_ptr", _i32p), p("out_dst", _i32p), p("out_logp", _f64p),
                        p("kind", _i32p), p("p0", _f64p), p("p1", _f64p), p("logw", _f64p))
     return desc, a
-
-
-def build_specialized(model, cache_dir=None):
-    """Compile the specialised kernel module of a baked `Model` (works without a GPU); returns its path."""
-    lib = load_library()
-    kinds, p0, p1 = model._device_params()
-    desc, keep = make_desc(model._baked, kinds, p0, p1)
-    buf = ctypes.create_string_buffer(4096)
-    rc = lib.pp_spec_build(ctypes.byref(desc), SRC_DIR.encode(), (cache_dir or SPEC_CACHE).encode(), buf, 4096)
-    if rc != PP_OK:
-        raise EngineError(rc, lib.pp_last_error().decode())
-    return buf.value.decode()
 
 
 def describe_schedule(model):
@@ -192,17 +174,6 @@ class Engine(object):
     def update_params(self, baked, kinds, p0, p1):
         desc = self._desc(baked, kinds, p0, p1)
         self._check(self._lib.pp_model_update_params(self._h, ctypes.byref(desc)))
-
-    def specialize(self, cache_dir=None):
-        """Compile (or load from the cache) the kernels specialised to this model's schedule and use them."""
-        self._check(self._lib.pp_model_specialize(self._h, SRC_DIR.encode(), (cache_dir or SPEC_CACHE).encode()))
-        return self
-
-    def use_specialized(self, on=True):
-        rc = self._lib.pp_model_use_specialized(self._h, 1 if on else 0)
-        if rc < 0:
-            self._check(rc)
-        return bool(rc)
 
     def set_workspace_limit(self, nbytes):
         self._check(self._lib.pp_model_set_workspace_limit(self._h, int(nbytes)))

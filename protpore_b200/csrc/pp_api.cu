@@ -102,13 +102,13 @@ int upload_model(pp_model* M) {
         g_arena_owner = nullptr;                                     // force a re-upload
         // global copies the kernels stage into shared memory: weights in lowered-edge order and
         // 4-double emission records per kernel family
-        std::vector<double> wl(n_low), wp(n_low), ev(4 * static_cast<size_t>(L.ne)), ef(4 * static_cast<size_t>(L.ne));
+        std::vector<double> wl(n_low), wp(n_low), ev(5 * static_cast<size_t>(L.ne)), ef(4 * static_cast<size_t>(L.ne));
         for (size_t i = 0; i < n_low; ++i) { wl[i] = L.edges_logp[0][i].val; wp[i] = L.edges_prob[0][i].val; }
         for (int k = 0; k < L.ne; ++k) {
             const EmisRec& R = L.emis[k];
-            double* a = &ev[4 * static_cast<size_t>(k)];
+            double* a = &ev[5 * static_cast<size_t>(k)];
             double* b = &ef[4 * static_cast<size_t>(k)];
-            a[0] = R.a0; a[1] = R.a1; a[2] = R.a2; a[3] = R.a3;
+            a[0] = R.a0; a[1] = R.a1; a[2] = R.a2; a[3] = R.a3; a[4] = R.logw;
             b[0] = R.a0; b[1] = R.kind == EMIS_NORMAL ? R.k2 : R.a1; b[2] = R.c2; b[3] = R.logw * 1.4426950408889634074;
         }
         PP_CUDA(upload(&M->d_wtab_logp, wl, s));
@@ -120,6 +120,7 @@ int upload_model(pp_model* M) {
     PP_CUDA(upload(&M->d_low_src, L.low_src, s));
     PP_CUDA(upload(&M->d_state_pword, L.state_pword, s));
     PP_CUDA(upload(&M->d_state_pshift, L.state_pshift, s));
+    PP_CUDA(upload(&M->d_state_pmul, L.state_pmul, s));
     PP_CUDA(upload(&M->d_in_ptr, M->in_ptr, s));
     PP_CUDA(upload(&M->d_in_src, M->in_src, s));
     PP_CUDA(upload(&M->d_in_logp, M->in_logp, s));
@@ -167,11 +168,11 @@ static LaneSched make_sched(const pp_model* M, bool logspace) {
     LaneSched S;
     const Lowered& L = M->low;
     for (int q = 0; q < 2; ++q) S.end_edges[q] = (logspace ? M->d_edges_logp[q] : M->d_edges_prob[q]).as<EdgeRec>();
-    S.warp_run_ranges = M->d_warp_run_ranges.as<int32_t>();
+    for (int i = 0; i < 8 * 6; ++i) S.run_ranges[i] = i < static_cast<int>(L.warp_run_ranges.size()) ? L.warp_run_ranges[i] : 0;
     S.wtab = (logspace ? M->d_wtab_logp : M->d_wtab_prob).as<double>();
     S.etab = (logspace ? M->d_etab_vit : M->d_etab_fwd).as<double>();
     S.n_low = static_cast<int32_t>(L.low_src.size());
-    S.logw_off = M->arena_emis;
+    S.etab_doubles = logspace ? 5 : 4;
     S.end_edge_begin = L.state_edge_begin[L.end];
     S.end_n_edges = L.state_n_edges[L.end];
     S.ptr_bits = L.ptr_bits;
@@ -232,18 +233,13 @@ static int host_offsets(pp_model* M, const int64_t* offsets, int64_t n_events, i
 
 template <typename ObsT>
 static int launch_viterbi(pp_model* M, const LaneBatch<ObsT>& B, const VitOut& O, int n_groups) {
-    if (M->spec.loaded() && M->use_spec) {
-        const int e = M->spec.viterbi(sizeof(ObsT) == 8, B.obs, B.offsets, B.order, B.group_len, B.group_row, O.score,
-                                      O.end_state, O.end_ord, O.ptr, n_groups, M->stream);
-        if (e != 0) { set_error("specialised Viterbi launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
-        ++M->launches;
-        return PP_OK;
-    }
     int brc = bind_arena(M);
     if (brc != PP_OK) return brc;
     const size_t smem = lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, 8);
-    PP_CUDA(cudaFuncSetAttribute(k_viterbi_lane<ObsT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_viterbi_lane<ObsT, 8><<<n_groups, 256, smem, M->stream>>>(make_sched(M, true), B, O);
+    PP_CUDA(cudaFuncSetAttribute(k_viterbi_lane<ObsT, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PP_CUDA(cudaFuncSetAttribute(k_viterbi_lane<ObsT, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (M->low.ptr_bits == 4) k_viterbi_lane<ObsT, 8, 4><<<n_groups, 256, smem, M->stream>>>(make_sched(M, true), B, O);
+    else k_viterbi_lane<ObsT, 8, 8><<<n_groups, 256, smem, M->stream>>>(make_sched(M, true), B, O);
     PP_CUDA(cudaGetLastError());
     ++M->launches;
     return PP_OK;
@@ -251,13 +247,6 @@ static int launch_viterbi(pp_model* M, const LaneBatch<ObsT>& B, const VitOut& O
 
 template <typename ObsT>
 static int launch_forward(pp_model* M, const LaneBatch<ObsT>& B, const FwdOut& O, int n_groups) {
-    if (M->spec.loaded() && M->use_spec) {
-        const int e = M->spec.forward(sizeof(ObsT) == 8, B.obs, B.offsets, B.order, B.group_len, B.group_row, O.logp,
-                                      n_groups, M->stream);
-        if (e != 0) { set_error("specialised forward launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
-        ++M->launches;
-        return PP_OK;
-    }
     int brc = bind_arena(M);
     if (brc != PP_OK) return brc;
     const size_t smem = lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, 8);
@@ -367,7 +356,7 @@ void pp_model_destroy(pp_model* M) {
     if (M->stream) cudaStreamSynchronize(M->stream);
     if (g_arena_owner == M) g_arena_owner = nullptr;
     DevBuf* bufs[] = {&M->d_edges_logp[0], &M->d_edges_logp[1], &M->d_edges_prob[0],
-                      &M->d_edges_prob[1], &M->d_emis, &M->d_warp_run_ranges, &M->d_wtab_logp, &M->d_wtab_prob, &M->d_etab_vit, &M->d_etab_fwd, &M->d_state_edge_begin, &M->d_low_src, &M->d_state_pword, &M->d_state_pshift,
+                      &M->d_edges_prob[1], &M->d_emis, &M->d_warp_run_ranges, &M->d_wtab_logp, &M->d_wtab_prob, &M->d_etab_vit, &M->d_etab_fwd, &M->d_state_edge_begin, &M->d_low_src, &M->d_state_pword, &M->d_state_pshift, &M->d_state_pmul,
                       &M->d_in_ptr, &M->d_in_src, &M->d_in_logp, &M->d_out_ptr, &M->d_out_dst, &M->d_out_logp,
                       &M->d_out_prob, &M->d_alive, &M->d_ws, &M->d_obs, &M->d_offsets, &M->d_order,
                       &M->d_group_len, &M->d_group_row, &M->d_score, &M->d_end_state, &M->d_end_ord, &M->d_path_len,
@@ -386,33 +375,7 @@ int pp_model_update_params(pp_model* M, const pp_model_desc* desc) {
     if (!err.empty()) { set_error("cannot refresh parameters: %s", err.c_str()); return PP_ERR_ARG; }
     copy_desc(M, desc);
     PP_CUDA(cudaSetDevice(M->device));
-    int rc = upload_model(M);
-    if (rc != PP_OK) return rc;
-    if (M->spec.loaded()) {
-        // emission KINDS are part of the specialised code (a point mass that became a Normal after an
-        // M-step changes the schedule header): rebuild when the header changed, else just refresh the table
-        if (generate_spec_header(M->low) != M->spec_header) {
-            spec_unload(&M->spec);
-            return pp_model_specialize(M, M->spec_src_dir.c_str(), M->spec_cache_dir.c_str());
-        }
-        const std::vector<double> w = spec_param_table(M->low);
-        const int e = M->spec.set_params(w.data(), static_cast<int>(w.size()), M->stream);
-        if (e != 0) { set_error("specialised parameter upload failed (%d)", e); return PP_ERR_CUDA; }
-        PP_CUDA(cudaStreamSynchronize(M->stream));
-    }
-    return PP_OK;
-}
-
-int pp_spec_build(const pp_model_desc* desc, const char* src_dir, const char* cache_dir, char* so_path_out, int64_t cap) {
-    if (!desc || !src_dir || !cache_dir) { set_error("null argument"); return PP_ERR_ARG; }
-    Lowered low;
-    std::string err = lower_model(*desc, 8, &low);
-    if (!err.empty()) { set_error("cannot lower model: %s", err.c_str()); return PP_ERR_UNSUPPORTED; }
-    std::string so, hash;
-    err = spec_build(low, src_dir, cache_dir, &so, &hash);
-    if (!err.empty()) { set_error("specialisation failed: %s", err.c_str()); return PP_ERR_UNSUPPORTED; }
-    if (so_path_out && cap > 0) std::snprintf(so_path_out, static_cast<size_t>(cap), "%s", so.c_str());
-    return PP_OK;
+    return upload_model(M);
 }
 
 int64_t pp_schedule_describe(const pp_model_desc* desc, char* buf, int64_t cap) {
@@ -425,36 +388,6 @@ int64_t pp_schedule_describe(const pp_model_desc* desc, char* buf, int64_t cap) 
     return static_cast<int64_t>(text.size());
 }
 
-int pp_model_specialize(pp_model* M, const char* src_dir, const char* cache_dir) {
-    if (!M || !src_dir || !cache_dir) { set_error("null argument"); return PP_ERR_ARG; }
-    PP_CUDA(cudaSetDevice(M->device));
-    if (lane_smem_bytes(M->low.n_slots, 8, 8) > M->smem_optin) {
-        set_error("model too large for the lane-per-event kernels; nothing to specialise");
-        return PP_ERR_UNSUPPORTED;
-    }
-    std::string so, hash;
-    std::string err = spec_build(M->low, src_dir, cache_dir, &so, &hash);
-    if (!err.empty()) { set_error("specialisation failed: %s", err.c_str()); return PP_ERR_UNSUPPORTED; }
-    SpecModule mod;
-    err = spec_load(so, M->low, &mod);
-    if (!err.empty()) { set_error("specialisation failed: %s", err.c_str()); return PP_ERR_UNSUPPORTED; }
-    mod.hash = hash;
-    const std::vector<double> w = spec_param_table(M->low);
-    const int e = mod.set_params(w.data(), static_cast<int>(w.size()), M->stream);
-    if (e != 0) { set_error("specialised parameter upload failed (%d)", e); return PP_ERR_CUDA; }
-    PP_CUDA(cudaStreamSynchronize(M->stream));
-    M->spec = mod;
-    M->spec_header = generate_spec_header(M->low);
-    M->spec_src_dir = src_dir;
-    M->spec_cache_dir = cache_dir;
-    return PP_OK;
-}
-
-int pp_model_use_specialized(pp_model* M, int on) {
-    if (!M) { set_error("null argument"); return PP_ERR_ARG; }
-    M->use_spec = on != 0;
-    return (M->spec.loaded() && M->use_spec) ? 1 : 0;
-}
 
 int pp_model_set_workspace_limit(pp_model* M, int64_t bytes) {
     if (!M || bytes <= 0) { set_error("bad workspace limit"); return PP_ERR_ARG; }
@@ -468,6 +401,15 @@ int64_t pp_viterbi_workspace_bytes(const pp_model* M, const int64_t* offsets_hos
     build_schedule(offsets_host, 0, n_events, &sc);
     return sc.total_rows * static_cast<int64_t>(M->low.n_ptr_words) * kLanes * 4;
 }
+
+#ifdef PP_PHASE_TIMING
+// debug build only (tools/phase_timing.py): per-warp phase clocks of k_viterbi_lane<float>, 8 warps x 8 slots
+int pp_debug_phase_cycles(unsigned long long* out, int reset) {
+    if (out) cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 64);
+    if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z); }
+    return 0;
+}
+#endif
 
 int64_t pp_launch_count(const pp_model* M) { return M ? M->launches : 0; }
 uint64_t pp_model_stream(const pp_model* M) { return M ? reinterpret_cast<uint64_t>(M->stream) : 0; }
@@ -571,7 +513,7 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
         // traceback pass 1: path lengths
         TraceArgs T{M->d_ws.as<uint32_t>(), M->d_order.as<int32_t>(), M->d_group_row.as<int64_t>(), d_off, d_score,
                     M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), M->d_state_edge_begin.as<int32_t>(),
-                    M->d_low_src.as<int32_t>(), M->d_state_pword.as<int32_t>(), M->d_state_pshift.as<int32_t>(),
+                    M->d_low_src.as<int32_t>(), M->d_state_pword.as<int32_t>(), M->d_state_pmul.as<int32_t>(), M->d_state_pshift.as<int32_t>(),
                     M->m, M->ne, M->start, M->low.end_final_only ? 1 : 0, M->low.n_ptr_words,
                     (1 << M->low.ptr_bits) - 1};
         const int nslots = sc.n_groups * kLanes;

@@ -126,8 +126,9 @@ struct TraceArgs {
     const int32_t* end_ord;
     const int32_t* state_edge_begin;   // [m]
     const int32_t* low_src;            // [lowered edges]
-    const int32_t* state_pword;        // [m] pointer word of a state's ordinal
-    const int32_t* state_pshift;       // [m] bit position inside the word
+    const int32_t* state_pword;        // [m] byte offset of lane 0's ordinal byte inside a pointer row
+    const int32_t* state_pmul;         // [m] bytes per lane of the unit holding it
+    const int32_t* state_pshift;       // [m] bit position inside that byte
     int32_t m, ne, start, end_final_only, n_ptr_words, ptr_mask;
 };
 
@@ -143,8 +144,8 @@ static __global__ void k_traceback(const TraceArgs T, int64_t* __restrict__ path
         return;
     }
     const int n = static_cast<int>(T.offsets[ev + 1] - T.offsets[ev]);
-    const uint32_t* base = T.ptr + (static_cast<size_t>(T.group_row[g]) * T.n_ptr_words) * kLanes + lane;
-    const size_t row_stride = static_cast<size_t>(T.n_ptr_words) * kLanes;
+    const size_t row_stride = static_cast<size_t>(T.n_ptr_words) * kLanes * 4;        // bytes
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(T.ptr) + static_cast<size_t>(T.group_row[g]) * row_stride;
     int64_t len = 1;
     int px = n, py = T.end_state[ev];
     int64_t pos = 0;
@@ -158,7 +159,7 @@ static __global__ void k_traceback(const TraceArgs T, int64_t* __restrict__ path
         if (out) out[pos--] = static_cast<uint16_t>(py);
         int ord;
         if (first && T.end_final_only) ord = T.end_ord[ev];
-        else ord = (base[static_cast<size_t>(px) * row_stride + static_cast<size_t>(T.state_pword[py]) * kLanes] >>
+        else ord = (base[static_cast<size_t>(px) * row_stride + T.state_pword[py] + lane * T.state_pmul[py]] >>
                     T.state_pshift[py]) & T.ptr_mask;
         first = false;
         const int src = T.low_src[T.state_edge_begin[py] + ord];

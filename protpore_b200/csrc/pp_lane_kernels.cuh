@@ -40,13 +40,24 @@ namespace pp {
 constexpr int kArenaDoubles = 7680;                       // 60 KB of the 64 KB constant bank
 static __constant__ double c_arena[kArenaDoubles];        // run records (+ log state weights)
 
+// Optional per-warp phase clocks (tools/phase_timing.py builds the library with -DPP_PHASE_TIMING): cycles a
+// warp spends working in phase B (silent / early), waiting at B's barrier, working in phase A, waiting at A's.
+#ifdef PP_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[8 * 8];
+#define PP_CLK(var) const long long var = clock64()
+#define PP_ACC(slot, a, b) phase_acc[slot] += static_cast<unsigned long long>((b) - (a))
+#else
+#define PP_CLK(var)
+#define PP_ACC(slot, a, b)
+#endif
+
 struct LaneSched {
     const EdgeRec* end_edges[2];     // lowered in-edges of the end state, per row parity (final score)
-    const int32_t* warp_run_ranges;  // [W][6]
+    int32_t run_ranges[8 * 6];       // per warp: {begin, end} of its late-emitting, silent and early-emitting runs
     const double* wtab;              // [n_low] transition weights in lowered-edge order: log p (Viterbi) or p (forward)
     const double* etab;              // [ne][4] emission records of this kernel family
     int32_t n_low;
-    int32_t logw_off;                // arena index of log(state.weight) per emitting state (Viterbi, rarely used)
+    int32_t etab_doubles;            // doubles per emission record (5 Viterbi, 4 forward)
     int32_t m, ne, ns, n_slots;
     int32_t start_slot_off;          // byte offset of the start state's slot
     int32_t end_slot_off;            // byte offset of the end state's slot
@@ -58,7 +69,7 @@ struct LaneSched {
 template <typename ObsT> struct TileCols { static constexpr int value = 128 / sizeof(ObsT); };
 
 __host__ __device__ inline size_t lane_smem_bytes2(int n_slots, int n_low, int ne, int warps) {
-    return static_cast<size_t>(n_slots) * kSlotBytes + static_cast<size_t>(n_low) * 8 + static_cast<size_t>(ne) * 32 +
+    return static_cast<size_t>(n_slots) * kSlotBytes + static_cast<size_t>(n_low) * 8 + static_cast<size_t>(ne) * 40 +
            static_cast<size_t>(32) * 33 * 4 + static_cast<size_t>(warps) * kLanes * sizeof(int32_t) + 64;
 }
 
@@ -74,37 +85,6 @@ __device__ __forceinline__ void sts64(uint32_t a, double v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 
-// traceback ordinals of consecutive items are packed into 32-bit words, one STG per full word
-struct PtrPack {
-    uint32_t* base;      // this lane's pointer row
-    int word;
-    uint32_t pw;
-    int sh, bits;
-    bool active;
-    __device__ __forceinline__ void flush() {
-        if (sh != 0 && active) base[static_cast<size_t>(word) * kLanes] = pw;
-        pw = 0;
-        sh = 0;
-    }
-    __device__ __forceinline__ void seat(int pword, int pshift) {
-        if (word != pword) {
-            flush();
-            word = pword;
-        }
-        sh = pshift;
-    }
-    __device__ __forceinline__ void push(uint32_t packed, int nbits) {       // never straddles a word (lowering)
-        pw |= packed << sh;
-        sh += nbits;
-        if (sh == 32) {
-            if (active) base[static_cast<size_t>(word) * kLanes] = pw;
-            ++word;
-            pw = 0;
-            sh = 0;
-        }
-    }
-};
-
 // induction state of one run: shared-memory addresses and byte strides
 template <int NE>
 struct RunPtrs {
@@ -112,9 +92,9 @@ struct RunPtrs {
     int ss[NE > 0 ? NE : 1];
     uint32_t dp, wp, ep;
     int ds, ws, es;
-    int kind, logw_i, logw_s;        // logw_i < 0: every log(state.weight) of the run is 0
+    int pbase;                       // byte offset of the next traceback unit inside the pointer row
     __device__ __forceinline__ void init(const RunRec& R, int par, uint32_t colb, uint32_t wtab, uint32_t etab,
-                                         int logw_off) {
+                                         int erec_bytes) {
 #pragma unroll
         for (int j = 0; j < NE; ++j) {
             ss[j] = R.src_stride[j];
@@ -124,11 +104,9 @@ struct RunPtrs {
         dp = colb + R.dst_off[par];
         ws = R.w_stride * 8;
         wp = wtab + R.w_base * 8;
-        es = R.e_stride * 32;
-        ep = etab + R.e_base * 32;
-        kind = R.kind;
-        logw_i = R.has_logw ? logw_off + R.e_base : -1;
-        logw_s = R.e_stride;
+        es = R.e_stride * erec_bytes;
+        ep = etab + R.e_base * erec_bytes;
+        pbase = R.pword;
     }
     __device__ __forceinline__ void advance(int g) {
 #pragma unroll
@@ -136,14 +114,17 @@ struct RunPtrs {
         dp += g * ds;
         wp += g * ws;
         ep += g * es;
-        if (logw_i >= 0) logw_i += g * logw_s;
     }
 };
 
-// exact float64 emission log-density from the shared-memory record {a0, a1, a2, a3} (see emission_log)
-__device__ __forceinline__ double smem_emission_log(int kind, uint32_t ep, double x) {
+constexpr int kVitEmisBytes = 40;    // Viterbi emission record {a0, a1, a2, a3, log(state.weight)}
+constexpr int kFwdEmisBytes = 32;    // forward emission record {a0, a1 | k2, c2, cu}
+
+// exact float64 emission log-density from the shared-memory record (see emission_log), + log(state.weight)
+template <int KIND>
+__device__ __forceinline__ double smem_emission_log(uint32_t ep, double x) {
     double r;
-    if (kind == EMIS_NORMAL) {
+    if (KIND == EMIS_NORMAL) {
         const double mu = lds64(ep), b = lds64(ep + 8), rinv = lds64(ep + 16), c = lds64(ep + 24);
         const double d = __dsub_rn(x, mu);
         const double d2 = __dmul_rn(d, d);
@@ -151,22 +132,23 @@ __device__ __forceinline__ double smem_emission_log(int kind, uint32_t ep, doubl
         const double rem = __fma_rn(-q0, b, d2);
         const double q = __fma_rn(rem, rinv, q0);
         r = __dsub_rn(c, q);
-    } else if (kind == EMIS_POINT) {
+    } else if (KIND == EMIS_POINT) {
         r = (fabs(__dsub_rn(x, lds64(ep))) < 1E-4) ? 0.0 : neg_inf();
     } else {
         const double a = lds64(ep), b = lds64(ep + 8);
         r = (x == a && x == b) ? 0.0 : ((x >= a && x <= b) ? lds64(ep + 24) : neg_inf());
     }
-    return r;
+    return __dadd_rn(r, lds64(ep + 32));
 }
 
 // forward record {a0, a1 | k2, c2, cu}: log2-domain emission of the linear-space sweep
-__device__ __forceinline__ double smem_emission_log2(int kind, uint32_t ep, double x) {
-    if (kind == EMIS_NORMAL) {
+template <int KIND>
+__device__ __forceinline__ double smem_emission_log2(uint32_t ep, double x) {
+    if (KIND == EMIS_NORMAL) {
         const double d = x - lds64(ep);
         return fma(-(d * d), lds64(ep + 8), lds64(ep + 16));
     }
-    if (kind == EMIS_POINT) return (fabs(x - lds64(ep)) < 1E-4) ? lds64(ep + 16) : neg_inf();
+    if (KIND == EMIS_POINT) return (fabs(x - lds64(ep)) < 1E-4) ? lds64(ep + 16) : neg_inf();
     const double a = lds64(ep), b = lds64(ep + 8);
     if (x == a && x == b) return lds64(ep + 24);
     return (x >= a && x <= b) ? lds64(ep + 16) : neg_inf();
@@ -174,51 +156,92 @@ __device__ __forceinline__ double smem_emission_log2(int kind, uint32_t ep, doub
 
 enum : int { MODE_EMIT = 0, MODE_SILENT = 1, MODE_CHAIN = 2 };
 
+// one coalesced store of the ordinals of a group: G items x BITS bits = 1, 2 or 4 bytes per lane
+template <int G, int BITS>
+__device__ __forceinline__ void store_ordinals(uint8_t* row, int& pbase, int lane, const uint32_t* arg, bool active) {
+    constexpr int UNIT = (G * BITS / 8) > 0 ? (G * BITS / 8) : 1;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) packed |= arg[g] << (g * BITS);
+    if (active) {
+        uint8_t* p = row + pbase + lane * UNIT;
+        if (UNIT == 1) *p = static_cast<uint8_t>(packed);
+        else if (UNIT == 2) *reinterpret_cast<uint16_t*>(p) = static_cast<uint16_t>(packed);
+        else *reinterpret_cast<uint32_t*>(p) = packed;
+    }
+    pbase += UNIT * kLanes;
+}
+
+// first maximum of s[lo, hi): a balanced tree of "right replaces left only if strictly greater" steps picks the
+// same index as the reference's left-to-right strict-'>' scan (the lowest index attaining the maximum), with a
+// dependent chain of log2(n) compare+select steps instead of n.
+template <int LO, int HI>
+struct FirstMax {
+    __device__ static __forceinline__ void run(const double* s, double& best, uint32_t& arg) {
+        constexpr int MID = (LO + HI) / 2;
+        double b2;
+        uint32_t a2;
+        FirstMax<LO, MID>::run(s, best, arg);
+        FirstMax<MID, HI>::run(s, b2, a2);
+        if (b2 > best) { best = b2; arg = a2; }
+    }
+};
+template <int LO>
+struct FirstMax<LO, LO + 1> {
+    __device__ static __forceinline__ void run(const double* s, double& best, uint32_t& arg) { best = s[LO]; arg = LO; }
+};
+
+struct VitCtx {
+    uint8_t* row;        // this row's traceback pointer bytes (group base; lane offset applied per unit)
+    int lane;
+    bool active;
+    double x;
+};
+
 // ------------------------------------------------------------------------------------------
 // Viterbi
 // ------------------------------------------------------------------------------------------
 // G consecutive items of a run.  MODE_CHAIN: the last edge of every item reads `prev`, the value of the
-// item before it.  The first candidate initialises (best, arg) directly: `s0 > -inf` can only be false
-// for s0 = -inf, which leaves the same (best, arg) = (-inf, 0) the reference ends up with.
-template <int NE, int MODE, int G>
-__device__ __forceinline__ void vit_group(RunPtrs<NE>& P, double x, bool start_row0, double& prev, PtrPack& pk) {
+// item before it.  Candidate j of an item is (v_j + t_j) + e for emitting items, v_j + t_j for silent ones,
+// exactly the reference's operations; the winner is the lowest index attaining the maximum, as the
+// reference's strict '>' scan leaves it (a candidate of -inf never displaces index 0 there either).
+template <int NE, int MODE, int G, int KIND, int BITS>
+__device__ __forceinline__ void vit_group(RunPtrs<NE>& P, const VitCtx& C, bool start_row0, double& prev) {
     constexpr int NL = (MODE == MODE_CHAIN) ? NE - 1 : NE;          // edges read from the column
-    double v[G][NL > 0 ? NL : 1], w[G][NE > 0 ? NE : 1], e[G], best[G];
+    double s[G][NL > 0 ? NL : 1], wl[G], e[G], best[G];
     uint32_t arg[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
 #pragma unroll
-        for (int j = 0; j < NL; ++j) v[g][j] = lds64(P.sp[j] + g * P.ss[j]);
+        for (int j = 0; j < NL; ++j) s[g][j] = lds64(P.sp[j] + g * P.ss[j]);
+    }
 #pragma unroll
-        for (int j = 0; j < NE; ++j) w[g][j] = lds64(P.wp + g * P.ws + j * 8);
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+        for (int j = 0; j < NL; ++j) s[g][j] = __dadd_rn(s[g][j], lds64(P.wp + g * P.ws + j * 8));
+        if (MODE == MODE_CHAIN) wl[g] = lds64(P.wp + g * P.ws + (NE - 1) * 8);
     }
     if (MODE == MODE_EMIT) {
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            e[g] = smem_emission_log(P.kind, P.ep + g * P.es, x);
-            e[g] = __dadd_rn(e[g], P.logw_i >= 0 ? c_arena[P.logw_i + g * P.logw_s] : 0.0);   // + log(state.weight)
+            e[g] = smem_emission_log<KIND>(P.ep + g * P.es, C.x);
+#pragma unroll
+            for (int j = 0; j < NL; ++j) s[g][j] = __dadd_rn(s[g][j], e[g]);
         }
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-        best[g] = neg_inf();
-        arg[g] = 0;
-#pragma unroll
-        for (int j = 0; j < NL; ++j) {
-            double s = __dadd_rn(v[g][j], w[g][j]);
-            if (MODE == MODE_EMIT) s = __dadd_rn(s, e[g]);
-            if (j == 0) {
-                best[g] = s;
-            } else if (s > best[g]) {
-                best[g] = s;
-                arg[g] = j;
-            }
+        if (NL > 0) {
+            FirstMax<0, (NL > 0 ? NL : 1)>::run(s[g], best[g], arg[g]);
+        } else {
+            best[g] = neg_inf();
+            arg[g] = 0;
         }
     }
     if (MODE == MODE_CHAIN) {
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const double t = __dadd_rn(prev, w[g][NE - 1]);
+            const double t = __dadd_rn(prev, wl[g]);
             if (NE == 1 || t > best[g]) {
                 best[g] = t;
                 arg[g] = NE - 1;
@@ -226,58 +249,61 @@ __device__ __forceinline__ void vit_group(RunPtrs<NE>& P, double x, bool start_r
             prev = best[g];
         }
     }
-    uint32_t packed = 0;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         if (start_row0) best[g] = 0.0;                // v[0, start] = 0 (3513-3514)
         sts64(P.dp + g * P.ds, best[g]);
-        packed |= arg[g] << (g * pk.bits);
     }
     if (MODE != MODE_CHAIN) prev = best[G - 1];
-    pk.push(packed, G * pk.bits);
+    store_ordinals<G, BITS>(C.row, P.pbase, C.lane, arg, C.active);
     P.advance(G);
 }
 
-template <int NE, int MODE>
-__device__ __forceinline__ void vit_items(RunPtrs<NE>& P, int count, double x, bool start_row0, double& prev,
-                                          PtrPack& pk) {
-    constexpr int G = (NE >= 3) ? 2 : 4;
-    int i = 0;
-    for (; i + G <= count; i += G) vit_group<NE, MODE, G>(P, x, start_row0, prev, pk);
-    for (; i < count; ++i) vit_group<NE, MODE, 1>(P, x, start_row0, prev, pk);
+template <int NE, int MODE, int KIND, int BITS>
+__device__ __forceinline__ void vit_items(RunPtrs<NE>& P, int count, const VitCtx& C, bool start_row0, double& prev) {
+    constexpr int G = run_group_size(NE);
+    int left = count;
+    for (; left >= G; left -= G) vit_group<NE, MODE, G, KIND, BITS>(P, C, start_row0, prev);
+    if (G > 2 && left >= 2) { vit_group<NE, MODE, 2, KIND, BITS>(P, C, start_row0, prev); left -= 2; }
+    if (left >= 1) vit_group<NE, MODE, 1, KIND, BITS>(P, C, start_row0, prev);
 }
 
-template <int NE>
+template <int NE, int BITS>
 __device__ __forceinline__ void vit_run_ne(const RunRec& R, int par, bool row0, uint32_t colb, uint32_t wtab,
-                                           uint32_t etab, double x, const LaneSched& S, PtrPack& pk) {
+                                           uint32_t etab, const VitCtx& C) {
     RunPtrs<NE> P;
-    P.init(R, par, colb, wtab, etab, S.logw_off);
-    pk.seat(R.pword, R.pshift);
+    P.init(R, par, colb, wtab, etab, kVitEmisBytes);
     double prev = 0.0;
     const int count = R.count;
-    if (R.kind <= EMIS_UNIFORM) {
-        vit_items<NE, MODE_EMIT>(P, count, x, false, prev, pk);
+    const int kind = R.kind;
+    if (kind == EMIS_NORMAL) {
+        vit_items<NE, MODE_EMIT, EMIS_NORMAL, BITS>(P, count, C, false, prev);
+    } else if (kind == EMIS_POINT) {
+        vit_items<NE, MODE_EMIT, EMIS_POINT, BITS>(P, count, C, false, prev);
+    } else if (kind == EMIS_UNIFORM) {
+        vit_items<NE, MODE_EMIT, EMIS_UNIFORM, BITS>(P, count, C, false, prev);
     } else if (NE > 0 && R.fwd) {
-        vit_group<NE, MODE_SILENT, 1>(P, x, false, prev, pk);       // chain head reads the column
-        vit_items<NE, MODE_CHAIN>(P, count - 1, x, false, prev, pk);
+        vit_group<NE, MODE_SILENT, 1, RUN_SILENT, BITS>(P, C, false, prev);       // chain head reads the column
+        vit_items<NE, MODE_CHAIN, RUN_SILENT, BITS>(P, count - 1, C, false, prev);
     } else {
-        vit_items<NE, MODE_SILENT>(P, count, x, row0 && R.kind == RUN_START, prev, pk);
+        vit_items<NE, MODE_SILENT, RUN_SILENT, BITS>(P, count, C, row0 && kind == RUN_START, prev);
     }
 }
 
+template <int BITS>
 __device__ __forceinline__ void vit_run(int r, int par, bool row0, uint32_t colb, uint32_t wtab, uint32_t etab,
-                                        double x, const LaneSched& S, PtrPack& pk) {
+                                        const VitCtx& C) {
     const RunRec& R = run_rec(r);
     switch (R.n_edges) {
-        case 0: vit_run_ne<0>(R, par, row0, colb, wtab, etab, x, S, pk); break;
-        case 1: vit_run_ne<1>(R, par, row0, colb, wtab, etab, x, S, pk); break;
-        case 2: vit_run_ne<2>(R, par, row0, colb, wtab, etab, x, S, pk); break;
-        case 3: vit_run_ne<3>(R, par, row0, colb, wtab, etab, x, S, pk); break;
-        case 4: vit_run_ne<4>(R, par, row0, colb, wtab, etab, x, S, pk); break;
-        case 5: vit_run_ne<5>(R, par, row0, colb, wtab, etab, x, S, pk); break;
-        case 6: vit_run_ne<6>(R, par, row0, colb, wtab, etab, x, S, pk); break;
-        case 7: vit_run_ne<7>(R, par, row0, colb, wtab, etab, x, S, pk); break;
-        default: vit_run_ne<8>(R, par, row0, colb, wtab, etab, x, S, pk); break;
+        case 0: vit_run_ne<0, BITS>(R, par, row0, colb, wtab, etab, C); break;
+        case 1: vit_run_ne<1, BITS>(R, par, row0, colb, wtab, etab, C); break;
+        case 2: vit_run_ne<2, BITS>(R, par, row0, colb, wtab, etab, C); break;
+        case 3: vit_run_ne<3, BITS>(R, par, row0, colb, wtab, etab, C); break;
+        case 4: vit_run_ne<4, BITS>(R, par, row0, colb, wtab, etab, C); break;
+        case 5: vit_run_ne<5, BITS>(R, par, row0, colb, wtab, etab, C); break;
+        case 6: vit_run_ne<6, BITS>(R, par, row0, colb, wtab, etab, C); break;
+        case 7: vit_run_ne<7, BITS>(R, par, row0, colb, wtab, etab, C); break;
+        default: vit_run_ne<8, BITS>(R, par, row0, colb, wtab, etab, C); break;
     }
 }
 
@@ -305,7 +331,7 @@ struct LaneSmem {
         col = smem;
         wtab = reinterpret_cast<double*>(smem + static_cast<size_t>(S.n_slots) * kSlotBytes);
         etab = wtab + S.n_low;
-        xt = reinterpret_cast<unsigned char*>(etab + static_cast<size_t>(S.ne) * 4);
+        xt = reinterpret_cast<unsigned char*>(etab + static_cast<size_t>(S.ne) * 5);
         wmax = reinterpret_cast<int32_t*>(xt + 32 * 33 * 4);
     }
 };
@@ -322,7 +348,7 @@ __device__ __forceinline__ void fill_tile2(ObsT* xt, const ObsT* __restrict__ ob
     }
 }
 
-template <typename ObsT, int W>
+template <typename ObsT, int W, int BITS>
 __global__ void __launch_bounds__(W * 32, 2)
 k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -330,7 +356,8 @@ k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
     constexpr int TC = TileCols<ObsT>::value;
     ObsT* xt = reinterpret_cast<ObsT*>(M.xt);
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // tells the compiler it is warp-uniform
     const int g = blockIdx.x;
     const int ev = B.order[g * kLanes + lane];
     const int64_t off = ev >= 0 ? B.offsets[ev] : 0;
@@ -340,50 +367,52 @@ k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
     const uint32_t colb = static_cast<uint32_t>(__cvta_generic_to_shared(colp));
     const uint32_t wtab = static_cast<uint32_t>(__cvta_generic_to_shared(M.wtab));
     const uint32_t etab = static_cast<uint32_t>(__cvta_generic_to_shared(M.etab));
-    uint32_t* prow = O.ptr + (static_cast<size_t>(B.group_row[g]) * S.n_ptr_words) * kLanes + lane;
-    const size_t row_stride = static_cast<size_t>(S.n_ptr_words) * kLanes;
+    const size_t row_stride = static_cast<size_t>(S.n_ptr_words) * kLanes * 4;                  // bytes per pointer row
+    uint8_t* prow = reinterpret_cast<uint8_t*>(O.ptr) + static_cast<size_t>(B.group_row[g]) * row_stride;
 
-    const int eb = S.warp_run_ranges[warp * 6 + 0], ee = S.warp_run_ranges[warp * 6 + 1];
-    const int sb = S.warp_run_ranges[warp * 6 + 3], se = S.warp_run_ranges[warp * 6 + 4];
+    const int ab = S.run_ranges[warp * 6 + 0], ae = S.run_ranges[warp * 6 + 1];     // A: late emitting
+    const int sb = S.run_ranges[warp * 6 + 2], se = S.run_ranges[warp * 6 + 3];     // B: silent
+    const int xb = S.run_ranges[warp * 6 + 4], xe = S.run_ranges[warp * 6 + 5];     // B: early emitting of the next row
 
     // stage the model: weights and emission records; row 0: v[0, :] = -inf, v[0, start] = 0 (3513-3514)
     for (int i = threadIdx.x; i < S.n_low; i += W * 32) M.wtab[i] = __ldg(S.wtab + i);
-    for (int i = threadIdx.x; i < S.ne * 4; i += W * 32) M.etab[i] = __ldg(S.etab + i);
+    for (int i = threadIdx.x; i < S.ne * S.etab_doubles; i += W * 32) M.etab[i] = __ldg(S.etab + i);
     double* col = reinterpret_cast<double*>(smem);
     for (int s = threadIdx.x; s < S.n_slots * kLanes; s += W * 32) col[s] = neg_inf();
     __syncthreads();
-    {   // silent closure of row 0 (3515-3542)
-        PtrPack pk{prow, -1, 0u, 0, S.ptr_bits, ev >= 0};
-        for (int u = sb; u < se; ++u) vit_run(u, 0, true, colb, wtab, etab, 0.0, S, pk);
-        pk.flush();
-    }
-    __syncthreads();
 
-    for (int r = 1; r <= nmax; ++r) {
+#ifdef PP_PHASE_TIMING
+    unsigned long long phase_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    double x = 0.0;                                          // observation of the row phase A works on
+    for (int r = 0;; ++r) {
+        // ---- phase B of row r: silent states of row r (3515-3542 for r = 0, 3564-3605 after) and the
+        //      early emitting states of row r + 1 (3545-3562), which only read emitting values of row r
         const int q = r & 1;
-        if (((r - 1) & (TC - 1)) == 0) {
-            fill_tile2<ObsT, W>(xt, B.obs, off, n, r - 1, warp, lane);
+        if (r < nmax && (r & (TC - 1)) == 0) {
+            fill_tile2<ObsT, W>(xt, B.obs, off, n, r, warp, lane);
             __syncthreads();
         }
-        const double x = static_cast<double>(xt[((r - 1) & (TC - 1)) * (kLanes + 1) + lane]);
-        const bool active = r <= n;
-        uint32_t* pr = prow + static_cast<size_t>(r) * row_stride;
+        PP_CLK(c0);
+        uint8_t* pr = prow + static_cast<size_t>(r) * row_stride;
         {
-            PtrPack pk{pr, -1, 0u, 0, S.ptr_bits, active};
-            for (int u = eb; u < ee; ++u) vit_run(u, q, false, colb, wtab, etab, x, S, pk);      // emitting (3545-3562)
-            pk.flush();
+            const VitCtx C{pr, lane, r == 0 ? ev >= 0 : r <= n, 0.0};
+            for (int u = sb; u < se; ++u) vit_run<BITS>(u, q, r == 0, colb, wtab, etab, C);
         }
-        __syncthreads();
-        {
-            PtrPack pk{pr, -1, 0u, 0, S.ptr_bits, active};
-            for (int u = sb; u < se; ++u) vit_run(u, q, false, colb, wtab, etab, x, S, pk);      // silent (3564-3605)
-            pk.flush();
+        PP_CLK(c1);
+        if (r < nmax) {
+            x = static_cast<double>(xt[(r & (TC - 1)) * (kLanes + 1) + lane]);       // obs[r] belongs to row r + 1
+            const VitCtx C{pr + row_stride, lane, r + 1 <= n, x};
+            for (int u = xb; u < xe; ++u) vit_run<BITS>(u, q ^ 1, false, colb, wtab, etab, C);
         }
+        PP_CLK(c2);
         __syncthreads();
+        PP_CLK(c3);
+        PP_ACC(0, c0, c1); PP_ACC(1, c1, c2); PP_ACC(2, c2, c3);
 
         // events whose last row this is: final score (3614-3619).  Warp 0 does it while the others
-        // already run the next row's emitting phase (they write E[q^1]; this reads E[q] and SIL).
-        if (warp == 0 && __any_sync(0xffffffffu, r == n)) {
+        // already run phase A of the next row (they write E[q^1]; this reads E[q] and SIL).
+        if (r >= 1 && warp == 0 && __any_sync(0xffffffffu, r == n)) {
             double score; int est = S.end_state, eord = 0;
             if (S.finite && S.end_final_only) {
                 vit_end_item((q ? S.end_edges[1] : S.end_edges[0]) + S.end_edge_begin, S.end_n_edges, colp, score, eord);
@@ -404,13 +433,32 @@ k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
                 O.end_ord[ev] = eord;
             }
         }
+        if (r == nmax) break;
+
+        // ---- phase A of row r + 1: late emitting states (they have a silent source of row r)
+        PP_CLK(c4);
+        {
+            const VitCtx C{pr + row_stride, lane, r + 1 <= n, x};
+            for (int u = ab; u < ae; ++u) vit_run<BITS>(u, q ^ 1, false, colb, wtab, etab, C);
+        }
+        PP_CLK(c5);
+        __syncthreads();
+        PP_CLK(c6);
+        PP_ACC(3, c4, c5); PP_ACC(4, c5, c6); PP_ACC(5, c3, c4);
+#ifdef PP_PHASE_TIMING
+        phase_acc[6] += 1;
+#endif
     }
+#ifdef PP_PHASE_TIMING
+    if (lane == 0)
+        for (int k = 0; k < 8; ++k) atomicAdd(&g_phase_cycles[warp * 8 + k], phase_acc[k]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
 // Forward (scaled linear space)
 // ------------------------------------------------------------------------------------------
-template <int NE, int MODE, int G>
+template <int NE, int MODE, int G, int KIND>
 __device__ __forceinline__ void fwd_group(RunPtrs<NE>& P, double x, double shiftd, bool start_row0, double& prev,
                                           int& mx) {
     constexpr int NL = (MODE == MODE_CHAIN) ? NE - 1 : NE;
@@ -423,14 +471,17 @@ __device__ __forceinline__ void fwd_group(RunPtrs<NE>& P, double x, double shift
         for (int j = 0; j < NE; ++j) w[g][j] = lds64(P.wp + g * P.ws + j * 8);
     }
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        acc[g] = 0.0;
+    for (int g = 0; g < G; ++g) {                 // two interleaved accumulators halve the dependent DFMA chain
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < NL; ++j) acc[g] = fma(v[g][j], w[g][j], acc[g]);
+        for (int j = 0; j < NL; j += 2) a0 = fma(v[g][j], w[g][j], a0);
+#pragma unroll
+        for (int j = 1; j < NL; j += 2) a1 = fma(v[g][j], w[g][j], a1);
+        acc[g] = a0 + a1;
     }
     if (MODE == MODE_EMIT) {
 #pragma unroll
-        for (int g = 0; g < G; ++g) acc[g] *= exp2_scaled(smem_emission_log2(P.kind, P.ep + g * P.es, x) + shiftd);
+        for (int g = 0; g < G; ++g) acc[g] *= exp2_scaled(smem_emission_log2<KIND>(P.ep + g * P.es, x) + shiftd);
     }
     if (MODE == MODE_CHAIN) {
 #pragma unroll
@@ -449,29 +500,35 @@ __device__ __forceinline__ void fwd_group(RunPtrs<NE>& P, double x, double shift
     P.advance(G);
 }
 
-template <int NE, int MODE>
+template <int NE, int MODE, int KIND>
 __device__ __forceinline__ void fwd_items(RunPtrs<NE>& P, int count, double x, double shiftd, bool start_row0,
                                           double& prev, int& mx) {
-    constexpr int G = (NE >= 3) ? 2 : 4;
-    int i = 0;
-    for (; i + G <= count; i += G) fwd_group<NE, MODE, G>(P, x, shiftd, start_row0, prev, mx);
-    for (; i < count; ++i) fwd_group<NE, MODE, 1>(P, x, shiftd, start_row0, prev, mx);
+    constexpr int G = run_group_size(NE);
+    int left = count;
+    for (; left >= G; left -= G) fwd_group<NE, MODE, G, KIND>(P, x, shiftd, start_row0, prev, mx);
+    if (G > 2 && left >= 2) { fwd_group<NE, MODE, 2, KIND>(P, x, shiftd, start_row0, prev, mx); left -= 2; }
+    if (left >= 1) fwd_group<NE, MODE, 1, KIND>(P, x, shiftd, start_row0, prev, mx);
 }
 
 template <int NE>
 __device__ __forceinline__ void fwd_run_ne(const RunRec& R, int par, bool row0, uint32_t colb, uint32_t wtab,
                                            uint32_t etab, double x, double shiftd, int& mx) {
     RunPtrs<NE> P;
-    P.init(R, par, colb, wtab, etab, 0);
+    P.init(R, par, colb, wtab, etab, kFwdEmisBytes);
     double prev = 0.0;
     const int count = R.count;
-    if (R.kind <= EMIS_UNIFORM) {
-        fwd_items<NE, MODE_EMIT>(P, count, x, shiftd, false, prev, mx);
+    const int kind = R.kind;
+    if (kind == EMIS_NORMAL) {
+        fwd_items<NE, MODE_EMIT, EMIS_NORMAL>(P, count, x, shiftd, false, prev, mx);
+    } else if (kind == EMIS_POINT) {
+        fwd_items<NE, MODE_EMIT, EMIS_POINT>(P, count, x, shiftd, false, prev, mx);
+    } else if (kind == EMIS_UNIFORM) {
+        fwd_items<NE, MODE_EMIT, EMIS_UNIFORM>(P, count, x, shiftd, false, prev, mx);
     } else if (NE > 0 && R.fwd) {
-        fwd_group<NE, MODE_SILENT, 1>(P, x, shiftd, false, prev, mx);
-        fwd_items<NE, MODE_CHAIN>(P, count - 1, x, shiftd, false, prev, mx);
+        fwd_group<NE, MODE_SILENT, 1, RUN_SILENT>(P, x, shiftd, false, prev, mx);
+        fwd_items<NE, MODE_CHAIN, RUN_SILENT>(P, count - 1, x, shiftd, false, prev, mx);
     } else {
-        fwd_items<NE, MODE_SILENT>(P, count, x, shiftd, row0 && R.kind == RUN_START, prev, mx);
+        fwd_items<NE, MODE_SILENT, RUN_SILENT>(P, count, x, shiftd, row0 && kind == RUN_START, prev, mx);
     }
 }
 
@@ -500,7 +557,8 @@ k_forward_lane(const LaneSched S, const LaneBatch<ObsT> B, const FwdOut O) {
     ObsT* xt = reinterpret_cast<ObsT*>(M.xt);
     int32_t* wmax = M.wmax;
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // tells the compiler it is warp-uniform
     const int g = blockIdx.x;
     const int ev = B.order[g * kLanes + lane];
     const int64_t off = ev >= 0 ? B.offsets[ev] : 0;
@@ -511,44 +569,51 @@ k_forward_lane(const LaneSched S, const LaneBatch<ObsT> B, const FwdOut O) {
     const uint32_t wtab = static_cast<uint32_t>(__cvta_generic_to_shared(M.wtab));
     const uint32_t etab = static_cast<uint32_t>(__cvta_generic_to_shared(M.etab));
 
-    const int eb = S.warp_run_ranges[warp * 6 + 0], ee = S.warp_run_ranges[warp * 6 + 1];
-    const int sb = S.warp_run_ranges[warp * 6 + 3], se = S.warp_run_ranges[warp * 6 + 4];
+    const int ab = S.run_ranges[warp * 6 + 0], ae = S.run_ranges[warp * 6 + 1];     // A: late emitting
+    const int sb = S.run_ranges[warp * 6 + 2], se = S.run_ranges[warp * 6 + 3];     // B: silent
+    const int xb = S.run_ranges[warp * 6 + 4], xe = S.run_ranges[warp * 6 + 5];     // B: early emitting of the next row
 
     for (int i = threadIdx.x; i < S.n_low; i += W * 32) M.wtab[i] = __ldg(S.wtab + i);
-    for (int i = threadIdx.x; i < S.ne * 4; i += W * 32) M.etab[i] = __ldg(S.etab + i);
+    for (int i = threadIdx.x; i < S.ne * S.etab_doubles; i += W * 32) M.etab[i] = __ldg(S.etab + i);
     double* col = reinterpret_cast<double*>(smem);
     for (int s = threadIdx.x; s < S.n_slots * kLanes; s += W * 32) col[s] = 0.0;
-    __syncthreads();
-    int mx = 0;                                   // max of the high words of this warp's new values
-    for (int u = sb; u < se; ++u) fwd_run(u, 0, true, colb, wtab, etab, 0.0, 0.0, mx);
-    wmax[warp * kLanes + lane] = mx;
+    wmax[warp * kLanes + lane] = 0;
     __syncthreads();
 
-    long long scale_total = 0;                    // sum of the power-of-two shifts applied so far
-    for (int r = 1; r <= nmax; ++r) {
+    // Scaling: the whole of row r + 1 is multiplied by 2^shift, shift chosen from the largest EMITTING value
+    // of row r (silent values of a row derive from its emitting values by probabilities <= 1).  Each warp
+    // tracks the maximum over the row-r values it produced (early ones in phase B of row r - 1, late ones in
+    // phase A of row r) and publishes it before the barrier that ends phase A.
+    long long scale_total = 0;                    // sum of the shifts of rows 1 .. r + 1
+    int mx = 0;                                   // max high word over this warp's emitting values of the next row
+    double x = 0.0, shiftd = 0.0;
+    for (int r = 0;; ++r) {
         const int q = r & 1;
-        // shift for this row from the previous row's maximum (exact power of two)
-        int Mx = 0;
+        const long long scale_row = scale_total;  // shifts applied up to row r (what the final score needs)
+        if (r < nmax) {
+            int Mx = 0;
 #pragma unroll
-        for (int w = 0; w < W; ++w) Mx = max(Mx, wmax[w * kLanes + lane]);
-        const int ex = (Mx >> 20) & 0x7ff;
-        int shift = (ex == 0 || ex == 0x7ff) ? 0 : (kFwdTargetExp + 1023 - ex);
-        shift = max(-900, min(900, shift));
-        scale_total += shift;
-        const double shiftd = static_cast<double>(shift);
-        if (((r - 1) & (TC - 1)) == 0) {
-            fill_tile2<ObsT, W>(xt, B.obs, off, n, r - 1, warp, lane);
-            __syncthreads();
+            for (int w = 0; w < W; ++w) Mx = max(Mx, wmax[w * kLanes + lane]);
+            const int ex = (Mx >> 20) & 0x7ff;
+            int shift = (ex == 0 || ex == 0x7ff) ? 0 : (kFwdTargetExp + 1023 - ex);
+            shift = max(-900, min(900, shift));
+            scale_total += shift;
+            shiftd = static_cast<double>(shift);
+            if ((r & (TC - 1)) == 0) {
+                fill_tile2<ObsT, W>(xt, B.obs, off, n, r, warp, lane);
+                __syncthreads();
+            }
         }
-        const double x = static_cast<double>(xt[((r - 1) & (TC - 1)) * (kLanes + 1) + lane]);
+        int mxs = 0;                              // silent values do not steer the scale
+        for (int u = sb; u < se; ++u) fwd_run(u, q, r == 0, colb, wtab, etab, 0.0, 0.0, mxs);    // silent (2847-2871, 2891-2926)
         mx = 0;
-        for (int u = eb; u < ee; ++u) fwd_run(u, q, false, colb, wtab, etab, x, shiftd, mx);      // emitting (2874-2889)
-        __syncthreads();
-        for (int u = sb; u < se; ++u) fwd_run(u, q, false, colb, wtab, etab, x, shiftd, mx);      // silent (2891-2926)
-        wmax[warp * kLanes + lane] = mx;
+        if (r < nmax) {
+            x = static_cast<double>(xt[(r & (TC - 1)) * (kLanes + 1) + lane]);
+            for (int u = xb; u < xe; ++u) fwd_run(u, q ^ 1, false, colb, wtab, etab, x, shiftd, mx);   // early emitting of row r + 1
+        }
         __syncthreads();
 
-        if (warp == 0 && __any_sync(0xffffffffu, r == n)) {          // log_probability (3378-3396)
+        if (r >= 1 && warp == 0 && __any_sync(0xffffffffu, r == n)) {          // log_probability (3378-3396)
             double P;
             if (S.finite && S.end_final_only) {
                 const EdgeRec* ep = (q ? S.end_edges[1] : S.end_edges[0]) + S.end_edge_begin;
@@ -571,10 +636,15 @@ k_forward_lane(const LaneSched S, const LaneBatch<ObsT> B, const FwdOut O) {
                 double lp;
                 if (P == 0.0) lp = neg_inf();
                 else if (!(P < __longlong_as_double(0x7FF0000000000000LL))) lp = __longlong_as_double(0x7FF8000000000000LL);
-                else lp = log(P) - static_cast<double>(scale_total) * 0.693147180559945309417;
+                else lp = log(P) - static_cast<double>(scale_row) * 0.693147180559945309417;
                 O.logp[ev] = lp;
             }
         }
+        if (r == nmax) break;
+
+        for (int u = ab; u < ae; ++u) fwd_run(u, q ^ 1, false, colb, wtab, etab, x, shiftd, mx);       // late emitting (2874-2889)
+        wmax[warp * kLanes + lane] = mx;
+        __syncthreads();
     }
 }
 

@@ -225,26 +225,40 @@ std::string lower_model(const pp_model_desc& d, int warps, Lowered* low) {
         }
     };
 
-    std::vector<std::vector<int>> emit_of(warps), sil_of(warps);
-    {   // emitting: sort by shape, then cut the sequence into W contiguous slices of equal cost
-        std::vector<int> order(ne);
-        std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    // Phases of one row r (steady state), separated by the two barriers of the row:
+    //   A  "late" emitting states of row r  -- those with a silent source, so they need silent(r-1);
+    //   B  silent states of row r, and next to them the "early" emitting states of row r+1 -- those
+    //      whose sources are all emitting states of row r, already complete after phase A's barrier.
+    // Early items fill the warps that have no silent chain to walk: in a profile HMM the chain owners
+    // are busy for the whole of phase B while everybody else would idle at the barrier.
+    std::vector<std::vector<int>> late_of(warps), early_of(warps), sil_of(warps);
+    std::vector<int> late, early;
+    for (int l = 0; l < ne; ++l) {
+        bool has_silent_src = false;
+        for (int k = 0; k < low->state_n_edges[l]; ++k)
+            if (low->low_src[low->state_edge_begin[l] + k] >= ne) has_silent_src = true;
+        (has_silent_src ? late : early).push_back(l);
+    }
+    auto shape_sort = [&](std::vector<int>* v) {
+        std::stable_sort(v->begin(), v->end(), [&](int a, int b) {
             if (low->state_n_edges[a] != low->state_n_edges[b]) return low->state_n_edges[a] > low->state_n_edges[b];
             return low->emis[a].kind < low->emis[b].kind;
         });
-        auto cost = [&](int l) { return 9L * low->state_n_edges[l] + (low->emis[l].kind == EMIS_NORMAL ? 22 : 14); };
-        long total = 0;
-        for (int l : order) total += cost(l);
-        long acc = 0;
+    };
+    auto emit_cost = [&](int l) { return 9L * low->state_n_edges[l] + (low->emis[l].kind == EMIS_NORMAL ? 22 : 14); };
+    shape_sort(&late);
+    shape_sort(&early);
+    {   // late: cut the shape-sorted sequence into W contiguous slices of equal cost
+        long total = 0, acc = 0;
+        for (int l : late) total += emit_cost(l);
         int w = 0;
-        for (int l : order) {
-            // move on when this warp has its share (keep at least the remaining warps non-empty-able)
+        for (int l : late) {
             if (w + 1 < warps && acc >= (total * (w + 1)) / warps) ++w;
-            emit_of[w].push_back(l);
-            acc += cost(l);
+            late_of[w].push_back(l);
+            acc += emit_cost(l);
         }
     }
+    std::vector<long> load_b(warps, 0);               // phase-B load per warp (silent work first)
     {   // silent: connected components of the silent sub-DAG, whole components per warp
         UnionFind uf(m);
         for (int l = ne; l < m; ++l) {
@@ -268,19 +282,19 @@ std::string lower_model(const pp_model_desc& d, int warps, Lowered* low) {
             long s = 0;
             for (int l : comps[c]) s += 9L * low->state_n_edges[l] + 8;
             // a chain is latency-bound: weigh long components far above their instruction count
-            return s + (comps[c].size() > 1 ? 30L * static_cast<long>(comps[c].size()) : 0L);
+            return s + (comps[c].size() > 1 ? 60L * static_cast<long>(comps[c].size()) : 0L);
         };
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
-        std::vector<long> load(warps, 0);
         std::vector<std::vector<int>> chains(warps), singles(warps);
         for (int c : order) {
-            int w = static_cast<int>(std::min_element(load.begin(), load.end()) - load.begin());
+            int w = static_cast<int>(std::min_element(load_b.begin(), load_b.end()) - load_b.begin());
             auto& dstv = comps[c].size() > 1 ? chains[w] : singles[w];
             for (int l : comps[c]) dstv.push_back(l);
-            load[w] += cost(c);
+            load_b[w] += cost(c);
         }
         for (int w = 0; w < warps; ++w) {
-            // independent single states first, sorted by (shape, index) so that they form runs; chains after
+            // chains first (the critical path starts at once), then the independent single states sorted by
+            // (shape, index) so that they form runs
             std::stable_sort(singles[w].begin(), singles[w].end(), [&](int a, int b) {
                 if (low->state_n_edges[a] != low->state_n_edges[b]) return low->state_n_edges[a] > low->state_n_edges[b];
                 return a < b;
@@ -289,42 +303,73 @@ std::string lower_model(const pp_model_desc& d, int warps, Lowered* low) {
             sil_of[w].insert(sil_of[w].end(), singles[w].begin(), singles[w].end());
         }
     }
-
-    // traceback pointer packing: ordinals of consecutive items of one (warp, phase) share 32-bit words
-    low->ptr_bits = low->max_item_edges <= 16 ? 4 : 8;
-    const int per_word = 32 / low->ptr_bits;
-    low->state_pword.assign(m, -1);
-    low->state_pshift.assign(m, 0);
-    int next_word = 0;
-    low->runs.clear();
-    low->warp_run_ranges.assign(static_cast<size_t>(warps) * 6, 0);
-    for (int w = 0; w < warps; ++w) {
-        for (int phase = 0; phase < 2; ++phase) {
-            const std::vector<int>& states = phase == 0 ? emit_of[w] : sil_of[w];
-            low->warp_run_ranges[w * 6 + phase * 3 + 0] = static_cast<int32_t>(low->runs.size());
-            make_runs(states, phase == 1, &low->runs);
-            low->warp_run_ranges[w * 6 + phase * 3 + 1] = static_cast<int32_t>(low->runs.size());
-            low->warp_run_ranges[w * 6 + phase * 3 + 2] = next_word;         // first pointer word of this (warp, phase)
-            // ordinal slots: consecutive within a run; every run starts on a multiple of 4 slots so that the
-            // kernels can pack the ordinals of 2 or 4 items with one shift (a group never straddles a word)
-            int slot = 0;
-            size_t si = 0;
-            for (int r = low->warp_run_ranges[w * 6 + phase * 3]; r < low->warp_run_ranges[w * 6 + phase * 3 + 1]; ++r) {
-                RunRec& R = low->runs[r];
-                // a chain run handles its head alone and then groups of 4: seat the head on slot = 3 (mod 4)
-                slot = R.fwd ? (((slot + 4) & ~3) - 1) : ((slot + 3) & ~3);
-                R.pword = next_word + slot / per_word;
-                R.pshift = (slot % per_word) * low->ptr_bits;
-                for (int i = 0; i < R.count; ++i, ++si, ++slot) {
-                    low->state_pword[states[si]] = next_word + slot / per_word;
-                    low->state_pshift[states[si]] = (slot % per_word) * low->ptr_bits;
-                }
-            }
-            next_word += (slot + per_word - 1) / per_word;
+    {   // early: fill the warps up to a common phase-B level (water-filling over the shape-sorted sequence)
+        long need = 0;
+        for (int l : early) need += emit_cost(l);
+        // smallest level such that sum_w max(0, level - load_b[w]) covers the early work
+        long lo = *std::min_element(load_b.begin(), load_b.end());
+        long hi = *std::max_element(load_b.begin(), load_b.end()) + need + 1;
+        while (lo < hi) {
+            const long mid = lo + (hi - lo) / 2;
+            long cap = 0;
+            for (long v : load_b) cap += std::max(0L, mid - v);
+            if (cap >= need) hi = mid; else lo = mid + 1;
+        }
+        const long level = lo;
+        int w = 0;
+        long acc = 0;
+        for (int l : early) {
+            while (w + 1 < warps && acc + load_b[w] >= level) { ++w; acc = 0; }
+            early_of[w].push_back(l);
+            acc += emit_cost(l);
         }
     }
-    low->n_ptr_words = next_word;
-    low->emit_of = emit_of;
+
+    // Traceback ordinals.  The kernels handle a run in GROUPS of 4 items (in-degree <= 2) or 2 items (more),
+    // then a remainder of one pair and/or one single; a chain run handles its head alone first.  Each group
+    // stores ITS ordinals with one coalesced store: a UNIT of 1, 2 or 4 bytes per lane, laid out as
+    // [unit][lane] -- so there is no packing state carried between items.  Ordinals take 4 bits when every
+    // item has <= 16 in-edges, else 8.
+    low->ptr_bits = low->max_item_edges <= 16 ? 4 : 8;
+    low->state_pword.assign(m, -1);
+    low->state_pmul.assign(m, 1);
+    low->state_pshift.assign(m, 0);
+    int row_bytes = 0;
+    low->runs.clear();
+    low->warp_run_ranges.assign(static_cast<size_t>(warps) * 6, 0);
+    auto place = [&](const std::vector<int>& states, size_t* si, int n_items) {      // one unit holding n_items ordinals
+        const int unit = std::max(1, n_items * low->ptr_bits / 8);
+        for (int k = 0; k < n_items; ++k, ++*si) {
+            const int bit = k * low->ptr_bits;
+            low->state_pword[states[*si]] = row_bytes + bit / 8;
+            low->state_pmul[states[*si]] = unit;
+            low->state_pshift[states[*si]] = bit % 8;
+        }
+        row_bytes += unit * kLanes;
+    };
+    for (int w = 0; w < warps; ++w) {
+        for (int list = 0; list < 3; ++list) {                  // 0: late emitting (A), 1: silent (B), 2: early emitting (B)
+            const std::vector<int>& states = list == 0 ? late_of[w] : (list == 1 ? sil_of[w] : early_of[w]);
+            low->warp_run_ranges[w * 6 + list * 2 + 0] = static_cast<int32_t>(low->runs.size());
+            make_runs(states, list == 1, &low->runs);
+            low->warp_run_ranges[w * 6 + list * 2 + 1] = static_cast<int32_t>(low->runs.size());
+            size_t si = 0;
+            for (int r = low->warp_run_ranges[w * 6 + list * 2]; r < low->warp_run_ranges[w * 6 + list * 2 + 1]; ++r) {
+                RunRec& R = low->runs[r];
+                R.pword = row_bytes;                             // byte offset of the run's first unit in a pointer row
+                R.pshift = 0;
+                int left = R.count;
+                if (R.fwd) { place(states, &si, 1); --left; }    // chain head
+                const int G = run_group_size(R.n_edges);
+                for (; left >= G; left -= G) place(states, &si, G);
+                if (left >= 2) { place(states, &si, 2); left -= 2; }
+                if (left >= 1) { place(states, &si, 1); left -= 1; }
+            }
+        }
+    }
+    low->n_ptr_words = (row_bytes + 127) / 128;                  // pointer-row stride in units of 32 lanes x 4 bytes
+    low->late_of = late_of;
+    low->early_of = early_of;
     low->sil_of = sil_of;
     return "";
 }

@@ -42,6 +42,8 @@ struct __attribute__((aligned(16))) EdgeRec {
 // A RUN: `count` items of one shape whose slots / weights / emission records advance by constant strides
 // (position k, k+1, ... of a profile).  Executed by one shape-templated loop body (pp_lane_kernels.cuh).
 constexpr int kMaxRunEdges = 8;
+// items a kernel handles at once in a run of this in-degree (kernels and lowering must agree)
+constexpr int run_group_size(int n_edges) { return n_edges <= 2 ? 4 : 2; }
 enum : int32_t { EMIS_NORMAL = 0, EMIS_POINT = 1, EMIS_UNIFORM = 2, RUN_SILENT = 3, RUN_START = 4 };
 struct __attribute__((aligned(16))) RunRec {
     int32_t kind;                                // EMIS_* for emitting items, RUN_SILENT, RUN_START (the start state)
@@ -52,7 +54,7 @@ struct __attribute__((aligned(16))) RunRec {
     int32_t dst_stride;                          // bytes per item
     int32_t w_base, w_stride;                    // weight-table index of the first item's first edge; per item
     int32_t e_base, e_stride;                    // emission-record index of the first item; per item
-    int32_t pword, pshift;                       // traceback ordinal of the first item: pointer word, bit position
+    int32_t pword, pshift;                       // pword: byte offset, inside a traceback pointer row, of the run's first unit
     int32_t has_logw;                            // some item of the run has log(state.weight) != 0
     int32_t pad[2];
     int32_t src_off[2][kMaxRunEdges];            // byte offset of each edge's first source slot, per row parity
@@ -76,13 +78,15 @@ struct Lowered {
     int32_t n_slots = 0;                         // ns + 2*ne column slots
     int32_t max_item_edges = 0;                  // over per-row items (end excluded if final-only)
     int32_t ptr_bits = 8;                        // traceback ordinal width: 4 if every item has <= 16 edges, else 8
-    int32_t n_ptr_words = 0;                     // 32-bit pointer words per lane per row
-    std::vector<int32_t> state_pword, state_pshift;   // per state (traceback lookup); -1 for a final-only end
-    std::vector<RunRec> runs;                    // warp-major: emitting runs then silent runs of each warp
-    std::vector<int32_t> warp_run_ranges;        // [warps][6]: {run_begin, run_end, first pointer word} x {emit, silent}
+    int32_t n_ptr_words = 0;                     // pointer-row stride in units of 128 bytes (32 lanes x 4 bytes)
+    // per state (traceback lookup): lane l finds the ordinal at byte state_pword + l * state_pmul of the row, shifted
+    // right by state_pshift; state_pword = -1 for a final-only end state
+    std::vector<int32_t> state_pword, state_pmul, state_pshift;
+    std::vector<RunRec> runs;                    // warp-major: late-emitting, silent, early-emitting runs of each warp
+    std::vector<int32_t> warp_run_ranges;        // [warps][6]: {run_begin, run_end} x {late emitting (A), silent (B), early emitting (B)}
     bool lane_ok = true;                         // false: some state has too many in-edges for the run kernels
     std::string lane_why;
-    std::vector<std::vector<int>> emit_of, sil_of;   // states per warp, in execution order
+    std::vector<std::vector<int>> late_of, sil_of, early_of;   // states per warp and list, in execution order
     std::vector<EdgeRec> edges_logp[2];          // per row parity, val = log p
     std::vector<EdgeRec> edges_prob[2];          // per row parity, val = p
     std::vector<int32_t> low_csr;                // index of each lowered edge in the IN-edge CSR
@@ -98,5 +102,7 @@ struct Lowered {
 std::string lower_model(const pp_model_desc& d, int warps, Lowered* out);
 // Refresh weights / emission parameters of an existing lowering (same topology).
 std::string refresh_params(const pp_model_desc& d, Lowered* low);
+// One line per warp and phase: the runs it executes (pp_describe.cpp).
+std::string describe_schedule(const Lowered& L);
 
 }  // namespace pp

@@ -5,7 +5,6 @@
 
 #include "pp_common.h"
 #include "pp_lowering.h"
-#include "pp_spec.h"
 
 // Kernel-time slots reported by pp_profile_get (milliseconds of the last batched call, summed over
 // its chunks, measured with CUDA events on the model's stream).
@@ -40,7 +39,7 @@ struct pp_model {
     std::vector<double> arena;            // host image of the constant arena: [runs | log p | p | emission records]
     int32_t arena_emis = 0;
     pp::DevBuf d_wtab_logp, d_wtab_prob, d_etab_vit, d_etab_fwd;
-    pp::DevBuf d_state_edge_begin, d_low_src, d_state_pword, d_state_pshift;
+    pp::DevBuf d_state_edge_begin, d_low_src, d_state_pword, d_state_pshift, d_state_pmul;
     // device copy of the baked CSR (state-parallel kernels, sampler)
     pp::DevBuf d_in_ptr, d_in_src, d_in_logp, d_out_ptr, d_out_dst, d_out_logp, d_out_prob, d_alive;
     pp::DevBuf d_lev_ptr, d_lev_states, d_rlev_ptr, d_rlev_states;
@@ -52,11 +51,6 @@ struct pp_model {
     pp::DevBuf d_score, d_end_state, d_end_ord, d_path_len, d_path_off, d_path, d_scan_tmp, d_logp;
     pp::DevBuf d_tab, d_xbuf, d_tab_off, d_list, d_counter, d_stats;
     size_t ws_limit = 0;
-
-    // model-specialised kernel module (pp_spec.h); used instead of the runtime-schedule kernels when loaded
-    pp::SpecModule spec;
-    bool use_spec = true;
-    std::string spec_header, spec_src_dir, spec_cache_dir;
 
     cudaEvent_t ev[2] = {nullptr, nullptr};
     double prof[PP_PROF_SLOTS] = {0};

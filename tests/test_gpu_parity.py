@@ -201,45 +201,3 @@ def test_pypore_apply_hmm(models):
     assert one[0] == g["vscore"][0] and one[1][0][1].name.endswith("-start")
     many = pypore.apply_hmm_batch(pev, model, 'viterbi')
     assert [m[0] for m in many] == list(g["vscore"][:6])
-
-
-@pytest.mark.parametrize("name", ["pro_001_py2", "toy_uniform", "toy_infinite", "synth_12"])
-def test_specialised_kernels_match_runtime_schedule_kernels(name):
-    """The model-specialised build (compile-time schedule) and the runtime-schedule build of the same
-    kernels give bit-identical Viterbi scores / paths and bit-identical forward log-probabilities."""
-    g = util.load_golden(name)
-    model = util.build_model(name)
-    eng = model.engine()
-    obs, offsets = _engine.pack_events(util.golden_events(g), np.float64)
-    assert not eng.use_specialized(True)                   # nothing loaded yet
-    s0, l0, p0 = eng.viterbi_batch(obs, offsets)
-    f0 = eng.forward_batch(obs, offsets)
-    eng.specialize()
-    assert eng.use_specialized(True)
-    s1, l1, p1 = eng.viterbi_batch(obs, offsets)
-    f1 = eng.forward_batch(obs, offsets)
-    assert np.array_equal(s0, s1) and np.array_equal(l0, l1) and np.array_equal(p0, p1)
-    assert np.array_equal(f0, f1, equal_nan=True)
-    assert np.array_equal(s1, g["vscore"])
-    assert util.close(f1, g["logp"]).all()
-    eng.use_specialized(False)
-    s2, _, _ = eng.viterbi_batch(obs, offsets)
-    assert np.array_equal(s2, s0)
-
-
-def test_specialised_kernels_follow_parameter_updates():
-    """Baum-Welch with the specialised build loaded: the constant table is refreshed (and the module rebuilt
-    when a point-mass emission turns into a Normal), results equal the runtime-schedule run."""
-    g = util.load_golden("synth_12")
-    evs = util.golden_events(g)
-    seqs = [evs[i] for i in g["bw_events"]]
-    a, b = util.build_model("synth_12"), util.build_model("synth_12")
-    b.engine().specialize()
-    ia = a.train(seqs, max_iterations=2, verbose=False)
-    ib = b.train(seqs, max_iterations=2, verbose=False)
-    assert ia == pytest.approx(ib, rel=1e-12, abs=1e-12)
-    ra = a.viterbi_batch(evs, dtype=np.float64, states=False)
-    rb = b.viterbi_batch(evs, dtype=np.float64, states=False)
-    assert b.engine().use_specialized(True)
-    for (sa, pa), (sb, pb) in zip(ra, rb):
-        assert sa == sb and ((pa is None and pb is None) or np.array_equal(pa, pb))
