@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprotpore_b200.so")
+LIB_PATH = os.environ.get("PROTPORE_B200_LIB", os.path.join(_HERE, "libprotpore_b200.so"))
 
 PP_OK, PP_ERR_ARG, PP_ERR_CUDA, PP_ERR_NOMEM, PP_ERR_UNSUPPORTED, PP_ERR_CAPACITY = 0, -1, -2, -3, -4, -5
 PP_MEM_HOST, PP_MEM_DEVICE = 0, 1

@@ -11,7 +11,7 @@
 #include <cstring>
 #include <new>
 
-#include "pp_lane_kernels.cuh"
+#include "pp_lane_types.h"
 #include "pp_model.h"
 
 namespace pp {
@@ -27,22 +27,20 @@ void set_error(const char* fmt, ...) {
     g_err = buf;
 }
 
-// The run kernels read their schedule from the __constant__ arena of this translation unit, which all
-// handles of the process share: it is (re)uploaded, stream-ordered, whenever the handle about to launch
-// is not the one whose image is resident.  Batched calls are synchronous, so a mutex around
-// upload + launch + synchronise is all the coordination two handles need.
-static const pp_model* g_arena_owner = nullptr;
+void lane_viterbi4_invalidate(const void*);
+void lane_viterbi8_invalidate(const void*);
+void lane_forward_invalidate(const void*);
+void lane_arena_invalidate(const void* owner) {
+    lane_viterbi4_invalidate(owner);
+    lane_viterbi8_invalidate(owner);
+    lane_forward_invalidate(owner);
+}
 
-static int bind_arena(pp_model* M) {
+static int check_lane_model(pp_model* M) {
     if (!M->low.lane_ok) { set_error("model cannot run on the lane-per-event kernels: %s", M->low.lane_why.c_str()); return PP_ERR_UNSUPPORTED; }
     if (M->arena.size() > static_cast<size_t>(kArenaDoubles)) {
         set_error("model schedule needs %zu bytes of constant memory (limit %d)", M->arena.size() * 8, kArenaDoubles * 8);
         return PP_ERR_UNSUPPORTED;
-    }
-    if (g_arena_owner != M) {
-        PP_CUDA(cudaMemcpyToSymbolAsync(c_arena, M->arena.data(), M->arena.size() * sizeof(double), 0,
-                                        cudaMemcpyHostToDevice, M->stream));
-        g_arena_owner = M;
     }
     return PP_OK;
 }
@@ -99,7 +97,7 @@ int upload_model(pp_model* M) {
         M->arena.assign(run_d + static_cast<size_t>(L.ne), 0.0);
         if (!L.runs.empty()) std::memcpy(M->arena.data(), L.runs.data(), L.runs.size() * sizeof(RunRec));
         for (int k = 0; k < L.ne; ++k) M->arena[run_d + k] = L.emis[k].logw;
-        g_arena_owner = nullptr;                                     // force a re-upload
+        lane_arena_invalidate(M);                                    // force a re-upload
         // global copies the kernels stage into shared memory: weights in lowered-edge order and
         // 4-double emission records per kernel family
         std::vector<double> wl(n_low), wp(n_low), ev(5 * static_cast<size_t>(L.ne)), ef(4 * static_cast<size_t>(L.ne));
@@ -168,7 +166,7 @@ static LaneSched make_sched(const pp_model* M, bool logspace) {
     LaneSched S;
     const Lowered& L = M->low;
     for (int q = 0; q < 2; ++q) S.end_edges[q] = (logspace ? M->d_edges_logp[q] : M->d_edges_prob[q]).as<EdgeRec>();
-    for (int i = 0; i < 8 * 6; ++i) S.run_ranges[i] = i < static_cast<int>(L.warp_run_ranges.size()) ? L.warp_run_ranges[i] : 0;
+    for (int i = 0; i < kMaxLaneWarps * 6; ++i) S.run_ranges[i] = i < static_cast<int>(L.warp_run_ranges.size()) ? L.warp_run_ranges[i] : 0;
     S.wtab = (logspace ? M->d_wtab_logp : M->d_wtab_prob).as<double>();
     S.etab = (logspace ? M->d_etab_vit : M->d_etab_fwd).as<double>();
     S.n_low = static_cast<int32_t>(L.low_src.size());
@@ -233,32 +231,31 @@ static int host_offsets(pp_model* M, const int64_t* offsets, int64_t n_events, i
 
 template <typename ObsT>
 static int launch_viterbi(pp_model* M, const LaneBatch<ObsT>& B, const VitOut& O, int n_groups) {
-    int brc = bind_arena(M);
-    if (brc != PP_OK) return brc;
-    const size_t smem = lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, 8);
-    PP_CUDA(cudaFuncSetAttribute(k_viterbi_lane<ObsT, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PP_CUDA(cudaFuncSetAttribute(k_viterbi_lane<ObsT, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (M->low.ptr_bits == 4) k_viterbi_lane<ObsT, 8, 4><<<n_groups, 256, smem, M->stream>>>(make_sched(M, true), B, O);
-    else k_viterbi_lane<ObsT, 8, 8><<<n_groups, 256, smem, M->stream>>>(make_sched(M, true), B, O);
-    PP_CUDA(cudaGetLastError());
+    int rc = check_lane_model(M);
+    if (rc != PP_OK) return rc;
+    const size_t smem = lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, kLaneWarps);
+    const LaneBatchAny A{B.obs, sizeof(ObsT) == 8 ? 1 : 0, B.offsets, B.order, B.group_len, B.group_row};
+    const int e = (M->low.ptr_bits == 4 ? lane_viterbi4_launch : lane_viterbi8_launch)(
+        make_sched(M, true), A, O, n_groups, smem, M->stream, M->arena.data(), M->arena.size(), M);
+    if (e != 0) { set_error("Viterbi kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
     ++M->launches;
     return PP_OK;
 }
 
 template <typename ObsT>
 static int launch_forward(pp_model* M, const LaneBatch<ObsT>& B, const FwdOut& O, int n_groups) {
-    int brc = bind_arena(M);
-    if (brc != PP_OK) return brc;
-    const size_t smem = lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, 8);
-    PP_CUDA(cudaFuncSetAttribute(k_forward_lane<ObsT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_forward_lane<ObsT, 8><<<n_groups, 256, smem, M->stream>>>(make_sched(M, false), B, O);
-    PP_CUDA(cudaGetLastError());
+    int rc = check_lane_model(M);
+    if (rc != PP_OK) return rc;
+    const size_t smem = lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, kLaneWarps);
+    const LaneBatchAny A{B.obs, sizeof(ObsT) == 8 ? 1 : 0, B.offsets, B.order, B.group_len, B.group_row};
+    const int e = lane_forward_launch(make_sched(M, false), A, O, n_groups, smem, M->stream, M->arena.data(), M->arena.size(), M);
+    if (e != 0) { set_error("forward kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
     ++M->launches;
     return PP_OK;
 }
 
 static int check_lane_fit(pp_model* M, int obs_bytes) {
-    const size_t smem = lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, 8);
+    const size_t smem = lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, kLaneWarps);
     (void)obs_bytes;
     if (smem > M->smem_optin) {
         set_error("model needs %zu bytes of shared memory per CTA for the lane-per-event kernels (limit %zu)", smem,
@@ -354,7 +351,7 @@ void pp_model_destroy(pp_model* M) {
     if (!M) return;
     cudaSetDevice(M->device);
     if (M->stream) cudaStreamSynchronize(M->stream);
-    if (g_arena_owner == M) g_arena_owner = nullptr;
+    lane_arena_invalidate(M);
     DevBuf* bufs[] = {&M->d_edges_logp[0], &M->d_edges_logp[1], &M->d_edges_prob[0],
                       &M->d_edges_prob[1], &M->d_emis, &M->d_warp_run_ranges, &M->d_wtab_logp, &M->d_wtab_prob, &M->d_etab_vit, &M->d_etab_fwd, &M->d_state_edge_begin, &M->d_low_src, &M->d_state_pword, &M->d_state_pshift, &M->d_state_pmul,
                       &M->d_in_ptr, &M->d_in_src, &M->d_in_logp, &M->d_out_ptr, &M->d_out_dst, &M->d_out_logp,
@@ -381,7 +378,7 @@ int pp_model_update_params(pp_model* M, const pp_model_desc* desc) {
 int64_t pp_schedule_describe(const pp_model_desc* desc, char* buf, int64_t cap) {
     if (!desc) { set_error("null argument"); return PP_ERR_ARG; }
     Lowered low;
-    std::string err = lower_model(*desc, 8, &low);
+    std::string err = lower_model(*desc, kLaneWarps, &low);
     if (!err.empty()) { set_error("cannot lower model: %s", err.c_str()); return PP_ERR_UNSUPPORTED; }
     const std::string text = describe_schedule(low);
     if (buf && cap > 0) std::snprintf(buf, static_cast<size_t>(cap), "%s", text.c_str());
@@ -403,12 +400,8 @@ int64_t pp_viterbi_workspace_bytes(const pp_model* M, const int64_t* offsets_hos
 }
 
 #ifdef PP_PHASE_TIMING
-// debug build only (tools/phase_timing.py): per-warp phase clocks of k_viterbi_lane<float>, 8 warps x 8 slots
-int pp_debug_phase_cycles(unsigned long long* out, int reset) {
-    if (out) cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 64);
-    if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z); }
-    return 0;
-}
+// debug build only (tools/phase_timing.py): per-warp phase clocks of the Viterbi lane kernel
+int pp_debug_phase_cycles(unsigned long long* out, int reset) { return lane_debug_phase_cycles(out, reset); }
 #endif
 
 int64_t pp_launch_count(const pp_model* M) { return M ? M->launches : 0; }

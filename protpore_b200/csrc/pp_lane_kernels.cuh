@@ -34,44 +34,22 @@
 // maximum, so the mantissas are untouched by rescaling (DESIGN.md "forward").
 #pragma once
 #include "pp_device_common.cuh"
+#include "pp_lane_types.h"
 
 namespace pp {
 
-constexpr int kArenaDoubles = 7680;                       // 60 KB of the 64 KB constant bank
-static __constant__ double c_arena[kArenaDoubles];        // run records (+ log state weights)
+static __constant__ double c_arena[kArenaDoubles];        // run records of the model whose image is resident
 
 // Optional per-warp phase clocks (tools/phase_timing.py builds the library with -DPP_PHASE_TIMING): cycles a
 // warp spends working in phase B (silent / early), waiting at B's barrier, working in phase A, waiting at A's.
 #ifdef PP_PHASE_TIMING
-__device__ unsigned long long g_phase_cycles[8 * 8];
+__device__ unsigned long long g_phase_cycles[16 * 8];
 #define PP_CLK(var) const long long var = clock64()
 #define PP_ACC(slot, a, b) phase_acc[slot] += static_cast<unsigned long long>((b) - (a))
 #else
 #define PP_CLK(var)
 #define PP_ACC(slot, a, b)
 #endif
-
-struct LaneSched {
-    const EdgeRec* end_edges[2];     // lowered in-edges of the end state, per row parity (final score)
-    int32_t run_ranges[8 * 6];       // per warp: {begin, end} of its late-emitting, silent and early-emitting runs
-    const double* wtab;              // [n_low] transition weights in lowered-edge order: log p (Viterbi) or p (forward)
-    const double* etab;              // [ne][4] emission records of this kernel family
-    int32_t n_low;
-    int32_t etab_doubles;            // doubles per emission record (5 Viterbi, 4 forward)
-    int32_t m, ne, ns, n_slots;
-    int32_t start_slot_off;          // byte offset of the start state's slot
-    int32_t end_slot_off;            // byte offset of the end state's slot
-    int32_t end_state, end_edge_begin, end_n_edges, finite, end_final_only;
-    int32_t n_ptr_words, ptr_bits;
-};
-
-// tile of staged observations: 32 columns for float32, 16 for float64 (same bytes)
-template <typename ObsT> struct TileCols { static constexpr int value = 128 / sizeof(ObsT); };
-
-__host__ __device__ inline size_t lane_smem_bytes2(int n_slots, int n_low, int ne, int warps) {
-    return static_cast<size_t>(n_slots) * kSlotBytes + static_cast<size_t>(n_low) * 8 + static_cast<size_t>(ne) * 40 +
-           static_cast<size_t>(32) * 33 * 4 + static_cast<size_t>(warps) * kLanes * sizeof(int32_t) + 64;
-}
 
 __device__ __forceinline__ const RunRec& run_rec(int i) { return reinterpret_cast<const RunRec*>(c_arena)[i]; }
 
@@ -336,25 +314,28 @@ struct LaneSmem {
     }
 };
 
-template <typename ObsT, int W>
-__device__ __forceinline__ void fill_tile2(ObsT* xt, const ObsT* __restrict__ obs, int64_t off, int n, int i0, int warp,
-                                           int lane) {
-    constexpr int TC = TileCols<ObsT>::value;                 // columns per tile; row stride TC + 1 elements
+template <int W>
+__device__ __forceinline__ void fill_tile2(double* xt, const void* __restrict__ obs, bool f64, int64_t off, int n, int i0,
+                                           int warp, int lane) {
+    constexpr int TC = kLaneTileCols;                         // columns per tile; row stride 32 + 1 doubles
     for (int j = warp * (32 / TC) + lane / TC; j < kLanes; j += W * (32 / TC)) {
         const int64_t oj = __shfl_sync(0xffffffffu, off, j);
         const int nj = __shfl_sync(0xffffffffu, n, j);
         const int c = i0 + (lane % TC);
-        xt[(lane % TC) * (kLanes + 1) + j] = (c < nj) ? __ldg(obs + oj + c) : ObsT(0);
+        double v = 0.0;
+        if (c < nj) v = f64 ? __ldg(static_cast<const double*>(obs) + oj + c)
+                            : static_cast<double>(__ldg(static_cast<const float*>(obs) + oj + c));
+        xt[(lane % TC) * (kLanes + 1) + j] = v;
     }
 }
 
-template <typename ObsT, int W, int BITS>
+template <int W, int BITS>
 __global__ void __launch_bounds__(W * 32, 2)
-k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
+k_viterbi_lane(const LaneSched S, const LaneBatchAny B, const VitOut O) {
     extern __shared__ __align__(16) unsigned char smem[];
     const LaneSmem M(smem, S);
-    constexpr int TC = TileCols<ObsT>::value;
-    ObsT* xt = reinterpret_cast<ObsT*>(M.xt);
+    constexpr int TC = kLaneTileCols;
+    double* xt = reinterpret_cast<double*>(M.xt);
 
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // tells the compiler it is warp-uniform
@@ -390,7 +371,7 @@ k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
         //      early emitting states of row r + 1 (3545-3562), which only read emitting values of row r
         const int q = r & 1;
         if (r < nmax && (r & (TC - 1)) == 0) {
-            fill_tile2<ObsT, W>(xt, B.obs, off, n, r, warp, lane);
+            fill_tile2<W>(xt, B.obs, B.obs_f64 != 0, off, n, r, warp, lane);
             __syncthreads();
         }
         PP_CLK(c0);
@@ -401,7 +382,7 @@ k_viterbi_lane(const LaneSched S, const LaneBatch<ObsT> B, const VitOut O) {
         }
         PP_CLK(c1);
         if (r < nmax) {
-            x = static_cast<double>(xt[(r & (TC - 1)) * (kLanes + 1) + lane]);       // obs[r] belongs to row r + 1
+            x = xt[(r & (TC - 1)) * (kLanes + 1) + lane];       // obs[r] belongs to row r + 1
             const VitCtx C{pr + row_stride, lane, r + 1 <= n, x};
             for (int u = xb; u < xe; ++u) vit_run<BITS>(u, q ^ 1, false, colb, wtab, etab, C);
         }
@@ -548,13 +529,13 @@ __device__ __forceinline__ void fwd_run(int r, int par, bool row0, uint32_t colb
     }
 }
 
-template <typename ObsT, int W>
+template <int W>
 __global__ void __launch_bounds__(W * 32, 2)
-k_forward_lane(const LaneSched S, const LaneBatch<ObsT> B, const FwdOut O) {
+k_forward_lane(const LaneSched S, const LaneBatchAny B, const FwdOut O) {
     extern __shared__ __align__(16) unsigned char smem[];
     const LaneSmem M(smem, S);
-    constexpr int TC = TileCols<ObsT>::value;
-    ObsT* xt = reinterpret_cast<ObsT*>(M.xt);
+    constexpr int TC = kLaneTileCols;
+    double* xt = reinterpret_cast<double*>(M.xt);
     int32_t* wmax = M.wmax;
 
     const int lane = threadIdx.x & 31;
@@ -600,7 +581,7 @@ k_forward_lane(const LaneSched S, const LaneBatch<ObsT> B, const FwdOut O) {
             scale_total += shift;
             shiftd = static_cast<double>(shift);
             if ((r & (TC - 1)) == 0) {
-                fill_tile2<ObsT, W>(xt, B.obs, off, n, r, warp, lane);
+                fill_tile2<W>(xt, B.obs, B.obs_f64 != 0, off, n, r, warp, lane);
                 __syncthreads();
             }
         }
@@ -608,7 +589,7 @@ k_forward_lane(const LaneSched S, const LaneBatch<ObsT> B, const FwdOut O) {
         for (int u = sb; u < se; ++u) fwd_run(u, q, r == 0, colb, wtab, etab, 0.0, 0.0, mxs);    // silent (2847-2871, 2891-2926)
         mx = 0;
         if (r < nmax) {
-            x = static_cast<double>(xt[(r & (TC - 1)) * (kLanes + 1) + lane]);
+            x = xt[(r & (TC - 1)) * (kLanes + 1) + lane];
             for (int u = xb; u < xe; ++u) fwd_run(u, q ^ 1, false, colb, wtab, etab, x, shiftd, mx);   // early emitting of row r + 1
         }
         __syncthreads();

@@ -1,0 +1,60 @@
+// pp_lane_types.h -- kernel-parameter structs and launch entry points of the lane-per-event kernels.
+// The kernels themselves (pp_lane_kernels.cuh) are instantiated in three translation units that compile in
+// parallel: pp_lane_viterbi4.cu (4-bit ordinals), pp_lane_viterbi8.cu (8-bit) and pp_lane_forward.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pp_device_common.cuh"
+
+namespace pp {
+
+constexpr int kArenaDoubles = 7680;                       // 60 KB of the 64 KB constant bank
+
+struct LaneSched {
+    const EdgeRec* end_edges[2];     // lowered in-edges of the end state, per row parity (final score)
+    int32_t run_ranges[kMaxLaneWarps * 6];       // per warp: {begin, end} of its late-emitting, silent and early-emitting runs
+    const double* wtab;              // [n_low] transition weights in lowered-edge order: log p (Viterbi) or p (forward)
+    const double* etab;              // [ne][4] emission records of this kernel family
+    int32_t n_low;
+    int32_t etab_doubles;            // doubles per emission record (5 Viterbi, 4 forward)
+    int32_t m, ne, ns, n_slots;
+    int32_t start_slot_off;          // byte offset of the start state's slot
+    int32_t end_slot_off;            // byte offset of the end state's slot
+    int32_t end_state, end_edge_begin, end_n_edges, finite, end_final_only;
+    int32_t n_ptr_words, ptr_bits;
+};
+
+// tile of staged observations: 32 columns for float32, 16 for float64 (same bytes)
+constexpr int kLaneTileCols = 16;   // the tile holds doubles whatever the input type: one kernel body for float32 and float64 events
+
+// type-erased batch: the same kernel serves float32 and float64 observations (halves the instantiations)
+struct LaneBatchAny {
+    const void* obs;
+    int32_t obs_f64;
+    const int64_t* offsets;
+    const int32_t* order;
+    const int32_t* group_len;
+    const int64_t* group_row;
+};
+
+__host__ __device__ inline size_t lane_smem_bytes2(int n_slots, int n_low, int ne, int warps) {
+    return static_cast<size_t>(n_slots) * kSlotBytes + static_cast<size_t>(n_low) * 8 + static_cast<size_t>(ne) * 40 +
+           static_cast<size_t>(32) * 33 * 4 + static_cast<size_t>(warps) * kLanes * sizeof(int32_t) + 64;
+}
+
+
+// Launchers.  Each kernel translation unit owns a __constant__ arena holding the run records of ONE model;
+// `arena` / `arena_doubles` / `owner` let it re-upload (stream-ordered) when another handle's image is resident.
+int lane_viterbi4_launch(const LaneSched& S, const LaneBatchAny& B, const VitOut& O, int n_groups, size_t smem,
+                         cudaStream_t stream, const double* arena, size_t arena_doubles, const void* owner);
+int lane_viterbi8_launch(const LaneSched& S, const LaneBatchAny& B, const VitOut& O, int n_groups, size_t smem,
+                         cudaStream_t stream, const double* arena, size_t arena_doubles, const void* owner);
+int lane_forward_launch(const LaneSched& S, const LaneBatchAny& B, const FwdOut& O, int n_groups, size_t smem,
+                        cudaStream_t stream, const double* arena, size_t arena_doubles, const void* owner);
+void lane_arena_invalidate(const void* owner);           // forget `owner` in every arena (model changed / destroyed)
+#ifdef PP_PHASE_TIMING
+int lane_debug_phase_cycles(unsigned long long* out, int reset);
+#endif
+
+}  // namespace pp

@@ -31,6 +31,14 @@
 namespace pp {
 
 constexpr int kLanes = 32;                       // events per CTA (one per lane)
+#ifndef PP_LANE_WARPS
+#define PP_LANE_WARPS 8
+#endif
+constexpr int kLaneWarps = PP_LANE_WARPS;        // warps per CTA of the lane kernels (the states of a column are split over them)
+constexpr int kMaxLaneWarps = 16;
+#ifndef PP_G_BIG
+#define PP_G_BIG 2
+#endif
 constexpr uint32_t kSlotBytes = kLanes * 8;      // one column slot: 32 doubles
 
 // ---- records shared by host and device ---------------------------------------------------
@@ -43,7 +51,7 @@ struct __attribute__((aligned(16))) EdgeRec {
 // (position k, k+1, ... of a profile).  Executed by one shape-templated loop body (pp_lane_kernels.cuh).
 constexpr int kMaxRunEdges = 8;
 // items a kernel handles at once in a run of this in-degree (kernels and lowering must agree)
-constexpr int run_group_size(int n_edges) { return n_edges <= 2 ? 4 : 2; }
+constexpr int run_group_size(int n_edges) { return n_edges <= 2 ? 4 : (n_edges <= 4 ? 2 : PP_G_BIG); }
 enum : int32_t { EMIS_NORMAL = 0, EMIS_POINT = 1, EMIS_UNIFORM = 2, RUN_SILENT = 3, RUN_START = 4 };
 struct __attribute__((aligned(16))) RunRec {
     int32_t kind;                                // EMIS_* for emitting items, RUN_SILENT, RUN_START (the start state)

@@ -25,7 +25,7 @@ struct pp_model {
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     size_t smem_optin = 0;
-    int warps = 8;
+    int warps = pp::kLaneWarps;
 
     // host copy of the baked description
     int32_t m = 0, ne = 0, n_edges = 0, start = 0, end = 0, finite = 0;

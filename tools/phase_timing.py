@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 csrc = os.path.join(ROOT, "protpore_b200", "csrc")
 out = os.path.join(ROOT, "protpore_b200", "libprotpore_b200_timing.so")
 if not os.path.exists(out) or "--build" in sys.argv:        # build in the CPU container: nvcc cross-compiles, the .so travels
-    subprocess.check_call(["make", "-B", "-C", csrc, "OUT=" + out, "NVFLAGS=-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a "
+    subprocess.check_call(["make", "-j6", "-C", csrc, "OUT=" + out, "OBJDIR=../_build_timing", "NVFLAGS=-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a "
                            "-Xcompiler -fPIC --expt-relaxed-constexpr -DPP_PHASE_TIMING"])
     if "--build" in sys.argv:
         sys.exit(0)
