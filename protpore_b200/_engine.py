@@ -128,6 +128,39 @@ def _is_device(a):
     return not isinstance(a, np.ndarray) and hasattr(a, "is_cuda") and a.is_cuda
 
 
+class _Pinned(object):
+    """Owner of one cudaHostAlloc block (freed when the last numpy view goes away)."""
+
+    def __init__(self, lib, nbytes):
+        self._lib, self.ptr = lib, lib.pp_host_alloc(int(nbytes))
+
+    def __del__(self):
+        if self.ptr:
+            self._lib.pp_host_free(self.ptr)
+            self.ptr = None
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in page-locked host memory (pp_host_alloc): host<->device copies run at link speed.
+    Falls back to pageable memory if the allocation fails (e.g. no CUDA runtime)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    if n == 0:
+        return np.empty(shape, dtype=dtype)
+    owner = _Pinned(load_library(), n * dtype.itemsize)
+    if not owner.ptr:
+        return np.empty(shape, dtype=dtype)
+    buf = (ctypes.c_char * (n * dtype.itemsize)).from_address(owner.ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    _PINNED_OWNERS[id(buf)] = (owner, buf)        # keep the block alive as long as the buffer object is referenced
+    import weakref
+    weakref.finalize(arr.base if arr.base is not None else arr, _PINNED_OWNERS.pop, id(buf), None)
+    return arr
+
+
+_PINNED_OWNERS = {}
+
+
 def pack_events(sequences, dtype=np.float32):
     """List of 1-D sequences -> (obs back to back, int64 offsets[n+1])."""
     lens = np.fromiter((len(s) for s in sequences), dtype=np.int64, count=len(sequences))
@@ -215,8 +248,11 @@ class Engine(object):
                                                _ptr(out)))
         return out
 
-    def viterbi_batch(self, obs, offsets, with_paths=True, capacity=None):
-        """(scores f64[n], path_len i64[n], paths u16[total] back to back in event order)."""
+    def viterbi_batch(self, obs, offsets, with_paths=True, capacity=None, out=None):
+        """(scores f64[n], path_len i64[n], paths u16[total] back to back in event order).
+
+        `out` = (scores, path_len, paths) lets a serving loop reuse its own (ideally pinned, see
+        `pinned_empty`) host buffers; len(paths) is then the path capacity."""
         n = len(offsets) - 1
         dev = _is_device(obs)
         if dev:
@@ -229,8 +265,10 @@ class Engine(object):
             obs = np.ascontiguousarray(obs)
             offsets = np.ascontiguousarray(offsets, dtype=np.int64)
             total_obs = len(obs)
-            scores, plen = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.int64)
+            scores, plen = (out[0], out[1]) if out is not None else (np.empty(n, dtype=np.float64), np.empty(n, dtype=np.int64))
             mem = PP_MEM_HOST
+        if out is not None:
+            capacity = len(out[2])
         cap = int(capacity) if capacity is not None else 3 * total_obs + 8 * n + 64
         total = ctypes.c_int64(0)
         while True:
@@ -240,7 +278,7 @@ class Engine(object):
                 import torch
                 paths = torch.empty(cap, dtype=torch.uint16, device=obs.device)
             else:
-                paths = np.empty(cap, dtype=np.uint16)
+                paths = out[2] if (out is not None and len(out[2]) >= cap) else np.empty(cap, dtype=np.uint16)
             rc = self._lib.pp_viterbi_batch(self._h, _ptr(obs), self._obs_dtype(obs), _ptr(offsets), n, mem,
                                             _ptr(scores), _ptr(plen), _ptr(paths), cap if with_paths else 0,
                                             ctypes.byref(total))

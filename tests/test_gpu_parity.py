@@ -201,3 +201,16 @@ def test_pypore_apply_hmm(models):
     assert one[0] == g["vscore"][0] and one[1][0][1].name.endswith("-start")
     many = pypore.apply_hmm_batch(pev, model, 'viterbi')
     assert [m[0] for m in many] == list(g["vscore"][:6])
+
+
+def test_distributed_baum_welch_single_process_equals_train():
+    """protpore_b200.parallel.train_baum_welch without a process group == Model.train (reference stopping rule)."""
+    from protpore_b200 import parallel
+    g = util.load_golden("toy")
+    evs = util.golden_events(g)
+    seqs = [evs[i] for i in g["bw_events"]]
+    a, b = util.build_model("toy"), util.build_model("toy")
+    ia = a.train(seqs, max_iterations=2, verbose=False)
+    ib = parallel.train_baum_welch(b, seqs, max_iterations=2, dtype=np.float64)
+    assert ia == pytest.approx(ib, rel=1e-9, abs=1e-9)
+    assert np.allclose(a.dense_transition_matrix(), b.dense_transition_matrix(), rtol=1e-10, atol=1e-12, equal_nan=True)
