@@ -254,15 +254,12 @@ static int launch_forward(pp_model* M, const LaneBatch<ObsT>& B, const FwdOut& O
     return PP_OK;
 }
 
-static int check_lane_fit(pp_model* M, int obs_bytes) {
+// The lane-per-event kernels need the float64 column of 32 events (+ weights, emission records) in shared
+// memory, every in-degree <= 8 and the run records in the constant arena; other models take the
+// state-parallel kernels.
+static bool lane_kernels_fit(const pp_model* M) {
     const size_t smem = lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, kLaneWarps);
-    (void)obs_bytes;
-    if (smem > M->smem_optin) {
-        set_error("model needs %zu bytes of shared memory per CTA for the lane-per-event kernels (limit %zu)", smem,
-                  M->smem_optin);
-        return PP_ERR_UNSUPPORTED;
-    }
-    return PP_OK;
+    return M->low.lane_ok && smem <= M->smem_optin && M->arena.size() <= static_cast<size_t>(kArenaDoubles);
 }
 
 // Splits [0, n_events) into chunks of whole events whose pointer table / staged observations fit.
@@ -435,8 +432,10 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     if (path_total) *path_total = 0;
     if (n_events == 0) return PP_OK;
     const size_t ob = obs_dtype == PP_F32 ? 4 : 8;
-    int rc = check_lane_fit(M, static_cast<int>(ob));
-    if (rc != PP_OK) return rc;
+    if (!lane_kernels_fit(M))                         // large model: exact state-parallel kernels
+        return viterbi_batch_state(M, obs, obs_dtype, offsets, n_events, mem, logp_out, path_len_out, path_out,
+                                   path_capacity, path_total);
+    int rc = PP_OK;
 
     std::vector<int64_t> store;
     const int64_t *h_off, *d_off;
@@ -579,8 +578,8 @@ int pp_forward_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     std::memset(M->prof, 0, sizeof M->prof);
     if (n_events == 0) return PP_OK;
     const size_t ob = obs_dtype == PP_F32 ? 4 : 8;
-    int rc = check_lane_fit(M, static_cast<int>(ob));
-    if (rc != PP_OK) return rc;
+    const bool lane = lane_kernels_fit(M);
+    int rc = PP_OK;
     std::vector<int64_t> store;
     const int64_t *h_off, *d_off;
     rc = host_offsets(M, offsets, n_events, mem, &store, &h_off, &d_off);
@@ -611,7 +610,9 @@ int pp_forward_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
         }
         FwdOut O{d_logp};
         Timer t(M, PP_PROF_FORWARD);
-        if (obs_dtype == PP_F32) {
+        if (!lane) {                                  // large model: every event takes the exact log-space kernel
+            PP_CUDA(cudaMemsetAsync(d_logp + e0, 0xFF, (e1 - e0) * sizeof(double), M->stream));     // all-ones = NaN
+        } else if (obs_dtype == PP_F32) {
             LaneBatch<float> B{static_cast<const float*>(d_obs_base), d_off, M->d_order.as<int32_t>(),
                                M->d_group_len.as<int32_t>(), M->d_group_row.as<int64_t>()};
             rc = launch_forward<float>(M, B, O, sc.n_groups);

@@ -132,6 +132,134 @@ int rerun_exact_forward(pp_model* M, const void* d_obs_base, int32_t obs_dtype, 
     return PP_OK;
 }
 
+// Batched Viterbi for models whose column does not fit the lane-per-event kernels (state-parallel, exact).
+int viterbi_batch_state(pp_model* M, const void* obs, int32_t obs_dtype, const int64_t* offsets, int64_t n_events,
+                        int32_t mem, double* logp_out, int64_t* path_len_out, uint16_t* path_out, int64_t path_capacity,
+                        int64_t* path_total) {
+    const size_t ob = obs_dtype == PP_F32 ? 4 : 8;
+    std::vector<int64_t> store;
+    const int64_t* h_off = offsets;
+    const int64_t* d_off = offsets;
+    if (mem == PP_MEM_DEVICE) {
+        store.resize(n_events + 1);
+        PP_CUDA(cudaMemcpy(store.data(), offsets, store.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        h_off = store.data();
+    } else {
+        PP_CUDA(M->d_offsets.reserve((n_events + 1) * sizeof(int64_t)));
+        PP_CUDA(cudaMemcpyAsync(M->d_offsets.p, offsets, (n_events + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, M->stream));
+        d_off = M->d_offsets.as<int64_t>();
+    }
+    for (int64_t e = 0; e < n_events; ++e)
+        if (h_off[e + 1] - h_off[e] < 1) { set_error("event %lld is empty", (long long)e); return PP_ERR_ARG; }
+    const void* d_obs = obs;
+    if (mem == PP_MEM_HOST) {
+        PP_CUDA(M->d_obs.reserve(h_off[n_events] * ob));
+        PP_CUDA(cudaMemcpyAsync(M->d_obs.p, obs, h_off[n_events] * ob, cudaMemcpyHostToDevice, M->stream));
+        d_obs = M->d_obs.p;
+    }
+    double* d_score = logp_out;
+    if (mem == PP_MEM_HOST) {
+        PP_CUDA(M->d_score.reserve(n_events * sizeof(double)));
+        d_score = M->d_score.as<double>();
+    }
+    PP_CUDA(M->d_end_state.reserve(n_events * sizeof(int32_t)));
+    PP_CUDA(M->d_path_len.reserve(n_events * sizeof(int64_t)));
+    PP_CUDA(M->d_path_off.reserve(n_events * sizeof(int64_t)));
+    std::vector<int32_t> n_edges(M->low.state_n_edges);
+    PP_CUDA(upload(&M->d_list, n_edges, M->stream));                 // [m] lowered in-degree per state
+    const StateModel S = make_state_model(M);
+    const StateVit V{M->d_state_edge_begin.as<int32_t>(), M->d_list.as<int32_t>(), M->d_low_src.as<int32_t>(),
+                     M->d_wtab_logp.as<double>(), M->low.end_final_only ? 1 : 0};
+    const size_t smem = 2 * static_cast<size_t>(M->m) * sizeof(double);
+    if (smem > M->smem_optin) { set_error("model has too many states (%d) for the state-parallel Viterbi kernel", M->m); return PP_ERR_UNSUPPORTED; }
+    int threads = 64;
+    while (threads < M->ne && threads < 1024) threads <<= 1;
+    std::vector<int64_t> h_len(n_events), h_poff, h_toff;
+    int64_t base = 0;
+    bool overflow = false;
+    cudaEventRecord(M->ev[0], M->stream);
+    for (int64_t e0 = 0; e0 < n_events;) {
+        // chunk of whole events whose uint16 pointer tables fit the workspace
+        int64_t e1 = e0;
+        size_t words = 0;
+        h_toff.clear();
+        while (e1 < n_events) {
+            const size_t w = static_cast<size_t>(h_off[e1 + 1] - h_off[e1] + 1) * M->m;
+            if (e1 > e0 && (words + w) * 2 > M->ws_limit) break;
+            h_toff.push_back(static_cast<int64_t>(words));
+            words += w;
+            ++e1;
+        }
+        if (words * 2 > M->ws_limit || M->d_ws.reserve(words * 2) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("one event needs %zu bytes of traceback workspace", words * 2);
+            return PP_ERR_NOMEM;
+        }
+        const int nev = static_cast<int>(e1 - e0);
+        PP_CUDA(upload(&M->d_tab_off, h_toff, M->stream));
+        const int grid = std::min(nev, M->sm_count * 4);
+        if (obs_dtype == PP_F32) {
+            if (set_dyn_smem(k_viterbi_state<float>, smem) != PP_OK) return PP_ERR_CUDA;
+            k_viterbi_state<float><<<grid, threads, smem, M->stream>>>(S, V, static_cast<const float*>(d_obs), d_off, (int)e0, nev,
+                M->d_tab_off.as<int64_t>(), M->d_ws.as<uint16_t>(), d_score, M->d_end_state.as<int32_t>());
+        } else {
+            if (set_dyn_smem(k_viterbi_state<double>, smem) != PP_OK) return PP_ERR_CUDA;
+            k_viterbi_state<double><<<grid, threads, smem, M->stream>>>(S, V, static_cast<const double*>(d_obs), d_off, (int)e0, nev,
+                M->d_tab_off.as<int64_t>(), M->d_ws.as<uint16_t>(), d_score, M->d_end_state.as<int32_t>());
+        }
+        PP_CUDA(cudaGetLastError());
+        ++M->launches;
+        k_traceback_state<<<(nev + 63) / 64, 64, 0, M->stream>>>(M->d_ws.as<uint16_t>(), M->d_tab_off.as<int64_t>(), d_off, (int)e0,
+            nev, d_score, M->d_end_state.as<int32_t>(), M->d_state_edge_begin.as<int32_t>(), M->d_low_src.as<int32_t>(), M->m,
+            M->ne, M->start, M->d_path_len.as<int64_t>(), nullptr, nullptr);
+        PP_CUDA(cudaGetLastError());
+        ++M->launches;
+        PP_CUDA(cudaMemcpyAsync(h_len.data() + e0, M->d_path_len.as<int64_t>() + e0, nev * sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
+        PP_CUDA(cudaStreamSynchronize(M->stream));
+        h_poff.assign(n_events, 0);
+        int64_t chunk_total = 0;
+        for (int64_t e = e0; e < e1; ++e) { h_poff[e] = chunk_total; chunk_total += h_len[e] > 0 ? h_len[e] : 0; }
+        if (path_out && !overflow && base + chunk_total <= path_capacity) {
+            PP_CUDA(cudaMemcpyAsync(M->d_path_off.as<int64_t>() + e0, h_poff.data() + e0, nev * sizeof(int64_t), cudaMemcpyHostToDevice, M->stream));
+            uint16_t* dst;
+            if (mem == PP_MEM_DEVICE) dst = path_out + base;
+            else {
+                PP_CUDA(M->d_path.reserve(static_cast<size_t>(chunk_total) * sizeof(uint16_t) + 16));
+                dst = M->d_path.as<uint16_t>();
+            }
+            k_traceback_state<<<(nev + 63) / 64, 64, 0, M->stream>>>(M->d_ws.as<uint16_t>(), M->d_tab_off.as<int64_t>(), d_off, (int)e0,
+                nev, d_score, M->d_end_state.as<int32_t>(), M->d_state_edge_begin.as<int32_t>(), M->d_low_src.as<int32_t>(), M->m,
+                M->ne, M->start, M->d_path_len.as<int64_t>(), M->d_path_off.as<int64_t>(), dst);
+            PP_CUDA(cudaGetLastError());
+            ++M->launches;
+            if (mem == PP_MEM_HOST && chunk_total > 0)
+                PP_CUDA(cudaMemcpyAsync(path_out + base, dst, static_cast<size_t>(chunk_total) * sizeof(uint16_t), cudaMemcpyDeviceToHost, M->stream));
+            PP_CUDA(cudaStreamSynchronize(M->stream));
+        } else if (path_out) {
+            overflow = true;
+        }
+        base += chunk_total;
+        e0 = e1;
+    }
+    cudaEventRecord(M->ev[1], M->stream);
+    if (mem == PP_MEM_HOST) {
+        PP_CUDA(cudaMemcpyAsync(logp_out, d_score, n_events * sizeof(double), cudaMemcpyDeviceToHost, M->stream));
+        std::memcpy(path_len_out, h_len.data(), n_events * sizeof(int64_t));
+    } else {
+        PP_CUDA(cudaMemcpyAsync(path_len_out, h_len.data(), n_events * sizeof(int64_t), cudaMemcpyHostToDevice, M->stream));
+    }
+    PP_CUDA(cudaStreamSynchronize(M->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, M->ev[0], M->ev[1]);
+    M->prof[PP_PROF_VITERBI] = ms;
+    if (path_total) *path_total = base;
+    if (overflow) {
+        set_error("path buffer too small: %lld elements needed, capacity %lld", (long long)base, (long long)path_capacity);
+        return PP_ERR_CAPACITY;
+    }
+    return PP_OK;
+}
+
 static int run_table(pp_model* M, const double* obs, int64_t n, int32_t mem, double* table_out, int mode) {
     if (!M || !obs || !table_out) { set_error("null argument"); return PP_ERR_ARG; }
     if (n < 1) { set_error("Invalid shape in axis 0: 0."); return PP_ERR_ARG; }      // yahmm.pyx:2836

@@ -219,6 +219,15 @@ std::string lower_model(const pp_model_desc& d, int warps, Lowered* low) {
                 for (size_t t = 1; t < seq.size(); ++t)
                     if (low->low_src[seq[t].wbase + a.ne - 1] != states[i + t - 1]) { all = false; break; }
                 r.fwd = all ? 1 : 0;
+                // 2: every side source is an emitting state -> the kernels may load the next group of links
+                //    before they store the current one (no link reads a silent slot written inside the run)
+                if (all) {
+                    bool side_emitting = true;
+                    for (size_t t = 0; t < seq.size(); ++t)
+                        for (int k = 0; k + 1 < a.ne; ++k)
+                            if (low->low_src[seq[t].wbase + k] >= ne) side_emitting = false;
+                    if (side_emitting) r.fwd = 2;
+                }
             }
             out->push_back(r);
             i = j;

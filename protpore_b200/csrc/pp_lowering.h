@@ -57,7 +57,8 @@ struct __attribute__((aligned(16))) RunRec {
     int32_t kind;                                // EMIS_* for emitting items, RUN_SILENT, RUN_START (the start state)
     int32_t n_edges;                             // in-edges per item (<= kMaxRunEdges), reference visiting order
     int32_t count;                               // items in the run
-    int32_t fwd;                                 // 1: the last edge reads the previous item of the run (a chain link)
+    int32_t fwd;                                 // >0: the last edge reads the previous item of the run (a chain link);
+                                                 // 2: and every other edge has an emitting source (prefetch-safe)
     int32_t dst_off[2];                          // byte offset of the first destination slot, per row parity
     int32_t dst_stride;                          // bytes per item
     int32_t w_base, w_stride;                    // weight-table index of the first item's first edge; per item

@@ -73,6 +73,10 @@ int upload_model(pp_model* M);
 int upload_state_model(pp_model* M);          // pp_aux.cu: level structure for the state-parallel kernels
 void release_state_model(pp_model* M);
 // Re-runs, with the exact log-space kernel, every event whose entry in d_logp is -inf or NaN.
+// State-parallel batched Viterbi (pp_aux.cu) for models too large for the lane-per-event kernels.
+int viterbi_batch_state(pp_model* M, const void* obs, int32_t obs_dtype, const int64_t* offsets, int64_t n_events,
+                        int32_t mem, double* logp_out, int64_t* path_len_out, uint16_t* path_out, int64_t path_capacity,
+                        int64_t* path_total);
 int rerun_exact_forward(pp_model* M, const void* d_obs_base, int32_t obs_dtype, const int64_t* d_off,
                         const int64_t* h_off, int64_t n_events, double* d_logp);
 

@@ -221,6 +221,123 @@ __global__ void k_forward_exact(const StateModel S, const ObsT* __restrict__ obs
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// State-parallel Viterbi (Model._viterbi, yahmm.pyx:3471-3652) for models whose column does not fit the
+// lane-per-event kernels: one CTA per event, one thread per state, two float64 rows in shared memory,
+// silent states level by level.  Every state scans its lowered in-edge list (reference visiting order) with
+// the reference's operations -- (v + t) + e / v + t, strict '>' -- so scores and paths are bit-identical
+// too; the winning ordinal per cell goes to HBM as uint16, [event][row][state].
+// ------------------------------------------------------------------------------------------
+struct StateVit {
+    const int32_t* edge_begin;   // [m] first lowered edge of a state
+    const int32_t* n_edges;      // [m]
+    const int32_t* low_src;      // [lowered edges]
+    const double* low_logp;      // [lowered edges]
+    int32_t end_final_only;
+};
+
+template <typename ObsT>
+__global__ void k_viterbi_state(const StateModel S, const StateVit V, const ObsT* __restrict__ obs,
+                                const int64_t* __restrict__ offsets, int ev0, int n_events,
+                                const int64_t* __restrict__ ptr_off, uint16_t* __restrict__ ptr,
+                                double* __restrict__ score_out, int32_t* __restrict__ end_state_out) {
+    extern __shared__ double rows[];                   // [2][m]
+    const int m = S.m, ne = S.ne, t = threadIdx.x, nt = blockDim.x;
+    for (int j = blockIdx.x; j < n_events; j += gridDim.x) {
+        const int ev = ev0 + j;
+        const int64_t off = offsets[ev];
+        const int n = static_cast<int>(offsets[ev + 1] - off);
+        uint16_t* tb = ptr + ptr_off[j];
+        double* cur = rows;
+        double* prv = rows + m;
+        for (int r = 0; r <= n; ++r) {
+            uint16_t* tr = tb + static_cast<size_t>(r) * m;
+            if (r == 0) {
+                for (int l = t; l < m; l += nt) cur[l] = (l == S.start) ? 0.0 : neg_inf();
+            } else {
+                const double x = static_cast<double>(obs[off + r - 1]);
+                for (int l = t; l < ne; l += nt) {                                   // 3545-3562
+                    const double e = emission_log(S.emis[l], x);
+                    double best = neg_inf();
+                    int arg = 0;
+                    const int b = V.edge_begin[l];
+                    for (int k = 0; k < V.n_edges[l]; ++k) {
+                        const double s = __dadd_rn(__dadd_rn(prv[V.low_src[b + k]], V.low_logp[b + k]), e);
+                        if (s > best) { best = s; arg = k; }
+                    }
+                    cur[l] = best;
+                    tr[l] = static_cast<uint16_t>(arg);
+                }
+            }
+            __syncthreads();
+            for (int lev = 0; lev < S.n_levels; ++lev) {                             // 3515-3542, 3564-3605
+                for (int i = S.lev_ptr[lev] + t; i < S.lev_ptr[lev + 1]; i += nt) {
+                    const int l = S.lev_states[i];
+                    if (r == 0 && l == S.start) continue;
+                    if (V.end_final_only && l == S.end && r != n) continue;
+                    double best = neg_inf();
+                    int arg = 0;
+                    const int b = V.edge_begin[l];
+                    for (int k = 0; k < V.n_edges[l]; ++k) {
+                        const double s = __dadd_rn(cur[V.low_src[b + k]], V.low_logp[b + k]);
+                        if (s > best) { best = s; arg = k; }
+                    }
+                    cur[l] = best;
+                    tr[l] = static_cast<uint16_t>(arg);
+                }
+                __syncthreads();
+            }
+            double* sw = cur; cur = prv; prv = sw;                                    // prv = the row just finished
+        }
+        if (t == 0) {                                                                // 3614-3619
+            int est = S.end;
+            double score;
+            if (S.finite == 1) {
+                score = prv[S.end];
+            } else {
+                est = 0;
+                score = prv[0];
+                for (int k = 1; k < m; ++k) if (prv[k] > score) { score = prv[k]; est = k; }
+            }
+            score_out[ev] = score;
+            end_state_out[ev] = est;
+        }
+        __syncthreads();
+    }
+}
+
+// traceback over the [event][row][state] uint16 table (3632-3646); pass 1 counts, pass 2 writes
+static __global__ void k_traceback_state(const uint16_t* __restrict__ ptr, const int64_t* __restrict__ ptr_off,
+                                         const int64_t* __restrict__ offsets, int ev0, int n_events,
+                                         const double* __restrict__ score, const int32_t* __restrict__ end_state,
+                                         const int32_t* __restrict__ edge_begin, const int32_t* __restrict__ low_src,
+                                         int m, int ne, int start, int64_t* __restrict__ path_len,
+                                         const int64_t* __restrict__ path_off, uint16_t* __restrict__ path) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_events) return;
+    const int ev = ev0 + j;
+    if (score[ev] == neg_inf()) {
+        if (!path) path_len[ev] = -1;
+        return;
+    }
+    const int n = static_cast<int>(offsets[ev + 1] - offsets[ev]);
+    const uint16_t* tb = ptr + ptr_off[j];
+    int px = n, py = end_state[ev];
+    int64_t len = 1, pos = 0;
+    uint16_t* out = nullptr;
+    if (path) { pos = path_len[ev] - 1; out = path + path_off[ev]; }
+    while (px != 0 || py != start) {
+        if (out) out[pos--] = static_cast<uint16_t>(py);
+        const int ord = tb[static_cast<size_t>(px) * m + py];
+        const int src = low_src[edge_begin[py] + ord];
+        if (py < ne) --px;
+        py = src;
+        ++len;
+    }
+    if (out) out[pos] = static_cast<uint16_t>(py);
+    else path_len[ev] = len;
+}
+
 // atomic min / max on doubles through the order-preserving integer view
 __device__ __forceinline__ void atomic_min_f64(double* addr, double v) {
     unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);

@@ -214,3 +214,44 @@ def test_distributed_baum_welch_single_process_equals_train():
     ib = parallel.train_baum_welch(b, seqs, max_iterations=2, dtype=np.float64)
     assert ia == pytest.approx(ib, rel=1e-9, abs=1e-9)
     assert np.allclose(a.dense_transition_matrix(), b.dense_transition_matrix(), rtol=1e-10, atol=1e-12, equal_nan=True)
+
+
+def test_large_model_takes_the_state_parallel_kernels():
+    """BASELINE config 4 shape: a ~2,000-state synthetic profile (skip / back-slip chains 334 long) does not fit
+    the lane-per-event kernels' shared-memory column; the state-parallel kernels serve it with the same bars:
+    Viterbi bit-exact, paths identical, forward within tolerance."""
+    from protpore_b200 import peptide_hmm
+    import protpore_b200.yahmm as y
+    model = peptide_hmm.model_maker(peptide_hmm.synthetic_profile(334, seed=11), "synth334", y, True)
+    assert len(model.states) == 6 * 334 - 1
+    assert "lane_ok 1" in _engine.describe_schedule(model)          # in-degrees fit, the column (3,000 slots) does not
+    orc = util.oracle_for(model)
+    lens = np.array([40, 700, 1, 333, 2500, 90])
+    evs = [np.asarray(x, dtype=np.float64) for x in events.sample_events(model, lens, seed=4)]
+    res = model.viterbi_batch(evs, dtype=np.float64, states=False)
+    lp = model.log_probability_batch(evs, dtype=np.float64)
+    for x, (score, path), l in zip(evs, res, lp):
+        s, p, margin = orc.viterbi(x, with_margin=True)
+        assert score == s
+        assert np.array_equal(path, p) or margin == 0.0
+        assert util.close([l], [orc.log_probability(x)], abs_tol=1e-8, rel_tol=1e-12).all()
+    # float32 observations give the same results as their float64 images
+    res32 = model.viterbi_batch([e.astype(np.float32) for e in evs], dtype=np.float32, states=False)
+    assert [r[0] for r in res32] == [r[0] for r in res]
+
+
+def test_mixed_length_batch_config5(models):
+    """BASELINE config 5 shape: 20-20,000 segments, log-uniform, length-bucketed: spot-check against the oracle."""
+    model = models["pro_001_py2"]
+    orc = util.oracle_for(model)
+    lens = events.log_uniform_lengths(400, 20, 20000, seed=8)
+    obs, offsets = model.engine().sample_events(lens, seed=21)
+    scores, plen, paths = model.engine().viterbi_batch(obs, offsets)
+    lp = model.engine().forward_batch(obs, offsets)
+    poff = np.concatenate([[0], np.cumsum(np.maximum(plen, 0))])
+    for e in list(np.argsort(lens)[-3:]) + list(np.argsort(lens)[:3]) + [7, 100, 250]:
+        x = obs[offsets[e]:offsets[e + 1]].astype(np.float64)
+        s, p, margin = orc.viterbi(x, with_margin=True)
+        assert scores[e] == s
+        assert np.array_equal(paths[poff[e]:poff[e + 1]], p) or margin == 0.0
+        assert util.close([lp[e]], [orc.log_probability(x)]).all()

@@ -27,9 +27,9 @@ obs, offsets = eng.sample_events(lens, seed=2)
 eng.viterbi_batch(obs, offsets, with_paths=False)
 lib.pp_debug_phase_cycles(None, 1)
 eng.viterbi_batch(obs, offsets, with_paths=False)
-buf = np.zeros(64, dtype=np.uint64)
+buf = np.zeros(128, dtype=np.uint64)
 lib.pp_debug_phase_cycles(buf.ctypes.data, 0)
-buf = buf.reshape(8, 8).astype(np.float64)
+buf = buf.reshape(16, 8).astype(np.float64)
 rows = buf[:, 6]
 print("warp  silent  early  waitB  finalgap  late(A)  waitA   (cycles per row, %d warp-rows)" % rows[0])
 for w in range(8):
