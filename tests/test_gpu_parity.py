@@ -255,3 +255,76 @@ def test_mixed_length_batch_config5(models):
         assert scores[e] == s
         assert np.array_equal(paths[poff[e]:poff[e + 1]], p) or margin == 0.0
         assert util.close([lp[e]], [orc.log_probability(x)]).all()
+
+
+def _random_model(rng, idx):
+    """Random small HMM: emitting states with Normal / point-mass / Uniform emissions, a silent DAG with chains,
+    sometimes infinite (no edge into end), random state weights -- the topologies PyPore/hmm.py-style builders make."""
+    import protpore_b200.yahmm as y
+    m = y.Model(name="rnd%d" % idx)
+    n_e, n_s = int(rng.randint(2, 9)), int(rng.randint(0, 7))
+    emit = []
+    for k in range(n_e):
+        kind = rng.randint(0, 4)
+        if kind <= 1:
+            d = y.NormalDistribution(float(rng.uniform(-3, 3)), float(rng.uniform(0.3, 2.0)))
+        elif kind == 2:
+            d = y.NormalDistribution(float(np.round(rng.uniform(-2, 2), 1)), 0.0)
+        else:
+            lo = float(rng.uniform(-4, 0))
+            d = y.UniformDistribution(lo, lo + float(rng.uniform(1, 6)))
+        emit.append(y.State(d, name="e%d" % k, weight=float(rng.choice([1.0, 1.0, 0.5, 2.0]))))
+    sil = [y.State(None, name="s%d" % k) for k in range(n_s)]
+    for s in emit + sil:
+        m.add_state(s)
+    finite = rng.rand() < 0.75
+    nodes = emit + sil
+    for a in [m.start] + nodes:
+        targets = []
+        for b in nodes + ([m.end] if finite else []):
+            if a is b and a.is_silent():
+                continue
+            if a.is_silent() and b is not m.end and b.is_silent():
+                # keep the silent sub-graph acyclic: start -> s_i -> s_j only for i < j
+                if a is not m.start and sil.index(a) >= sil.index(b):
+                    continue
+            if rng.rand() < (0.45 if b is not m.end else 0.6):
+                targets.append(b)
+        if not targets:
+            targets = [emit[int(rng.randint(n_e))]]
+        p = rng.dirichlet(np.ones(len(targets)))
+        for b, pb in zip(targets, p):
+            m.add_transition(a, b, float(pb))
+    m.bake()
+    return m
+
+
+def test_random_models_against_oracle():
+    """60 random HMMs x 12 random events each: Viterbi bit-exact (paths identical unless the oracle reports an exact
+    tie), forward / tables within tolerance, impossible events in-band."""
+    rng = np.random.RandomState(2026)
+    checked = 0
+    for idx in range(60):
+        model = _random_model(rng, idx)
+        if model.silent_start == 0:
+            continue
+        orc = util.oracle_for(model)
+        evs = []
+        for _ in range(12):
+            n = int(rng.randint(1, 40))
+            x = rng.uniform(-4, 4, size=n)
+            evs.append(np.round(x, 1) if rng.rand() < 0.4 else x)      # rounded values can hit the point masses
+        res = model.viterbi_batch(evs, dtype=np.float64, states=False)
+        lp = model.log_probability_batch(evs, dtype=np.float64)
+        for x, (score, path), l in zip(evs, res, lp):
+            s, p, margin = orc.viterbi(x, with_margin=True)
+            assert score == s, (idx, score, s)
+            assert (path is None) == (p is None)
+            if p is not None:
+                assert np.array_equal(path, p) or margin == 0.0, idx
+            assert util.close([l], [orc.log_probability(x)], abs_tol=1e-5, rel_tol=1e-7).all(), (idx, l, orc.log_probability(x))
+            checked += 1
+        x = evs[0]
+        assert util.close(model.forward(x), orc.forward(x), abs_tol=1e-9, rel_tol=1e-12).all()
+        assert util.close(model.backward(x), orc.backward(x), abs_tol=1e-9, rel_tol=1e-12).all()
+    assert checked > 500
