@@ -69,7 +69,7 @@ __device__ __forceinline__ double emission_log(const EmisRec& R, double x) {
     } else if (R.kind == EMIS_POINT) {
         r = (fabs(__dsub_rn(x, R.a0)) < 1E-4) ? 0.0 : neg_inf();
     } else {
-        r = (x == R.a0 && x == R.a1) ? 0.0 : ((x >= R.a0 && x <= R.a1) ? R.a3 : neg_inf());
+        r = (x >= R.a0 && x <= R.a1) ? R.a3 : neg_inf();      // a3 = 0 when a0 == a1 (host), the x == a == b branch
     }
     return __dadd_rn(r, R.logw);
 }

@@ -113,8 +113,9 @@ __device__ __forceinline__ double smem_emission_log(uint32_t ep, double x) {
     } else if (KIND == EMIS_POINT) {
         r = (fabs(__dsub_rn(x, lds64(ep))) < 1E-4) ? 0.0 : neg_inf();
     } else {
-        const double a = lds64(ep), b = lds64(ep + 8);
-        r = (x == a && x == b) ? 0.0 : ((x >= a && x <= b) ? lds64(ep + 24) : neg_inf());
+        // a3 = log(1/(b-a)), or 0 when a == b (then "in range" means x == a == b, the reference's first branch)
+        const double a = lds64(ep), b = lds64(ep + 8), c = lds64(ep + 24);
+        r = (x >= a && x <= b) ? c : neg_inf();
     }
     return __dadd_rn(r, lds64(ep + 32));
 }
@@ -127,9 +128,8 @@ __device__ __forceinline__ double smem_emission_log2(uint32_t ep, double x) {
         return fma(-(d * d), lds64(ep + 8), lds64(ep + 16));
     }
     if (KIND == EMIS_POINT) return (fabs(x - lds64(ep)) < 1E-4) ? lds64(ep + 16) : neg_inf();
-    const double a = lds64(ep), b = lds64(ep + 8);
-    if (x == a && x == b) return lds64(ep + 24);
-    return (x >= a && x <= b) ? lds64(ep + 16) : neg_inf();
+    const double a = lds64(ep), b = lds64(ep + 8), c = lds64(ep + 16);     // c2 covers a == b as well (host)
+    return (x >= a && x <= b) ? c : neg_inf();
 }
 
 enum : int { MODE_EMIT = 0, MODE_SILENT = 1, MODE_CHAIN = 2 };

@@ -37,7 +37,8 @@ std::string fill_emissions(const pp_model_desc& d, Lowered* low) {
             e.kind = EMIS_UNIFORM;
             e.a0 = p0;
             e.a1 = p1;
-            e.a3 = ref_log(1.0 / (p1 - p0));                   // (261); a == b is caught by x==a==b first
+            // (261); a == b: the reference returns 0 for x == a == b (257-259), and nothing else is in range
+            e.a3 = (p1 == p0) ? 0.0 : ref_log(1.0 / (p1 - p0));
             e.c2 = (e.a3 + lw) * kLog2e;
         } else {
             return "emission kind " + std::to_string(d.emit_kind[k]) + " of state " + std::to_string(k) +
