@@ -78,14 +78,19 @@ __device__ __forceinline__ double emission_log(const EmisRec& R, double x) {
 // rel. error ~2^-22); the integer part is written straight into the exponent field.  Below 2^-1000
 // the factor is flushed to zero, above 2^1000 it becomes +inf (caught by the caller's status).
 __device__ __forceinline__ double exp2_scaled(double t) {
-    if (!(t > -1000.0)) return 0.0;                  // also catches -inf and NaN
-    if (t > 1000.0) return __longlong_as_double(0x7FF0000000000000LL);
-    const double n = rint(t);
-    const float f = static_cast<float>(t - n);
+    // clamp instead of branching: below -1000 the result is made an exact 0, above 1000 it saturates to 2^1000 * p
+    // (the caller's row maximum then reaches inf / NaN and the event is re-run by the exact kernel)
+    const double tc = fmin(fmax(t, -1001.0), 1000.0);          // fmax(NaN, -1001) = -1001 -> 0
+    // round to nearest integer with the 1.5 * 2^52 trick: two DADDs, the integer lands in the low word
+    const double magic = 6755399441055744.0;
+    const double tm = tc + magic;
+    const int n = __double2loint(tm);
+    const float f = static_cast<float>(tc - (tm - magic));
     float p;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(f));
-    const int hi = (static_cast<int>(n) + 1023) << 20;
-    return static_cast<double>(p) * __hiloint2double(hi, 0);
+    const double scale = __hiloint2double((n + 1023) << 20, 0);
+    const double r = static_cast<double>(p) * scale;
+    return (t > -1000.0) ? r : 0.0;
 }
 
 __device__ __forceinline__ double emission_log2(const EmisRec& R, double x) {
