@@ -485,27 +485,44 @@ class Model(object):
                 raise NotImplementedError("{} cannot be re-estimated from GPU sufficient statistics".format(dist.name))
         self._push_params()
 
-    def _viterbi_counts(self, sequences):
-        """Hard-assignment statistics from batched Viterbi paths (yahmm.pyx:4329-4357)."""
-        m = len(self.states)
-        counts = numpy.zeros((m, m), dtype=numpy.int64)
-        emitted = [[] for _ in range(self.silent_start)]
+    def _train_viterbi(self, sequences, transition_pseudocount, use_pseudocount, edge_inertia, distribution_inertia):
+        """Hard-assignment training (yahmm.pyx:4329-4357): tag every sequence with ONE batched Viterbi call, then
+        train on the (sequence, path) pairs as labelled data."""
+        pairs = []
         for seq, (score, path) in zip(sequences, self.viterbi_batch(sequences, dtype=numpy.float64, states=False)):
             if path is None:
+                print("Warning: skipped impossible sequence {}".format(seq))
                 continue
-            i = 0
-            for a, c in zip(path[:-1], path[1:]):
-                counts[a, c] += 1
-                if c < self.silent_start:
-                    emitted[c].append(seq[i])
-                    i += 1
-        return counts, emitted
+            pairs.append((seq, [self.states[k] for k in path]))
+        self._train_labelled(pairs, transition_pseudocount, use_pseudocount, edge_inertia, distribution_inertia)
 
-    def _apply_counts(self, counts, emitted, transition_pseudocount, use_pseudocount, edge_inertia,
-                      distribution_inertia):
-        """Shared M-step of Viterbi / labelled training (yahmm.pyx:4425-4499)."""
+    def _train_labelled(self, sequences, transition_pseudocount, use_pseudocount, edge_inertia, distribution_inertia):
+        """Training on (sequence, state path) pairs (yahmm.pyx:4359-4499)."""
         b = self._baked
         m = len(self.states)
+        indices = {s: i for i, s in enumerate(self.states)}
+        counts = numpy.zeros((m, m), dtype=numpy.int64)
+        symbols = [[] for _ in range(m)]
+        for seq, labels in sequences:
+            counts[self.start_index, indices[labels[0]]] += 1
+            for x, y in zip(labels[:-1], labels[1:]):
+                counts[indices[x], indices[y]] += 1
+            counts[indices[labels[-1]], self.end_index] += 1
+            i = 0
+            for label in labels:
+                if label.is_silent():
+                    continue
+                k = indices[label]
+                symbols[k].append(seq[i])
+                for li in b.tied_idx[b.tied_ptr[k]:b.tied_ptr[k + 1]]:
+                    symbols[int(li)].append(seq[i])
+                i += 1
+        sizes = b.tied_edge_group_size                      # tied edges pool their counts (4425-4440)
+        for g in range(len(sizes) - 1):
+            members = [(int(b.tied_edges_starts[l]), int(b.tied_edges_ends[l])) for l in range(sizes[g], sizes[g + 1])]
+            total = sum(counts[k] for k in members)
+            for k in members:
+                counts[k] = total
         norm = numpy.zeros(m)
         for k in range(m):
             for l in range(b.out_ptr[k], b.out_ptr[k + 1]):
@@ -520,29 +537,15 @@ class Model(object):
                 if norm[li] > 0:
                     p = (counts[li, k] + transition_pseudocount + b.in_pseudo[l] * use_pseudocount) / norm[li]
                     b.in_logp[l] = log(math.exp(b.in_logp[l]) * edge_inertia + p * (1 - edge_inertia))
-        for k in range(self.silent_start):
-            if len(emitted[k]) > 0:
-                self.states[k].distribution.from_sample(numpy.asarray(emitted[k]), inertia=distribution_inertia)
+        visited = numpy.zeros(self.silent_start, dtype=bool)
+        for k in range(self.silent_start):                  # once per tied group (4481-4499)
+            if visited[k]:
+                continue
+            visited[k] = True
+            for li in b.tied_idx[b.tied_ptr[k]:b.tied_ptr[k + 1]]:
+                visited[int(li)] = True
+            self.states[k].distribution.from_sample(numpy.asarray(symbols[k]), inertia=distribution_inertia)
         self._push_params()
-
-    def _train_viterbi(self, sequences, transition_pseudocount, use_pseudocount, edge_inertia, distribution_inertia):
-        counts, emitted = self._viterbi_counts(sequences)
-        self._apply_counts(counts, emitted, transition_pseudocount, use_pseudocount, edge_inertia, distribution_inertia)
-
-    def _train_labelled(self, sequences, transition_pseudocount, use_pseudocount, edge_inertia, distribution_inertia):
-        m = len(self.states)
-        indices = {s: i for i, s in enumerate(self.states)}
-        counts = numpy.zeros((m, m), dtype=numpy.int64)
-        emitted = [[] for _ in range(self.silent_start)]
-        for seq, path in sequences:
-            i = 0
-            for a, c in zip(path[:-1], path[1:]):
-                ka, kc = indices[a], indices[c]
-                counts[ka, kc] += 1
-                if kc < self.silent_start:
-                    emitted[kc].append(seq[i])
-                    i += 1
-        self._apply_counts(counts, emitted, transition_pseudocount, use_pseudocount, edge_inertia, distribution_inertia)
 
     # ---- text format (yahmm.pyx:3744-3936) -------------------------------------------------------
     def write(self, stream):

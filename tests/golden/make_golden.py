@@ -166,6 +166,14 @@ def main():
             out["bw_dense"] = tmodel.dense_transition_matrix()
             out["bw_params"] = np.array([[float(p) for p in s.distribution.parameters[:2]]
                                          for s in tmodel.states[:tmodel.silent_start]])
+            # Viterbi (hard-assignment) training on the same events (yahmm.pyx:4329-4499)
+            vmodel = build(ref)
+            with redirect_stdout(io.StringIO()):
+                vimp = vmodel.train(seqs, algorithm='viterbi', verbose=False)
+            out["vt_improvement"] = np.array([vimp])
+            out["vt_dense"] = vmodel.dense_transition_matrix()
+            out["vt_params"] = np.array([[float(p) for p in s.distribution.parameters[:2]]
+                                         for s in vmodel.states[:vmodel.silent_start]])
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, "events", len(evs), "obs", len(out["obs"]), "impossible", int(np.sum(~np.isfinite(out["vscore"]))))
 

@@ -328,3 +328,20 @@ def test_random_models_against_oracle():
         assert util.close(model.forward(x), orc.forward(x), abs_tol=1e-9, rel_tol=1e-12).all()
         assert util.close(model.backward(x), orc.backward(x), abs_tol=1e-9, rel_tol=1e-12).all()
     assert checked > 500
+
+
+@pytest.mark.parametrize("name", ["pro_001_py2", "toy", "synth_12"])
+def test_viterbi_training_matches_golden(name):
+    """Model.train(algorithm='viterbi') (yahmm.pyx:4329-4499): paths from ONE batched Viterbi call, host M-step."""
+    g = util.load_golden(name)
+    model = util.build_model(name)
+    evs = util.golden_events(g)
+    seqs = [evs[i] for i in g["bw_events"]]
+    imp = model.train(seqs, algorithm='viterbi', verbose=False)
+    assert imp == pytest.approx(float(g["vt_improvement"][0]), rel=1e-7, abs=1e-6)
+    dense = model.dense_transition_matrix()
+    fin = np.isfinite(g["vt_dense"])
+    assert np.array_equal(np.isfinite(dense), fin)
+    assert np.allclose(dense[fin], g["vt_dense"][fin], rtol=1e-10, atol=1e-12)
+    params = np.array([[float(p) for p in s.distribution.parameters[:2]] for s in model.states[:model.silent_start]])
+    assert np.allclose(params, g["vt_params"], rtol=1e-9, atol=1e-12)
