@@ -152,6 +152,13 @@ def main():
             if et is not None:
                 out["fb_et_%d" % j] = et
                 out["fb_ew_%d" % j] = ew
+        # posterior decoding (yahmm.pyx:3654-3742) on the table events
+        for j, i in enumerate(small):
+            with redirect_stdout(io.StringIO()):
+                ms, mp = rmodel.maximum_a_posteriori(evs[i])
+            if mp is not None:
+                out["map_score_%d" % j] = np.array([ms])
+                out["map_path_%d" % j] = np.array([k for k, _ in mp], dtype=np.int32)
         # one Baum-Welch iteration on the possible events among the first 30 (fresh model: train mutates)
         if name in ("pro_001_py2", "toy", "synth_12"):
             tmodel = build(ref)

@@ -345,3 +345,80 @@ def test_viterbi_training_matches_golden(name):
     assert np.allclose(dense[fin], g["vt_dense"][fin], rtol=1e-10, atol=1e-12)
     params = np.array([[float(p) for p in s.distribution.parameters[:2]] for s in model.states[:model.silent_start]])
     assert np.allclose(params, g["vt_params"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", util.MODEL_NAMES)
+def test_maximum_a_posteriori_matches_golden(models, name):
+    g = util.load_golden(name)
+    model = models[name]
+    evs = util.golden_events(g)
+    for j, i in enumerate(g["table_events"]):
+        score, path = model.maximum_a_posteriori(evs[i])
+        if "map_score_%d" % j not in g:
+            assert score is None and path is None
+            continue
+        assert score == pytest.approx(float(g["map_score_%d" % j][0]), rel=1e-9, abs=1e-9)
+        assert [k for k, _ in path] == list(g["map_path_%d" % j])
+
+
+def test_config1_thousand_free_running_events(models):
+    """BASELINE config 1: 1,000 events by free-running Model.sample() (mean ~15 segments): Viterbi + forward
+    log-probability, full parity against the oracle (pinned to the compiled reference) on every event."""
+    import random
+    model = models["pro_001_py2"]
+    orc = util.oracle_for(model)
+    random.seed(20261019)
+    evs = []
+    while len(evs) < 1000:
+        x = np.asarray(np.asarray(model.sample(), dtype=np.float32), dtype=np.float64)
+        if len(x):
+            evs.append(x)
+    res = model.viterbi_batch(evs, dtype=np.float64, states=False)
+    lp = model.log_probability_batch(evs, dtype=np.float64)
+    n_seg = 0
+    for x, (score, path), l in zip(evs, res, lp):
+        s, p, margin = orc.viterbi(x, with_margin=True)
+        assert score == s
+        assert np.array_equal(path, p) or margin == 0.0
+        assert util.close([l], [orc.log_probability(x)]).all()
+        n_seg += len(x)
+    assert 5 < n_seg / 1000.0 < 40
+
+
+def test_tied_states_and_labelled_training():
+    """Tied emission distributions (shared object) and tied edge groups: forward_backward(tie=True) pools
+    posteriors (yahmm.pyx:3325-3361); labelled training follows yahmm.pyx:4359-4499.  Checked against a direct
+    numpy evaluation of the same formulas from the oracle's tables."""
+    import protpore_b200.yahmm as y
+    shared = y.NormalDistribution(1.0, 0.7)
+    m = y.Model(name="tied")
+    a = y.State(shared, name="a"); b = y.State(shared, name="b"); c = y.State(y.NormalDistribution(4.0, 1.0), name="c")
+    for s in (a, b, c):
+        m.add_state(s)
+    m.add_transition(m.start, a, 0.6); m.add_transition(m.start, c, 0.4)
+    m.add_transition(a, b, 0.5, group="g"); m.add_transition(a, a, 0.3); m.add_transition(a, m.end, 0.2)
+    m.add_transition(b, c, 0.5, group="g"); m.add_transition(b, b, 0.3); m.add_transition(b, m.end, 0.2)
+    m.add_transition(c, a, 0.5); m.add_transition(c, c, 0.3); m.add_transition(c, m.end, 0.2)
+    m.bake()
+    x = np.array([0.8, 1.3, 3.9, 4.2, 1.1, 0.7])
+    et, ew = m.forward_backward(x, tie=False)
+    et2, ew2 = m.forward_backward(x, tie=True)
+    ia, ib = [s.name for s in m.states].index("a"), [s.name for s in m.states].index("b")
+    pooled = np.logaddexp(ew[:, ia], ew[:, ib])
+    assert np.allclose(ew2[:, ia], pooled, rtol=1e-12, atol=1e-12) and np.allclose(ew2[:, ib], pooled, rtol=1e-12, atol=1e-12)
+    assert np.allclose(et, et2)
+    # labelled training: counts along the given path (plus start -> first, last -> end), tied edges pooled
+    path = [m.start, a, a, c, c, a, b, m.end]
+    before = m.dense_transition_matrix().copy()
+    m.train([(x, path)], algorithm='labelled', verbose=False)
+    dense = m.dense_transition_matrix()
+    names = [s.name for s in m.states]
+    i = {n: names.index(n) for n in names}
+    # group "g" = {a->b, b->c}: counts 1 and 0 -> both 1; a's out-edges: a->b 1, a->a 1, a->end 0 (path ends in b->end)
+    assert np.exp(dense[i["a"], i["b"]]) == pytest.approx(0.5) and np.exp(dense[i["a"], i["a"]]) == pytest.approx(0.5)
+    assert np.isneginf(dense[i["a"], m.end_index])
+    # b: b->c pooled count 1, b->end 1 -> 0.5 each
+    assert np.exp(dense[i["b"], i["c"]]) == pytest.approx(0.5) and np.exp(dense[i["b"], m.end_index]) == pytest.approx(0.5)
+    # the shared distribution was re-estimated once from the symbols of a AND b
+    assert shared.parameters[0] == pytest.approx(np.mean([0.8, 1.3, 1.1, 0.7]))
+    assert before.shape == dense.shape
