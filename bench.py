@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="score", choices=["score", "baum-welch"],
+                    help="score: forward + Viterbi (config 2, the contract line); baum-welch: one distributed BW iteration (config 3)")
+    ap.add_argument("--bw-events", type=int, default=20000, help="events per GPU of the baum-welch workload")
     return ap.parse_args()
 
 
@@ -142,6 +145,55 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
 
 
+def bench_baum_welch(args, model, rank, world, local):
+    """Config 3 shape: forward-backward statistics + one Baum-Welch iteration, events sharded over the GPUs, the
+    packed statistics allreduced over NCCL (protpore_b200.parallel), identical M-step on every rank."""
+    import torch
+    import torch.distributed as dist
+    from protpore_b200 import events, parallel
+    eng = model.engine()
+    lens = events.uniform_lengths(args.bw_events, args.min_len, args.max_len, seed=args.seed + rank)
+    obs, off = eng.sample_events(lens, seed=args.seed + 2000 + rank)
+    seqs = [obs[off[i]:off[i + 1]] for i in range(len(lens))]
+    cells = 2.0 * float(lens.sum()) * len(model.states)                 # a forward and a backward pass
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+    for _ in range(min(args.warmup, 1)):
+        parallel.baum_welch_iteration(model, seqs[:200])
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ll, used = parallel.baum_welch_iteration(model, seqs)
+    sync()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t[0])
+    # every rank must hold the identical model after the allreduced M-step
+    dense = torch.from_numpy(np.nan_to_num(model.dense_transition_matrix(), neginf=-1e300)).cuda()
+    lo, hi = dense.clone(), dense.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    identical = bool(torch.equal(lo, hi))
+    if rank == 0:
+        print(json.dumps({"metric": "Baum-Welch iteration (forward-backward statistics + NCCL allreduce + M-step), cell updates per second",
+                          "value": cells * world * args.steps / dt / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                          "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "ours",
+                          "config": {"workload": "pro_001, {} events/GPU of {}-{} segments, one Baum-Welch iteration; exact "
+                                     "state-parallel log-space kernel (k_fb_accumulate)".format(args.bw_events, args.min_len, args.max_len),
+                                     "allreduce_doubles": int(model.edge_count() + 3 * model.silent_start + 2)},
+                          "events_used": used, "sum_loglik": ll, "ranks_hold_identical_model": identical,
+                          "gpu_launches": int(eng.launch_count())}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -176,6 +228,8 @@ def main():
     model = peptide_hmm.pro_001_model()
     eng = model.engine()
     m, E = len(model.states), model.edge_count()
+    if args.workload == "baum-welch":
+        return bench_baum_welch(args, model, rank, world, local)
     from protpore_b200 import _engine as _eng
     ptr_bytes_row = int(_eng.describe_schedule(model).split("ptr_row_bytes")[1].split()[0]) / 32.0   # per event-row
 
