@@ -381,7 +381,7 @@ std::string lower_model(const pp_model_desc& d, int warps, Lowered* low) {
     low->late_of = late_of;
     low->early_of = early_of;
     low->sil_of = sil_of;
-    return "";
+    return lower_backward(d, low);
 }
 
 std::string refresh_params(const pp_model_desc& d, Lowered* low) {
@@ -393,7 +393,7 @@ std::string refresh_params(const pp_model_desc& d, Lowered* low) {
             low->edges_logp[q][i].val = d.in_logp[low->low_csr[i]];
             low->edges_prob[q][i].val = std::exp(d.in_logp[low->low_csr[i]]);
         }
-    return "";
+    return lower_backward(d, low);
 }
 
 }  // namespace pp

@@ -105,12 +105,19 @@ struct Lowered {
     std::vector<int32_t> sil_level;              // per state: 0 for emitting, else 1 + longest silent-pred chain
     int32_t n_levels = 0;
     std::vector<EmisRec> emis;
+    // backward sweep (pp_lowering_bw.cpp): runs over the out-edge CSR, lists {H items, silent, emitting} per warp
+    bool bw_ok = false;
+    std::vector<RunRec> bw_runs;
+    std::vector<int32_t> bw_ranges;              // [warps][6]
+    std::vector<double> bw_wtab;                 // transition probabilities in backward-lowered edge order (+ a 1.0)
 };
 
 // Returns "" on success, otherwise why the model cannot be lowered.
 std::string lower_model(const pp_model_desc& d, int warps, Lowered* out);
 // Refresh weights / emission parameters of an existing lowering (same topology).
 std::string refresh_params(const pp_model_desc& d, Lowered* low);
+// Run schedule of the backward sweep; sets low->bw_ok (false: the exact state-parallel kernels serve the model).
+std::string lower_backward(const pp_model_desc& d, Lowered* low);
 // One line per warp and phase: the runs it executes (pp_describe.cpp).
 std::string describe_schedule(const Lowered& L);
 
