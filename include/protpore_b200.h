@@ -92,8 +92,9 @@ int64_t pp_viterbi_workspace_bytes(const pp_model *model, const int64_t *offsets
 /*
  * Batched Model.log_probability (yahmm.pyx:3366-3396 over Model._forward, 2810-2930):
  * logp_out[e] = log P(event e | model), float64, -inf if impossible.
- * Computed by the scaled linear-space fp32 column kernel with exact power-of-two rescaling
- * (DESIGN.md "forward"); |error| <= 1e-3 nats abs or 1e-6 rel against the float64 reference.
+ * Computed by the scaled linear-space float64 column kernel with exact power-of-two rescaling
+ * (DESIGN.md "forward"; emission factors through MUFU.EX2, rel. error ~2^-22 each); measured worst error
+ * < 1e-7 relative against the float64 reference, inside the 1e-3 abs / 1e-6 rel bar.
  */
 int pp_forward_batch(pp_model *model, const void *obs, int32_t obs_dtype, const int64_t *offsets,
                      int64_t n_events, int32_t mem, double *logp_out);
@@ -133,10 +134,20 @@ int pp_backward_table(pp_model *model, const double *obs, int64_t n, int32_t mem
  *   posteriors_out         : optional (may be NULL): log emission weights, float64, event e row i
  *                            state k at [(offsets[e] + i) * silent_start + k]  (3304-3321)
  * Accumulators are read-modify-write so a caller can sum shards before an allreduce.
+ * Without posteriors_out, models the lane-per-event kernels serve run on k_fb_lane (scaled linear-space forward
+ * and backward sweeps, float64, float64-accurate emissions; statistics within ~1e-11 relative of the exact
+ * log-space kernel); events it cannot resolve, other models, and calls that ask for posteriors take the exact
+ * state-parallel log-space kernel.
  */
 int pp_forward_backward_batch(pp_model *model, const void *obs, int32_t obs_dtype, const int64_t *offsets,
                               int64_t n_events, int32_t mem, double *logp_out, double *edge_counts,
                               double *emit_moments, double *emit_minmax, double *posteriors_out);
+
+/* How the LAST pp_forward_backward_batch call on this handle was served: out[0] = 1 lane-per-event kernel
+ * (pp_lane_fb.cuh), 0 exact state-parallel kernel only, 2 lane kernel failed its numeric checks and the batch was
+ * redone by the exact kernel; out[1] = events the lane kernel handed to the exact kernel (scaled sweep could not
+ * resolve them); out[2] = events whose backward sweep failed the checks. */
+int pp_forward_backward_info(const pp_model *model, int64_t *out3);
 
 /*
  * Length-conditioned ancestral sampler used to make synthetic events:

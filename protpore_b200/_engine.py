@@ -59,6 +59,7 @@ ABI = [
                                         ctypes.c_int64, _i64p]),
     ("pp_forward_table", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
     ("pp_backward_table", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
+    ("pp_forward_backward_info", ctypes.c_int, [_vp, _i64p]),
     ("pp_forward_backward_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, ctypes.c_int64, ctypes.c_int32, _vp,
                                                  _vp, _vp, _vp, _vp]),
     ("pp_sample_events", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int32, _vp]),
@@ -306,23 +307,43 @@ class Engine(object):
     def forward_backward_batch(self, obs, offsets, posteriors=False, accum=None):
         """E-step statistics: (logp[n], edge_counts[E] (out-CSR order), moments[ne,3], minmax[ne,2], posteriors|None).
 
-        `accum` = (edge_counts, moments, minmax) to keep accumulating into (host arrays)."""
-        obs = np.ascontiguousarray(obs)
-        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        `accum` = (edge_counts, moments, minmax) to keep accumulating into.  numpy in -> numpy out; torch CUDA
+        tensors in -> torch out (the statistics stay on the device, ready for the NCCL allreduce)."""
         n = len(offsets) - 1
-        logp = np.empty(n, dtype=np.float64)
-        if accum is None:
-            edge = np.zeros(self.n_edges, dtype=np.float64)
-            mom = np.zeros((self.ne, 3), dtype=np.float64)
-            mm = np.empty((self.ne, 2), dtype=np.float64)
-            mm[:, 0], mm[:, 1] = np.inf, -np.inf
+        if _is_device(obs):
+            import torch
+            mk = lambda shape, fill: torch.full(shape, fill, dtype=torch.float64, device=obs.device)
+            logp = mk((n,), 0.0)
+            if accum is None:
+                edge, mom, mm = mk((self.n_edges,), 0.0), mk((self.ne, 3), 0.0), mk((self.ne, 2), 0.0)
+                mm[:, 0], mm[:, 1] = float("inf"), float("-inf")
+            else:
+                edge, mom, mm = accum
+            post = mk((int(obs.numel()), self.ne), 0.0) if posteriors else None
+            mem = PP_MEM_DEVICE
+            torch.cuda.current_stream(obs.device).synchronize()       # the handle enqueues on its own stream
         else:
-            edge, mom, mm = accum
-        post = np.empty((len(obs), self.ne), dtype=np.float64) if posteriors else None
+            obs = np.ascontiguousarray(obs)
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+            logp = np.empty(n, dtype=np.float64)
+            if accum is None:
+                edge = np.zeros(self.n_edges, dtype=np.float64)
+                mom = np.zeros((self.ne, 3), dtype=np.float64)
+                mm = np.empty((self.ne, 2), dtype=np.float64)
+                mm[:, 0], mm[:, 1] = np.inf, -np.inf
+            else:
+                edge, mom, mm = accum
+            post = np.empty((len(obs), self.ne), dtype=np.float64) if posteriors else None
+            mem = PP_MEM_HOST
         self._check(self._lib.pp_forward_backward_batch(self._h, _ptr(obs), self._obs_dtype(obs), _ptr(offsets), n,
-                                                        PP_MEM_HOST, _ptr(logp), _ptr(edge), _ptr(mom), _ptr(mm),
-                                                        _ptr(post)))
+                                                        mem, _ptr(logp), _ptr(edge), _ptr(mom), _ptr(mm), _ptr(post)))
         return logp, edge, mom, mm, post
+
+    def forward_backward_info(self):
+        """How the last forward_backward_batch was served: {'path': 'lane' | 'exact' | 'lane-failed', 'rejects', 'failed'}."""
+        out = (ctypes.c_int64 * 3)()
+        self._check(self._lib.pp_forward_backward_info(self._h, out))
+        return {"path": ("exact", "lane", "lane-failed")[int(out[0])], "rejects": int(out[1]), "failed": int(out[2])}
 
     def sample_events(self, lengths, seed=0, device_out=False):
         """Length-conditioned synthetic events: (obs float32, offsets int64)."""

@@ -30,7 +30,9 @@ void set_error(const char* fmt, ...) {
 void lane_viterbi4_invalidate(const void*);
 void lane_viterbi8_invalidate(const void*);
 void lane_forward_invalidate(const void*);
+void lane_fb_invalidate(const void*);
 void lane_arena_invalidate(const void* owner) {
+    lane_fb_invalidate(owner);
     lane_viterbi4_invalidate(owner);
     lane_viterbi8_invalidate(owner);
     lane_forward_invalidate(owner);
@@ -114,6 +116,17 @@ int upload_model(pp_model* M) {
         PP_CUDA(upload(&M->d_etab_vit, ev, s));
         PP_CUDA(upload(&M->d_etab_fwd, ef, s));
     }
+    if (L.bw_ok) {                                                   // forward-backward lane kernel: forward runs | backward runs
+        const size_t nf = L.runs.size() * sizeof(RunRec) / 8, nb = L.bw_runs.size() * sizeof(RunRec) / 8;
+        M->arena_fb.assign(nf + nb, 0.0);
+        if (nf) std::memcpy(M->arena_fb.data(), L.runs.data(), nf * 8);
+        if (nb) std::memcpy(M->arena_fb.data() + nf, L.bw_runs.data(), nb * 8);
+        PP_CUDA(upload(&M->d_bw_wtab, L.bw_wtab, s));
+        PP_CUDA(upload(&M->d_acc_map, L.acc_map, s));
+        PP_CUDA(upload(&M->d_acc_log2, L.acc_log2, s));
+    } else {
+        M->arena_fb.clear();
+    }
     PP_CUDA(upload(&M->d_state_edge_begin, L.state_edge_begin, s));
     PP_CUDA(upload(&M->d_low_src, L.low_src, s));
     PP_CUDA(upload(&M->d_state_pword, L.state_pword, s));
@@ -162,7 +175,7 @@ static int copy_desc(pp_model* M, const pp_model_desc* d) {
     return PP_OK;
 }
 
-static LaneSched make_sched(const pp_model* M, bool logspace) {
+LaneSched make_sched(const pp_model* M, bool logspace) {
     LaneSched S;
     const Lowered& L = M->low;
     for (int q = 0; q < 2; ++q) S.end_edges[q] = (logspace ? M->d_edges_logp[q] : M->d_edges_prob[q]).as<EdgeRec>();
@@ -354,7 +367,8 @@ void pp_model_destroy(pp_model* M) {
                       &M->d_in_ptr, &M->d_in_src, &M->d_in_logp, &M->d_out_ptr, &M->d_out_dst, &M->d_out_logp,
                       &M->d_out_prob, &M->d_alive, &M->d_ws, &M->d_obs, &M->d_offsets, &M->d_order,
                       &M->d_group_len, &M->d_group_row, &M->d_score, &M->d_end_state, &M->d_end_ord, &M->d_path_len,
-                      &M->d_path_off, &M->d_path, &M->d_scan_tmp, &M->d_logp};
+                      &M->d_path_off, &M->d_path, &M->d_scan_tmp, &M->d_logp, &M->d_bw_wtab, &M->d_acc_map,
+                      &M->d_acc_log2, &M->d_fb_acc, &M->d_fb_scratch, &M->d_fb_ctl, &M->d_fb_minmax};
     for (DevBuf* b : bufs) b->release();
     release_state_model(M);
     if (M->ev[0]) cudaEventDestroy(M->ev[0]);

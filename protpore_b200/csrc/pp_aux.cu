@@ -2,12 +2,16 @@
 // (pp_state_kernels.cuh): full forward / backward tables, batched forward-backward statistics,
 // the exact re-run path of the linear-space forward sweep, and the synthetic-event sampler.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
+#include "pp_lane_types.h"
 #include "pp_model.h"
 #include "pp_state_kernels.cuh"
 
 namespace pp {
+
+LaneSched make_sched(const pp_model* M, bool logspace);        // pp_api.cu
 
 static StateModel make_state_model(const pp_model* M) {
     StateModel S;
@@ -312,6 +316,103 @@ int pp_backward_table(pp_model* M, const double* obs, int64_t n, int32_t mem, do
     return run_table(M, obs, n, mem, table_out, 1);
 }
 
+
+// Lane-per-event forward-backward (pp_lane_fb.cuh).  Returns PP_OK and sets *done: 1 = statistics added (events the
+// scaled sweep rejected are listed in d_list / *n_rejects for the exact kernel), 0 = the path does not apply or its
+// checks failed and the caller must run the whole batch on the exact kernel.
+static int fb_batch_lane(pp_model* M, const void* d_obs, int32_t obs_dtype, const int64_t* d_off, const int64_t* h_off,
+                         int64_t n_events, int64_t maxlen, double* d_logp, double* d_edge, double* d_mom, double* d_mm,
+                         int* done, int32_t* n_rejects) {
+    *done = 0;
+    *n_rejects = 0;
+    const Lowered& L = M->low;
+    if (!L.bw_ok || !L.lane_ok || M->arena_fb.empty() || M->arena_fb.size() > static_cast<size_t>(kArenaDoubles)) return PP_OK;
+    const int n_w = static_cast<int>(std::max(L.low_src.size(), L.bw_wtab.size()));
+    const size_t smem = lane_fb_smem(L.n_slots, n_w, L.ne);
+    if (smem > M->smem_optin) return PP_OK;
+    const int row_slots = L.ns + L.ne + 1;
+    const size_t cta_scratch = static_cast<size_t>(maxlen + 1) * row_slots * kSlotBytes;
+    Schedule sc;
+    build_schedule(h_off, 0, n_events, &sc);
+    int grid = std::min(sc.n_groups, 2 * M->sm_count);
+    const size_t budget = M->ws_limit;
+    if (cta_scratch * static_cast<size_t>(grid) > budget) grid = static_cast<int>(budget / cta_scratch);
+    if (grid < 1) return PP_OK;
+    if (M->d_fb_scratch.reserve(cta_scratch * grid) != cudaSuccess) { cudaGetLastError(); return PP_OK; }
+    const size_t acc_bytes = static_cast<size_t>(grid) * L.n_acc_slots * kLanes * sizeof(double);
+    PP_CUDA(M->d_fb_acc.reserve(acc_bytes));
+    PP_CUDA(M->d_fb_ctl.reserve(64));
+    PP_CUDA(M->d_fb_minmax.reserve(2 * static_cast<size_t>(L.ne) * sizeof(double)));
+    PP_CUDA(upload(&M->d_order, sc.order, M->stream));
+    PP_CUDA(upload(&M->d_group_len, sc.group_len, M->stream));
+    PP_CUDA(cudaMemsetAsync(M->d_fb_acc.p, 0, acc_bytes, M->stream));
+    PP_CUDA(cudaMemsetAsync(M->d_fb_ctl.p, 0, 64, M->stream));
+    {
+        std::vector<double> mm(2 * static_cast<size_t>(L.ne));
+        for (int k = 0; k < L.ne; ++k) { mm[2 * k] = INFINITY; mm[2 * k + 1] = -INFINITY; }
+        PP_CUDA(cudaMemcpyAsync(M->d_fb_minmax.p, mm.data(), mm.size() * sizeof(double), cudaMemcpyHostToDevice, M->stream));
+        PP_CUDA(cudaStreamSynchronize(M->stream));                 // mm is a stack-lifetime staging buffer
+    }
+    LaneSched S = make_sched(M, false);
+    FbSched F;
+    const int nf = static_cast<int>(L.runs.size());
+    for (int i = 0; i < kMaxLaneWarps * 6; ++i) F.run_ranges[i] = i < static_cast<int>(L.bw_ranges.size()) ? L.bw_ranges[i] + nf : 0;
+    for (int i = 0; i < kMaxLaneWarps; ++i) F.acc_base[i] = i < static_cast<int>(L.acc_base.size()) ? L.acc_base[i] : 0;
+    F.wtab = M->d_bw_wtab.as<double>();
+    F.n_w = static_cast<int32_t>(L.bw_wtab.size());
+    F.n_acc_slots = L.n_acc_slots;
+    F.row_slots = row_slots;
+    F.n_groups = sc.n_groups;
+    F.scratch = M->d_fb_scratch.as<unsigned char>();
+    F.scratch_stride = cta_scratch;
+    F.acc = M->d_fb_acc.as<double>();
+    F.counter = M->d_fb_ctl.as<int32_t>();
+    F.fail = M->d_fb_ctl.as<int32_t>() + 1;
+    F.logp = d_logp;
+    F.minmax = M->d_fb_minmax.as<double>();
+    const LaneBatchAny B{d_obs, obs_dtype == PP_F64 ? 1 : 0, d_off, M->d_order.as<int32_t>(), M->d_group_len.as<int32_t>(), nullptr};
+    int e = lane_fb_launch(S, F, B, grid, smem, M->stream, M->arena_fb.data(), M->arena_fb.size(), M);
+    if (e != 0) { set_error("forward-backward kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
+    ++M->launches;
+    int32_t ctl[16] = {0};
+    PP_CUDA(cudaMemcpyAsync(ctl, M->d_fb_ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, M->stream));
+    PP_CUDA(cudaStreamSynchronize(M->stream));
+    if (ctl[1] != 0 && std::getenv("PP_DEBUG_FB")) {
+        const double* dv = reinterpret_cast<const double*>(ctl + 8);
+        std::fprintf(stderr, "[pp] k_fb_lane: %d failed events; first: reason %d event %d (n or row %d) values %.17g %.17g %.17g %.17g\n",
+                     ctl[1], ctl[2], ctl[3], ctl[4], dv[0], dv[1], dv[2], dv[3]);
+    }
+    if (ctl[1] != 0) {                                              // a backward sweep failed its checks: exact path
+        M->fb_info[0] = 2;
+        M->fb_info[2] = ctl[1];
+        return PP_OK;
+    }
+    e = lane_fb_finalize(F.acc, grid, L.n_acc_slots, M->d_acc_map.as<int32_t>(), M->d_acc_log2.as<int32_t>(), M->n_edges,
+                         L.ne, d_edge, d_mom, F.minmax, d_mm, M->stream);
+    if (e != 0) { set_error("forward-backward finalize failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
+    M->launches += 2;
+    // events the scaled sweep rejected (P^ == 0, inf, NaN)
+    PP_CUDA(M->d_list.reserve(n_events * sizeof(int32_t)));
+    PP_CUDA(M->d_counter.reserve(16));
+    PP_CUDA(cudaMemsetAsync(M->d_counter.p, 0, 4, M->stream));
+    k_collect_flagged<<<static_cast<unsigned>((n_events + 255) / 256), 256, 0, M->stream>>>(
+        d_logp, n_events, M->d_list.as<int32_t>(), M->d_counter.as<int32_t>());
+    PP_CUDA(cudaGetLastError());
+    ++M->launches;
+    PP_CUDA(cudaMemcpyAsync(n_rejects, M->d_counter.p, 4, cudaMemcpyDeviceToHost, M->stream));
+    PP_CUDA(cudaStreamSynchronize(M->stream));
+    *done = 1;
+    M->fb_info[0] = 1;
+    M->fb_info[1] = *n_rejects;
+    return PP_OK;
+}
+
+int pp_forward_backward_info(const pp_model* M, int64_t* out3) {
+    if (!M || !out3) { set_error("null argument"); return PP_ERR_ARG; }
+    for (int i = 0; i < 3; ++i) out3[i] = M->fb_info[i];
+    return PP_OK;
+}
+
 int pp_forward_backward_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int64_t* offsets, int64_t n_events,
                               int32_t mem, double* logp_out, double* edge_counts, double* emit_moments,
                               double* emit_minmax, double* posteriors_out) {
@@ -371,30 +472,41 @@ int pp_forward_backward_batch(pp_model* M, const void* obs, int32_t obs_dtype, c
             d_post = M->d_ws.as<double>();
         }
     }
-    const int grid = static_cast<int>(std::min<int64_t>(n_events, static_cast<int64_t>(M->sm_count) * 4));
-    const int64_t stride = 2 * (maxlen + 1) * M->m;
-    const size_t need = static_cast<size_t>(grid) * stride * sizeof(double);
-    if (need > M->ws_limit || M->d_tab.reserve(need) != cudaSuccess) {
-        cudaGetLastError();
-        set_error("forward-backward needs %zu bytes of table workspace", need);
-        return PP_ERR_NOMEM;
-    }
-    PP_CUDA(M->d_xbuf.reserve(static_cast<size_t>(grid) * maxlen * sizeof(double)));
-    const int threads = std::max(128, state_threads(M));
-    const size_t smem = static_cast<size_t>(ne) * sizeof(double) + 16;
-    const StateModel S = make_state_model(M);
     cudaEventRecord(M->ev[0], M->stream);
-    if (obs_dtype == PP_F32) {
-        if (set_dyn_smem(k_fb_accumulate<float>, smem) != PP_OK) return PP_ERR_CUDA;
-        k_fb_accumulate<float><<<grid, threads, smem, M->stream>>>(S, static_cast<const float*>(d_obs), d_off, (int)n_events,
-            M->d_tab.as<double>(), stride, M->d_xbuf.as<double>(), maxlen, d_logp, d_edge, d_mom, d_mm, d_post);
-    } else {
-        if (set_dyn_smem(k_fb_accumulate<double>, smem) != PP_OK) return PP_ERR_CUDA;
-        k_fb_accumulate<double><<<grid, threads, smem, M->stream>>>(S, static_cast<const double*>(d_obs), d_off, (int)n_events,
-            M->d_tab.as<double>(), stride, M->d_xbuf.as<double>(), maxlen, d_logp, d_edge, d_mom, d_mm, d_post);
+    M->fb_info[0] = M->fb_info[1] = M->fb_info[2] = 0;
+    int lane_done = 0;
+    int32_t n_rej = 0;
+    if (!posteriors_out) {
+        int rc = fb_batch_lane(M, d_obs, obs_dtype, d_off, h_off, n_events, maxlen, d_logp, d_edge, d_mom, d_mm, &lane_done, &n_rej);
+        if (rc != PP_OK) return rc;
     }
-    PP_CUDA(cudaGetLastError());
-    ++M->launches;
+    const int64_t n_exact = lane_done ? n_rej : n_events;
+    const int32_t* d_evlist = lane_done ? M->d_list.as<int32_t>() : nullptr;
+    if (n_exact > 0) {
+        const int grid = static_cast<int>(std::min<int64_t>(n_exact, static_cast<int64_t>(M->sm_count) * 4));
+        const int64_t stride = 2 * (maxlen + 1) * M->m;
+        const size_t need = static_cast<size_t>(grid) * stride * sizeof(double);
+        if (need > M->ws_limit || M->d_tab.reserve(need) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("forward-backward needs %zu bytes of table workspace", need);
+            return PP_ERR_NOMEM;
+        }
+        PP_CUDA(M->d_xbuf.reserve(static_cast<size_t>(grid) * maxlen * sizeof(double)));
+        const int threads = std::max(128, state_threads(M));
+        const size_t smem = static_cast<size_t>(ne) * sizeof(double) + 16;
+        const StateModel S = make_state_model(M);
+        if (obs_dtype == PP_F32) {
+            if (set_dyn_smem(k_fb_accumulate<float>, smem) != PP_OK) return PP_ERR_CUDA;
+            k_fb_accumulate<float><<<grid, threads, smem, M->stream>>>(S, static_cast<const float*>(d_obs), d_off, (int)n_exact,
+                M->d_tab.as<double>(), stride, M->d_xbuf.as<double>(), maxlen, d_logp, d_edge, d_mom, d_mm, d_post, d_evlist);
+        } else {
+            if (set_dyn_smem(k_fb_accumulate<double>, smem) != PP_OK) return PP_ERR_CUDA;
+            k_fb_accumulate<double><<<grid, threads, smem, M->stream>>>(S, static_cast<const double*>(d_obs), d_off, (int)n_exact,
+                M->d_tab.as<double>(), stride, M->d_xbuf.as<double>(), maxlen, d_logp, d_edge, d_mom, d_mm, d_post, d_evlist);
+        }
+        PP_CUDA(cudaGetLastError());
+        ++M->launches;
+    }
     cudaEventRecord(M->ev[1], M->stream);
     if (mem == PP_MEM_HOST) {
         PP_CUDA(cudaMemcpyAsync(logp_out, d_logp, n_events * sizeof(double), cudaMemcpyDeviceToHost, M->stream));

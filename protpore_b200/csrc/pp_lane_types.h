@@ -52,6 +52,29 @@ int lane_viterbi8_launch(const LaneSched& S, const LaneBatchAny& B, const VitOut
                          cudaStream_t stream, const double* arena, size_t arena_doubles, const void* owner);
 int lane_forward_launch(const LaneSched& S, const LaneBatchAny& B, const FwdOut& O, int n_groups, size_t smem,
                         cudaStream_t stream, const double* arena, size_t arena_doubles, const void* owner);
+// lane-per-event forward-backward kernel (pp_lane_fb.cuh)
+struct FbSched {
+    int32_t run_ranges[kMaxLaneWarps * 6];   // per warp: {begin, end} of its H, silent and emitting runs (arena indices)
+    int32_t acc_base[kMaxLaneWarps];
+    const double* wtab;                      // backward weights (probabilities) in backward-lowered edge order
+    int32_t n_w;
+    int32_t n_acc_slots;
+    int32_t row_slots;                       // ns + ne + 1 (the last slot holds S_r)
+    int32_t n_groups;
+    unsigned char* scratch;                  // per CTA: (max_len + 1) rows of row_slots * 256 bytes
+    size_t scratch_stride;                   // bytes per CTA
+    double* acc;                             // per CTA: n_acc_slots * 32 doubles, zeroed by the host
+    int32_t* counter;                        // work-stealing group counter (zeroed by the host)
+    int32_t* fail;                           // number of events whose backward sweep failed its checks
+    double* logp;                            // [n_events]
+    double* minmax;                          // [2 * ne] min / max over events that gave the state non-zero weight
+};
+size_t lane_fb_smem(int n_slots, int n_w, int ne);
+int lane_fb_launch(const LaneSched& S, const FbSched& F, const LaneBatchAny& B, int grid, size_t smem, cudaStream_t stream,
+                   const double* arena, size_t arena_doubles, const void* owner);
+int lane_fb_finalize(const double* acc, int n_ctas, int n_slots, const int32_t* acc_map, const int32_t* acc_log2,
+                     int n_edges, int ne, double* edge_counts, double* emit_moments, const double* minmax_tmp,
+                     double* emit_minmax, cudaStream_t stream);
 void lane_arena_invalidate(const void* owner);           // forget `owner` in every arena (model changed / destroyed)
 #ifdef PP_PHASE_TIMING
 int lane_debug_phase_cycles(unsigned long long* out, int reset);

@@ -386,6 +386,19 @@ std::string lower_model(const pp_model_desc& d, int warps, Lowered* low) {
 
 std::string refresh_params(const pp_model_desc& d, Lowered* low) {
     if (d.n_states != low->m || d.silent_start != low->ne || d.n_edges != low->n_edges) return "topology changed";
+    // A changed emission KIND (a Normal whose sigma was 0 gets the min_std clamp in the M-step, yahmm.pyx:513, and
+    // leaves the point-mass branch) changes the shape of the runs: lower again from scratch.
+    for (int k = 0; k < d.silent_start; ++k) {
+        const int kind = d.emit_kind[k] == PP_EMIT_UNIFORM ? EMIS_UNIFORM : (d.emit_p1[k] == 0.0 ? EMIS_POINT : EMIS_NORMAL);
+        if (d.emit_kind[k] == PP_EMIT_NORMAL || d.emit_kind[k] == PP_EMIT_UNIFORM) {
+            if (kind != low->emis[k].kind) {
+                Lowered fresh;
+                std::string e = lower_model(d, low->warps, &fresh);
+                if (e.empty()) *low = std::move(fresh);
+                return e;
+            }
+        }
+    }
     std::string err = fill_emissions(d, low);
     if (!err.empty()) return err;
     for (int q = 0; q < 2; ++q)

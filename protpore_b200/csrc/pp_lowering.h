@@ -52,6 +52,12 @@ struct __attribute__((aligned(16))) EdgeRec {
 constexpr int kMaxRunEdges = 8;
 // items a kernel handles at once in a run of this in-degree (kernels and lowering must agree)
 constexpr int run_group_size(int n_edges) { return n_edges <= 2 ? 4 : (n_edges <= 4 ? 2 : PP_G_BIG); }
+// forward-backward accumulation: per-lane terms are lane-transposed in chunks of kAccChunk (then 4, 2, 1)
+#ifndef PP_ACC_LOG2
+#define PP_ACC_LOG2 3
+#endif
+constexpr int kAccLog2 = PP_ACC_LOG2;
+constexpr int kAccChunk = 1 << kAccLog2;
 enum : int32_t { EMIS_NORMAL = 0, EMIS_POINT = 1, EMIS_UNIFORM = 2, RUN_SILENT = 3, RUN_START = 4 };
 struct __attribute__((aligned(16))) RunRec {
     int32_t kind;                                // EMIS_* for emitting items, RUN_SILENT, RUN_START (the start state)
@@ -110,6 +116,13 @@ struct Lowered {
     std::vector<RunRec> bw_runs;
     std::vector<int32_t> bw_ranges;              // [warps][6]
     std::vector<double> bw_wtab;                 // transition probabilities in backward-lowered edge order (+ a 1.0)
+    std::vector<int32_t> bw_edge;                // out-edge CSR index of each entry of bw_wtab (-1: the constant 1.0)
+    // accumulation slots of the forward-backward kernel (pp_lane_fb.cuh): every chunk of <= kAccChunk per-lane terms is
+    // lane-transposed and added into one 32-double slot; lane L of a slot of 2^s terms holds term L >> (5 - s)
+    std::vector<int32_t> acc_base;               // [warps] first slot of the warp (program order: silent list, emitting list)
+    std::vector<int32_t> acc_map;                // [n_acc_slots * 32] statistic index per (slot, lane), -1 = unused
+    std::vector<int32_t> acc_log2;               // [n_acc_slots] s
+    int32_t n_acc_slots = 0;                     // statistic index: out-edge e | n_edges + 3 k + {0, 1, 2} (sum w, w x, w x^2)
 };
 
 // Returns "" on success, otherwise why the model cannot be lowered.

@@ -76,6 +76,11 @@ std::string lower_backward(const pp_model_desc& d, Lowered* low) {
     low->bw_ok = false;
     low->bw_runs.clear();
     low->bw_wtab.clear();
+    low->bw_edge.clear();
+    low->acc_base.clear();
+    low->acc_map.clear();
+    low->acc_log2.clear();
+    low->n_acc_slots = 0;
     const int m = d.n_states, ne = d.silent_start, ns = m - ne, W = low->warps;
     if (!low->lane_ok || !(d.finite == 1 && low->end_final_only)) return "";        // exact kernels serve these
     const int SIL = 0, EB = ns, HB = ns + ne;                      // slot bases
@@ -89,6 +94,7 @@ std::string lower_backward(const pp_model_desc& d, Lowered* low) {
         o->dst = k < ne ? EB + k : SIL + (k - ne);
         int chain_edge = -1;
         std::vector<std::pair<int, double>> edges;               // (slot, weight)
+        std::vector<int> eids;                                   // out-edge CSR index, same order
         for (int pass = 0; pass < 2; ++pass)                      // emitting targets first, then silent ones
             for (int e = d.out_ptr[k]; e < d.out_ptr[k + 1]; ++e) {
                 const int l = d.out_dst[e];
@@ -96,17 +102,26 @@ std::string lower_backward(const pp_model_desc& d, Lowered* low) {
                 if (k >= ne && l >= ne && l < k + 1) continue;    // silent -> silent only to larger indices (3026, 3108)
                 if (l == chain_prev) { chain_edge = e; continue; }
                 edges.emplace_back(slot_of_value(l), std::exp(d.out_logp[e]));
+                eids.push_back(e);
             }
-        if (chain_edge >= 0) edges.emplace_back(slot_of_value(chain_prev), std::exp(d.out_logp[chain_edge]));
+        if (chain_edge >= 0) {
+            edges.emplace_back(slot_of_value(chain_prev), std::exp(d.out_logp[chain_edge]));
+            eids.push_back(chain_edge);
+        }
         if (edges.size() > static_cast<size_t>(kMaxRunEdges)) return false;
         o->wbase = static_cast<int>(low->bw_wtab.size());
-        for (auto& sw : edges) { o->src[o->ne++] = sw.first; low->bw_wtab.push_back(sw.second); }
+        for (size_t i = 0; i < edges.size(); ++i) {
+            o->src[o->ne++] = edges[i].first;
+            low->bw_wtab.push_back(edges[i].second);
+            low->bw_edge.push_back(eids[i]);
+        }
         return true;
     };
 
     // ---- list 0: H items (one per emitting state), list 2: emitting b items --------------------------------
     const int one_idx = static_cast<int>(low->bw_wtab.size());
     low->bw_wtab.push_back(1.0);
+    low->bw_edge.push_back(-1);
     std::vector<BDesc> h_items, e_items;
     {
         std::vector<int> order(ne);
@@ -188,14 +203,53 @@ std::string lower_backward(const pp_model_desc& d, Lowered* low) {
         }
         return out;
     };
+    // Accumulation slots: replay the kernel's group decomposition (fbb_items in pp_lane_fb.cuh) over the runs of the
+    // silent and emitting lists; the terms of a group are {edge terms of item 0, [w, wx, wxx], item 1 ...}.
+    auto add_chunks = [&](const std::vector<int32_t>& terms) {
+        size_t i = 0;
+        for (int s = kAccLog2; s >= 0; --s) {
+            const size_t c = size_t(1) << s;
+            while (terms.size() - i >= c) {
+                low->acc_log2.push_back(s);
+                for (int lane = 0; lane < kLanes; ++lane) low->acc_map.push_back(terms[i + (lane >> (5 - s))]);
+                i += c;
+            }
+        }
+    };
+    auto map_run = [&](const RunRec& r, bool emit) {
+        const int NE = r.n_edges, G = run_group_size(NE);
+        int item = 0;
+        auto group = [&](int g) {
+            std::vector<int32_t> terms;
+            for (int q = 0; q < g; ++q, ++item) {
+                for (int j = 0; j < NE; ++j) terms.push_back(low->bw_edge[r.w_base + item * r.w_stride + j]);
+                if (emit) {
+                    const int k = r.e_base + item * r.e_stride;
+                    for (int t = 0; t < 3; ++t) terms.push_back(d.n_edges + 3 * k + t);
+                }
+            }
+            if (!terms.empty()) add_chunks(terms);
+        };
+        int left = r.count;
+        if (!emit && NE > 0 && r.fwd) { group(1); --left; }       // chain head
+        for (; left >= G; left -= G) group(G);
+        if (G > 2 && left >= 2) { group(2); left -= 2; }
+        if (left >= 1) group(1);
+    };
+    low->acc_base.assign(W, 0);
     for (int w = 0; w < W; ++w) {
         const std::vector<BDesc> lists[3] = {slice(h_items, w), sil_of[w], slice(e_items, w)};
+        low->acc_base[w] = static_cast<int32_t>(low->acc_log2.size());
         for (int list = 0; list < 3; ++list) {
-            low->bw_ranges[w * 6 + list * 2] = static_cast<int32_t>(low->bw_runs.size());
+            const size_t r0 = low->bw_runs.size();
+            low->bw_ranges[w * 6 + list * 2] = static_cast<int32_t>(r0);
             build_runs(lists[list], list == 1, &low->bw_runs);
             low->bw_ranges[w * 6 + list * 2 + 1] = static_cast<int32_t>(low->bw_runs.size());
+            if (list > 0)
+                for (size_t r = r0; r < low->bw_runs.size(); ++r) map_run(low->bw_runs[r], list == 2);
         }
     }
+    low->n_acc_slots = static_cast<int32_t>(low->acc_log2.size());
     low->bw_ok = true;
     return "";
 }

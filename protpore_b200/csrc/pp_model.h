@@ -50,6 +50,10 @@ struct pp_model {
     pp::DevBuf d_obs, d_offsets, d_order, d_group_len, d_group_row;
     pp::DevBuf d_score, d_end_state, d_end_ord, d_path_len, d_path_off, d_path, d_scan_tmp, d_logp;
     pp::DevBuf d_tab, d_xbuf, d_tab_off, d_list, d_counter, d_stats;
+    // lane-per-event forward-backward (pp_lane_fb.cuh)
+    int64_t fb_info[3] = {0, 0, 0};       // pp_forward_backward_info
+    std::vector<double> arena_fb;         // constant-arena image: forward runs, then backward runs
+    pp::DevBuf d_bw_wtab, d_acc_map, d_acc_log2, d_fb_acc, d_fb_scratch, d_fb_ctl, d_fb_minmax;
     size_t ws_limit = 0;
 
     cudaEvent_t ev[2] = {nullptr, nullptr};

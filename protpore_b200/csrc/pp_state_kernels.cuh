@@ -371,11 +371,13 @@ __global__ void k_fb_accumulate(const StateModel S, const ObsT* __restrict__ obs
                                 int n_events, double* __restrict__ scratch, int64_t scratch_stride,
                                 double* __restrict__ xbuf, int64_t xbuf_stride, double* __restrict__ logp_out,
                                 double* __restrict__ edge_counts, double* __restrict__ emit_moments,
-                                double* __restrict__ emit_minmax, double* __restrict__ posteriors) {
+                                double* __restrict__ emit_minmax, double* __restrict__ posteriors,
+                                const int32_t* __restrict__ list) {
     extern __shared__ double e_row[];
     __shared__ double s_lo, s_hi;
     const int m = S.m, ne = S.ne, t = threadIdx.x, nt = blockDim.x;
-    for (int ev = blockIdx.x; ev < n_events; ev += gridDim.x) {
+    for (int idx = blockIdx.x; idx < n_events; idx += gridDim.x) {
+        const int ev = list ? list[idx] : idx;                 // optional event list (re-run of the lane kernel's rejects)
         const int64_t off = offsets[ev];
         const int n = static_cast<int>(offsets[ev + 1] - off);
         double* x = xbuf + static_cast<size_t>(blockIdx.x) * xbuf_stride;

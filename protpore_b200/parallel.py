@@ -98,6 +98,24 @@ def baum_welch_iteration(model, local_sequences, transition_pseudocount=0, use_p
     return float(extra[0]), int(extra[1])
 
 
+def baum_welch_iteration_packed(model, obs, offsets, transition_pseudocount=0, use_pseudocount=False, edge_inertia=0.0,
+                                distribution_inertia=0.0):
+    """`baum_welch_iteration` on events already packed CSR-style (`obs` back to back, `offsets[n + 1]`): numpy arrays
+    or torch CUDA tensors resident on the model's GPU.  One batched E-step call, one packed allreduce, the M-step."""
+    logp, edge, mom, mm, _ = model.engine().forward_backward_batch(obs, offsets)
+    if not isinstance(logp, np.ndarray):                      # device tensors: reduce the per-event values there
+        import torch
+        ok = torch.isfinite(logp)
+        extra = np.array([float(logp[ok].sum()), float(ok.sum())], dtype=np.float64)
+        edge, mom, mm = edge.cpu().numpy(), mom.cpu().numpy(), mm.cpu().numpy()
+    else:
+        ok = np.isfinite(logp)
+        extra = np.array([float(logp[ok].sum()), float(ok.sum())], dtype=np.float64)
+    allreduce_statistics(edge, mom, mm, extra)
+    model.apply_m_step(edge, mom, mm, transition_pseudocount, int(use_pseudocount), edge_inertia, distribution_inertia)
+    return float(extra[0]), int(extra[1])
+
+
 def train_baum_welch(model, local_sequences, stop_threshold=1e-9, min_iterations=0, max_iterations=None, verbose=False,
                      **kwargs):
     """Distributed `Model.train(..., algorithm='baum-welch')`: same stopping rule as the reference

@@ -422,3 +422,97 @@ def test_tied_states_and_labelled_training():
     # the shared distribution was re-estimated once from the symbols of a AND b
     assert shared.parameters[0] == pytest.approx(np.mean([0.8, 1.3, 1.1, 0.7]))
     assert before.shape == dense.shape
+
+
+def test_lane_forward_backward_statistics(models):
+    """Baum-Welch E-step on the lane-per-event kernel (pp_lane_fb.cuh) against the oracle's bw_accumulate
+    (yahmm.pyx:4107-4236) and against the exact state-parallel kernel, including impossible events and an outlier
+    that the scaled sweep hands to the exact kernel."""
+    model = models["pro_001_py2"]
+    eng = model.engine()
+    assert "bw_ok 1" in _engine.describe_schedule(model)
+    lens = events.uniform_lengths(300, 1, 400, seed=7)
+    obs, offsets = eng.sample_events(lens, seed=99)
+    obs = obs.astype(np.float64)
+    obs[offsets[5]:offsets[5] + 1] = 250.0                      # underflows every linear-space factor: exact re-run
+    obs[offsets[9] + 2] = 119.5                                  # far outlier the scaled sweep still resolves
+    logp, edge, mom, mm, _ = eng.forward_backward_batch(obs, offsets)
+    info = eng.forward_backward_info()
+    assert info["path"] == "lane" and info["rejects"] >= 1 and info["failed"] == 0
+    # exact kernel: asking for the posteriors keeps the batch on the state-parallel path
+    logp_x, edge_x, mom_x, mm_x, _ = eng.forward_backward_batch(obs, offsets, posteriors=True)
+    assert eng.forward_backward_info()["path"] == "exact"
+    assert np.array_equal(np.isfinite(logp), np.isfinite(logp_x))
+    fin = np.isfinite(logp)
+    assert np.allclose(logp[fin], logp_x[fin], rtol=1e-12, atol=1e-9)
+    assert np.allclose(edge, edge_x, rtol=1e-9, atol=1e-12)
+    assert np.allclose(mom, mom_x, rtol=1e-9, atol=1e-11)
+    assert np.array_equal(mm, mm_x)
+    # oracle on a subset (float64 CPU restatement of the reference)
+    orc = util.oracle_for(model)
+    sub = list(range(0, 300, 6))
+    seqs = [obs[offsets[e]:offsets[e + 1]] for e in sub]
+    so, oo = np.concatenate(seqs), np.concatenate([[0], np.cumsum([len(s) for s in seqs])])
+    lp_s, edge_s, mom_s, mm_s, _ = eng.forward_backward_batch(so, oo)
+    exp_t, mom_o, mm_o, lz = orc.bw_accumulate(seqs)
+    b = model._baked
+    src = np.repeat(np.arange(len(model.states)), np.diff(b.out_ptr))
+    assert np.allclose(edge_s, exp_t[src, b.out_idx], rtol=1e-9, atol=1e-12)
+    assert np.allclose(mom_s, mom_o, rtol=1e-9, atol=1e-11)
+    assert np.array_equal(mm_s, mm_o)
+    assert np.allclose(lp_s, lz, rtol=1e-12, atol=1e-9)
+
+
+def test_lane_forward_backward_accumulates_and_is_composition_invariant(models):
+    """Accumulators are read-modify-write; statistics of a batch = sum over its halves (different bucketing)."""
+    model = models["pro_001_py2"]
+    eng = model.engine()
+    lens = events.log_uniform_lengths(500, 1, 700, seed=3)
+    obs, offsets = eng.sample_events(lens, seed=5)
+    _, edge, mom, mm, _ = eng.forward_backward_batch(obs, offsets)
+    assert eng.forward_backward_info()["path"] == "lane"
+    h = 250
+    o1, f1 = obs[:offsets[h]], offsets[:h + 1]
+    o2, f2 = obs[offsets[h]:], offsets[h:] - offsets[h]
+    _, e1, m1, mm1, _ = eng.forward_backward_batch(o1, f1)
+    acc = (e1, m1, mm1)
+    _, e2, m2, mm2, _ = eng.forward_backward_batch(o2, f2, accum=acc)
+    assert np.allclose(e2, edge, rtol=1e-11, atol=1e-13) and np.allclose(m2, mom, rtol=1e-11, atol=1e-12)
+    assert np.array_equal(mm2, mm)
+    # posterior mass: sum_k gamma_r[k] = 1 for every observation, so sum of `sum w` = number of observations
+    assert abs(mom[:, 0].sum() - len(obs)) < 1e-6 * len(obs)
+
+
+def test_kernels_follow_a_changed_emission_kind():
+    """After one Baum-Welch iteration on sampled events the sigma == 0 insert states get the min_std clamp
+    (yahmm.pyx:513) and leave the point-mass branch: the run schedule must be lowered again.  The lane kernels of
+    the updated model are checked against the exact state-parallel tables and the oracle, and a second iteration
+    still runs on the lane forward-backward kernel."""
+    model = util.build_model("pro_001_py2")
+    eng = model.engine()
+    lens = events.uniform_lengths(400, 20, 200, seed=11)
+    obs, offsets = eng.sample_events(lens, seed=12)
+    seqs = [obs[offsets[i]:offsets[i + 1]].astype(np.float64) for i in range(len(lens))]
+    from protpore_b200 import parallel
+    parallel.baum_welch_iteration(model, seqs)
+    sig = np.array([float(s.distribution.parameters[1]) for s in model.states[:model.silent_start]
+                    if s.distribution.name == "NormalDistribution"])
+    assert (sig > 0).all() and (sig == 0.01).any()              # some insert state moved off sigma == 0
+    eng = model.engine()
+    orc = util.oracle_for(model)
+    lp = model.log_probability_batch(seqs[:40], dtype=np.float64)
+    vit = model.viterbi_batch(seqs[:40], dtype=np.float64, states=False)
+    for i in range(40):
+        assert util.close([lp[i]], [orc.log_probability(seqs[i])]).all()
+        s, p, margin = orc.viterbi(seqs[i], with_margin=True)
+        assert vit[i][0] == s and (np.array_equal(vit[i][1], p) or margin == 0.0)
+    logp, edge, mom, mm, _ = eng.forward_backward_batch(obs.astype(np.float64), offsets)
+    assert eng.forward_backward_info()["path"] == "lane"
+    exp_t, mom_o, mm_o, lz = orc.bw_accumulate(seqs[:60])
+    so = np.concatenate(seqs[:60])
+    oo = np.concatenate([[0], np.cumsum([len(s) for s in seqs[:60]])])
+    _, edge_s, mom_s, mm_s, _ = eng.forward_backward_batch(so, oo)
+    b = model._baked
+    src = np.repeat(np.arange(len(model.states)), np.diff(b.out_ptr))
+    assert np.allclose(edge_s, exp_t[src, b.out_idx], rtol=1e-9, atol=1e-12)
+    assert np.allclose(mom_s, mom_o, rtol=1e-9, atol=1e-11)
