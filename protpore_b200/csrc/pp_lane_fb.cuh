@@ -45,7 +45,9 @@ __device__ __forceinline__ void stcg64(void* p, double v) { __stcg(static_cast<d
 // 2^g by a degree-6 Taylor polynomial of exp(g ln 2), 2^(j/32) from a shared-memory table, 2^n into the exponent.
 // Below 2^-1000 the factor is an exact 0.
 __device__ __forceinline__ double exp2_acc(double t, uint32_t t2tab) {
-    const double tc = fmin(fmax(t, -1001.0), 1000.0);
+    // no clamp: t <= log2(max density) + 900 < 1000 by construction; for t <= -1000 (or -inf / NaN) the intermediate
+    // values are meaningless but never used -- the final select returns an exact 0
+    const double tc = t;
     const double magic = 6755399441055744.0;
     const double tm = tc + magic;
     const int n = __double2loint(tm);
@@ -63,7 +65,7 @@ __device__ __forceinline__ double exp2_acc(double t, uint32_t t2tab) {
     const double tv = lds64(t2tab + static_cast<uint32_t>(j + 16) * 8u);
     const double scale = __hiloint2double((n + 1023) << 20, 0);
     const double r = (p * tv) * scale;
-    return (t > -1000.0) ? r : 0.0;
+    return (t > -1000.0) ? r : 0.0;               // false for NaN as well
 }
 
 template <int W>
@@ -240,18 +242,27 @@ struct BwdCtx {
     uint32_t flags;      // shared-memory address of the per-state "some lane gave it weight" ballots
 };
 
-template <int NE, int MODE, int G, bool EMIT>
+// One group of G items of a backward run.
+//   STORE: the items' values b^_r[k] = sum_j w_j * value_j are computed and written to the column
+//          (MODE_CHAIN: the last edge reads the previous item's value from a register);
+//   ACC:   the per-lane terms g * w_j * value_j (and g * b^_r[k] * (1, x, x^2) for EMIT items) go through the
+//          transpose-reduce into the warp's accumulation slots.
+// List 1 (silent values) is <STORE, !ACC>; list 2 is <STORE, ACC, EMIT> for emitting states and <!STORE, ACC> for the
+// accumulate-only items of the silent states, which re-read the finished column.
+template <int NE, int MODE, int G, bool EMIT, bool ACC, bool STORE>
 __device__ __forceinline__ void fbb_group(RunPtrs<NE>& P, const unsigned char*& fp, int gs, int& st, int sts,
                                           AccCtx& A, const BwdCtx& C, double& prev, int& mx) {
     constexpr int NL = (MODE == MODE_CHAIN) ? NE - 1 : NE;
     constexpr int NT1 = NE + (EMIT ? 3 : 0);
-    constexpr int NT = G * NT1;
+    constexpr int NT = ACC ? G * NT1 : 0;
     constexpr int NS = acc_slots_for(NT);
     double a[NS > 0 ? NS : 1], fh[G];
+    if (ACC) {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) a[i] = ldcg64(A.p + i * kLanes);           // issued first: L2 latency hides behind the group
+        for (int i = 0; i < NS; ++i) a[i] = ldcg64(A.p + i * kLanes);       // issued first: L2 latency hides behind the group
 #pragma unroll
-    for (int g = 0; g < G; ++g) fh[g] = ldcg64(fp + g * gs);
+        for (int g = 0; g < G; ++g) fh[g] = ldcg64(fp + g * gs);
+    }
     double v[G][NL > 0 ? NL : 1], w[G][NE > 0 ? NE : 1], acc[G];
     double t[NT > 0 ? NT : 1];
 #pragma unroll
@@ -261,70 +272,85 @@ __device__ __forceinline__ void fbb_group(RunPtrs<NE>& P, const unsigned char*& 
 #pragma unroll
         for (int j = 0; j < NE; ++j) w[g][j] = lds64(P.wp + g * P.ws + j * 8);
     }
+    if (ACC) {
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        double a0 = 0.0, a1 = 0.0;
+        for (int g = 0; g < G; ++g) {
+            double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < NL; ++j) {
-            const double p = v[g][j] * w[g][j];
-            t[g * NT1 + j] = p;
-            if (j & 1) a1 += p; else a0 += p;
+            for (int j = 0; j < NL; ++j) {
+                const double p = v[g][j] * w[g][j];
+                t[g * NT1 + j] = p;
+                if (STORE) { if (j & 1) a1 += p; else a0 += p; }
+            }
+            acc[g] = a0 + a1;
         }
-        acc[g] = a0 + a1;
+    } else {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < NL; j += 2) a0 = fma(v[g][j], w[g][j], a0);
+#pragma unroll
+            for (int j = 1; j < NL; j += 2) a1 = fma(v[g][j], w[g][j], a1);
+            acc[g] = a0 + a1;
+        }
     }
     if (MODE == MODE_CHAIN) {
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const double p = prev * w[g][NE - 1];
-            t[g * NT1 + NE - 1] = p;
-            acc[g] += p;
+            acc[g] = fma(prev, w[g][NE - 1], acc[g]);
             prev = acc[g];
         }
     }
+    if (STORE) {
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        sts64(P.dp + g * P.ds, acc[g]);
-        if (EMIT) mx = max(mx, __double2hiint(acc[g]));
+        for (int g = 0; g < G; ++g) {
+            sts64(P.dp + g * P.ds, acc[g]);
+            if (EMIT) mx = max(mx, __double2hiint(acc[g]));
+        }
+        if (MODE != MODE_CHAIN) prev = acc[G - 1];
     }
-    if (MODE != MODE_CHAIN) prev = acc[G - 1];
+    if (ACC) {
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        const double gk = fh[g] * C.c;
+        for (int g = 0; g < G; ++g) {
+            const double gk = fh[g] * C.c;
 #pragma unroll
-        for (int j = 0; j < NE; ++j) t[g * NT1 + j] *= gk;
-        if (EMIT) {
-            const double gam = gk * acc[g];
-            const double gx = gam * C.xb;
-            t[g * NT1 + NE] = gam;
-            t[g * NT1 + NE + 1] = gx;
-            t[g * NT1 + NE + 2] = gx * C.xb;
-            const uint32_t b = __ballot_sync(0xffffffffu, gam > 0.0);
-            if (A.lane == 0 && b != 0u) {
-                const uint32_t fa = C.flags + static_cast<uint32_t>(st + g * sts) * 4u;
-                uint32_t old;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(old) : "r"(fa) : "memory");
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(fa), "r"(old | b) : "memory");
+            for (int j = 0; j < NE; ++j) t[g * NT1 + j] *= gk;
+            if (EMIT) {
+                const double gam = gk * acc[g];
+                const double gx = gam * C.xb;
+                t[g * NT1 + NE] = gam;
+                t[g * NT1 + NE + 1] = gx;
+                t[g * NT1 + NE + 2] = gx * C.xb;
+                const uint32_t b = __ballot_sync(0xffffffffu, gam > 0.0);
+                if (A.lane == 0 && b != 0u) {
+                    const uint32_t fa = C.flags + static_cast<uint32_t>(st + g * sts) * 4u;
+                    uint32_t old;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(old) : "r"(fa) : "memory");
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(fa), "r"(old | b) : "memory");
+                }
             }
         }
+        if (NT > 0) AccChunks<NT, kAccLog2, 0>::run(t, a, A);
+        A.p += NS * kLanes;
+        fp += G * gs;
+        st += G * sts;
     }
-    if (NT > 0) AccChunks<NT, kAccLog2, 0>::run(t, a, A);
-    A.p += NS * kLanes;
-    fp += G * gs;
-    st += G * sts;
     P.advance(G);
 }
 
-template <int NE, int MODE, bool EMIT>
+template <int NE, int MODE, bool EMIT, bool ACC, bool STORE>
 __device__ __forceinline__ void fbb_items(RunPtrs<NE>& P, const unsigned char*& fp, int gs, int& st, int sts, int count,
                                           AccCtx& A, const BwdCtx& C, double& prev, int& mx) {
     constexpr int G = run_group_size(NE);
     int left = count;
-    for (; left >= G; left -= G) fbb_group<NE, MODE, G, EMIT>(P, fp, gs, st, sts, A, C, prev, mx);
-    if (G > 2 && left >= 2) { fbb_group<NE, MODE, 2, EMIT>(P, fp, gs, st, sts, A, C, prev, mx); left -= 2; }
-    if (left >= 1) fbb_group<NE, MODE, 1, EMIT>(P, fp, gs, st, sts, A, C, prev, mx);
+    for (; left >= G; left -= G) fbb_group<NE, MODE, G, EMIT, ACC, STORE>(P, fp, gs, st, sts, A, C, prev, mx);
+    if (G > 2 && left >= 2) { fbb_group<NE, MODE, 2, EMIT, ACC, STORE>(P, fp, gs, st, sts, A, C, prev, mx); left -= 2; }
+    if (left >= 1) fbb_group<NE, MODE, 1, EMIT, ACC, STORE>(P, fp, gs, st, sts, A, C, prev, mx);
 }
 
-template <int NE, bool EMIT>
+// LIST 1: silent values; LIST 2: accumulating items (emitting: value + statistics; RUN_ACC: statistics only)
+template <int NE, int LIST>
 __device__ __forceinline__ void fbb_run_ne(const RunRec& R, uint32_t colb, uint32_t wtab, const unsigned char* grow,
                                            AccCtx& A, const BwdCtx& C, int& mx) {
     RunPtrs<NE> P;
@@ -334,28 +360,34 @@ __device__ __forceinline__ void fbb_run_ne(const RunRec& R, uint32_t colb, uint3
     int st = R.e_base;
     const int sts = R.e_stride;
     double prev = 0.0;
-    if (!EMIT && NE > 0 && R.fwd) {
-        fbb_group<NE, MODE_SILENT, 1, EMIT>(P, fp, gs, st, sts, A, C, prev, mx);      // chain head reads the column
-        fbb_items<NE, MODE_CHAIN, EMIT>(P, fp, gs, st, sts, R.count - 1, A, C, prev, mx);
+    if (LIST == 1) {
+        if (NE > 0 && R.fwd) {
+            fbb_group<NE, MODE_SILENT, 1, false, false, true>(P, fp, gs, st, sts, A, C, prev, mx);   // chain head reads the column
+            fbb_items<NE, MODE_CHAIN, false, false, true>(P, fp, gs, st, sts, R.count - 1, A, C, prev, mx);
+        } else {
+            fbb_items<NE, MODE_SILENT, false, false, true>(P, fp, gs, st, sts, R.count, A, C, prev, mx);
+        }
+    } else if (R.kind == RUN_ACC) {
+        fbb_items<NE, MODE_SILENT, false, true, false>(P, fp, gs, st, sts, R.count, A, C, prev, mx);
     } else {
-        fbb_items<NE, MODE_SILENT, EMIT>(P, fp, gs, st, sts, R.count, A, C, prev, mx);
+        fbb_items<NE, MODE_SILENT, true, true, true>(P, fp, gs, st, sts, R.count, A, C, prev, mx);
     }
 }
 
-template <bool EMIT>
+template <int LIST>
 __device__ __forceinline__ void fbb_run(int r, uint32_t colb, uint32_t wtab, const unsigned char* grow, AccCtx& A,
                                         const BwdCtx& C, int& mx) {
     const RunRec& R = run_rec(r);
     switch (R.n_edges) {
-        case 0: fbb_run_ne<0, EMIT>(R, colb, wtab, grow, A, C, mx); break;
-        case 1: fbb_run_ne<1, EMIT>(R, colb, wtab, grow, A, C, mx); break;
-        case 2: fbb_run_ne<2, EMIT>(R, colb, wtab, grow, A, C, mx); break;
-        case 3: fbb_run_ne<3, EMIT>(R, colb, wtab, grow, A, C, mx); break;
-        case 4: fbb_run_ne<4, EMIT>(R, colb, wtab, grow, A, C, mx); break;
-        case 5: fbb_run_ne<5, EMIT>(R, colb, wtab, grow, A, C, mx); break;
-        case 6: fbb_run_ne<6, EMIT>(R, colb, wtab, grow, A, C, mx); break;
-        case 7: fbb_run_ne<7, EMIT>(R, colb, wtab, grow, A, C, mx); break;
-        default: fbb_run_ne<8, EMIT>(R, colb, wtab, grow, A, C, mx); break;
+        case 0: fbb_run_ne<0, LIST>(R, colb, wtab, grow, A, C, mx); break;
+        case 1: fbb_run_ne<1, LIST>(R, colb, wtab, grow, A, C, mx); break;
+        case 2: fbb_run_ne<2, LIST>(R, colb, wtab, grow, A, C, mx); break;
+        case 3: fbb_run_ne<3, LIST>(R, colb, wtab, grow, A, C, mx); break;
+        case 4: fbb_run_ne<4, LIST>(R, colb, wtab, grow, A, C, mx); break;
+        case 5: fbb_run_ne<5, LIST>(R, colb, wtab, grow, A, C, mx); break;
+        case 6: fbb_run_ne<6, LIST>(R, colb, wtab, grow, A, C, mx); break;
+        case 7: fbb_run_ne<7, LIST>(R, colb, wtab, grow, A, C, mx); break;
+        default: fbb_run_ne<8, LIST>(R, colb, wtab, grow, A, C, mx); break;
     }
 }
 
@@ -479,6 +511,8 @@ k_fb_lane(const LaneSched S, const FbSched F, const LaneBatchAny B) {
         for (int i = threadIdx.x; i < S.ne; i += W * 32) s_flags[i] = 0u;
         wmax[warp * kLanes + lane] = 0;
         if (warp == 0) { s_invp[lane] = 0.0; s_sn[lane] = 0.0; }
+        for (int k = warp; k < S.ne; k += W)                     // f^_0[emitting] = 0: the sweep never writes row 0's emitting slots
+            stcg64(scratch + static_cast<size_t>(S.ns + k) * kSlotBytes, 0.0);
         __syncthreads();
 
         double xlo = __longlong_as_double(0x7FF0000000000000LL), xhi = neg_inf();
@@ -564,6 +598,12 @@ k_fb_lane(const LaneSched S, const FbSched F, const LaneBatchAny B) {
             T += static_cast<double>(shift);
             const unsigned char* grow = scratch + static_cast<size_t>(r) * row_bytes;
             const double sr = ldcg64(grow + scale_off);
+            if (r > 0) {                                         // pull row r - 1 of the scratch into L2 while row r is processed
+                const unsigned char* nrow = F.scratch + static_cast<size_t>(blockIdx.x) * F.scratch_stride +
+                                            static_cast<size_t>(r - 1) * row_bytes;
+                for (uint32_t o = threadIdx.x * 128u; o < static_cast<uint32_t>(row_bytes); o += W * 32 * 128u)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + o));
+            }
             for (int u = hb; u < he; ++u) fbh_run(u, colb, etab, xa, static_cast<double>(shift), t2tab);
             if (warp == 0) *reinterpret_cast<double*>(colp + S.end_slot_off) = (r == n && valid) ? 1.0 : 0.0;
             {
@@ -589,11 +629,10 @@ k_fb_lane(const LaneSched S, const FbSched F, const LaneBatchAny B) {
             const BwdCtx C{c, xbv, flagsa};
             AccCtx A{acc_cta + static_cast<size_t>(F.acc_base[warp]) * kLanes, lane};
             int mxs = 0;
-            for (int u = tb; u < te; ++u) fbb_run<false>(u, colb, wtab, grow, A, C, mxs);
+            for (int u = tb; u < te; ++u) fbb_run<1>(u, colb, wtab, grow, A, C, mxs);
             __syncthreads();
             mx = 0;
-            if (r > 0)                                           // row 0 has no emitting column (f_0[emitting] = 0, never stored)
-                for (int u = eb; u < ee; ++u) fbb_run<true>(u, colb, wtab, grow, A, C, mx);
+            for (int u = eb; u < ee; ++u) fbb_run<2>(u, colb, wtab, grow, A, C, mx);
             wmax[warp * kLanes + lane] = mx;
             __syncthreads();
             xa = xbv;

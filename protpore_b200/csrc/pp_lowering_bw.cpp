@@ -86,64 +86,65 @@ std::string lower_backward(const pp_model_desc& d, Lowered* low) {
     const int SIL = 0, EB = ns, HB = ns + ne;                      // slot bases
     low->bw_ranges.assign(static_cast<size_t>(W) * 6, 0);
 
+    // An item before its weights are placed: out-edges as (slot the edge reads, out-edge CSR index).
+    struct Item {
+        BDesc d;
+        int eid[kMaxRunEdges];
+    };
     auto slot_of_value = [&](int l) { return l < ne ? HB + l : SIL + (l - ne); };  // what a predecessor reads for target l
-    auto out_items = [&](int k, int chain_prev, BDesc* o) -> bool {
-        o->ne = 0;
-        o->state = k;
-        o->kind = RUN_SILENT;
-        o->dst = k < ne ? EB + k : SIL + (k - ne);
-        int chain_edge = -1;
-        std::vector<std::pair<int, double>> edges;               // (slot, weight)
-        std::vector<int> eids;                                   // out-edge CSR index, same order
+    auto make_item = [&](int k, int chain_prev, int kind, Item* o) -> bool {
+        o->d = BDesc{};
+        o->d.state = k;
+        o->d.kind = kind;
+        o->d.dst = k < ne ? EB + k : SIL + (k - ne);
+        int chain_edge = -1, n = 0;
         for (int pass = 0; pass < 2; ++pass)                      // emitting targets first, then silent ones
             for (int e = d.out_ptr[k]; e < d.out_ptr[k + 1]; ++e) {
                 const int l = d.out_dst[e];
                 if ((pass == 0) != (l < ne)) continue;
                 if (k >= ne && l >= ne && l < k + 1) continue;    // silent -> silent only to larger indices (3026, 3108)
                 if (l == chain_prev) { chain_edge = e; continue; }
-                edges.emplace_back(slot_of_value(l), std::exp(d.out_logp[e]));
-                eids.push_back(e);
+                if (n >= kMaxRunEdges) return false;
+                o->d.src[n] = slot_of_value(l);
+                o->eid[n++] = e;
             }
         if (chain_edge >= 0) {
-            edges.emplace_back(slot_of_value(chain_prev), std::exp(d.out_logp[chain_edge]));
-            eids.push_back(chain_edge);
+            if (n >= kMaxRunEdges) return false;
+            o->d.src[n] = slot_of_value(chain_prev);
+            o->eid[n++] = chain_edge;
         }
-        if (edges.size() > static_cast<size_t>(kMaxRunEdges)) return false;
-        o->wbase = static_cast<int>(low->bw_wtab.size());
-        for (size_t i = 0; i < edges.size(); ++i) {
-            o->src[o->ne++] = edges[i].first;
-            low->bw_wtab.push_back(edges[i].second);
-            low->bw_edge.push_back(eids[i]);
-        }
+        o->d.ne = n;
         return true;
     };
+    // family order: items with the same in-degree and the same slots relative to their own go next to each other,
+    // so that positions k, k+1, ... of a profile become one affine run
+    auto family_less = [](const Item& a, const Item& b) {
+        if (a.d.ne != b.d.ne) return a.d.ne > b.d.ne;
+        for (int j = 0; j < a.d.ne; ++j) {
+            const int ra = a.d.src[j] - a.d.dst, rb = b.d.src[j] - b.d.dst;
+            if (ra != rb) return ra < rb;
+        }
+        return false;
+    };
+    auto item_cost = [](const Item& x, bool acc, bool emit) {
+        long c = 12 + 5L * x.d.ne;
+        if (acc) c += 7L * (x.d.ne + (emit ? 3 : 0)) + 8;
+        return c;
+    };
 
-    // ---- list 0: H items (one per emitting state), list 2: emitting b items --------------------------------
-    const int one_idx = static_cast<int>(low->bw_wtab.size());
-    low->bw_wtab.push_back(1.0);
-    low->bw_edge.push_back(-1);
-    std::vector<BDesc> h_items, e_items;
+    // ---- list 0: H items (one per emitting state) ------------------------------------------------------------
+    std::vector<Item> h_items;
     {
         std::vector<int> order(ne);
         std::iota(order.begin(), order.end(), 0);
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return low->emis[a].kind < low->emis[b].kind; });
         for (int l : order) {
-            BDesc h{};
-            h.kind = low->emis[l].kind; h.ne = 1; h.dst = HB + l; h.state = l; h.src[0] = EB + l; h.wbase = one_idx;
+            Item h{};
+            h.d.kind = low->emis[l].kind; h.d.ne = 1; h.d.dst = HB + l; h.d.state = l; h.d.src[0] = EB + l; h.eid[0] = -1;
             h_items.push_back(h);
         }
-        std::vector<BDesc> tmp;
-        for (int k = 0; k < ne; ++k) {
-            BDesc e{};
-            if (!out_items(k, -1, &e)) return "";
-            tmp.push_back(e);
-        }
-        std::vector<int> eo(ne);
-        std::iota(eo.begin(), eo.end(), 0);
-        std::stable_sort(eo.begin(), eo.end(), [&](int a, int b) { return tmp[a].ne > tmp[b].ne; });
-        for (int k : eo) e_items.push_back(tmp[k]);
     }
-    // ---- list 1: silent items, components of the silent sub-DAG, descending index ------------------------------
+    // ---- list 1: silent VALUES, no accumulation: the components of the silent sub-DAG in descending index ------
     std::vector<std::vector<int>> comps;
     {
         UnionFind uf(m);
@@ -162,49 +163,87 @@ std::string lower_backward(const pp_model_desc& d, Lowered* low) {
             comps[comp_of[r]].push_back(k);
         }
     }
-    auto cost_items = [&](const std::vector<BDesc>& v) { long s = 0; for (auto& x : v) s += 4L * x.ne + 8; return s; };
-    std::vector<std::vector<BDesc>> sil_of(W);
+    std::vector<std::vector<Item>> sil_of(W);
     {
         std::vector<int> order(comps.size());
         std::iota(order.begin(), order.end(), 0);
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return comps[a].size() > comps[b].size(); });
         std::vector<long> load(W, 0);
-        std::vector<std::vector<BDesc>> chains(W), singles(W);
+        std::vector<std::vector<Item>> chains(W), singles(W);
         for (int c : order) {
             const int w = static_cast<int>(std::min_element(load.begin(), load.end()) - load.begin());
             int prev = -1;
             for (int k : comps[c]) {
-                BDesc s{};
-                if (!out_items(k, prev, &s)) return "";
+                Item s{};
+                if (!make_item(k, prev, RUN_SILENT, &s)) return "";
                 (comps[c].size() > 1 ? chains[w] : singles[w]).push_back(s);
                 prev = k;
-                load[w] += 4L * s.ne + 8 + (comps[c].size() > 1 ? 40 : 0);
+                load[w] += item_cost(s, false, false) + (comps[c].size() > 1 ? 30 : 0);
             }
         }
         for (int w = 0; w < W; ++w) {
-            std::stable_sort(singles[w].begin(), singles[w].end(), [](const BDesc& a, const BDesc& b) {
-                if (a.ne != b.ne) return a.ne > b.ne;
-                return a.state > b.state;
-            });
+            std::stable_sort(singles[w].begin(), singles[w].end(), family_less);
             sil_of[w] = chains[w];
             sil_of[w].insert(sil_of[w].end(), singles[w].begin(), singles[w].end());
         }
     }
-    // ---- deal lists 0 and 2 to the warps in contiguous, cost-balanced slices; emit runs -------------------------
-    auto slice = [&](const std::vector<BDesc>& items, int w) {
-        const long total = cost_items(items);
-        std::vector<BDesc> out;
-        long acc = 0;
+    // ---- list 2: everything that accumulates: emitting items (value + statistics) and, for every silent state, an
+    //      accumulate-only item that re-reads the finished column (keeps the serial chains of list 1 short) --------
+    std::vector<Item> acc_items;
+    {
+        std::vector<Item> em, sa;
+        for (int k = 0; k < ne; ++k) {
+            Item e{};
+            if (!make_item(k, -1, RUN_SILENT, &e)) return "";
+            em.push_back(e);
+        }
+        std::vector<Item> singles;                              // chains keep their chain order (affine), singles by family
+        std::vector<int> order(comps.size());
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return comps[a].size() > comps[b].size(); });
+        for (int c : order)
+            for (int k : comps[c]) {
+                Item a{};
+                if (!make_item(k, -1, RUN_ACC, &a)) return "";
+                if (a.d.ne == 0) continue;
+                (comps[c].size() > 1 ? sa : singles).push_back(a);
+            }
+        std::stable_sort(singles.begin(), singles.end(), family_less);
+        sa.insert(sa.end(), singles.begin(), singles.end());
+        std::stable_sort(em.begin(), em.end(), family_less);
+        acc_items = em;
+        acc_items.insert(acc_items.end(), sa.begin(), sa.end());
+    }
+    // ---- place the weights in final list order (constant weight stride inside a run), deal lists 0 and 2 to the
+    //      warps in contiguous cost-balanced slices, emit runs and accumulation slots -------------------------------
+    const int one_idx = static_cast<int>(low->bw_wtab.size());
+    low->bw_wtab.push_back(1.0);
+    low->bw_edge.push_back(-1);
+    auto place = [&](std::vector<Item>& items, bool is_h) {
+        for (Item& x : items) {
+            if (is_h) { x.d.wbase = one_idx; continue; }
+            x.d.wbase = static_cast<int>(low->bw_wtab.size());
+            for (int j = 0; j < x.d.ne; ++j) {
+                low->bw_wtab.push_back(std::exp(d.out_logp[x.eid[j]]));
+                low->bw_edge.push_back(x.eid[j]);
+            }
+        }
+    };
+    auto slice = [&](const std::vector<Item>& items, int w, bool acc) {
+        long total = 0;
+        for (const Item& x : items) total += item_cost(x, acc, x.d.kind != RUN_ACC);
+        std::vector<Item> out;
+        long run = 0;
         int cur = 0;
-        for (const BDesc& x : items) {
-            if (cur + 1 < W && acc >= (total * (cur + 1)) / W) ++cur;
+        for (const Item& x : items) {
+            if (cur + 1 < W && run >= (total * (cur + 1)) / W) ++cur;
             if (cur == w) out.push_back(x);
-            acc += 4L * x.ne + 8;
+            run += item_cost(x, acc, x.d.kind != RUN_ACC);
         }
         return out;
     };
-    // Accumulation slots: replay the kernel's group decomposition (fbb_items in pp_lane_fb.cuh) over the runs of the
-    // silent and emitting lists; the terms of a group are {edge terms of item 0, [w, wx, wxx], item 1 ...}.
+    // Accumulation slots: replay the kernel's group decomposition (fbb_items in pp_lane_fb.cuh) over the runs of
+    // list 2; the terms of a group are {edge terms of item 0, [w, wx, wxx], item 1 ...}.
     auto add_chunks = [&](const std::vector<int32_t>& terms) {
         size_t i = 0;
         for (int s = kAccLog2; s >= 0; --s) {
@@ -216,7 +255,8 @@ std::string lower_backward(const pp_model_desc& d, Lowered* low) {
             }
         }
     };
-    auto map_run = [&](const RunRec& r, bool emit) {
+    auto map_run = [&](const RunRec& r) {
+        const bool emit = r.kind != RUN_ACC;
         const int NE = r.n_edges, G = run_group_size(NE);
         int item = 0;
         auto group = [&](int g) {
@@ -231,22 +271,24 @@ std::string lower_backward(const pp_model_desc& d, Lowered* low) {
             if (!terms.empty()) add_chunks(terms);
         };
         int left = r.count;
-        if (!emit && NE > 0 && r.fwd) { group(1); --left; }       // chain head
         for (; left >= G; left -= G) group(G);
         if (G > 2 && left >= 2) { group(2); left -= 2; }
         if (left >= 1) group(1);
     };
     low->acc_base.assign(W, 0);
     for (int w = 0; w < W; ++w) {
-        const std::vector<BDesc> lists[3] = {slice(h_items, w), sil_of[w], slice(e_items, w)};
+        std::vector<Item> lists[3] = {slice(h_items, w, false), sil_of[w], slice(acc_items, w, true)};
         low->acc_base[w] = static_cast<int32_t>(low->acc_log2.size());
         for (int list = 0; list < 3; ++list) {
+            place(lists[list], list == 0);
+            std::vector<BDesc> seq;
+            for (const Item& x : lists[list]) seq.push_back(x.d);
             const size_t r0 = low->bw_runs.size();
             low->bw_ranges[w * 6 + list * 2] = static_cast<int32_t>(r0);
-            build_runs(lists[list], list == 1, &low->bw_runs);
+            build_runs(seq, list == 1, &low->bw_runs);
             low->bw_ranges[w * 6 + list * 2 + 1] = static_cast<int32_t>(low->bw_runs.size());
-            if (list > 0)
-                for (size_t r = r0; r < low->bw_runs.size(); ++r) map_run(low->bw_runs[r], list == 2);
+            if (list == 2)
+                for (size_t r = r0; r < low->bw_runs.size(); ++r) map_run(low->bw_runs[r]);
         }
     }
     low->n_acc_slots = static_cast<int32_t>(low->acc_log2.size());
