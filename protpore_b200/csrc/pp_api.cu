@@ -371,6 +371,17 @@ void pp_model_destroy(pp_model* M) {
                       &M->d_acc_log2, &M->d_fb_acc, &M->d_fb_scratch, &M->d_fb_ctl, &M->d_fb_minmax};
     for (DevBuf* b : bufs) b->release();
     release_state_model(M);
+    for (int b = 0; b < 2; ++b) {
+        pp_model::PipeSlot& P = M->ps[b];
+        DevBuf* pb[] = {&P.obs, &P.ws, &P.path, &P.order, &P.group_len, &P.group_row, &P.list, &P.counter};
+        for (DevBuf* x : pb) x->release();
+        cudaEvent_t evs[] = {P.in_done, P.a_done, P.tb_done, P.out_done};
+        for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    }
+    for (cudaEvent_t e : M->evpool) cudaEventDestroy(e);
+    if (M->h_pin) cudaFreeHost(M->h_pin);
+    if (M->s_in) cudaStreamDestroy(M->s_in);
+    if (M->s_out) cudaStreamDestroy(M->s_out);
     if (M->ev[0]) cudaEventDestroy(M->ev[0]);
     if (M->ev[1]) cudaEventDestroy(M->ev[1]);
     if (M->stream) cudaStreamDestroy(M->stream);
@@ -435,6 +446,60 @@ void* pp_host_alloc(int64_t bytes) {
 void pp_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ---------------------------------------------------------------------------------------------
+// Chunk pipeline shared by pp_viterbi_batch and pp_forward_batch.  A batch is cut into chunks of whole events; chunk c
+// uses buffer slot c & 1.  Per chunk, in enqueue order:
+//   s_in    : upload of the chunk's bucketing arrays and (host buffers) its observations            -> in_done
+//   stream  : phase A = sweep kernel(s) + whatever produces the scalar the host needs (path total,
+//             number of events for the exact re-run), copied to pinned memory                        -> a_done
+//   host    : waits for a_done of chunk c - 1 only AFTER phase A of chunk c is enqueued, so the GPU never idles
+//   stream  : phase B of chunk c - 1 (traceback write pass / exact re-run)                           -> tb_done
+//   s_out   : device -> host copy of the chunk's paths                                              -> out_done
+// so copies in, sweeps and copies out of neighbouring chunks overlap.
+static int pipe_init(pp_model* M) {
+    if (M->s_in) return PP_OK;
+    PP_CUDA(cudaStreamCreateWithFlags(&M->s_in, cudaStreamNonBlocking));
+    PP_CUDA(cudaStreamCreateWithFlags(&M->s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        PP_CUDA(cudaEventCreateWithFlags(&M->ps[b].in_done, cudaEventDisableTiming));
+        PP_CUDA(cudaEventCreateWithFlags(&M->ps[b].a_done, cudaEventDisableTiming));
+        PP_CUDA(cudaEventCreateWithFlags(&M->ps[b].tb_done, cudaEventDisableTiming));
+        PP_CUDA(cudaEventCreateWithFlags(&M->ps[b].out_done, cudaEventDisableTiming));
+    }
+    PP_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&M->h_pin), 16 * sizeof(int64_t), cudaHostAllocDefault));
+    return PP_OK;
+}
+
+static cudaEvent_t pool_event(pp_model* M) {
+    if (M->evnext == M->evpool.size()) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        M->evpool.push_back(e);
+    }
+    return M->evpool[M->evnext++];
+}
+// timed span on a stream, resolved by spans_collect after the call's final synchronisation
+struct SpanGuard {
+    pp_model* M;
+    cudaStream_t s;
+    cudaEvent_t b;
+    SpanGuard(pp_model* m, int slot, cudaStream_t st) : M(m), s(st) {
+        cudaEvent_t a = pool_event(M);
+        b = pool_event(M);
+        cudaEventRecord(a, s);
+        M->spans.push_back({a, b, slot});
+    }
+    ~SpanGuard() { cudaEventRecord(b, s); }
+};
+static void spans_collect(pp_model* M) {
+    for (const pp_model::Span& sp : M->spans) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) M->prof[sp.slot] += ms;
+    }
+    cudaGetLastError();
+    M->spans.clear();
+    M->evnext = 0;
+}
+
 int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int64_t* offsets, int64_t n_events,
                      int32_t mem, double* logp_out, int64_t* path_len_out, uint16_t* path_out, int64_t path_capacity,
                      int64_t* path_total) {
@@ -449,7 +514,9 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     if (!lane_kernels_fit(M))                         // large model: exact state-parallel kernels
         return viterbi_batch_state(M, obs, obs_dtype, offsets, n_events, mem, logp_out, path_len_out, path_out,
                                    path_capacity, path_total);
-    int rc = PP_OK;
+    int rc = pipe_init(M);
+    if (rc != PP_OK) return rc;
+    const bool host = mem == PP_MEM_HOST;
 
     std::vector<int64_t> store;
     const int64_t *h_off, *d_off;
@@ -458,7 +525,7 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
 
     double* d_score;
     int64_t* d_plen;
-    if (mem == PP_MEM_DEVICE) {
+    if (!host) {
         d_score = logp_out;
         d_plen = path_len_out;
     } else {
@@ -470,110 +537,144 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     PP_CUDA(M->d_end_state.reserve(n_events * sizeof(int32_t)));
     PP_CUDA(M->d_end_ord.reserve(n_events * sizeof(int32_t)));
     PP_CUDA(M->d_path_off.reserve((n_events + 1) * sizeof(int64_t)));
+    PP_CUDA(cudaStreamSynchronize(M->stream));            // offsets are on the device before s_in / kernels use them
 
     const size_t row_bytes = static_cast<size_t>(M->low.n_ptr_words) * kLanes * sizeof(uint32_t);
-    const std::vector<int64_t> cuts =
-        make_chunks(h_off, n_events, row_bytes, M->ws_limit, mem == PP_MEM_HOST ? ob : 0, size_t(4) << 30);
+    // two chunks in flight: each gets half the workspace; host batches are cut fine enough for the copies to overlap
+    const std::vector<int64_t> cuts = make_chunks(h_off, n_events, row_bytes, M->ws_limit / 2, host ? ob : 0, size_t(96) << 20);
+    const int n_chunks = static_cast<int>(cuts.size()) - 1;
     int64_t base = 0;
     bool overflow = false;
     Schedule sc;
-    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+    struct ChunkInfo { int64_t e0, e1; int n_groups; };
+    std::vector<ChunkInfo> info(n_chunks);
+
+    auto trace_args = [&](int c) {
+        pp_model::PipeSlot& P = M->ps[c & 1];
+        return TraceArgs{P.ws.as<uint32_t>(), P.order.as<int32_t>(), P.group_row.as<int64_t>(), d_off, d_score,
+                         M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), M->d_state_edge_begin.as<int32_t>(),
+                         M->d_low_src.as<int32_t>(), M->d_state_pword.as<int32_t>(), M->d_state_pmul.as<int32_t>(),
+                         M->d_state_pshift.as<int32_t>(), M->m, M->ne, M->start, M->low.end_final_only ? 1 : 0,
+                         M->low.n_ptr_words, (1 << M->low.ptr_bits) - 1};
+    };
+    // phase B of chunk c: the host learns the chunk's path total, then the write pass and the copy out
+    auto finish = [&](int c) -> int {
+        pp_model::PipeSlot& P = M->ps[c & 1];
+        PP_CUDA(cudaEventSynchronize(P.a_done));
+        const int64_t last_off = M->h_pin[(c & 1) * 2], last_len = M->h_pin[(c & 1) * 2 + 1];
+        const int64_t chunk_total = last_off + (last_len > 0 ? last_len : 0);
+        const int nslots = info[c].n_groups * kLanes;
+        if (path_out && !overflow && base + chunk_total <= path_capacity) {
+            uint16_t* dst;
+            if (!host) dst = path_out + base;
+            else {
+                PP_CUDA(cudaStreamWaitEvent(M->stream, P.out_done, 0));      // the slot's previous copy out has left the buffer
+                PP_CUDA(P.path.reserve(static_cast<size_t>(chunk_total) * sizeof(uint16_t) + 16));
+                dst = P.path.as<uint16_t>();
+            }
+            {
+                SpanGuard t(M, PP_PROF_TRACEBACK, M->stream);
+                k_traceback<<<(nslots + 127) / 128, 128, 0, M->stream>>>(trace_args(c), d_plen, M->d_path_off.as<int64_t>(), dst, nslots);
+            }
+            PP_CUDA(cudaGetLastError());
+            ++M->launches;
+            PP_CUDA(cudaEventRecord(P.tb_done, M->stream));
+            if (host && chunk_total > 0) {
+                PP_CUDA(cudaStreamWaitEvent(M->s_out, P.tb_done, 0));
+                SpanGuard t(M, PP_PROF_D2H, M->s_out);
+                PP_CUDA(cudaMemcpyAsync(path_out + base, dst, static_cast<size_t>(chunk_total) * sizeof(uint16_t),
+                                        cudaMemcpyDeviceToHost, M->s_out));
+            }
+            if (host) PP_CUDA(cudaEventRecord(P.out_done, M->s_out));
+        } else {
+            PP_CUDA(cudaEventRecord(P.tb_done, M->stream));
+            if (path_out) overflow = true;
+        }
+        base += chunk_total;
+        return PP_OK;
+    };
+
+    for (int c = 0; c < n_chunks; ++c) {
+        pp_model::PipeSlot& P = M->ps[c & 1];
         const int64_t e0 = cuts[c], e1 = cuts[c + 1];
         auto t0 = std::chrono::steady_clock::now();
         build_schedule(h_off, e0, e1, &sc);
         M->prof[PP_PROF_SCHEDULE_HOST_MS] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        info[c] = {e0, e1, sc.n_groups};
         const size_t ws = static_cast<size_t>(sc.total_rows) * row_bytes;
         if (ws > M->ws_limit) {
             set_error("one event needs %zu bytes of traceback workspace (limit %zu)", ws, M->ws_limit);
+            cudaDeviceSynchronize();
             return PP_ERR_NOMEM;
         }
-        if (M->d_ws.reserve(ws) != cudaSuccess) { cudaGetLastError(); set_error("cannot allocate %zu bytes of workspace", ws); return PP_ERR_NOMEM; }
-        PP_CUDA(upload(&M->d_order, sc.order, M->stream));
-        PP_CUDA(upload(&M->d_group_len, sc.group_len, M->stream));
-        PP_CUDA(upload(&M->d_group_row, sc.group_row, M->stream));
-
-        const void* d_obs_base = obs;                    // indexable with the GLOBAL offsets
-        if (mem == PP_MEM_HOST) {
-            const size_t nob = static_cast<size_t>(h_off[e1] - h_off[e0]) * ob;
-            PP_CUDA(M->d_obs.reserve(nob));
-            Timer t(M, PP_PROF_H2D);
-            PP_CUDA(cudaMemcpyAsync(M->d_obs.p, static_cast<const char*>(obs) + h_off[e0] * ob, nob, cudaMemcpyHostToDevice, M->stream));
-            t.stop();
-            d_obs_base = static_cast<const char*>(M->d_obs.p) - h_off[e0] * ob;
+        // ---- copy in (the slot's buffers were last used by chunk c - 2: its traceback must be through)
+        PP_CUDA(cudaStreamWaitEvent(M->s_in, P.tb_done, 0));
+        if (P.ws.cap < ws) {                                  // growing the table frees memory: nothing may be in flight on it
+            PP_CUDA(cudaStreamSynchronize(M->stream));
+            if (P.ws.reserve(ws) != cudaSuccess) { cudaGetLastError(); set_error("cannot allocate %zu bytes of workspace", ws); return PP_ERR_NOMEM; }
         }
-        VitOut O{d_score, M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), M->d_ws.as<uint32_t>()};
+        PP_CUDA(upload(&P.order, sc.order, M->s_in));
+        PP_CUDA(upload(&P.group_len, sc.group_len, M->s_in));
+        PP_CUDA(upload(&P.group_row, sc.group_row, M->s_in));
+        const void* d_obs_base = obs;                        // indexable with the GLOBAL offsets
+        if (host) {
+            const size_t nob = static_cast<size_t>(h_off[e1] - h_off[e0]) * ob;
+            PP_CUDA(P.obs.reserve(nob));
+            SpanGuard t(M, PP_PROF_H2D, M->s_in);
+            PP_CUDA(cudaMemcpyAsync(P.obs.p, static_cast<const char*>(obs) + h_off[e0] * ob, nob, cudaMemcpyHostToDevice, M->s_in));
+            d_obs_base = static_cast<const char*>(P.obs.p) - h_off[e0] * ob;
+        }
+        PP_CUDA(cudaEventRecord(P.in_done, M->s_in));
+        // ---- phase A: sweep, path lengths, exclusive scan, the chunk's total to pinned memory
+        PP_CUDA(cudaStreamWaitEvent(M->stream, P.in_done, 0));
+        VitOut O{d_score, M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), P.ws.as<uint32_t>()};
         {
-            Timer t(M, PP_PROF_VITERBI);
+            SpanGuard t(M, PP_PROF_VITERBI, M->stream);
             if (obs_dtype == PP_F32) {
-                LaneBatch<float> B{static_cast<const float*>(d_obs_base), d_off, M->d_order.as<int32_t>(),
-                                   M->d_group_len.as<int32_t>(), M->d_group_row.as<int64_t>()};
+                LaneBatch<float> B{static_cast<const float*>(d_obs_base), d_off, P.order.as<int32_t>(),
+                                   P.group_len.as<int32_t>(), P.group_row.as<int64_t>()};
                 rc = launch_viterbi<float>(M, B, O, sc.n_groups);
             } else {
-                LaneBatch<double> B{static_cast<const double*>(d_obs_base), d_off, M->d_order.as<int32_t>(),
-                                    M->d_group_len.as<int32_t>(), M->d_group_row.as<int64_t>()};
+                LaneBatch<double> B{static_cast<const double*>(d_obs_base), d_off, P.order.as<int32_t>(),
+                                    P.group_len.as<int32_t>(), P.group_row.as<int64_t>()};
                 rc = launch_viterbi<double>(M, B, O, sc.n_groups);
             }
-            t.stop();
-            if (rc != PP_OK) return rc;
         }
-        // traceback pass 1: path lengths
-        TraceArgs T{M->d_ws.as<uint32_t>(), M->d_order.as<int32_t>(), M->d_group_row.as<int64_t>(), d_off, d_score,
-                    M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), M->d_state_edge_begin.as<int32_t>(),
-                    M->d_low_src.as<int32_t>(), M->d_state_pword.as<int32_t>(), M->d_state_pmul.as<int32_t>(), M->d_state_pshift.as<int32_t>(),
-                    M->m, M->ne, M->start, M->low.end_final_only ? 1 : 0, M->low.n_ptr_words,
-                    (1 << M->low.ptr_bits) - 1};
-        const int nslots = sc.n_groups * kLanes;
-        int64_t chunk_total = 0;
+        if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
         {
-            Timer t(M, PP_PROF_TRACEBACK);
-            k_traceback<<<(nslots + 127) / 128, 128, 0, M->stream>>>(T, d_plen, nullptr, nullptr, nslots);
+            SpanGuard t(M, PP_PROF_TRACEBACK, M->stream);
+            const int nslots = sc.n_groups * kLanes;
+            k_traceback<<<(nslots + 127) / 128, 128, 0, M->stream>>>(trace_args(c), d_plen, nullptr, nullptr, nslots);
             PP_CUDA(cudaGetLastError());
             ++M->launches;
-            // exclusive scan of max(len, 0) over the chunk's events (original order)
-            const int64_t ne = e1 - e0;
+            const int64_t ne = e1 - e0;                       // exclusive scan of max(len, 0) over the chunk's events
             auto it = thrust::make_transform_iterator(static_cast<const int64_t*>(d_plen + e0), ClampLen());
             size_t tmp = 0;
             int64_t* d_poff = M->d_path_off.as<int64_t>() + e0;
             PP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, d_poff, static_cast<int>(ne), M->stream));
-            PP_CUDA(M->d_scan_tmp.reserve(tmp + 16));
+            if (M->d_scan_tmp.cap < tmp + 16) {
+                PP_CUDA(cudaStreamSynchronize(M->stream));
+                PP_CUDA(M->d_scan_tmp.reserve(tmp + 16));
+            }
             PP_CUDA(cub::DeviceScan::ExclusiveSum(M->d_scan_tmp.p, tmp, it, d_poff, static_cast<int>(ne), M->stream));
             ++M->launches;
-            int64_t last_off = 0, last_len = 0;
-            PP_CUDA(cudaMemcpyAsync(&last_off, d_poff + ne - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
-            PP_CUDA(cudaMemcpyAsync(&last_len, d_plen + e1 - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
-            PP_CUDA(cudaStreamSynchronize(M->stream));
-            chunk_total = last_off + (last_len > 0 ? last_len : 0);
-            if (path_out && !overflow && base + chunk_total <= path_capacity) {
-                uint16_t* dst;
-                if (mem == PP_MEM_DEVICE) dst = path_out + base;
-                else {
-                    PP_CUDA(M->d_path.reserve(static_cast<size_t>(chunk_total) * sizeof(uint16_t) + 16));
-                    dst = M->d_path.as<uint16_t>();
-                }
-                k_traceback<<<(nslots + 127) / 128, 128, 0, M->stream>>>(T, d_plen, M->d_path_off.as<int64_t>(), dst, nslots);
-                PP_CUDA(cudaGetLastError());
-                ++M->launches;
-                t.stop();
-                if (mem == PP_MEM_HOST && chunk_total > 0) {
-                    Timer t2(M, PP_PROF_D2H);
-                    PP_CUDA(cudaMemcpyAsync(path_out + base, dst, static_cast<size_t>(chunk_total) * sizeof(uint16_t),
-                                            cudaMemcpyDeviceToHost, M->stream));
-                    t2.stop();
-                }
-            } else {
-                t.stop();
-                if (path_out) overflow = true;
-            }
+            PP_CUDA(cudaMemcpyAsync(M->h_pin + (c & 1) * 2, d_poff + ne - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
+            PP_CUDA(cudaMemcpyAsync(M->h_pin + (c & 1) * 2 + 1, d_plen + e1 - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
         }
-        base += chunk_total;
+        PP_CUDA(cudaEventRecord(P.a_done, M->stream));
+        if (c >= 1) { rc = finish(c - 1); if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; } }
     }
-    if (mem == PP_MEM_HOST) {
-        Timer t(M, PP_PROF_D2H);
+    rc = finish(n_chunks - 1);
+    if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
+    if (host) {
+        SpanGuard t(M, PP_PROF_D2H, M->stream);
         PP_CUDA(cudaMemcpyAsync(logp_out, d_score, n_events * sizeof(double), cudaMemcpyDeviceToHost, M->stream));
         PP_CUDA(cudaMemcpyAsync(path_len_out, d_plen, n_events * sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
-        t.stop();
     }
     PP_CUDA(cudaStreamSynchronize(M->stream));
+    PP_CUDA(cudaStreamSynchronize(M->s_out));
+    PP_CUDA(cudaStreamSynchronize(M->s_in));
+    spans_collect(M);
     if (path_total) *path_total = base;
     if (overflow) {
         set_error("path buffer too small: %lld elements needed, capacity %lld", (long long)base, (long long)path_capacity);
@@ -593,60 +694,84 @@ int pp_forward_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     if (n_events == 0) return PP_OK;
     const size_t ob = obs_dtype == PP_F32 ? 4 : 8;
     const bool lane = lane_kernels_fit(M);
-    int rc = PP_OK;
+    const bool host = mem == PP_MEM_HOST;
+    int rc = pipe_init(M);
+    if (rc != PP_OK) return rc;
     std::vector<int64_t> store;
     const int64_t *h_off, *d_off;
     rc = host_offsets(M, offsets, n_events, mem, &store, &h_off, &d_off);
     if (rc != PP_OK) return rc;
     double* d_logp = logp_out;
-    if (mem == PP_MEM_HOST) {
+    if (host) {
         PP_CUDA(M->d_logp.reserve(n_events * sizeof(double)));
         d_logp = M->d_logp.as<double>();
     }
-    const std::vector<int64_t> cuts = make_chunks(h_off, n_events, 0, 0, mem == PP_MEM_HOST ? ob : 0, size_t(4) << 30);
+    PP_CUDA(cudaStreamSynchronize(M->stream));
+    const std::vector<int64_t> cuts = make_chunks(h_off, n_events, 0, 0, host ? ob : 0, size_t(96) << 20);
+    const int n_chunks = static_cast<int>(cuts.size()) - 1;
     Schedule sc;
-    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+    std::vector<const void*> obs_base(n_chunks);
+    // phase B of chunk c: events the scaled sweep could not resolve (P == 0, inf, NaN) go through the exact kernel
+    auto finish = [&](int c) -> int {
+        pp_model::PipeSlot& P = M->ps[c & 1];
+        PP_CUDA(cudaEventSynchronize(P.a_done));
+        const int64_t e0 = cuts[c], e1 = cuts[c + 1];
+        int r = exact_forward_run(M, c & 1, obs_base[c], obs_dtype, d_off + e0, h_off + e0, e1 - e0, d_logp + e0);
+        PP_CUDA(cudaEventRecord(P.tb_done, M->stream));
+        return r;
+    };
+    for (int c = 0; c < n_chunks; ++c) {
+        pp_model::PipeSlot& P = M->ps[c & 1];
         const int64_t e0 = cuts[c], e1 = cuts[c + 1];
         auto t0 = std::chrono::steady_clock::now();
-        build_schedule(h_off, e0, e1, &sc);
+        if (lane) build_schedule(h_off, e0, e1, &sc);
         M->prof[PP_PROF_SCHEDULE_HOST_MS] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        PP_CUDA(upload(&M->d_order, sc.order, M->stream));
-        PP_CUDA(upload(&M->d_group_len, sc.group_len, M->stream));
-        PP_CUDA(upload(&M->d_group_row, sc.group_row, M->stream));
-        const void* d_obs_base = obs;
-        if (mem == PP_MEM_HOST) {
+        PP_CUDA(cudaStreamWaitEvent(M->s_in, P.tb_done, 0));
+        if (lane) {
+            PP_CUDA(upload(&P.order, sc.order, M->s_in));
+            PP_CUDA(upload(&P.group_len, sc.group_len, M->s_in));
+            PP_CUDA(upload(&P.group_row, sc.group_row, M->s_in));
+        }
+        obs_base[c] = obs;
+        if (host) {
             const size_t nob = static_cast<size_t>(h_off[e1] - h_off[e0]) * ob;
-            PP_CUDA(M->d_obs.reserve(nob));
-            Timer t(M, PP_PROF_H2D);
-            PP_CUDA(cudaMemcpyAsync(M->d_obs.p, static_cast<const char*>(obs) + h_off[e0] * ob, nob, cudaMemcpyHostToDevice, M->stream));
-            t.stop();
-            d_obs_base = static_cast<const char*>(M->d_obs.p) - h_off[e0] * ob;
+            PP_CUDA(P.obs.reserve(nob));
+            SpanGuard t(M, PP_PROF_H2D, M->s_in);
+            PP_CUDA(cudaMemcpyAsync(P.obs.p, static_cast<const char*>(obs) + h_off[e0] * ob, nob, cudaMemcpyHostToDevice, M->s_in));
+            obs_base[c] = static_cast<const char*>(P.obs.p) - h_off[e0] * ob;
         }
+        PP_CUDA(cudaEventRecord(P.in_done, M->s_in));
+        PP_CUDA(cudaStreamWaitEvent(M->stream, P.in_done, 0));
         FwdOut O{d_logp};
-        Timer t(M, PP_PROF_FORWARD);
-        if (!lane) {                                  // large model: every event takes the exact log-space kernel
-            PP_CUDA(cudaMemsetAsync(d_logp + e0, 0xFF, (e1 - e0) * sizeof(double), M->stream));     // all-ones = NaN
-        } else if (obs_dtype == PP_F32) {
-            LaneBatch<float> B{static_cast<const float*>(d_obs_base), d_off, M->d_order.as<int32_t>(),
-                               M->d_group_len.as<int32_t>(), M->d_group_row.as<int64_t>()};
-            rc = launch_forward<float>(M, B, O, sc.n_groups);
-        } else {
-            LaneBatch<double> B{static_cast<const double*>(d_obs_base), d_off, M->d_order.as<int32_t>(),
-                                M->d_group_len.as<int32_t>(), M->d_group_row.as<int64_t>()};
-            rc = launch_forward<double>(M, B, O, sc.n_groups);
+        {
+            SpanGuard t(M, PP_PROF_FORWARD, M->stream);
+            if (!lane) {                                  // large model: every event takes the exact log-space kernel
+                PP_CUDA(cudaMemsetAsync(d_logp + e0, 0xFF, (e1 - e0) * sizeof(double), M->stream));     // all-ones = NaN
+            } else if (obs_dtype == PP_F32) {
+                LaneBatch<float> B{static_cast<const float*>(obs_base[c]), d_off, P.order.as<int32_t>(),
+                                   P.group_len.as<int32_t>(), P.group_row.as<int64_t>()};
+                rc = launch_forward<float>(M, B, O, sc.n_groups);
+            } else {
+                LaneBatch<double> B{static_cast<const double*>(obs_base[c]), d_off, P.order.as<int32_t>(),
+                                    P.group_len.as<int32_t>(), P.group_row.as<int64_t>()};
+                rc = launch_forward<double>(M, B, O, sc.n_groups);
+            }
         }
-        t.stop();
-        if (rc != PP_OK) return rc;
-        // events the scaled sweep could not resolve (P == 0, inf, NaN) go through the exact kernel
-        rc = rerun_exact_forward(M, d_obs_base, obs_dtype, d_off + e0, h_off + e0, e1 - e0, d_logp + e0);
-        if (rc != PP_OK) return rc;
+        if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
+        rc = exact_forward_collect(M, c & 1, d_logp + e0, e1 - e0);
+        if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
+        PP_CUDA(cudaEventRecord(P.a_done, M->stream));
+        if (c >= 1) { rc = finish(c - 1); if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; } }
     }
-    if (mem == PP_MEM_HOST) {
-        Timer t(M, PP_PROF_D2H);
+    rc = finish(n_chunks - 1);
+    if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
+    if (host) {
+        SpanGuard t(M, PP_PROF_D2H, M->stream);
         PP_CUDA(cudaMemcpyAsync(logp_out, d_logp, n_events * sizeof(double), cudaMemcpyDeviceToHost, M->stream));
-        t.stop();
     }
     PP_CUDA(cudaStreamSynchronize(M->stream));
+    PP_CUDA(cudaStreamSynchronize(M->s_in));
+    spans_collect(M);
     return PP_OK;
 }
 

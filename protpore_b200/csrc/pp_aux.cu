@@ -136,6 +136,52 @@ int rerun_exact_forward(pp_model* M, const void* d_obs_base, int32_t obs_dtype, 
     return PP_OK;
 }
 
+int exact_forward_collect(pp_model* M, int slot, const double* d_logp, int64_t n_events) {
+    pp_model::PipeSlot& P = M->ps[slot];
+    PP_CUDA(P.list.reserve(n_events * sizeof(int32_t)));
+    PP_CUDA(P.counter.reserve(16));
+    PP_CUDA(cudaMemsetAsync(P.counter.p, 0, 4, M->stream));
+    k_collect_flagged<<<static_cast<unsigned>((n_events + 255) / 256), 256, 0, M->stream>>>(
+        d_logp, n_events, P.list.as<int32_t>(), P.counter.as<int32_t>());
+    PP_CUDA(cudaGetLastError());
+    ++M->launches;
+    PP_CUDA(cudaMemcpyAsync(M->h_pin + 8 + slot, P.counter.p, 4, cudaMemcpyDeviceToHost, M->stream));
+    return PP_OK;
+}
+
+int exact_forward_run(pp_model* M, int slot, const void* d_obs_base, int32_t obs_dtype, const int64_t* d_off,
+                      const int64_t* h_off, int64_t n_events, double* d_logp) {
+    pp_model::PipeSlot& P = M->ps[slot];
+    const int32_t n_list = *reinterpret_cast<const int32_t*>(M->h_pin + 8 + slot);
+    if (n_list == 0) return PP_OK;
+    int64_t maxlen = 0;
+    for (int64_t e = 0; e < n_events; ++e) maxlen = std::max(maxlen, h_off[e + 1] - h_off[e]);
+    const int grid = static_cast<int>(std::min<int64_t>(n_list, static_cast<int64_t>(M->sm_count) * 4));
+    const int64_t stride = (maxlen + 1) * M->m;
+    const size_t need = static_cast<size_t>(grid) * stride * sizeof(double);
+    if (need > M->ws_limit || M->d_tab.reserve(need) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("exact forward re-run needs %zu bytes of workspace", need);
+        return PP_ERR_NOMEM;
+    }
+    PP_CUDA(M->d_xbuf.reserve(static_cast<size_t>(grid) * maxlen * sizeof(double)));
+    const int threads = state_threads(M);
+    const size_t smem = static_cast<size_t>(M->ne) * sizeof(double) + 16;
+    const StateModel S = make_state_model(M);
+    if (obs_dtype == PP_F32) {
+        if (set_dyn_smem(k_forward_exact<float>, smem) != PP_OK) return PP_ERR_CUDA;
+        k_forward_exact<float><<<grid, threads, smem, M->stream>>>(S, static_cast<const float*>(d_obs_base), d_off,
+            P.list.as<int32_t>(), n_list, M->d_tab.as<double>(), stride, M->d_xbuf.as<double>(), maxlen, d_logp);
+    } else {
+        if (set_dyn_smem(k_forward_exact<double>, smem) != PP_OK) return PP_ERR_CUDA;
+        k_forward_exact<double><<<grid, threads, smem, M->stream>>>(S, static_cast<const double*>(d_obs_base), d_off,
+            P.list.as<int32_t>(), n_list, M->d_tab.as<double>(), stride, M->d_xbuf.as<double>(), maxlen, d_logp);
+    }
+    PP_CUDA(cudaGetLastError());
+    ++M->launches;
+    return PP_OK;
+}
+
 // Batched Viterbi for models whose column does not fit the lane-per-event kernels (state-parallel, exact).
 int viterbi_batch_state(pp_model* M, const void* obs, int32_t obs_dtype, const int64_t* offsets, int64_t n_events,
                         int32_t mem, double* logp_out, int64_t* path_len_out, uint16_t* path_out, int64_t path_capacity,

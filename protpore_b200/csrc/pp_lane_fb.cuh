@@ -29,7 +29,7 @@ namespace pp {
 
 constexpr int kFbTargetExp = 480;        // row maxima of both sweeps are steered to ~2^480 (c_r ~ 2^-960 stays normal)
 constexpr int kFbTileCols = 8;
-constexpr int kT2Entries = 33;           // 2^(j/32), j = -16 .. 16
+constexpr int kT2Entries = 17;           // 2^(j/16), j = -8 .. 8 (136 bytes: bank-conflict free but for -8 / 8)
 
 
 __host__ __device__ inline size_t fb_smem_bytes(int n_slots, int n_w, int ne, int warps) {
@@ -41,7 +41,7 @@ __host__ __device__ inline size_t fb_smem_bytes(int n_slots, int n_w, int ne, in
 __device__ __forceinline__ double ldcg64(const void* p) { return __ldcg(static_cast<const double*>(p)); }
 __device__ __forceinline__ void stcg64(void* p, double v) { __stcg(static_cast<double*>(p), v); }
 
-// 2^t for t in the log2 domain, float64-accurate (rel. error ~3e-16): t = n + j/32 + g, |g| <= 1/64;
+// 2^t for t in the log2 domain, float64-accurate (rel. error ~6e-16): t = n + j/16 + g, |g| <= 1/32;
 // 2^g by a degree-6 Taylor polynomial of exp(g ln 2), 2^(j/32) from a shared-memory table, 2^n into the exponent.
 // Below 2^-1000 the factor is an exact 0.
 __device__ __forceinline__ double exp2_acc(double t, uint32_t t2tab) {
@@ -52,9 +52,9 @@ __device__ __forceinline__ double exp2_acc(double t, uint32_t t2tab) {
     const double tm = tc + magic;
     const int n = __double2loint(tm);
     const double fr = tc - (tm - magic);                       // [-0.5, 0.5]
-    const double um = fma(fr, 32.0, magic);
-    const int j = __double2loint(um);                           // [-16, 16]
-    const double g = fma(-(um - magic), 0.03125, fr);           // [-1/64, 1/64]
+    const double um = fma(fr, 16.0, magic);
+    const int j = __double2loint(um);                           // [-8, 8]
+    const double g = fma(-(um - magic), 0.0625, fr);            // [-1/32, 1/32]
     const double z = g * 0.693147180559945309417;
     double p = fma(z, 1.0 / 720.0, 1.0 / 120.0);
     p = fma(p, z, 1.0 / 24.0);
@@ -62,10 +62,17 @@ __device__ __forceinline__ double exp2_acc(double t, uint32_t t2tab) {
     p = fma(p, z, 0.5);
     p = fma(p, z, 1.0);
     p = fma(p, z, 1.0);
-    const double tv = lds64(t2tab + static_cast<uint32_t>(j + 16) * 8u);
+    const double tv = lds64(t2tab + static_cast<uint32_t>(j + 8) * 8u);
     const double scale = __hiloint2double((n + 1023) << 20, 0);
     const double r = (p * tv) * scale;
     return (t > -1000.0) ? r : 0.0;               // false for NaN as well
+}
+
+// membership test of the point-mass / uniform densities (the value is the run's shared 2^(c2 + shift))
+template <int KIND>
+__device__ __forceinline__ bool emis_in_range(uint32_t ep, double x) {
+    if (KIND == EMIS_POINT) return fabs(x - lds64(ep)) < 1E-4;
+    return x >= lds64(ep) && x <= lds64(ep + 8);
 }
 
 template <int W>
@@ -91,9 +98,9 @@ struct FwdCtx {
     uint32_t t2tab;
 };
 
-template <int NE, int MODE, int G, int KIND>
+template <int NE, int MODE, int G, int KIND, bool SH = false>
 __device__ __forceinline__ void fbf_group(RunPtrs<NE>& P, unsigned char*& gp, int gs, const FwdCtx& C, bool start_row0,
-                                          double& prev, int& mx) {
+                                          double& prev, int& mx, double E = 0.0) {
     constexpr int NL = (MODE == MODE_CHAIN) ? NE - 1 : NE;
     double v[G][NL > 0 ? NL : 1], w[G][NE > 0 ? NE : 1], acc[G];
 #pragma unroll
@@ -114,8 +121,10 @@ __device__ __forceinline__ void fbf_group(RunPtrs<NE>& P, unsigned char*& gp, in
     }
     if (MODE == MODE_EMIT) {
 #pragma unroll
-        for (int g = 0; g < G; ++g)
-            acc[g] *= exp2_acc(smem_emission_log2<KIND>(P.ep + g * P.es, C.x) + C.shiftd, C.t2tab);
+        for (int g = 0; g < G; ++g) {
+            if (SH) acc[g] = emis_in_range<KIND>(P.ep + g * P.es, C.x) ? acc[g] * E : 0.0;
+            else acc[g] *= exp2_acc(smem_emission_log2<KIND>(P.ep + g * P.es, C.x) + C.shiftd, C.t2tab);
+        }
     }
     if (MODE == MODE_CHAIN) {
 #pragma unroll
@@ -136,14 +145,14 @@ __device__ __forceinline__ void fbf_group(RunPtrs<NE>& P, unsigned char*& gp, in
     P.advance(G);
 }
 
-template <int NE, int MODE, int KIND>
+template <int NE, int MODE, int KIND, bool SH = false>
 __device__ __forceinline__ void fbf_items(RunPtrs<NE>& P, unsigned char*& gp, int gs, int count, const FwdCtx& C,
-                                          bool start_row0, double& prev, int& mx) {
+                                          bool start_row0, double& prev, int& mx, double E = 0.0) {
     constexpr int G = run_group_size(NE);
     int left = count;
-    for (; left >= G; left -= G) fbf_group<NE, MODE, G, KIND>(P, gp, gs, C, start_row0, prev, mx);
-    if (G > 2 && left >= 2) { fbf_group<NE, MODE, 2, KIND>(P, gp, gs, C, start_row0, prev, mx); left -= 2; }
-    if (left >= 1) fbf_group<NE, MODE, 1, KIND>(P, gp, gs, C, start_row0, prev, mx);
+    for (; left >= G; left -= G) fbf_group<NE, MODE, G, KIND, SH>(P, gp, gs, C, start_row0, prev, mx, E);
+    if (G > 2 && left >= 2) { fbf_group<NE, MODE, 2, KIND, SH>(P, gp, gs, C, start_row0, prev, mx, E); left -= 2; }
+    if (left >= 1) fbf_group<NE, MODE, 1, KIND, SH>(P, gp, gs, C, start_row0, prev, mx, E);
 }
 
 template <int NE>
@@ -158,10 +167,16 @@ __device__ __forceinline__ void fbf_run_ne(const RunRec& R, int par, bool row0, 
     const int kind = R.kind;
     if (kind == EMIS_NORMAL) {
         fbf_items<NE, MODE_EMIT, EMIS_NORMAL>(P, gp, gs, count, C, false, prev, mx);
-    } else if (kind == EMIS_POINT) {
-        fbf_items<NE, MODE_EMIT, EMIS_POINT>(P, gp, gs, count, C, false, prev, mx);
-    } else if (kind == EMIS_UNIFORM) {
-        fbf_items<NE, MODE_EMIT, EMIS_UNIFORM>(P, gp, gs, count, C, false, prev, mx);
+    } else if (kind == EMIS_POINT || kind == EMIS_UNIFORM) {
+        if (R.shared_c2) {                                    // one exponentiation per run and row
+            const double E = exp2_acc(lds64(P.ep + 16) + C.shiftd, C.t2tab);
+            if (kind == EMIS_POINT) fbf_items<NE, MODE_EMIT, EMIS_POINT, true>(P, gp, gs, count, C, false, prev, mx, E);
+            else fbf_items<NE, MODE_EMIT, EMIS_UNIFORM, true>(P, gp, gs, count, C, false, prev, mx, E);
+        } else if (kind == EMIS_POINT) {
+            fbf_items<NE, MODE_EMIT, EMIS_POINT>(P, gp, gs, count, C, false, prev, mx);
+        } else {
+            fbf_items<NE, MODE_EMIT, EMIS_UNIFORM>(P, gp, gs, count, C, false, prev, mx);
+        }
     } else if (NE > 0 && R.fwd) {
         fbf_group<NE, MODE_SILENT, 1, RUN_SILENT>(P, gp, gs, C, false, prev, mx);
         fbf_items<NE, MODE_CHAIN, RUN_SILENT>(P, gp, gs, count - 1, C, false, prev, mx);
@@ -392,25 +407,32 @@ __device__ __forceinline__ void fbb_run(int r, uint32_t colb, uint32_t wtab, con
 }
 
 // H[l] = p_l(x_r) 2^shift * b^_{r+1}[l] for the emitting states of a run (list 0 of pp_lowering_bw.cpp)
-template <int KIND>
+template <int KIND, bool SH = false>
 __device__ __forceinline__ void fbh_items(const RunRec& R, uint32_t colb, uint32_t etab, double x, double shiftd,
                                           uint32_t t2tab) {
     uint32_t sp = colb + R.src_off[0][0], dp = colb + R.dst_off[0];
     uint32_t ep = etab + R.e_base * kFwdEmisBytes;
     const int ss = R.src_stride[0], ds = R.dst_stride, es = R.e_stride * kFwdEmisBytes;
     int left = R.count;
+    double E = 0.0;
+    if (SH) E = exp2_acc(lds64(ep + 16) + shiftd, t2tab);
     for (; left >= 4; left -= 4) {
         double b[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) b[g] = lds64(sp + g * ss);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) b[g] *= exp2_acc(smem_emission_log2<KIND>(ep + g * es, x) + shiftd, t2tab);
+        for (int g = 0; g < 4; ++g) {
+            if (SH) b[g] = emis_in_range<KIND>(ep + g * es, x) ? b[g] * E : 0.0;
+            else b[g] *= exp2_acc(smem_emission_log2<KIND>(ep + g * es, x) + shiftd, t2tab);
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) sts64(dp + g * ds, b[g]);
         sp += 4 * ss; dp += 4 * ds; ep += 4 * es;
     }
     for (; left >= 1; --left) {
-        const double b = lds64(sp) * exp2_acc(smem_emission_log2<KIND>(ep, x) + shiftd, t2tab);
+        double b = lds64(sp);
+        if (SH) b = emis_in_range<KIND>(ep, x) ? b * E : 0.0;
+        else b *= exp2_acc(smem_emission_log2<KIND>(ep, x) + shiftd, t2tab);
         sts64(dp, b);
         sp += ss; dp += ds; ep += es;
     }
@@ -419,6 +441,8 @@ __device__ __forceinline__ void fbh_items(const RunRec& R, uint32_t colb, uint32
 __device__ __forceinline__ void fbh_run(int r, uint32_t colb, uint32_t etab, double x, double shiftd, uint32_t t2tab) {
     const RunRec& R = run_rec(r);
     if (R.kind == EMIS_NORMAL) fbh_items<EMIS_NORMAL>(R, colb, etab, x, shiftd, t2tab);
+    else if (R.shared_c2 && R.kind == EMIS_POINT) fbh_items<EMIS_POINT, true>(R, colb, etab, x, shiftd, t2tab);
+    else if (R.shared_c2) fbh_items<EMIS_UNIFORM, true>(R, colb, etab, x, shiftd, t2tab);
     else if (R.kind == EMIS_POINT) fbh_items<EMIS_POINT>(R, colb, etab, x, shiftd, t2tab);
     else fbh_items<EMIS_UNIFORM>(R, colb, etab, x, shiftd, t2tab);
 }
@@ -492,7 +516,7 @@ k_fb_lane(const LaneSched S, const FbSched F, const LaneBatchAny B) {
     const int eb = F.run_ranges[warp * 6 + 4], ee = F.run_ranges[warp * 6 + 5];     //           emitting
 
     for (int i = threadIdx.x; i < S.ne * 4; i += W * 32) s_etab[i] = __ldg(S.etab + i);
-    for (int i = threadIdx.x; i < kT2Entries; i += W * 32) s_t2[i] = exp2(static_cast<double>(i - 16) * 0.03125);
+    for (int i = threadIdx.x; i < kT2Entries; i += W * 32) s_t2[i] = exp2(static_cast<double>(i - 8) * 0.0625);
 
     for (;;) {
         __syncthreads();                                         // previous group is done with shared memory

@@ -381,7 +381,19 @@ std::string lower_model(const pp_model_desc& d, int warps, Lowered* low) {
     low->late_of = late_of;
     low->early_of = early_of;
     low->sil_of = sil_of;
+    mark_shared_c2(*low, &low->runs);
     return lower_backward(d, low);
+}
+
+void mark_shared_c2(const Lowered& low, std::vector<RunRec>* runs) {
+    for (RunRec& r : *runs) {
+        r.shared_c2 = 0;
+        if (r.kind != EMIS_POINT && r.kind != EMIS_UNIFORM) continue;
+        bool same = true;
+        const double c0 = low.emis[r.e_base].c2;
+        for (int t = 1; t < r.count && same; ++t) same = low.emis[r.e_base + t * r.e_stride].c2 == c0;
+        r.shared_c2 = same ? 1 : 0;
+    }
 }
 
 std::string refresh_params(const pp_model_desc& d, Lowered* low) {
@@ -406,6 +418,7 @@ std::string refresh_params(const pp_model_desc& d, Lowered* low) {
             low->edges_logp[q][i].val = d.in_logp[low->low_csr[i]];
             low->edges_prob[q][i].val = std::exp(d.in_logp[low->low_csr[i]]);
         }
+    mark_shared_c2(*low, &low->runs);
     return lower_backward(d, low);
 }
 

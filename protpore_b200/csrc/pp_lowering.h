@@ -72,7 +72,9 @@ struct __attribute__((aligned(16))) RunRec {
     int32_t e_base, e_stride;                    // emission-record index of the first item; per item
     int32_t pword, pshift;                       // pword: byte offset, inside a traceback pointer row, of the run's first unit
     int32_t has_logw;                            // some item of the run has log(state.weight) != 0
-    int32_t pad[2];
+    int32_t shared_c2;                           // emitting run of point-mass / uniform states whose log2 densities are all equal:
+                                                 // the linear-space sweeps exponentiate once per run and row
+    int32_t pad;
     int32_t src_off[2][kMaxRunEdges];            // byte offset of each edge's first source slot, per row parity
     int32_t src_stride[kMaxRunEdges];            // bytes per item
 };
@@ -130,6 +132,8 @@ struct Lowered {
 std::string lower_model(const pp_model_desc& d, int warps, Lowered* out);
 // Refresh weights / emission parameters of an existing lowering (same topology).
 std::string refresh_params(const pp_model_desc& d, Lowered* low);
+// Sets RunRec::shared_c2 of the emitting runs in `runs` from the current emission records.
+void mark_shared_c2(const Lowered& low, std::vector<RunRec>* runs);
 // Run schedule of the backward sweep; sets low->bw_ok (false: the exact state-parallel kernels serve the model).
 std::string lower_backward(const pp_model_desc& d, Lowered* low);
 // One line per warp and phase: the runs it executes (pp_describe.cpp).

@@ -292,6 +292,7 @@ std::string lower_backward(const pp_model_desc& d, Lowered* low) {
         }
     }
     low->n_acc_slots = static_cast<int32_t>(low->acc_log2.size());
+    mark_shared_c2(*low, &low->bw_runs);                       // only the H runs carry an emission kind
     low->bw_ok = true;
     return "";
 }

@@ -56,6 +56,19 @@ struct pp_model {
     pp::DevBuf d_bw_wtab, d_acc_map, d_acc_log2, d_fb_acc, d_fb_scratch, d_fb_ctl, d_fb_minmax;
     size_t ws_limit = 0;
 
+    // chunk pipeline of the batched host/device calls (pp_api.cu): copy-in and copy-out streams beside the compute
+    // stream, two slots of per-chunk buffers, pinned scalars the host polls, a pool of timing events
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    struct PipeSlot {
+        pp::DevBuf obs, ws, path, order, group_len, group_row, list, counter;
+        cudaEvent_t in_done = nullptr, a_done = nullptr, tb_done = nullptr, out_done = nullptr;
+    } ps[2];
+    int64_t* h_pin = nullptr;             // [16] pinned
+    struct Span { cudaEvent_t a, b; int slot; };
+    std::vector<cudaEvent_t> evpool;
+    size_t evnext = 0;
+    std::vector<Span> spans;
+
     cudaEvent_t ev[2] = {nullptr, nullptr};
     double prof[PP_PROF_SLOTS] = {0};
     int64_t launches = 0;
@@ -83,5 +96,11 @@ int viterbi_batch_state(pp_model* M, const void* obs, int32_t obs_dtype, const i
                         int64_t* path_total);
 int rerun_exact_forward(pp_model* M, const void* d_obs_base, int32_t obs_dtype, const int64_t* d_off,
                         const int64_t* h_off, int64_t n_events, double* d_logp);
+// The same in two halves for the chunk pipeline: enqueue the collection of the flagged events of a chunk (list, counter
+// and the pinned copy of the counter belong to pipeline slot `slot`), later -- after the caller has waited for the
+// slot's a_done event -- run the exact kernel on them.
+int exact_forward_collect(pp_model* M, int slot, const double* d_logp, int64_t n_events);
+int exact_forward_run(pp_model* M, int slot, const void* d_obs_base, int32_t obs_dtype, const int64_t* d_off,
+                      const int64_t* h_off, int64_t n_events, double* d_logp);
 
 }  // namespace pp
