@@ -158,6 +158,44 @@ int pp_forward_backward_info(const pp_model *model, int64_t *out3);
 int pp_sample_events(pp_model *model, const int64_t *offsets, int64_t n_events, uint64_t seed, int32_t mem,
                      float *obs_out);
 
+/*
+ * ---- Segmentation: raw current -> segments -> segment means (the step before the HMM path) ----------------
+ * Batched FastStatSplit.parse (PyPore/cparsers.pyx:103-203; the class SpeedyStatSplit wraps it,
+ * PyPore/parsers.py:505-534; called per event at peptide_hmm_v0.0.1.py:443-446).  Model-independent: these
+ * entry points take a CUDA device ordinal instead of a model handle.
+ *
+ * pp_statsplit_min_gain: the gain threshold FastStatSplit.__init__ derives (cparsers.pyx:56-101); pass 0 for an
+ * argument the Python caller left at None.  Pure host arithmetic.
+ */
+typedef struct pp_statsplit_params {
+    int64_t min_width, max_width, window_width;   /* samples; the reference's defaults are 100, 1000000, 10000 */
+    double min_gain;                              /* threshold on the log-variance gain (already doubled, 101) */
+} pp_statsplit_params;
+
+double pp_statsplit_min_gain(int64_t window_width, double min_gain_per_sample, double false_positive_rate,
+                             double prior_segments_per_second, double sampling_freq, double cutoff_freq);
+
+/*
+ * current[offsets[e] .. offsets[e+1]) is the float64 current of event e.  Outputs, CSR-style like the HMM calls:
+ *   seg_offsets[n_events + 1] : segments of event e are [seg_offsets[e], seg_offsets[e+1])  -- this array and
+ *                               seg_mean / seg_mean_f32 are exactly the `offsets` / `obs` of pp_viterbi_batch
+ *   seg_start[j]              : first sample of segment j, relative to its event (0 for an event's first segment;
+ *                               the others are the reference's breakpoints, ascending)
+ *   seg_mean[j], seg_std[j]   : Segment.mean / Segment.std (PyPore/core.py:209-214), float64; each may be NULL
+ *   seg_mean_f32[j]           : the mean rounded to float32 (the batched HMM calls' input type); may be NULL
+ *   capacity                  : entries the seg_* arrays can hold;  *seg_total receives the number needed
+ * seg_start == NULL runs the counting pass only (seg_offsets and *seg_total are filled).  PP_ERR_CAPACITY if the
+ * arrays are too small.  Breakpoints are bit-identical to the reference's except where two candidate gains of one
+ * window agree to ~1e-13 relative (CUDA's float64 log is accurate to 1 ulp, glibc's is not the same function).
+ */
+int pp_statsplit_batch(const pp_statsplit_params *prm, int device, const double *current, const int64_t *offsets,
+                       int64_t n_events, int32_t mem, int64_t *seg_offsets, int32_t *seg_start, double *seg_mean,
+                       double *seg_std, float *seg_mean_f32, int64_t capacity, int64_t *seg_total);
+
+/* Device time of the last pp_statsplit_batch on `device`: out3 = {k_statsplit ms, k_segments ms, kernels launched
+ * since the library was loaded}. */
+int pp_statsplit_profile(int device, double *out3);
+
 /* Number of usable CUDA devices (0 without a driver/GPU; never fails). */
 int pp_device_count(void);
 

@@ -11,6 +11,14 @@ PY="${PYTHON:-python3}"
 mkdir -p "$OUT"
 EXT="$($PY -c 'import sysconfig;print(sysconfig.get_config_var("EXT_SUFFIX"))')"
 SO="$OUT/yahmm$EXT"
+# the segmenter of SURVEY 8f-1 (PyPore/cparsers.pyx, FastStatSplit); same recipe, its own extension
+SO2="$OUT/cparsers$EXT"
+if [ -f "$REF/PyPore/cparsers.pyx" ] && { [ ! -f "$SO2" ] || [ "$REF/PyPore/cparsers.pyx" -nt "$SO2" ] || [ "${1:-}" = "--force" ]; }; then
+  $PY -m cython -2 "$REF/PyPore/cparsers.pyx" -o "$OUT/cparsers.c"
+  gcc -O2 -fPIC -shared -w -I"$($PY -c 'import numpy;print(numpy.get_include())')" \
+      -I"$($PY -c 'import sysconfig;print(sysconfig.get_paths()["include"])')" "$OUT/cparsers.c" -o "$SO2"
+  echo "oracle/_ref: built $SO2"
+fi
 if [ -f "$SO" ] && [ "$SO" -nt "$REF/yahmm/yahmm.pyx" ] && [ "${1:-}" != "--force" ]; then
   echo "oracle/_ref: up to date ($SO)"; exit 0
 fi

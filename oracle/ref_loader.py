@@ -52,3 +52,42 @@ def load_reference_yahmm():
         sys.modules.update({k: v for k, v in saved.items() if v is not None})
     _cached = mod
     return mod
+
+
+_cached_cparsers = None
+
+
+def cparsers_available():
+    return bool(glob.glob(os.path.join(_REF_DIR, "cparsers*.so")))
+
+
+def load_reference_cparsers():
+    """The compiled, unmodified PyPore/cparsers.pyx (FastStatSplit).  While it is imported `core` resolves to the
+    stub in oracle/stubs/pypore_core/ and itertools gets the Python-2 name `izip` (cparsers.pyx:16-17)."""
+    global _cached_cparsers
+    if _cached_cparsers is not None:
+        return _cached_cparsers
+    hits = sorted(glob.glob(os.path.join(_REF_DIR, "cparsers*.so")))
+    if not hits:
+        raise ImportError("oracle/_ref/cparsers*.so not built; run oracle/build_ref.sh")
+    import itertools
+    had_izip = hasattr(itertools, "izip")
+    if not had_izip:
+        itertools.izip = zip
+    saved_core = sys.modules.pop("core", None)
+    stub = os.path.join(_STUBS, "pypore_core")
+    sys.path.insert(0, stub)
+    try:
+        loader = importlib.machinery.ExtensionFileLoader("cparsers", hits[0])
+        spec = importlib.util.spec_from_file_location("cparsers", hits[0], loader=loader)
+        mod = importlib.util.module_from_spec(spec)
+        loader.exec_module(mod)
+    finally:
+        sys.path.remove(stub)
+        sys.modules.pop("core", None)
+        if saved_core is not None:
+            sys.modules["core"] = saved_core
+        if not had_izip:
+            del itertools.izip
+    _cached_cparsers = mod
+    return mod

@@ -4,6 +4,7 @@ Public surface (mirrors the one hot path of mitenjain/protpore):
   protpore_b200.yahmm        drop-in `yahmm` (Model / State / distributions), sweeps on the GPU
   protpore_b200.peptide_hmm  `HMM_Constructor`, `model_maker`, `prediction`, `kmer_current_map`
   protpore_b200.pypore       `Segment`, `Event.apply_hmm`, `apply_hmm_batch`
+  protpore_b200.parsers      `SpeedyStatSplit` / `FastStatSplit` (raw current -> segments), `parse_batch`
   protpore_b200.parallel     one-process-per-GPU sharding + NCCL allreduce for Baum-Welch
 """
 import sys

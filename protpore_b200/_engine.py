@@ -33,6 +33,12 @@ class PPModelDesc(ctypes.Structure):
                 ("emit_kind", _i32p), ("emit_p0", _f64p), ("emit_p1", _f64p), ("emit_logw", _f64p)]
 
 
+class PPStatSplitParams(ctypes.Structure):
+    """struct pp_statsplit_params (include/protpore_b200.h)."""
+    _fields_ = [("min_width", ctypes.c_int64), ("max_width", ctypes.c_int64), ("window_width", ctypes.c_int64),
+                ("min_gain", ctypes.c_double)]
+
+
 class EngineError(RuntimeError):
     def __init__(self, code, message):
         RuntimeError.__init__(self, "protpore_b200 error {}: {}".format(code, message))
@@ -64,6 +70,10 @@ ABI = [
                                                  _vp, _vp, _vp, _vp]),
     ("pp_sample_events", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int32, _vp]),
     ("pp_profile_get", ctypes.c_int, [_vp, _f64p, ctypes.c_int32]),
+    ("pp_statsplit_min_gain", ctypes.c_double, [ctypes.c_int64] + [ctypes.c_double] * 5),
+    ("pp_statsplit_batch", ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp, _vp,
+                                          _vp, ctypes.c_int64, _i64p]),
+    ("pp_statsplit_profile", ctypes.c_int, [ctypes.c_int, _f64p]),
     ("pp_launch_count", ctypes.c_int64, [_vp]),
     ("pp_model_stream", ctypes.c_uint64, [_vp]),
 ]
@@ -361,3 +371,71 @@ class Engine(object):
         obs = np.empty(int(offsets[-1]), dtype=np.float32)
         self._check(self._lib.pp_sample_events(self._h, _ptr(offsets), len(lengths), int(seed), PP_MEM_HOST, _ptr(obs)))
         return obs, offsets
+
+
+def statsplit_min_gain(window_width, min_gain_per_sample=None, false_positive_rate=None, prior_segments_per_second=None,
+                       sampling_freq=1.e5, cutoff_freq=None):
+    """pp_statsplit_min_gain: FastStatSplit.__init__'s threshold (cparsers.pyx:56-101).  Host arithmetic, no GPU."""
+    return load_library().pp_statsplit_min_gain(int(window_width), float(min_gain_per_sample or 0.0),
+                                                float(false_positive_rate or 0.0),
+                                                float(prior_segments_per_second or 0.0), float(sampling_freq),
+                                                float(cutoff_freq or 0.0))
+
+
+def statsplit_batch(current, offsets, min_width, max_width, window_width, min_gain, device=0, want_std=True,
+                    want_f32=False, capacity=None):
+    """pp_statsplit_batch.  `current` / `offsets`: numpy (host) or torch-CUDA (device) buffers, float64 / int64.
+    Returns (seg_offsets, seg_start, seg_mean, seg_std | None, seg_mean_f32 | None) of the same kind as the input."""
+    lib = load_library()
+    prm = PPStatSplitParams(int(min_width), int(max_width), int(window_width), float(min_gain))
+    n_events = len(offsets) - 1
+    total = ctypes.c_int64(0)
+    on_device = _is_device(current)
+    if on_device:
+        import torch
+        dev = current.device
+        assert current.dtype == torch.float64 and offsets.dtype == torch.int64 and offsets.is_cuda
+        seg_offsets = torch.empty(n_events + 1, dtype=torch.int64, device=dev)
+        mem = PP_MEM_DEVICE
+        device = dev.index if dev.index is not None else device
+
+        def alloc(n, dt):
+            return torch.empty(n, dtype={"i4": torch.int32, "f8": torch.float64, "f4": torch.float32}[dt], device=dev)
+    else:
+        current = np.ascontiguousarray(current, dtype=np.float64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        seg_offsets = np.empty(n_events + 1, dtype=np.int64)
+        mem = PP_MEM_HOST
+
+        def alloc(n, dt):
+            return np.empty(n, dtype=dt)
+
+    def call(cap, bufs):
+        rc = lib.pp_statsplit_batch(ctypes.byref(prm), int(device), _ptr(current), _ptr(offsets), n_events, mem,
+                                    _ptr(seg_offsets), _ptr(bufs[0]), _ptr(bufs[1]), _ptr(bufs[2]), _ptr(bufs[3]), cap,
+                                    ctypes.byref(total))
+        return rc
+
+    def make(cap):
+        return [alloc(cap, "i4"), alloc(cap, "f8"), alloc(cap, "f8") if want_std else None,
+                alloc(cap, "f4") if want_f32 else None]
+
+    if capacity is None:                      # an event of n samples has at most n // min_width + 1 segments
+        lens = (offsets[1:] - offsets[:-1])
+        capacity = int((lens // max(1, int(min_width))).sum()) + n_events
+    bufs = make(int(capacity))
+    rc = call(int(capacity), bufs)
+    if rc == PP_ERR_CAPACITY:
+        bufs = make(total.value)
+        rc = call(total.value, bufs)
+    if rc != PP_OK:
+        raise EngineError(rc, lib.pp_last_error().decode())
+    n = total.value
+    return (seg_offsets, bufs[0][:n], bufs[1][:n], None if bufs[2] is None else bufs[2][:n],
+            None if bufs[3] is None else bufs[3][:n])
+
+
+def statsplit_profile(device=0):
+    out = (ctypes.c_double * 3)()
+    load_library().pp_statsplit_profile(int(device), out)
+    return {"statsplit_ms": out[0], "segments_ms": out[1], "launches": int(out[2])}

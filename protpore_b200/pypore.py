@@ -44,6 +44,12 @@ class Event(Segment):
     def segment_means(self):
         return np.array([seg.mean for seg in self.segments])
 
+    def parse(self, parser, hmm=None):
+        """Split the event's current into segments (PyPore/DataTypes.py:292-332 without the hmm-merging branch)."""
+        self.segments = parser.parse(self.current)
+        self.n = len(self.segments)
+        return self.segments
+
     def apply_hmm(self, hmm, algorithm='viterbi'):
         """`getattr(hmm, algorithm)(segment means)` (PyPore/DataTypes.py:349-355, 62-68)."""
         return getattr(hmm, algorithm)(self.segment_means())

@@ -1,0 +1,159 @@
+"""FastStatSplit segmenter: the CPU oracle against golden vectors of the compiled reference, the host
+logic, and -- on a GPU -- the CUDA path through the C ABI against both."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import statsplit_oracle as so, ref_loader
+from protpore_b200 import _engine, parsers
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "statsplit.npz")
+
+
+def golden_cases():
+    g = np.load(GOLDEN)
+    for name in g["names"]:
+        name = str(name)
+        kw = json.loads(str(g[name + "__kw"]))
+        yield (name, kw, g[name + "__current"].astype(np.float64), float(g[name + "__min_gain"]),
+               g[name + "__starts"], g[name + "__means"], g[name + "__stds"])
+
+
+def staircase(rng, n_levels, lo, hi):
+    return np.concatenate([rng.normal(rng.uniform(25, 50), rng.uniform(0.4, 2.5), size=int(rng.integers(lo, hi)))
+                           for _ in range(n_levels)])
+
+
+CLI = dict(min_width=250, max_width=1000, window_width=2000, min_gain_per_sample=0.05)
+
+
+# ---------------------------------------------------------------------------------------- CPU: oracle, host logic
+def test_oracle_matches_golden_bit_for_bit():
+    n = 0
+    for name, kw, cur, gain, starts, means, stds in golden_cases():
+        gkw = {k: v for k, v in kw.items() if k not in ("min_width", "max_width")}
+        assert so.min_gain(**gkw) == gain, name
+        bp = so.parse(cur, kw["min_width"], kw["max_width"], kw["window_width"], gain=gain)
+        assert np.array_equal(np.concatenate([[0], bp]), starts), name
+        assert np.array_equal(so.segment_means(cur, bp), means), name
+        n += 1
+    assert n == 9
+
+
+def test_host_threshold_matches_golden():
+    """pp_statsplit_min_gain is host arithmetic: callable without a GPU, and bit-identical to the reference."""
+    for name, kw, cur, gain, starts, means, stds in golden_cases():
+        p = parsers.FastStatSplit(**kw)
+        assert p.min_gain == gain, name
+    with pytest.raises(AssertionError):
+        parsers.FastStatSplit(min_width=100, max_width=50)                     # cparsers.pyx:69-70
+    with pytest.raises(AssertionError):
+        parsers.SpeedyStatSplit(min_width=100, window_width=150)               # cparsers.pyx:71-72
+
+
+@pytest.mark.reference
+def test_oracle_matches_compiled_reference_on_fresh_events():
+    if not ref_loader.cparsers_available():
+        pytest.skip("oracle/_ref/cparsers*.so not built")
+    cp = ref_loader.load_reference_cparsers()
+    rng = np.random.default_rng(5)
+    for trial in range(12):
+        kw = CLI if trial % 2 == 0 else dict(min_width=60, max_width=3000, window_width=600,
+                                             prior_segments_per_second=25., false_positive_rate=10.)
+        cur = staircase(rng, int(rng.integers(2, 30)), 80, 1300)
+        ref = cp.FastStatSplit(**kw)
+        segs = ref.parse(cur)
+        bp = so.parse(cur, kw["min_width"], kw["max_width"], kw["window_width"], gain=ref.min_gain)
+        assert list(bp) == [s.start for s in segs][1:]
+        assert np.array_equal(so.segment_means(cur, bp), [s.mean for s in segs])
+
+
+def test_segmenter_fails_loudly_without_gpu():
+    if _engine.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_engine.EngineError):
+        parsers.SpeedyStatSplit(**CLI).parse(np.ones(1000))
+
+
+# ---------------------------------------------------------------------------------------- GPU: parity through the ABI
+def _check_event(cur, kw, gain, starts_gpu, means_gpu, stds_gpu, label):
+    bp, stats = so.parse(cur, kw["min_width"], kw["max_width"], kw["window_width"], gain=gain, with_stats=True)
+    want = np.concatenate([[0], bp])
+    if not np.array_equal(starts_gpu, want):
+        # the only accepted difference: a window whose two best gains tie within the accuracy of log()
+        assert stats[0] < 1e-9, (label, stats[0], starts_gpu, want)
+        return False
+    edges = np.append(want, len(cur))
+    m = np.array([np.mean(cur[a:b]) for a, b in zip(edges[:-1], edges[1:])])
+    s = np.array([np.std(cur[a:b]) for a, b in zip(edges[:-1], edges[1:])])
+    assert np.allclose(means_gpu, m, rtol=1e-12, atol=0), label
+    assert np.allclose(stds_gpu, s, rtol=1e-9, atol=1e-12), label
+    return True
+
+
+@pytest.mark.gpu
+def test_gpu_matches_golden():
+    for name, kw, cur, gain, starts, means, stds in golden_cases():
+        segs = parsers.SpeedyStatSplit(**kw).parse(cur)
+        got = np.array([s.start for s in segs])
+        assert np.array_equal(got, starts), name
+        assert np.allclose([s.mean for s in segs], means, rtol=1e-12, atol=0), name
+        assert np.allclose([s.std for s in segs], stds, rtol=1e-9, atol=1e-12), name
+        assert [s.end for s in segs] == list(starts[1:]) + [len(cur)]
+        assert all(len(s.current) == s.duration for s in segs)
+
+
+@pytest.mark.gpu
+def test_gpu_batch_matches_oracle_ragged():
+    rng = np.random.default_rng(11)
+    currents = [staircase(rng, int(rng.integers(1, 25)), 60, 1400) for _ in range(70)]
+    currents += [np.array([3.0]), rng.normal(40, 1, size=499), rng.normal(40, 1, size=501), rng.normal(40, 1, size=2)]
+    for kw in (CLI, dict(min_width=40, max_width=800, window_width=300)):
+        p = parsers.FastStatSplit(**kw)
+        off, start, mean, std, f32 = p.segment_means_batch(currents, want_std=True, want_f32=True)
+        assert off[0] == 0 and len(off) == len(currents) + 1
+        same = 0
+        for e, cur in enumerate(currents):
+            a, b = off[e], off[e + 1]
+            same += _check_event(cur, kw, p.min_gain, start[a:b], mean[a:b], std[a:b], (kw["min_width"], e))
+        assert same >= len(currents) - 1
+        assert np.array_equal(f32, mean.astype(np.float32))
+        # the batch call and the one-event call agree exactly
+        one = p.parse(currents[3])
+        assert [s.start for s in one] == list(start[off[3]:off[4]])
+
+
+@pytest.mark.gpu
+def test_gpu_device_resident_feeds_the_hmm():
+    """Device buffers in, device buffers out; seg_offsets / seg_mean_f32 go straight into the batched Viterbi."""
+    import torch
+    from protpore_b200 import peptide_hmm
+    rng = np.random.default_rng(3)
+    currents = [staircase(rng, int(rng.integers(3, 12)), 260, 700) for _ in range(40)]
+    cur, off = _engine.pack_events(currents, dtype=np.float64)
+    p = parsers.SpeedyStatSplit(**CLI)
+    h = p.segment_means_batch((cur, off), want_std=False, want_f32=True)
+    d = p.segment_means_batch((torch.from_numpy(cur).cuda(), torch.from_numpy(off).cuda()), want_std=False, want_f32=True)
+    assert np.array_equal(d[0].cpu().numpy(), h[0]) and np.array_equal(d[1].cpu().numpy(), h[1])
+    assert np.array_equal(d[2].cpu().numpy(), h[2]) and np.array_equal(d[4].cpu().numpy(), h[4])
+    model = peptide_hmm.pro_001_model()
+    eng = model.engine()
+    s_dev, l_dev, _ = eng.viterbi_batch(d[4], d[0], with_paths=False)
+    s_host, l_host, _ = eng.viterbi_batch(h[4], h[0], with_paths=False)
+    assert np.array_equal(np.asarray(s_dev.cpu() if hasattr(s_dev, "cpu") else s_dev), np.asarray(s_host))
+
+
+@pytest.mark.gpu
+def test_gpu_capacity_and_errors():
+    rng = np.random.default_rng(2)
+    cur, off = _engine.pack_events([staircase(rng, 10, 300, 600) for _ in range(5)], dtype=np.float64)
+    p = parsers.FastStatSplit(**CLI)
+    full = _engine.statsplit_batch(cur, off, p.min_width, p.max_width, p.window_width, p.min_gain)
+    small = _engine.statsplit_batch(cur, off, p.min_width, p.max_width, p.window_width, p.min_gain, capacity=2)   # retried
+    assert np.array_equal(full[1], small[1])
+    with pytest.raises(_engine.EngineError):
+        _engine.statsplit_batch(cur, np.array([0, 0, len(cur)]), p.min_width, p.max_width, p.window_width, p.min_gain)
+    with pytest.raises(_engine.EngineError):
+        _engine.statsplit_batch(cur, off, 0, 10, 20, 1.0)
