@@ -41,8 +41,10 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="score", choices=["score", "baum-welch"],
-                    help="score: forward + Viterbi (config 2, the contract line); baum-welch: one distributed BW iteration (config 3)")
+    ap.add_argument("--workload", default="score", choices=["score", "baum-welch", "segment"],
+                    help="score: forward + Viterbi (config 2, the contract line); baum-welch: one distributed BW iteration "
+                         "(config 3); segment: the FastStatSplit segmenter in front of the path (SURVEY 8f-1)")
+    ap.add_argument("--seg-events", type=int, default=20000, help="events per GPU of the segment workload (~18k samples each)")
     ap.add_argument("--bw-events", type=int, default=20000, help="events per GPU of the baum-welch workload")
     return ap.parse_args()
 
@@ -198,6 +200,138 @@ def bench_baum_welch(args, model, rank, world, local):
         dist.destroy_process_group()
     return 0
 
+# ---------------------------------------------------------------------------------------------
+# segment workload: raw current -> FastStatSplit breakpoints -> segment means
+# ---------------------------------------------------------------------------------------------
+SEG_KW = dict(min_width=250, max_width=1000, window_width=2000, min_gain_per_sample=0.05)   # peptide_hmm_v0.0.1.py:311-313, 426
+SEG_METRIC = "FastStatSplit segmentation of raw nanopore current (min_width 250, max_width 1000, window 2000), samples per second"
+
+
+def _seg_cpu_worker(args):
+    kind, shard, reps = args
+    if kind == "reference":
+        from oracle import ref_loader
+        parser = ref_loader.load_reference_cparsers().FastStatSplit(**SEG_KW)
+        fn = parser.parse
+    else:
+        from oracle import statsplit_oracle as so
+        gain = so.min_gain(window_width=SEG_KW["window_width"], min_gain_per_sample=SEG_KW["min_gain_per_sample"])
+        fn = lambda c: so.segment_means(c, so.parse(c, SEG_KW["min_width"], SEG_KW["max_width"], SEG_KW["window_width"], gain=gain))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for c in shard:
+            fn(c)
+    return time.perf_counter() - t0
+
+
+def seg_cpu(seed, per_worker=24, reps=200):
+    """The compiled reference segmenter (oracle/_ref/cparsers) on every host core over a bounded sample."""
+    import multiprocessing as mp
+    from oracle import ref_loader
+    kind = "reference" if ref_loader.cparsers_available() else "port"
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(seed)
+    evs = [np.concatenate([rng.normal(rng.uniform(25, 50), rng.uniform(0.4, 2.5), size=int(rng.integers(260, 1500)))
+                           for _ in range(21)]) for _ in range(cores * per_worker)]
+    samples = float(sum(len(c) for c in evs)) * reps
+    with mp.get_context("fork").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        pool.map(_seg_cpu_worker, [(kind, evs[w::cores], reps) for w in range(cores)])
+        dt = time.perf_counter() - t0
+    return dict(value=samples / dt / 1e9, unit="Gsamples/s", cores=cores, kind=kind, seconds=dt,
+                sample="{} synthetic events of ~18k samples x {} passes ({:.3g} samples), FastStatSplit.parse per event, "
+                       "{} worker processes".format(len(evs), reps, samples, cores)), dt
+
+
+def bench_segment(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    from protpore_b200 import parsers, _engine
+    dev = torch.device("cuda", local)
+    g = torch.Generator(device=dev).manual_seed(args.seed + rank)
+    n_ev, n_lev = args.seg_events, 21
+    dur = torch.randint(260, 1500, (n_ev, n_lev), generator=g, device=dev)
+    mu = 25 + 25 * torch.rand((n_ev, n_lev), generator=g, device=dev, dtype=torch.float64)
+    sd = 0.4 + 2.1 * torch.rand((n_ev, n_lev), generator=g, device=dev, dtype=torch.float64)
+    off = torch.zeros(n_ev + 1, dtype=torch.int64, device=dev)
+    off[1:] = torch.cumsum(dur.sum(1), 0)
+    total = int(off[-1])
+    cur = torch.repeat_interleave(mu.flatten(), dur.flatten()) + \
+        torch.repeat_interleave(sd.flatten(), dur.flatten()) * torch.randn(total, generator=g, device=dev, dtype=torch.float64)
+    parser = parsers.SpeedyStatSplit(device=local, **SEG_KW)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = parser.segment_means_batch((cur, off), want_std=False, want_f32=True)
+    n_seg = int(out[0][-1])
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _engine.statsplit_profile(local)["launches"]
+    barrier()
+    t0 = time.perf_counter()
+    k_ms = [0.0, 0.0, 0.0]
+    for _ in range(args.steps):
+        out = parser.segment_means_batch((cur, off), want_std=False, want_f32=True)
+        pr = _engine.statsplit_profile(local)
+        k_ms[0] += pr["statsplit_ms"]
+        k_ms[1] += pr["segments_ms"]
+        k_ms[2] += pr["cumsum_ms"]
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.summary()
+    launches = _engine.statsplit_profile(local)["launches"] - launches0
+    # e2e: pinned host current in, host segment arrays out
+    cur_h, off_h = cur.cpu().pin_memory().numpy(), off.cpu().numpy()
+    parser.segment_means_batch((cur_h, off_h), want_std=False, want_f32=True)
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        oh = parser.segment_means_batch((cur_h, off_h), want_std=False, want_f32=True)
+    barrier()
+    dt2 = time.perf_counter() - t1
+    t = torch.tensor([dt, dt2], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt, dt2 = float(t[0]), float(t[1])
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        ms = k_ms[0] / args.steps
+        # algorithmic HBM bytes per sample of k_statsplit: 8 read (current) + 16 written (c, c2) + 16 read back by the window
+        # scans (at least once; the windows overlap by half, the rest hits L1/L2) + 1 byte of the split map
+        alg = 41.0 * total
+        cpu = None if args.no_cpu_baseline else seg_cpu(args.seed)[0]
+        print(json.dumps({
+            "metric": SEG_METRIC, "value": total * world * args.steps / dt / 1e9, "unit": "Gsamples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "ours",
+            "config": {"workload": "{} events/GPU of 21 levels x 260-1500 samples (~18k samples, the CLI's slice), Gaussian "
+                                   "noise sd 0.4-2.5 pA, device-resident float64 current".format(n_ev),
+                       "samples_per_gpu": total, "segments_per_gpu": n_seg, "parallelism": "events sharded, dp{}".format(world),
+                       "l2_policy": "current + cumulative sums ({:.1f} GB) exceed the 126 MB L2".format(total * 24 / 1e9)},
+            "kernel_ms_per_step": {"k_cumsum": k_ms[2] / args.steps, "k_statsplit": ms, "k_segments": k_ms[1] / args.steps},
+            "roofline": {"bound": "hbm", "kernel": "k_statsplit", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg, "launch_ms": ms,
+                         "note": "fp64 log/divide bound, not HBM bound: ~2.3 candidate positions per sample, 2 logs + 4 divisions each"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": total * world * e2e_steps / dt2 / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": int(cur_h.nbytes + off_h.nbytes),
+                    "d2h_bytes_per_step": int(sum(a.nbytes for a in oh if a is not None)), "ms_per_step": dt2 / e2e_steps * 1e3},
+            "gpu_launches": int(launches), "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
 
 def main():
     args = parse()
@@ -205,6 +339,17 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if args.impl == "reference" and args.workload == "segment":
+        if rank != 0:
+            return 0
+        cpu, dt = seg_cpu(args.seed)
+        print(json.dumps({"metric": SEG_METRIC, "value": cpu["value"], "unit": "Gsamples/s", "n_gpus": args.gpus,
+                          "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+                          "config": {"workload": "synthetic events of ~18k samples; bounded CPU sample"}, "cpu_baseline": cpu,
+                          "e2e": {"value": cpu["value"], "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return 0
     if args.impl == "reference":
         if rank != 0:
             return 0
@@ -228,6 +373,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.workload == "segment":
+        return bench_segment(args, rank, world, local)
     import protpore_b200.yahmm as y
     y.Model.device = local
     model = peptide_hmm.pro_001_model()

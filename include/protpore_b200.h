@@ -192,9 +192,9 @@ int pp_statsplit_batch(const pp_statsplit_params *prm, int device, const double 
                        int64_t n_events, int32_t mem, int64_t *seg_offsets, int32_t *seg_start, double *seg_mean,
                        double *seg_std, float *seg_mean_f32, int64_t capacity, int64_t *seg_total);
 
-/* Device time of the last pp_statsplit_batch on `device`: out3 = {k_statsplit ms, k_segments ms, kernels launched
- * since the library was loaded}. */
-int pp_statsplit_profile(int device, double *out3);
+/* Device time of the last pp_statsplit_batch on `device`: out4 = {k_statsplit ms, k_segments ms, kernels launched
+ * since the library was loaded, k_cumsum ms}. */
+int pp_statsplit_profile(int device, double *out4);
 
 /* Number of usable CUDA devices (0 without a driver/GPU; never fails). */
 int pp_device_count(void);

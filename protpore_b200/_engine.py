@@ -436,6 +436,6 @@ def statsplit_batch(current, offsets, min_width, max_width, window_width, min_ga
 
 
 def statsplit_profile(device=0):
-    out = (ctypes.c_double * 3)()
+    out = (ctypes.c_double * 4)()
     load_library().pp_statsplit_profile(int(device), out)
-    return {"statsplit_ms": out[0], "segments_ms": out[1], "launches": int(out[2])}
+    return {"statsplit_ms": out[0], "segments_ms": out[1], "launches": int(out[2]), "cumsum_ms": out[3]}

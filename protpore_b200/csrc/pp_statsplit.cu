@@ -6,20 +6,18 @@
 // (_best_split_stepwise 157-178, _recursive_split 180-203) and hands the segment means to the HMM
 // (peptide_hmm_v0.0.1.py:443-466).  Here one CTA owns one event:
 //
-//   k_statsplit   phase 1  cumulative sums.  numpy.cumsum is a SEQUENTIAL float64 accumulation and every gain
-//                          is a difference of its entries, so the order of the additions is part of the result:
-//                          tiles of the current are staged in shared memory with coalesced loads, ONE thread
-//                          accumulates c and one thread (of another warp) c2 in the reference's order, and the
-//                          tile goes back to HBM/L2 with coalesced stores.  The serial part costs 2 of 256
-//                          threads; the other CTAs resident on the SM fill the issue slots meanwhile.
-//                 phase 2  the recursion as an explicit interval stack in shared memory.  A window scan is
+//   k_cumsum      cumulative sums.  numpy.cumsum is a SEQUENTIAL float64 accumulation and every gain is a difference
+//                 of its entries, so the order of the additions is part of the result: a chain cannot be
+//                 parallelised, but the 2 x n_events chains are independent.  One LANE owns one chain (a warp takes
+//                 16 events: lanes 0-15 accumulate c, lanes 16-31 c2 of the same events); 16 x 32-sample tiles are
+//                 staged through shared memory so that every global load and store is a coalesced 256-byte row.
+//   k_statsplit   (one CTA per event) the recursion as an explicit interval stack in shared memory.  A window scan is
 //                          parallel over the candidate positions: float64 gain with explicitly rounded
 //                          operations (no FMA contraction) and a (gain, position) arg-max whose tie rule --
 //                          lowest position among equal gains, gain strictly above the threshold -- is what the
-//                          reference's ascending strict-'>' scan leaves.  Splits are marked in a byte map, which
-//                          makes the output order (ascending = the reference's in-order concatenation) free.
-//   k_segments    compacts the byte map into segment starts (block scan) and reduces every segment to mean / std
-//                 with one warp per segment (Segment.mean / .std, PyPore/core.py:209-214).
+//                          reference's ascending strict-'>' scan leaves.  Splits go to an unordered per-event list.
+//   k_segments    rank-sorts the list (ascending = the reference's in-order concatenation) and reduces every segment to
+//                 mean / std with one warp per segment (Segment.mean / .std, PyPore/core.py:209-214).
 //
 // Float64 `log` here is CUDA's (<= 1 ulp), the reference's is glibc's: a window whose two best gains agree to
 // ~1e-13 relative could split elsewhere.  The CPU oracle reports that margin per event; tests accept a different
@@ -36,7 +34,8 @@ namespace pp {
 namespace {
 
 constexpr int kSegThreads = 256;
-constexpr int kSegTile = 512;          // samples staged per cumulative-sum tile
+constexpr int kCsWarps = 2;            // warps per CTA of k_cumsum
+constexpr int kCsEvents = 16;          // events per warp of k_cumsum (lane = event + 16 * {c, c2})
 constexpr int kSegStack = 1024;        // pending intervals per event (depth-first: bounded by the recursion depth)
 
 struct SegParams {
@@ -48,9 +47,21 @@ __device__ __forceinline__ bool better(double g, int i, double bg, int bi) {
     return g > bg || (g == bg && i >= 0 && i < bi);
 }
 
-// cparsers.pyx:157-178 -- all threads of the CTA call this with the same arguments and get the same answer
+// a / b for an integer-valued b with y = RN(1 / b): q0 = RN(a y), r = a - q0 b (exact in an FMA), q = RN(q0 + r y) is the
+// correctly rounded quotient (Markstein) -- 3 instructions instead of the ~35 of a float64 divide.  Checked bit for bit
+// against IEEE division on the GPU (tests/test_statsplit.py::test_gpu_division_by_reciprocal_is_exact).
+__device__ __forceinline__ double div_rcp(double a, double b, double y) {
+    const double q0 = __dmul_rn(a, y);
+    const double r = __fma_rn(-q0, b, a);
+    return __fma_rn(r, y, q0);
+}
+
+// cparsers.pyx:157-178 -- all threads of the CTA call this with the same arguments and get the same answer.
+// TABLE: s_rcp[n] = RN(1 / n) for n <= window_width is resident in shared memory (every segment length of a scan is
+// an integer below the window width); otherwise the reciprocal is computed per position.
+template <bool TABLE>
 __device__ int best_split_stepwise(const SegParams& P, const double* __restrict__ c, const double* __restrict__ c2,
-                                   int start, int end, double* s_gain, int* s_idx) {
+                                   int start, int end, double* s_gain, int* s_idx, const double* s_rcp) {
     if (end - start <= 2 * P.min_width) return -1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // var_c (31-38) with c[-1] = c2[-1] = 0: x - 0.0 and n - 0 are exact, so the start == 0 branch is the same arithmetic
@@ -65,10 +76,12 @@ __device__ int best_split_stepwise(const SegParams& P, const double* __restrict_
     for (int i = start + P.min_width + tid; i < end + 1 - P.min_width; i += kSegThreads) {
         const double ci = c[i - 1], c2i = c2[i - 1];
         const double nl = static_cast<double>(i - start), nh = static_cast<double>(end - i);
-        const double ml = __ddiv_rn(__dsub_rn(ci, cb), nl);
-        const double vl = __dsub_rn(__ddiv_rn(__dsub_rn(c2i, c2b), nl), __dmul_rn(ml, ml));
-        const double mh = __ddiv_rn(__dsub_rn(ce, ci), nh);
-        const double vh = __dsub_rn(__ddiv_rn(__dsub_rn(c2e, c2i), nh), __dmul_rn(mh, mh));
+        const double yl = TABLE ? s_rcp[i - start] : __drcp_rn(nl);
+        const double yh = TABLE ? s_rcp[end - i] : __drcp_rn(nh);
+        const double ml = div_rcp(__dsub_rn(ci, cb), nl, yl);
+        const double vl = __dsub_rn(div_rcp(__dsub_rn(c2i, c2b), nl, yl), __dmul_rn(ml, ml));
+        const double mh = div_rcp(__dsub_rn(ce, ci), nh, yh);
+        const double vh = __dsub_rn(div_rcp(__dsub_rn(c2e, c2i), nh, yh), __dmul_rn(mh, mh));
         const double low = __dmul_rn(nl, log(vl));
         const double high = __dmul_rn(nh, log(vh));
         const double gain = __dsub_rn(var_summed, __dadd_rn(low, high));
@@ -91,53 +104,114 @@ __device__ int best_split_stepwise(const SegParams& P, const double* __restrict_
     return ri;
 }
 
+// test hook: q[i] = a[i] / b[i] by IEEE division and by div_rcp; returns the number of mismatching bit patterns
+__global__ void k_div_check(const double* __restrict__ a, const int* __restrict__ b, int n, unsigned long long* bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double bd = static_cast<double>(b[i]);
+    const double q = __ddiv_rn(a[i], bd), p = div_rcp(a[i], bd, __drcp_rn(bd));
+    if (__double_as_longlong(q) != __double_as_longlong(p) && !(q == 0.0 && p == 0.0)) {   // a = -0.0 gives +0.0: log(+-0) is the same -inf
+        atomicAdd(bad, 1ULL); atomicMin(bad + 1, static_cast<unsigned long long>(i)); }
+}
+
+// c = cumsum(x), c2 = cumsum(x * x), sequential float64 per event (cparsers.pyx:110-111)
+__global__ void __launch_bounds__(kCsWarps * 32)
+k_cumsum(const double* __restrict__ current, const int64_t* __restrict__ offsets, int n_events, double* __restrict__ cs,
+         double* __restrict__ cs2) {
+    constexpr int ROW = 33;                                    // 32 samples + 1: lanes of different events hit different banks
+    constexpr int ARR = kCsEvents * ROW + 1;                   // c2 rows shifted by one bank pair against the c rows
+    __shared__ double s_in[kCsWarps][kCsEvents * ROW];
+    __shared__ double s_out[kCsWarps][2 * ARR];
+    __shared__ int64_t s_off[kCsWarps][kCsEvents];
+    __shared__ int s_n[kCsWarps][kCsEvents];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* xin = s_in[warp];
+    double* xout = s_out[warp];
+    const int ev0 = (blockIdx.x * kCsWarps + warp) * kCsEvents;
+    if (ev0 >= n_events) return;
+    const int my_e = lane & (kCsEvents - 1), arr = lane >> 4;
+    int64_t my_off = 0;
+    int my_n = 0;
+    if (ev0 + my_e < n_events) {
+        my_off = offsets[ev0 + my_e];
+        my_n = static_cast<int>(offsets[ev0 + my_e + 1] - my_off);
+    }
+    int nmax = my_n;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+    if (lane < kCsEvents) { s_off[warp][lane] = my_off; s_n[warp][lane] = my_n; }
+    __syncwarp();
+    // software pipeline: the 16 row loads of tile t + 1 are in flight while the lanes walk tile t
+    double pre[kCsEvents];
+#pragma unroll
+    for (int e = 0; e < kCsEvents; ++e) pre[e] = lane < s_n[warp][e] ? current[s_off[warp][e] + lane] : 0.0;
+    double s = 0.0;
+    for (int t0 = 0; t0 < nmax; t0 += 32) {
+#pragma unroll
+        for (int e = 0; e < kCsEvents; ++e) xin[e * ROW + lane] = pre[e];
+        __syncwarp();
+        if (t0 + 32 < nmax) {
+            const int i = t0 + 32 + lane;
+#pragma unroll
+            for (int e = 0; e < kCsEvents; ++e) pre[e] = i < s_n[warp][e] ? current[s_off[warp][e] + i] : 0.0;
+        }
+        const int cnt = min(32, my_n - t0);
+        const double* xr = xin + my_e * ROW;
+        double* outr = xout + arr * ARR + my_e * ROW;
+        if (t0 == 0 && cnt > 0) {                              // c[0] = x[0] (no 0.0 + x: keeps a -0.0)
+            const double v = xr[0];
+            s = arr ? __dmul_rn(v, v) : v;
+            outr[0] = s;
+        }
+#pragma unroll 8
+        for (int k = (t0 == 0 ? 1 : 0); k < 32; ++k) {
+            if (k < cnt) {
+                const double v = xr[k];
+                s = __dadd_rn(s, arr ? __dmul_rn(v, v) : v);
+                outr[k] = s;
+            }
+        }
+        __syncwarp();
+        const int i = t0 + lane;
+#pragma unroll
+        for (int e = 0; e < kCsEvents; ++e) {                  // 2 x 16 rows back, coalesced
+            if (i < s_n[warp][e]) {
+                const int64_t oe = s_off[warp][e];
+                cs[oe + i] = xout[e * ROW + lane];
+                cs2[oe + i] = xout[ARR + e * ROW + lane];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <bool TABLE>
 __global__ void __launch_bounds__(kSegThreads)
-k_statsplit(const SegParams P, const double* __restrict__ current, const int64_t* __restrict__ offsets, int n_events,
-            double* __restrict__ cs, double* __restrict__ cs2, unsigned char* __restrict__ marks,
+k_statsplit(const SegParams P, const int64_t* __restrict__ offsets, int n_events,
+            const double* __restrict__ cs, const double* __restrict__ cs2, int32_t* __restrict__ splits,
             int32_t* __restrict__ seg_count, int32_t* __restrict__ status) {
-    __shared__ double s_x[kSegTile], s_c[kSegTile], s_c2[kSegTile];
     __shared__ int2 s_stack[kSegStack];
     __shared__ double s_gain[kSegThreads / 32];
     __shared__ int s_idx[kSegThreads / 32];
     __shared__ int s_sp, s_fail;
+    extern __shared__ double s_rcp[];
     const int tid = threadIdx.x;
+    if (TABLE) {
+        for (int k = tid; k <= P.window_width; k += kSegThreads) s_rcp[k] = k > 0 ? __drcp_rn(static_cast<double>(k)) : 0.0;
+        __syncthreads();
+    }
     for (int ev = blockIdx.x; ev < n_events; ev += gridDim.x) {
         const int64_t off = offsets[ev];
         const int n = static_cast<int>(offsets[ev + 1] - off);
-        const double* x = current + off;
-        double* c = cs + off;
-        double* c2 = cs2 + off;
-        unsigned char* mk = marks + off;
+        const double* c = cs + off;
+        const double* c2 = cs2 + off;
+        int32_t* sl = splits + (off / P.min_width + ev);       // room for n / min_width + 1 entries per event: sum floor(n_j / w) <= floor(off / w)
 
-        // ---- phase 1: c = cumsum(x), c2 = cumsum(x * x), sequential float64 (cparsers.pyx:110-111)
-        double run = 0.0;                   // thread 0 carries c, thread 32 carries c2
-        for (int t0 = 0; t0 < n; t0 += kSegTile) {
-            const int cnt = min(kSegTile, n - t0);
-            for (int k = tid; k < cnt; k += kSegThreads) s_x[k] = x[t0 + k];
-            __syncthreads();
-            if (tid == 0) {
-                double s = run;
-                int k = 0;
-                if (t0 == 0) { s = s_x[0]; s_c[0] = s; k = 1; }
-#pragma unroll 8
-                for (; k < cnt; ++k) { s = __dadd_rn(s, s_x[k]); s_c[k] = s; }
-                run = s;
-            } else if (tid == 32) {
-                double s = run;
-                int k = 0;
-                if (t0 == 0) { s = __dmul_rn(s_x[0], s_x[0]); s_c2[0] = s; k = 1; }
-#pragma unroll 8
-                for (; k < cnt; ++k) { s = __dadd_rn(s, __dmul_rn(s_x[k], s_x[k])); s_c2[k] = s; }
-                run = s;
-            }
-            __syncthreads();
-            for (int k = tid; k < cnt; k += kSegThreads) { c[t0 + k] = s_c[k]; c2[t0 + k] = s_c2[k]; }
-        }
         if (tid == 0) { s_stack[0] = make_int2(0, n); s_sp = 1; s_fail = 0; }
         int n_splits = 0;                   // thread 0 only
-        __syncthreads();                    // the sums are visible to the whole CTA from here on
+        __syncthreads();
 
-        // ---- phase 2: _recursive_split (180-203) with an explicit stack, left part first
+        // _recursive_split (180-203) with an explicit stack, left part first
         while (true) {
             const int sp = s_sp;
             if (sp == 0) break;
@@ -154,7 +228,7 @@ k_statsplit(const SegParams P, const double* __restrict__ current, const int64_t
                     break;
                 }
                 const int pe = static_cast<int>(min(static_cast<long long>(end), ps + P.window_width));
-                split_at = best_split_stepwise(P, c, c2, static_cast<int>(ps), pe, s_gain, s_idx);
+                split_at = best_split_stepwise<TABLE>(P, c, c2, static_cast<int>(ps), pe, s_gain, s_idx, s_rcp);
                 if (split_at >= 0) break;
             }
             if (split_at == -1 && static_cast<long long>(end) - start > P.max_width)          // 198-201
@@ -167,8 +241,7 @@ k_statsplit(const SegParams P, const double* __restrict__ current, const int64_t
                         s_fail = 1;                                  // stack exhausted or a split that cannot terminate
                         top = 0;
                     } else {
-                        mk[split_at] = 1;
-                        ++n_splits;
+                        sl[n_splits++] = split_at;
                         s_stack[top++] = make_int2(split_at, end);
                         if (!right_only) s_stack[top++] = make_int2(start, split_at);
                     }
@@ -185,39 +258,33 @@ k_statsplit(const SegParams P, const double* __restrict__ current, const int64_t
     }
 }
 
-// byte map -> segment starts, then mean / std of every segment (one warp per segment)
+// unordered split list -> ascending segment starts (rank sort; the splits of an event are distinct), then mean / std of
+// every segment with one warp per segment
+constexpr int kSegSortCap = 2048;
 __global__ void __launch_bounds__(kSegThreads)
-k_segments(const double* __restrict__ current, const int64_t* __restrict__ offsets, int n_events,
-           const unsigned char* __restrict__ marks, const int64_t* __restrict__ seg_offsets,
+k_segments(const double* __restrict__ current, const int64_t* __restrict__ offsets, int n_events, int min_width,
+           const int32_t* __restrict__ splits, const int64_t* __restrict__ seg_offsets,
            int32_t* __restrict__ seg_start, double* __restrict__ seg_mean, double* __restrict__ seg_std,
            float* __restrict__ seg_mean_f32) {
-    __shared__ int s_warp[kSegThreads / 32];
-    __shared__ int s_base;
+    __shared__ int s_split[kSegSortCap];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int ev = blockIdx.x; ev < n_events; ev += gridDim.x) {
         const int64_t off = offsets[ev];
         const int n = static_cast<int>(offsets[ev + 1] - off);
         const int64_t so = seg_offsets[ev];
         const int n_seg = static_cast<int>(seg_offsets[ev + 1] - so);
-        const unsigned char* mk = marks + off;
-        if (tid == 0) { s_base = 1; seg_start[so] = 0; }
+        const int k = n_seg - 1;
+        const int32_t* sl = splits + (off / min_width + ev);
+        const bool in_smem = k <= kSegSortCap;
+        if (in_smem) for (int j = tid; j < k; j += kSegThreads) s_split[j] = sl[j];
+        if (tid == 0) seg_start[so] = 0;
         __syncthreads();
-        for (int t0 = 0; t0 < n; t0 += kSegThreads) {
-            const int i = t0 + tid;
-            const bool m = i < n && mk[i] != 0;
-            const unsigned b = __ballot_sync(0xffffffffu, m);
-            if (lane == 0) s_warp[warp] = __popc(b);
-            __syncthreads();
-            int before = s_base;
-            for (int w = 0; w < warp; ++w) before += s_warp[w];
-            if (m) seg_start[so + before + __popc(b & ((1u << lane) - 1u))] = i;
-            __syncthreads();
-            if (tid == 0) {
-                int t = 0;
-                for (int w = 0; w < kSegThreads / 32; ++w) t += s_warp[w];
-                s_base += t;
-            }
-            __syncthreads();
+        for (int j = tid; j < k; j += kSegThreads) {
+            const int v = in_smem ? s_split[j] : sl[j];
+            int rank = 0;
+            if (in_smem) for (int q = 0; q < k; ++q) rank += s_split[q] < v;
+            else for (int q = 0; q < k; ++q) rank += sl[q] < v;
+            seg_start[so + 1 + rank] = v;
         }
         __threadfence_block();
         __syncthreads();
@@ -249,11 +316,11 @@ k_segments(const double* __restrict__ current, const int64_t* __restrict__ offse
 struct SegCtx {
     int device = -1;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int sm_count = 0;
     DevBuf d_cur, d_off, d_c, d_c2, d_marks, d_count, d_status, d_segoff, d_start, d_mean, d_std, d_mean32;
     int64_t launches = 0;
-    float last_ms[2] = {0.f, 0.f};
+    float last_ms[3] = {0.f, 0.f, 0.f};
 };
 std::mutex g_seg_mutex;
 std::vector<SegCtx*> g_seg_ctx;
@@ -355,10 +422,9 @@ int pp_statsplit_batch(const pp_statsplit_params* prm, int device, const double*
     }
     PP_CUDA(C->d_c.reserve(static_cast<size_t>(total) * 8));
     PP_CUDA(C->d_c2.reserve(static_cast<size_t>(total) * 8));
-    PP_CUDA(C->d_marks.reserve(static_cast<size_t>(total)));
+    PP_CUDA(C->d_marks.reserve(static_cast<size_t>(total / prm->min_width + ne + 1) * 4));       // split lists
     PP_CUDA(C->d_count.reserve(static_cast<size_t>(ne) * 4));
     PP_CUDA(C->d_status.reserve(16));
-    PP_CUDA(cudaMemsetAsync(C->d_marks.p, 0, static_cast<size_t>(total), s));
     PP_CUDA(cudaMemsetAsync(C->d_status.p, 0, 16, s));
 
     SegParams P;
@@ -367,11 +433,27 @@ int pp_statsplit_batch(const pp_statsplit_params* prm, int device, const double*
     P.window_width = static_cast<int>(prm->window_width);
     P.step = static_cast<int>(prm->window_width / 2);
     P.min_gain = prm->min_gain;
-    const int grid = std::min(ne, C->sm_count * 8);
+    // reciprocal table in shared memory while it leaves room for >= 5 CTAs per SM
+    const bool table = prm->window_width <= 4096;
+    const size_t dyn = table ? static_cast<size_t>(prm->window_width + 1) * 8 : 0;
+    int per_sm = 4;
+    if (table) PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_statsplit<true>, kSegThreads, dyn));
+    else PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_statsplit<false>, kSegThreads, dyn));
+    const int grid = std::min(ne, C->sm_count * std::max(1, per_sm));
     PP_CUDA(cudaEventRecord(C->ev[0], s));
-    k_statsplit<<<grid, kSegThreads, 0, s>>>(P, d_cur, d_off, ne, C->d_c.as<double>(), C->d_c2.as<double>(),
-                                             C->d_marks.as<unsigned char>(), C->d_count.as<int32_t>(),
-                                             C->d_status.as<int32_t>());
+    k_cumsum<<<(ne + kCsWarps * kCsEvents - 1) / (kCsWarps * kCsEvents), kCsWarps * 32, 0, s>>>(
+        d_cur, d_off, ne, C->d_c.as<double>(), C->d_c2.as<double>());
+    PP_CUDA(cudaGetLastError());
+    PP_CUDA(cudaEventRecord(C->ev[4], s));
+    ++C->launches;
+    if (table)
+        k_statsplit<true><<<grid, kSegThreads, dyn, s>>>(P, d_off, ne, C->d_c.as<double>(), C->d_c2.as<double>(),
+                                                         C->d_marks.as<int32_t>(), C->d_count.as<int32_t>(),
+                                                         C->d_status.as<int32_t>());
+    else
+        k_statsplit<false><<<grid, kSegThreads, 0, s>>>(P, d_off, ne, C->d_c.as<double>(), C->d_c2.as<double>(),
+                                                        C->d_marks.as<int32_t>(), C->d_count.as<int32_t>(),
+                                                        C->d_status.as<int32_t>());
     PP_CUDA(cudaGetLastError());
     PP_CUDA(cudaEventRecord(C->ev[1], s));
     ++C->launches;
@@ -416,7 +498,7 @@ int pp_statsplit_batch(const pp_statsplit_params* prm, int device, const double*
         if (seg_mean_f32) { PP_CUDA(C->d_mean32.reserve(static_cast<size_t>(n_seg) * 4)); d_mean32 = C->d_mean32.as<float>(); }
     }
     PP_CUDA(cudaEventRecord(C->ev[2], s));
-    k_segments<<<grid, kSegThreads, 0, s>>>(d_cur, d_off, ne, C->d_marks.as<unsigned char>(), d_segoff, d_start, d_mean,
+    k_segments<<<grid, kSegThreads, 0, s>>>(d_cur, d_off, ne, P.min_width, C->d_marks.as<int32_t>(), d_segoff, d_start, d_mean,
                                             d_std, d_mean32);
     PP_CUDA(cudaGetLastError());
     PP_CUDA(cudaEventRecord(C->ev[3], s));
@@ -428,20 +510,40 @@ int pp_statsplit_batch(const pp_statsplit_params* prm, int device, const double*
         if (seg_mean_f32) PP_CUDA(cudaMemcpyAsync(seg_mean_f32, d_mean32, static_cast<size_t>(n_seg) * 4, cudaMemcpyDeviceToHost, s));
     }
     PP_CUDA(cudaStreamSynchronize(s));
-    PP_CUDA(cudaEventElapsedTime(&C->last_ms[0], C->ev[0], C->ev[1]));
+    PP_CUDA(cudaEventElapsedTime(&C->last_ms[2], C->ev[0], C->ev[4]));
+    PP_CUDA(cudaEventElapsedTime(&C->last_ms[0], C->ev[4], C->ev[1]));
     PP_CUDA(cudaEventElapsedTime(&C->last_ms[1], C->ev[2], C->ev[3]));
     return PP_OK;
 }
 
-int pp_statsplit_profile(int device, double* out3) {
+// Test hook (not in the public header): counts a[i] / b[i] results of the reciprocal division that differ from IEEE division.
+int pp_debug_div_check(int device, const double* a_host, const int32_t* b_host, int64_t n, int64_t* mismatches) {
+    if (!a_host || !b_host || !mismatches || n < 0) { set_error("null argument"); return PP_ERR_ARG; }
+    PP_CUDA(cudaSetDevice(device));
+    double* da = nullptr; int* db = nullptr; unsigned long long* dbad = nullptr; unsigned long long bad[2] = {0, ~0ULL};
+    PP_CUDA(cudaMalloc(&da, n * 8 + 8)); PP_CUDA(cudaMalloc(&db, n * 4 + 8)); PP_CUDA(cudaMalloc(&dbad, 16));
+    PP_CUDA(cudaMemcpy(da, a_host, n * 8, cudaMemcpyHostToDevice));
+    PP_CUDA(cudaMemcpy(db, b_host, n * 4, cudaMemcpyHostToDevice));
+    PP_CUDA(cudaMemcpy(dbad, bad, 16, cudaMemcpyHostToDevice));
+    if (n > 0) k_div_check<<<static_cast<unsigned>((n + 255) / 256), 256>>>(da, db, static_cast<int>(n), dbad);
+    PP_CUDA(cudaMemcpy(bad, dbad, 16, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dbad);
+    mismatches[0] = static_cast<int64_t>(bad[0]);
+    mismatches[1] = static_cast<int64_t>(bad[1]);
+    return PP_OK;
+}
+
+int pp_statsplit_profile(int device, double* out4) {
+    double* out3 = out4;
     if (!out3) { set_error("null argument"); return PP_ERR_ARG; }
     std::lock_guard<std::mutex> lock(g_seg_mutex);
-    out3[0] = out3[1] = out3[2] = 0.0;
+    out3[0] = out3[1] = out3[2] = out3[3] = 0.0;
     for (SegCtx* c : g_seg_ctx)
         if (c->device == device) {
             out3[0] = c->last_ms[0];
             out3[1] = c->last_ms[1];
             out3[2] = static_cast<double>(c->launches);
+            out3[3] = c->last_ms[2];
         }
     return PP_OK;
 }

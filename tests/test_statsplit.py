@@ -157,3 +157,36 @@ def test_gpu_capacity_and_errors():
         _engine.statsplit_batch(cur, np.array([0, 0, len(cur)]), p.min_width, p.max_width, p.window_width, p.min_gain)
     with pytest.raises(_engine.EngineError):
         _engine.statsplit_batch(cur, off, 0, 10, 20, 1.0)
+
+
+@pytest.mark.gpu
+def test_gpu_division_by_reciprocal_is_exact():
+    """k_statsplit divides by segment lengths through a reciprocal (3 instructions); it must be IEEE division bit for bit."""
+    import ctypes
+    lib = _engine.load_library()
+    rng = np.random.default_rng(9)
+    n = 1 << 22
+    b = np.concatenate([np.arange(1, 1 << 20), rng.integers(1, 2 ** 31 - 1, size=n - (1 << 20) + 1)]).astype(np.int32)
+    mant = rng.integers(0, 1 << 52, size=n, dtype=np.uint64)
+    expo = rng.integers(1023 - 40, 1023 + 60, size=n, dtype=np.uint64)
+    sign = rng.integers(0, 2, size=n, dtype=np.uint64)
+    a = ((sign << np.uint64(63)) | (expo << np.uint64(52)) | mant).view(np.float64)
+    a[:4096] = np.repeat(rng.normal(0, 1e6, size=64), 64) * b[:4096]          # exact and near-exact quotients
+    a[4096:4100] = [0.0, -0.0, 1.0, 3.0]
+    bad = (ctypes.c_int64 * 2)()                      # {mismatches, first mismatching index}; +-0 counts as equal
+    lib.pp_debug_div_check.restype = ctypes.c_int
+    lib.pp_debug_div_check.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
+    assert lib.pp_debug_div_check(0, a.ctypes.data, b.ctypes.data, n, bad) == 0
+    assert bad[0] == 0, (bad[0], a[bad[1]], b[bad[1]])
+
+
+@pytest.mark.gpu
+def test_gpu_wide_window_takes_the_tableless_kernel():
+    """window_width > 4096: reciprocals per position instead of the shared-memory table; same breakpoints."""
+    rng = np.random.default_rng(21)
+    currents = [staircase(rng, 12, 900, 4000) for _ in range(6)]
+    kw = dict(min_width=100, max_width=1000000, window_width=10000)                 # the reference's defaults
+    p = parsers.FastStatSplit(**kw)
+    off, start, mean, std, _ = p.segment_means_batch(currents, want_std=True)
+    for e, cur in enumerate(currents):
+        assert _check_event(cur, kw, p.min_gain, start[off[e]:off[e + 1]], mean[off[e]:off[e + 1]], std[off[e]:off[e + 1]], e)
