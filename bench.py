@@ -489,8 +489,16 @@ def main():
     bytes_col = ptr_bytes_row + 4                        # packed traceback ordinals written + one float32 mean read
     vit_bytes = float(total_obs) * bytes_col
     achieved = vit_bytes / (vit_ms * 1e-3) / 1e9
+    # measured DRAM traffic of one launch (ncu capture of this exact batch, committed under profiles/); null for other batches
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_viterbi_lane"]
+        if (tr["events"], tr["min_len"], tr["max_len"], tr["seed"]) == (args.events, args.min_len, args.max_len, args.seed):
+            traffic = float(tr["dram_bytes_read"] + tr["dram_bytes_write"])
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": "k_viterbi_lane", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-            "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": None,
+            "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": traffic,
             "algorithmic_bytes_per_launch": vit_bytes, "launch_ms": vit_ms}
     b = model._baked
     ne = model.silent_start

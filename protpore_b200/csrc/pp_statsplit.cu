@@ -34,7 +34,7 @@ namespace pp {
 namespace {
 
 constexpr int kSegThreads = 256;
-constexpr int kCsWarps = 2;            // warps per CTA of k_cumsum
+constexpr int kCsWarps = 4;            // warps per CTA of k_cumsum
 constexpr int kCsEvents = 16;          // events per warp of k_cumsum (lane = event + 16 * {c, c2})
 constexpr int kSegStack = 1024;        // pending intervals per event (depth-first: bounded by the recursion depth)
 
@@ -114,19 +114,19 @@ __global__ void k_div_check(const double* __restrict__ a, const int* __restrict_
         atomicAdd(bad, 1ULL); atomicMin(bad + 1, static_cast<unsigned long long>(i)); }
 }
 
-// c = cumsum(x), c2 = cumsum(x * x), sequential float64 per event (cparsers.pyx:110-111)
+// c = cumsum(x), c2 = cumsum(x * x), sequential float64 per event (cparsers.pyx:110-111).
+// Shared memory per warp: [c | c2][16 events][32 samples + 1]; the staging pass writes x and x * x, every lane then
+// accumulates ITS row in place, and the rows go back to global memory as coalesced 256-byte stores.
 __global__ void __launch_bounds__(kCsWarps * 32)
 k_cumsum(const double* __restrict__ current, const int64_t* __restrict__ offsets, int n_events, double* __restrict__ cs,
          double* __restrict__ cs2) {
     constexpr int ROW = 33;                                    // 32 samples + 1: lanes of different events hit different banks
     constexpr int ARR = kCsEvents * ROW + 1;                   // c2 rows shifted by one bank pair against the c rows
-    __shared__ double s_in[kCsWarps][kCsEvents * ROW];
-    __shared__ double s_out[kCsWarps][2 * ARR];
+    __shared__ double s_tile[kCsWarps][2 * ARR];
     __shared__ int64_t s_off[kCsWarps][kCsEvents];
     __shared__ int s_n[kCsWarps][kCsEvents];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* xin = s_in[warp];
-    double* xout = s_out[warp];
+    double* t = s_tile[warp];
     const int ev0 = (blockIdx.x * kCsWarps + warp) * kCsEvents;
     if (ev0 >= n_events) return;
     const int my_e = lane & (kCsEvents - 1), arr = lane >> 4;
@@ -136,49 +136,63 @@ k_cumsum(const double* __restrict__ current, const int64_t* __restrict__ offsets
         my_off = offsets[ev0 + my_e];
         my_n = static_cast<int>(offsets[ev0 + my_e + 1] - my_off);
     }
-    int nmax = my_n;
+    int nmax = my_n, nmin = my_n;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+    for (int o = 8; o > 0; o >>= 1) {
+        nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+        nmin = min(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
+    }
     if (lane < kCsEvents) { s_off[warp][lane] = my_off; s_n[warp][lane] = my_n; }
     __syncwarp();
+    int64_t offe[kCsEvents];
+#pragma unroll
+    for (int e = 0; e < kCsEvents; ++e) offe[e] = s_off[warp][e] + lane;
     // software pipeline: the 16 row loads of tile t + 1 are in flight while the lanes walk tile t
     double pre[kCsEvents];
 #pragma unroll
-    for (int e = 0; e < kCsEvents; ++e) pre[e] = lane < s_n[warp][e] ? current[s_off[warp][e] + lane] : 0.0;
+    for (int e = 0; e < kCsEvents; ++e) pre[e] = lane < s_n[warp][e] ? current[offe[e]] : 0.0;
     double s = 0.0;
+    double* r = t + arr * ARR + my_e * ROW;                    // this lane's row
     for (int t0 = 0; t0 < nmax; t0 += 32) {
+        const bool full = t0 + 32 <= nmin;                     // no row ends inside this tile (warp-uniform)
 #pragma unroll
-        for (int e = 0; e < kCsEvents; ++e) xin[e * ROW + lane] = pre[e];
+        for (int e = 0; e < kCsEvents; ++e) {
+            t[e * ROW + lane] = pre[e];
+            t[ARR + e * ROW + lane] = __dmul_rn(pre[e], pre[e]);
+        }
         __syncwarp();
-        if (t0 + 32 < nmax) {
+        if (t0 + 64 <= nmin) {
+#pragma unroll
+            for (int e = 0; e < kCsEvents; ++e) pre[e] = current[offe[e] + t0 + 32];
+        } else if (t0 + 32 < nmax) {
             const int i = t0 + 32 + lane;
 #pragma unroll
-            for (int e = 0; e < kCsEvents; ++e) pre[e] = i < s_n[warp][e] ? current[s_off[warp][e] + i] : 0.0;
+            for (int e = 0; e < kCsEvents; ++e) pre[e] = i < s_n[warp][e] ? current[offe[e] + t0 + 32] : 0.0;
         }
-        const int cnt = min(32, my_n - t0);
-        const double* xr = xin + my_e * ROW;
-        double* outr = xout + arr * ARR + my_e * ROW;
-        if (t0 == 0 && cnt > 0) {                              // c[0] = x[0] (no 0.0 + x: keeps a -0.0)
-            const double v = xr[0];
-            s = arr ? __dmul_rn(v, v) : v;
-            outr[0] = s;
-        }
-#pragma unroll 8
-        for (int k = (t0 == 0 ? 1 : 0); k < 32; ++k) {
-            if (k < cnt) {
-                const double v = xr[k];
-                s = __dadd_rn(s, arr ? __dmul_rn(v, v) : v);
-                outr[k] = s;
-            }
+        if (full && t0 > 0) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) { s = __dadd_rn(s, r[k]); r[k] = s; }
+        } else {
+            const int cnt = min(32, my_n - t0);
+            int k = 0;
+            if (t0 == 0 && cnt > 0) { s = r[0]; k = 1; }       // c[0] = x[0] (no 0.0 + x: keeps a -0.0)
+            for (; k < cnt; ++k) { s = __dadd_rn(s, r[k]); r[k] = s; }
         }
         __syncwarp();
-        const int i = t0 + lane;
+        if (full) {
 #pragma unroll
-        for (int e = 0; e < kCsEvents; ++e) {                  // 2 x 16 rows back, coalesced
-            if (i < s_n[warp][e]) {
-                const int64_t oe = s_off[warp][e];
-                cs[oe + i] = xout[e * ROW + lane];
-                cs2[oe + i] = xout[ARR + e * ROW + lane];
+            for (int e = 0; e < kCsEvents; ++e) {              // 2 x 16 rows back, coalesced
+                cs[offe[e] + t0] = t[e * ROW + lane];
+                cs2[offe[e] + t0] = t[ARR + e * ROW + lane];
+            }
+        } else {
+            const int i = t0 + lane;
+#pragma unroll
+            for (int e = 0; e < kCsEvents; ++e) {
+                if (i < s_n[warp][e]) {
+                    cs[offe[e] + t0] = t[e * ROW + lane];
+                    cs2[offe[e] + t0] = t[ARR + e * ROW + lane];
+                }
             }
         }
         __syncwarp();
