@@ -46,7 +46,7 @@ typedef enum pp_status {
 
 typedef enum pp_mem { PP_MEM_HOST = 0, PP_MEM_DEVICE = 1 } pp_mem;
 typedef enum pp_dtype { PP_F32 = 0, PP_F64 = 1 } pp_dtype;
-typedef enum pp_emission_kind { PP_EMIT_NORMAL = 0, PP_EMIT_UNIFORM = 1 } pp_emission_kind;
+typedef enum pp_emission_kind { PP_EMIT_NORMAL = 0, PP_EMIT_UNIFORM = 1, PP_EMIT_TABLE = 2 } pp_emission_kind;
 
 /*
  * Baked model, exactly the arrays Model.bake produces (yahmm.pyx:2280-2655):
@@ -56,6 +56,8 @@ typedef enum pp_emission_kind { PP_EMIT_NORMAL = 0, PP_EMIT_UNIFORM = 1 } pp_emi
  *   emit_kind/p0/p1          = distribution family and parameters of each emitting state
  *                              (Normal: mean, std -- std == 0 selects the point-mass branch,
  *                              yahmm.pyx:383-387; Uniform: start, end, yahmm.pyx:257-262)
+ *                              PP_EMIT_TABLE: any other Distribution (yahmm.pyx:525-1917) -- its log-densities are
+ *                              supplied per batch through pp_model_set_emission_table, p0/p1 unused
  *   emit_logw                = state_weights = log(state.weight) (yahmm.pyx:2515-2517)
  */
 typedef struct pp_model_desc {
@@ -77,6 +79,16 @@ void pp_model_destroy(pp_model *model);
 
 /* New parameters, same topology (after a Baum-Welch M-step, yahmm.pyx:4277-4327). */
 int pp_model_update_params(pp_model *model, const pp_model_desc *desc);
+
+/*
+ * Emission table for states of kind PP_EMIT_TABLE: the reference fills e[i, k] = dist_k.log_probability(x_i) for
+ * every observation before each sweep (yahmm.pyx:2836-2840); the caller does that for the families the kernels do not
+ * evaluate themselves and hands the matrix over: table[r * silent_start + k] is the log-density of emitting state k
+ * for observation r of the `obs` array of the batched calls that follow (log(state.weight) is added by the kernels;
+ * columns of non-table states are ignored).  A host table is copied to the device; a device table must stay valid
+ * until it is replaced.  NULL clears it.  Models with table states run on the exact state-parallel kernels.
+ */
+int pp_model_set_emission_table(pp_model *model, const double *table, int64_t n_rows, int32_t mem);
 
 /* Text dump of the run schedule the kernels execute for this model (one line per warp and phase); needs no
  * GPU.  Returns the length of the full text (buf may be NULL to query it), < 0 on error. */

@@ -58,6 +58,7 @@ ABI = [
     ("pp_model_destroy", None, [_vp]),
     ("pp_model_update_params", ctypes.c_int, [_vp, ctypes.POINTER(PPModelDesc)]),
     ("pp_model_set_workspace_limit", ctypes.c_int, [_vp, ctypes.c_int64]),
+    ("pp_model_set_emission_table", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32]),
     ("pp_schedule_describe", ctypes.c_int64, [ctypes.POINTER(PPModelDesc), ctypes.c_char_p, ctypes.c_int64]),
     ("pp_viterbi_workspace_bytes", ctypes.c_int64, [_vp, _vp, ctypes.c_int64]),
     ("pp_forward_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
@@ -218,6 +219,20 @@ class Engine(object):
     def update_params(self, baked, kinds, p0, p1):
         desc = self._desc(baked, kinds, p0, p1)
         self._check(self._lib.pp_model_update_params(self._h, ctypes.byref(desc)))
+
+    def set_emission_table(self, table):
+        """pp_model_set_emission_table: float64 [rows, silent_start] log-densities of the table states for the `obs` of
+        the calls that follow (numpy: copied to the device; torch CUDA tensor: used in place); None clears it."""
+        if table is None:
+            self._check(self._lib.pp_model_set_emission_table(self._h, None, 0, PP_MEM_HOST))
+            self._table_keep = None
+            return
+        dev = _is_device(table)
+        if not dev:
+            table = np.ascontiguousarray(table, dtype=np.float64)
+        self._table_keep = table if dev else None
+        self._check(self._lib.pp_model_set_emission_table(self._h, _ptr(table), int(table.shape[0]),
+                                                          PP_MEM_DEVICE if dev else PP_MEM_HOST))
 
     def set_workspace_limit(self, nbytes):
         self._check(self._lib.pp_model_set_workspace_limit(self._h, int(nbytes)))

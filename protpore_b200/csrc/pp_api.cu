@@ -172,6 +172,8 @@ static int copy_desc(pp_model* M, const pp_model_desc* d) {
     M->emit_p0.assign(d->emit_p0, d->emit_p0 + d->silent_start);
     M->emit_p1.assign(d->emit_p1, d->emit_p1 + d->silent_start);
     M->emit_logw.assign(d->emit_logw, d->emit_logw + d->silent_start);
+    M->has_table_states = false;
+    for (int k = 0; k < d->silent_start; ++k) M->has_table_states |= d->emit_kind[k] == PP_EMIT_TABLE;
     return PP_OK;
 }
 
@@ -368,7 +370,7 @@ void pp_model_destroy(pp_model* M) {
                       &M->d_out_prob, &M->d_alive, &M->d_ws, &M->d_obs, &M->d_offsets, &M->d_order,
                       &M->d_group_len, &M->d_group_row, &M->d_score, &M->d_end_state, &M->d_end_ord, &M->d_path_len,
                       &M->d_path_off, &M->d_path, &M->d_scan_tmp, &M->d_logp, &M->d_bw_wtab, &M->d_acc_map,
-                      &M->d_acc_log2, &M->d_fb_acc, &M->d_fb_scratch, &M->d_fb_ctl, &M->d_fb_minmax};
+                      &M->d_acc_log2, &M->d_fb_acc, &M->d_fb_scratch, &M->d_fb_ctl, &M->d_fb_minmax, &M->d_etab_own};
     for (DevBuf* b : bufs) b->release();
     release_state_model(M);
     for (int b = 0; b < 2; ++b) {
@@ -395,6 +397,25 @@ int pp_model_update_params(pp_model* M, const pp_model_desc* desc) {
     copy_desc(M, desc);
     PP_CUDA(cudaSetDevice(M->device));
     return upload_model(M);
+}
+
+int pp_model_set_emission_table(pp_model* M, const double* table, int64_t n_rows, int32_t mem) {
+    if (!M || n_rows < 0) { set_error("null or negative argument"); return PP_ERR_ARG; }
+    if (mem != PP_MEM_HOST && mem != PP_MEM_DEVICE) { set_error("bad mem"); return PP_ERR_ARG; }
+    PP_CUDA(cudaSetDevice(M->device));
+    if (!table) { M->etab = nullptr; M->etab_rows = 0; return PP_OK; }
+    if (mem == PP_MEM_DEVICE) {
+        M->etab = table;
+    } else {
+        const size_t bytes = static_cast<size_t>(n_rows) * M->ne * sizeof(double);
+        PP_CUDA(cudaStreamSynchronize(M->stream));            // an earlier sweep may still read the old copy
+        PP_CUDA(M->d_etab_own.reserve(bytes + 16));
+        PP_CUDA(cudaMemcpyAsync(M->d_etab_own.p, table, bytes, cudaMemcpyHostToDevice, M->stream));
+        PP_CUDA(cudaStreamSynchronize(M->stream));
+        M->etab = M->d_etab_own.as<double>();
+    }
+    M->etab_rows = n_rows;
+    return PP_OK;
 }
 
 int64_t pp_schedule_describe(const pp_model_desc* desc, char* buf, int64_t cap) {
@@ -700,6 +721,8 @@ int pp_forward_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     std::vector<int64_t> store;
     const int64_t *h_off, *d_off;
     rc = host_offsets(M, offsets, n_events, mem, &store, &h_off, &d_off);
+    if (rc != PP_OK) return rc;
+    rc = pp_check_emission_table(M, h_off[n_events]);
     if (rc != PP_OK) return rc;
     double* d_logp = logp_out;
     if (host) {

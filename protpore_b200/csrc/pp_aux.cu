@@ -19,6 +19,7 @@ static StateModel make_state_model(const pp_model* M) {
     S.out_ptr = M->d_out_ptr.as<int32_t>(); S.out_dst = M->d_out_dst.as<int32_t>();
     S.in_logp = M->d_in_logp.as<double>(); S.out_logp = M->d_out_logp.as<double>();
     S.emis = M->d_emis.as<EmisRec>();
+    S.etab = M->etab;
     S.lev_ptr = M->d_lev_ptr.as<int32_t>(); S.lev_states = M->d_lev_states.as<int32_t>();
     S.rlev_ptr = M->d_rlev_ptr.as<int32_t>(); S.rlev_states = M->d_rlev_states.as<int32_t>();
     S.m = M->m; S.ne = M->ne; S.start = M->start; S.end = M->end; S.finite = M->finite;
@@ -201,6 +202,7 @@ int viterbi_batch_state(pp_model* M, const void* obs, int32_t obs_dtype, const i
     }
     for (int64_t e = 0; e < n_events; ++e)
         if (h_off[e + 1] - h_off[e] < 1) { set_error("event %lld is empty", (long long)e); return PP_ERR_ARG; }
+    { const int trc = pp_check_emission_table(M, h_off[n_events]); if (trc != PP_OK) return trc; }
     const void* d_obs = obs;
     if (mem == PP_MEM_HOST) {
         PP_CUDA(M->d_obs.reserve(h_off[n_events] * ob));
@@ -315,6 +317,7 @@ static int run_table(pp_model* M, const double* obs, int64_t n, int32_t mem, dou
     if (n < 1) { set_error("Invalid shape in axis 0: 0."); return PP_ERR_ARG; }      // yahmm.pyx:2836
     if (mem != PP_MEM_HOST && mem != PP_MEM_DEVICE) { set_error("bad mem"); return PP_ERR_ARG; }
     PP_CUDA(cudaSetDevice(M->device));
+    { const int trc = pp_check_emission_table(M, n); if (trc != PP_OK) return trc; }
     const size_t cells = static_cast<size_t>(n + 1) * M->m;
     const double* d_obs = obs;
     double* d_tab = table_out;
@@ -492,6 +495,7 @@ int pp_forward_backward_batch(pp_model* M, const void* obs, int32_t obs_dtype, c
         maxlen = std::max(maxlen, len);
     }
     const int64_t total_obs = h_off[n_events];
+    { const int trc = pp_check_emission_table(M, total_obs); if (trc != PP_OK) return trc; }
     const void* d_obs = obs;
     double *d_logp = logp_out, *d_edge = edge_counts, *d_mom = emit_moments, *d_mm = emit_minmax, *d_post = posteriors_out;
     const size_t n_stats = static_cast<size_t>(E) + 5 * static_cast<size_t>(ne);
@@ -574,6 +578,7 @@ int pp_sample_events(pp_model* M, const int64_t* offsets, int64_t n_events, uint
     if (!M || !offsets || !obs_out) { set_error("null argument"); return PP_ERR_ARG; }
     if (mem != PP_MEM_HOST && mem != PP_MEM_DEVICE) { set_error("bad mem"); return PP_ERR_ARG; }
     PP_CUDA(cudaSetDevice(M->device));
+    if (M->has_table_states) { set_error("states with table emissions cannot be sampled on the device"); return PP_ERR_UNSUPPORTED; }
     if (n_events == 0) return PP_OK;
     const int64_t* d_off = offsets;
     float* d_out = obs_out;

@@ -11,6 +11,10 @@ std::string describe_schedule(const Lowered& L) {
     std::ostringstream o;
     o << "states " << L.m << " emitting " << L.ne << " silent " << L.ns << " slots " << L.n_slots << " runs " << L.runs.size()
       << " ptr_bits " << L.ptr_bits << " ptr_row_bytes " << L.n_ptr_words * 128 << " lane_ok " << (L.lane_ok ? 1 : 0) << "\n";
+    if (!L.lane_ok) {                                   // no run schedule: the state-parallel kernels serve this model
+        o << "state-parallel kernels only: " << L.lane_why << "\n";
+        return o.str();
+    }
     for (int w = 0; w < L.warps; ++w) {
         for (int list = 0; list < 3; ++list) {
             const int b = L.warp_run_ranges[w * 6 + list * 2], e = L.warp_run_ranges[w * 6 + list * 2 + 1];

@@ -40,6 +40,8 @@ std::string fill_emissions(const pp_model_desc& d, Lowered* low) {
             // (261); a == b: the reference returns 0 for x == a == b (257-259), and nothing else is in range
             e.a3 = (p1 == p0) ? 0.0 : ref_log(1.0 / (p1 - p0));
             e.c2 = (e.a3 + lw) * kLog2e;
+        } else if (d.emit_kind[k] == PP_EMIT_TABLE) {
+            e.kind = EMIS_TABLE;                                // density comes from the caller's table; only logw is kept
         } else {
             return "emission kind " + std::to_string(d.emit_kind[k]) + " of state " + std::to_string(k) +
                    " has no device lowering";
@@ -179,6 +181,8 @@ std::string lower_model(const pp_model_desc& d, int warps, Lowered* low) {
         if (low->end_final_only && l == d.end_index) continue;
         if (low->state_n_edges[l] > kMaxRunEdges) { low->lane_ok = false; low->lane_why = "state " + std::to_string(l) + " has more than 8 usable in-edges"; }
     }
+    for (int k = 0; k < ne; ++k)
+        if (low->emis[k].kind == EMIS_TABLE) { low->lane_ok = false; low->lane_why = "state " + std::to_string(k) + " takes its emissions from a table (state-parallel kernels only)"; }
     if (!low->lane_ok) return "";                 // only the state-parallel kernels can take this model
     auto make_runs = [&](const std::vector<int>& states, bool silent, std::vector<RunRec>* out) {
         size_t i = 0;
@@ -413,11 +417,14 @@ std::string refresh_params(const pp_model_desc& d, Lowered* low) {
     }
     std::string err = fill_emissions(d, low);
     if (!err.empty()) return err;
+    for (int k = 0; k < d.silent_start; ++k)                      // a state that switched to / from table emissions: lower again
+        if ((d.emit_kind[k] == PP_EMIT_TABLE) != (low->emis[k].kind == EMIS_TABLE)) return lower_model(d, low->warps, low);
     for (int q = 0; q < 2; ++q)
         for (size_t i = 0; i < low->low_csr.size(); ++i) {
             low->edges_logp[q][i].val = d.in_logp[low->low_csr[i]];
             low->edges_prob[q][i].val = std::exp(d.in_logp[low->low_csr[i]]);
         }
+    if (!low->lane_ok) return "";
     mark_shared_c2(*low, &low->runs);
     return lower_backward(d, low);
 }

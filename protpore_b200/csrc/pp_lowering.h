@@ -59,7 +59,8 @@ constexpr int run_group_size(int n_edges) { return n_edges <= 2 ? 4 : (n_edges <
 constexpr int kAccLog2 = PP_ACC_LOG2;
 constexpr int kAccChunk = 1 << kAccLog2;
 enum : int32_t { EMIS_NORMAL = 0, EMIS_POINT = 1, EMIS_UNIFORM = 2, RUN_SILENT = 3, RUN_START = 4,
-                 RUN_ACC = 5 /* backward: accumulate-only item of a silent state */ };
+                 RUN_ACC = 5 /* backward: accumulate-only item of a silent state */,
+                 EMIS_TABLE = 6 /* log-density read from the caller's emission table (pp_model_set_emission_table) */ };
 struct __attribute__((aligned(16))) RunRec {
     int32_t kind;                                // EMIS_* for emitting items, RUN_SILENT, RUN_START (the start state)
     int32_t n_edges;                             // in-edges per item (<= kMaxRunEdges), reference visiting order

@@ -55,6 +55,11 @@ struct pp_model {
     std::vector<double> arena_fb;         // constant-arena image: forward runs, then backward runs
     pp::DevBuf d_bw_wtab, d_acc_map, d_acc_log2, d_fb_acc, d_fb_scratch, d_fb_ctl, d_fb_minmax;
     size_t ws_limit = 0;
+    // emission table of PP_EMIT_TABLE states (pp_model_set_emission_table): device pointer, rows, owned copy of a host table
+    const double* etab = nullptr;
+    int64_t etab_rows = 0;
+    pp::DevBuf d_etab_own;
+    bool has_table_states = false;
 
     // chunk pipeline of the batched host/device calls (pp_api.cu): copy-in and copy-out streams beside the compute
     // stream, two slots of per-chunk buffers, pinned scalars the host polls, a pool of timing events
@@ -104,3 +109,14 @@ int exact_forward_run(pp_model* M, int slot, const void* d_obs_base, int32_t obs
                       const int64_t* h_off, int64_t n_events, double* d_logp);
 
 }  // namespace pp
+
+// Models with PP_EMIT_TABLE states need a table covering every observation row of the batch.
+inline int pp_check_emission_table(const pp_model* M, int64_t rows_needed) {
+    if (!M->has_table_states) return PP_OK;
+    if (!M->etab || M->etab_rows < rows_needed) {
+        pp::set_error("model has table-emission states: call pp_model_set_emission_table with >= %lld rows first (have %lld)",
+                      (long long)rows_needed, (long long)(M->etab ? M->etab_rows : 0));
+        return PP_ERR_ARG;
+    }
+    return PP_OK;
+}

@@ -22,12 +22,21 @@ struct StateModel {
     const int32_t *in_ptr, *in_src, *out_ptr, *out_dst;
     const double *in_logp, *out_logp;
     const EmisRec* emis;
+    const double* etab;          // caller's emission table [row][ne] for EMIS_TABLE states (row = index into obs), or null
     const int32_t* lev_ptr;      // [n_levels + 1] silent states grouped by forward level (ascending)
     const int32_t* lev_states;
     const int32_t* rlev_ptr;     // [n_rlevels + 1] silent states grouped by reverse level
     const int32_t* rlev_states;
     int32_t m, ne, start, end, finite, n_levels, n_rlevels;
 };
+
+// e[i, l] (yahmm.pyx:2836-2840): evaluated here for Normal / point-mass / Uniform states, read from the caller's table
+// for every other family; `row` is the observation's index in the batch's obs array
+__device__ __forceinline__ double emit_state(const StateModel& S, int l, double x, int64_t row) {
+    const EmisRec& R = S.emis[l];
+    if (R.kind == EMIS_TABLE) return __dadd_rn(S.etab[row * S.ne + l], R.logw);
+    return emission_log(R, x);
+}
 
 __device__ __forceinline__ double pair_lse(double x, double y) {       // yahmm.pyx:52-70
     const double inf = __longlong_as_double(0x7FF0000000000000LL);
@@ -40,7 +49,7 @@ __device__ __forceinline__ double pair_lse(double x, double y) {       // yahmm.
 
 // One event per CTA.  table: (n+1) x m row-major float64.  e_row: scratch [ne] per CTA.
 __device__ inline void forward_table_event(const StateModel& S, const double* __restrict__ x, int n, double* f,
-                                           double* e_row) {
+                                           double* e_row, int64_t row0) {
     const int m = S.m, ne = S.ne;
     const int t = threadIdx.x, nt = blockDim.x;
     for (int l = t; l < m; l += nt) f[l] = (l == S.start) ? 0.0 : neg_inf();
@@ -66,7 +75,7 @@ __device__ inline void forward_table_event(const StateModel& S, const double* __
         for (int l = t; l < ne; l += nt) {                               // 2874-2889
             double lp = neg_inf();
             for (int k = S.in_ptr[l]; k < S.in_ptr[l + 1]; ++k) lp = pair_lse(lp, fi[S.in_src[k]] + S.in_logp[k]);
-            fn[l] = lp + emission_log(S.emis[l], xi);
+            fn[l] = lp + emit_state(S, l, xi, row0 + i);
         }
         __syncthreads();
         for (int lev = 0; lev < S.n_levels; ++lev) {
@@ -101,7 +110,7 @@ __device__ inline double logp_from_forward(const StateModel& S, const double* f,
 }
 
 __device__ inline void backward_table_event(const StateModel& S, const double* __restrict__ x, int n, double* b,
-                                            double* e_row) {
+                                            double* e_row, int64_t row0) {
     const int m = S.m, ne = S.ne;
     const int t = threadIdx.x, nt = blockDim.x;
     double* bn = b + static_cast<size_t>(n) * m;
@@ -141,7 +150,7 @@ __device__ inline void backward_table_event(const StateModel& S, const double* _
         double* bi = b + static_cast<size_t>(i) * m;
         const double* bp = b + static_cast<size_t>(i + 1) * m;
         const double xi = x[i];
-        for (int l = t; l < ne; l += nt) e_row[l] = emission_log(S.emis[l], xi);
+        for (int l = t; l < ne; l += nt) e_row[l] = emit_state(S, l, xi, row0 + i);
         __syncthreads();
         for (int lev = 0; lev < S.n_rlevels; ++lev) {
             for (int j = S.rlev_ptr[lev] + t; j < S.rlev_ptr[lev + 1]; j += nt) {
@@ -193,8 +202,8 @@ __global__ void k_table(const StateModel S, const ObsT* __restrict__ obs, const 
         for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = static_cast<double>(obs[off + i]);
         __syncthreads();
         double* tab = tables + table_off[ev];
-        if (mode == 0) forward_table_event(S, x, n, tab, e_row);
-        else backward_table_event(S, x, n, tab, e_row);
+        if (mode == 0) forward_table_event(S, x, n, tab, e_row, off);
+        else backward_table_event(S, x, n, tab, e_row, off);
         __syncthreads();
     }
 }
@@ -215,7 +224,7 @@ __global__ void k_forward_exact(const StateModel S, const ObsT* __restrict__ obs
         for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = static_cast<double>(obs[off + i]);
         __syncthreads();
         double* f = scratch + static_cast<size_t>(blockIdx.x) * scratch_stride;
-        forward_table_event(S, x, n, f, e_row);
+        forward_table_event(S, x, n, f, e_row, off);
         if (threadIdx.x == 0) logp_out[ev] = logp_from_forward(S, f, n);
         __syncthreads();
     }
@@ -257,7 +266,7 @@ __global__ void k_viterbi_state(const StateModel S, const StateVit V, const ObsT
             } else {
                 const double x = static_cast<double>(obs[off + r - 1]);
                 for (int l = t; l < ne; l += nt) {                                   // 3545-3562
-                    const double e = emission_log(S.emis[l], x);
+                    const double e = emit_state(S, l, x, off + r - 1);
                     double best = neg_inf();
                     int arg = 0;
                     const int b = V.edge_begin[l];
@@ -385,11 +394,11 @@ __global__ void k_fb_accumulate(const StateModel S, const ObsT* __restrict__ obs
         __syncthreads();
         double* f = scratch + static_cast<size_t>(blockIdx.x) * scratch_stride;
         double* b = f + static_cast<size_t>(n + 1) * m;
-        forward_table_event(S, x, n, f, e_row);
+        forward_table_event(S, x, n, f, e_row, off);
         const double lsp = logp_from_forward(S, f, n);
         if (t == 0) logp_out[ev] = lsp;
         if (lsp == neg_inf() || lsp != lsp) { __syncthreads(); continue; }
-        backward_table_event(S, x, n, b, e_row);
+        backward_table_event(S, x, n, b, e_row, off);
         if (t == 0) {
             double lo = x[0], hi = x[0];
             for (int i = 1; i < n; ++i) { lo = fmin(lo, x[i]); hi = fmax(hi, x[i]); }
@@ -405,9 +414,8 @@ __global__ void k_fb_accumulate(const StateModel S, const ObsT* __restrict__ obs
             const double tl = S.out_logp[eidx];
             double acc = 0.0;
             if (li < ne) {
-                const EmisRec R = S.emis[li];
                 for (int i = 0; i < n; ++i) {
-                    const double term = f[static_cast<size_t>(i) * m + k] + tl + emission_log(R, x[i]) +
+                    const double term = f[static_cast<size_t>(i) * m + k] + tl + emit_state(S, li, x[i], off + i) +
                                         b[static_cast<size_t>(i + 1) * m + li];
                     if (term != neg_inf()) acc += exp(term - lsp);
                 }

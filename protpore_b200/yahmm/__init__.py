@@ -4,7 +4,9 @@ Same public names as the reference module: `Model`, `State`, the distributions, 
 `log_probability`.  The dynamic-programming sweeps behind `Model` run on the GPU through the C ABI in
 include/protpore_b200.h; see protpore_b200/yahmm/model.py.
 """
-from .distributions import (Distribution, NormalDistribution, UniformDistribution)  # noqa: F401
+from .distributions import (Distribution, NormalDistribution, UniformDistribution, LogNormalDistribution,  # noqa: F401
+                            ExponentialDistribution, LambdaDistribution, GaussianKernelDensity,
+                            UniformKernelDensity, TriangleKernelDensity, MixtureDistribution)
 from .state import State  # noqa: F401
 from .model import Model, log, exp, log_probability  # noqa: F401
 

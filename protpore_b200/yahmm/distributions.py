@@ -6,9 +6,11 @@ Mirrors the reference interface (yahmm.pyx:101-231 `Distribution`, 233-348 `Unif
 for single-symbol queries, sampling and the Baum-Welch M-step); the per-observation evaluation on
 the hot path happens inside the CUDA column kernels from the lowered (kind, p0, p1) table.
 
-Only the two families the pro_001 peptide model uses are device-lowerable this round.  Any other
-`Distribution` subclass can still be put in a `State` and baked; asking the GPU path to score it
-raises `NotImplementedError`, never a CPU fallback.
+The two families the pro_001 peptide model uses are evaluated inside the kernels.  Every other family
+(LogNormal, Exponential, Lambda, the Gaussian / Uniform / Triangle kernel densities PyPore/hmm.py and
+PyPore/alignment.py use, Mixture, or any user subclass) is a TABLE state: the host fills the emission
+matrix column e[:, k] = log_probability(x) for the batch, exactly what the reference does before every sweep
+(yahmm.pyx:2836-2840), and the dynamic programming still runs on the GPU (exact state-parallel kernels).
 """
 import math
 import random
@@ -83,9 +85,14 @@ class Distribution(object):
 
     # ---- device lowering hook (new) -----------------------------------
     def device_params(self):
-        """(kind, p0, p1) for the CUDA emission table, or raise if this family is host-only."""
-        raise NotImplementedError(
-            "{} has no sm_100a emission kernel yet (only Normal/Uniform are lowered)".format(self.name))
+        """(kind, p0, p1) of the C ABI's emission description.  Normal and Uniform are evaluated inside the kernels;
+        every other family is kind 2 (PP_EMIT_TABLE): the host evaluates `log_probability_many` over the batch's
+        observations, as the reference fills its emission matrix (yahmm.pyx:2836-2840), and the kernels read the table."""
+        return (2, 0.0, 0.0)
+
+    def log_probability_many(self, symbols):
+        """log_probability of every element of a 1-D array (families override this with a vectorised form)."""
+        return numpy.array([self.log_probability(x) for x in symbols], dtype=numpy.float64)
 
 
 class UniformDistribution(Distribution):
@@ -225,3 +232,199 @@ class NormalDistribution(Distribution):
 
     def device_params(self):
         return KIND_NORMAL, float(self.parameters[0]), float(self.parameters[1])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Families the kernels read from the emission table.  Same constructor arguments, `parameters`,
+# `log_probability`, `sample` and `from_sample` as the reference; no device lowering of their own.
+# ---------------------------------------------------------------------------------------------------------------
+class LogNormalDistribution(Distribution):
+    """yahmm.pyx:525-688."""
+
+    def __init__(self, mu, sigma, frozen=False):
+        Distribution.__init__(self)
+        self.parameters = [mu, sigma]
+        self.name = "LogNormalDistribution"
+        self.frozen = frozen
+
+    def log_probability(self, symbol):
+        mu, sigma = self.parameters                                            # 547-556
+        return -math.log(symbol * sigma * SQRT_2_PI) - 0.5 * ((math.log(symbol) - mu) / sigma) ** 2
+
+    def sample(self):
+        return numpy.random.lognormal(*self.parameters)
+
+    def from_sample(self, items, weights=None, inertia=0.0, min_std=0.01):
+        if len(items) == 0 or self.frozen:
+            return
+        items = numpy.asarray(items)
+        weights = numpy.ones_like(items) if weights is None else numpy.asarray(weights)
+        if weights.sum() == 0:
+            return
+        mean = numpy.average(numpy.log(items), weights=weights)               # 595-613
+        if len(weights[weights != 0]) > 1:
+            std = math.sqrt(numpy.average((numpy.log(items) - mean) ** 2, weights=weights))
+        else:
+            std = 0
+        std = max(std, min_std)
+        prior_mean, prior_std = self.parameters
+        self.parameters = [prior_mean * inertia + mean * (1 - inertia), prior_std * inertia + std * (1 - inertia)]
+
+
+class ExponentialDistribution(Distribution):
+    """yahmm.pyx:726-842."""
+
+    def __init__(self, rate, frozen=False):
+        Distribution.__init__(self)
+        self.parameters = [rate]
+        self.name = "ExponentialDistribution"
+        self.frozen = frozen
+
+    def log_probability(self, symbol):
+        return _log(self.parameters[0]) - self.parameters[0] * symbol          # 741-746
+
+    def log_probability_many(self, symbols):
+        return _log(self.parameters[0]) - self.parameters[0] * numpy.asarray(symbols, dtype=numpy.float64)
+
+    def sample(self):
+        return random.expovariate(*self.parameters)
+
+    def from_sample(self, items, weights=None, inertia=0.0):
+        if len(items) == 0 or self.frozen:
+            return
+        items = numpy.asarray(items)
+        weights = numpy.ones_like(items) if weights is None else numpy.asarray(weights)
+        if weights.sum() == 0:
+            return
+        rate = 1.0 / numpy.average(items, weights=weights)
+        self.parameters[0] = self.parameters[0] * inertia + rate * (1 - inertia)
+
+
+class LambdaDistribution(Distribution):
+    """A log-density given as a Python callable (yahmm.pyx:1326-1356)."""
+
+    def __init__(self, lambda_funct, frozen=True):
+        Distribution.__init__(self)
+        self.parameters = [lambda_funct]
+        self.name = "LambdaDistribution"
+        self.frozen = frozen
+
+    def log_probability(self, symbol):
+        return self.parameters[0](symbol)
+
+
+class _KernelDensity(Distribution):
+    """Points, bandwidth, weights (normalised to sum 1); shared by the three kernel densities."""
+
+    def __init__(self, points, bandwidth=1, weights=None, frozen=False):
+        Distribution.__init__(self)
+        points = numpy.asarray(points)
+        n = len(points)
+        if weights is not None and len(weights) > 0:
+            weights = numpy.array(weights) / numpy.sum(weights)
+        else:
+            weights = numpy.ones(n) / n
+        self.parameters = [points, bandwidth, weights]
+        self.frozen = frozen
+
+    def _kernel(self, diff):
+        raise NotImplementedError
+
+    def log_probability(self, symbol):
+        # sequential accumulation over the points in stored order, as the reference's loop (1395-1416)
+        total = 0.0
+        points, _, weights = self.parameters
+        contrib = self._kernel(points - symbol)
+        for c, w in zip(contrib, weights):
+            total += c * w
+        return _log(total)
+
+    def log_probability_many(self, symbols):
+        return numpy.array([self.log_probability(float(x)) for x in symbols], dtype=numpy.float64)
+
+    def from_sample(self, points, weights=None, inertia=0.0):
+        if self.frozen:
+            return
+        points = numpy.asarray(points)
+        n = len(points)
+        if weights is not None and len(weights) > 0:
+            weights = numpy.array(weights) / numpy.sum(weights)
+        else:
+            weights = numpy.ones(n) / n
+        if inertia == 0.0:
+            self.parameters[0] = points
+            self.parameters[2] = weights
+        else:
+            self.parameters[0] = numpy.concatenate((self.parameters[0], points))
+            self.parameters[2] = numpy.concatenate((self.parameters[2] * inertia, weights * (1 - inertia)))
+
+
+class GaussianKernelDensity(_KernelDensity):
+    """yahmm.pyx:1358-1456: log sum_i w_i exp(-0.5 ((p_i - x) / bandwidth)^2) / sqrt(2 pi)."""
+
+    def __init__(self, points, bandwidth=1, weights=None, frozen=False):
+        _KernelDensity.__init__(self, points, bandwidth, weights, frozen)
+        self.name = "GaussianKernelDensity"
+
+    def _kernel(self, diff):
+        return (1.0 / SQRT_2_PI) * numpy.exp(-0.5 * (diff / self.parameters[1]) ** 2)
+
+    def sample(self):
+        mu = numpy.random.choice(self.parameters[0], p=self.parameters[2])
+        return random.gauss(mu, self.parameters[1])
+
+
+class UniformKernelDensity(_KernelDensity):
+    """yahmm.pyx:1458-1559: a point counts 1 when |p_i - x| <= bandwidth."""
+
+    def __init__(self, points, bandwidth=1, weights=None, frozen=False):
+        _KernelDensity.__init__(self, points, bandwidth, weights, frozen)
+        self.name = "UniformKernelDensity"
+
+    def _kernel(self, diff):
+        return (numpy.abs(diff) <= self.parameters[1]).astype(numpy.float64)
+
+    def sample(self):
+        mu = numpy.random.choice(self.parameters[0], p=self.parameters[2])
+        return random.uniform(mu - self.parameters[1], mu + self.parameters[1])
+
+
+class TriangleKernelDensity(_KernelDensity):
+    """yahmm.pyx:1561-1660: max(0, bandwidth - |p_i - x|) per point."""
+
+    def __init__(self, points, bandwidth=1, weights=None, frozen=False):
+        _KernelDensity.__init__(self, points, bandwidth, weights, frozen)
+        self.name = "TriangleKernelDensity"
+
+    def _kernel(self, diff):
+        return numpy.maximum(self.parameters[1] - numpy.abs(diff), 0.0)
+
+    def sample(self):
+        mu = numpy.random.choice(self.parameters[0], p=self.parameters[2])
+        return random.triangular(mu - self.parameters[1], mu + self.parameters[1], mu)
+
+
+class MixtureDistribution(Distribution):
+    """Weighted mixture of other distributions (yahmm.pyx:1662-1821)."""
+
+    def __init__(self, distributions, weights=None, frozen=False):
+        Distribution.__init__(self)
+        n = len(distributions)
+        if weights is not None and len(weights) > 0:
+            weights = numpy.array(weights) / numpy.sum(weights)
+        else:
+            weights = numpy.ones(n) / n
+        self.parameters = [distributions, weights]
+        self.name = "MixtureDistribution"
+        self.frozen = frozen
+
+    def log_probability(self, symbol):
+        d, w = self.parameters                                                 # 1704-1706
+        return _log(numpy.sum([math.exp(d[i].log_probability(symbol)) * w[i] for i in range(len(d))]))
+
+    def sample(self):
+        i = random.random()
+        for d, w in zip(*self.parameters):
+            if w > i:
+                return d.sample()
+            i -= w

@@ -57,7 +57,7 @@ def log_probability(model, samples):
     """Log-sum-exp of the per-sequence log probabilities (yahmm.pyx:93-99), one batched GPU call."""
     batch = getattr(model, "log_probability_batch", None)
     if batch is not None and len(samples) > 0 and not isinstance(samples[0], tuple):
-        return reduce(_pair_lse, [float(v) for v in batch(samples)])
+        return reduce(_pair_lse, [float(v) for v in batch(samples, dtype=numpy.float64)])   # the reference's precision
     return reduce(_pair_lse, map(model.log_probability, samples))
 
 
@@ -178,6 +178,25 @@ class Model(object):
             self._engine = Engine(self._baked, kinds, p0, p1, device=self.device)
         return self._engine
 
+    def _sweep_engine(self, obs):
+        """The engine, with the emission table of this batch in place when the model has states whose family the
+        kernels do not evaluate themselves (kind 2): column k = log_probability of state k's
+        distribution for every observation, the matrix the reference fills at yahmm.pyx:2836-2840."""
+        eng = self.engine()
+        kinds = self._device_params()[0]
+        table_states = [k for k, kind in enumerate(kinds) if kind == 2]
+        if table_states:
+            x = numpy.asarray(obs.cpu() if hasattr(obs, "cpu") else obs, dtype=numpy.float64)
+            table = numpy.zeros((len(x), self.silent_start), dtype=numpy.float64)
+            done = {}
+            for k in table_states:
+                dist = self.states[k].distribution
+                if id(dist) not in done:                       # tied states share one distribution object
+                    done[id(dist)] = dist.log_probability_many(x)
+                table[:, k] = done[id(dist)]
+            eng.set_emission_table(table)
+        return eng
+
     def _push_params(self):
         if self._engine is not None:
             kinds, p0, p1 = self._device_params()
@@ -201,11 +220,11 @@ class Model(object):
     # ---- single-sequence API (same signatures and return values as the reference) --------------
     def forward(self, sequence):
         """Full forward table, (n+1) x m log probabilities (yahmm.pyx:2780-2930)."""
-        return self.engine().forward_table(self._seq(sequence))
+        return self._sweep_engine(self._seq(sequence)).forward_table(self._seq(sequence))
 
     def backward(self, sequence):
         """Full backward table, (n+1) x m log probabilities (yahmm.pyx:2932-3156)."""
-        return self.engine().backward_table(self._seq(sequence))
+        return self._sweep_engine(self._seq(sequence)).backward_table(self._seq(sequence))
 
     def _logp_from_forward(self, f, n):
         if self._baked.finite == 1:
@@ -220,7 +239,7 @@ class Model(object):
         if path:
             return self._log_probability_of_path(numpy.array(sequence), path)
         x = self._seq(sequence)
-        return self._logp_from_forward(self.engine().forward_table(x), len(x))
+        return self._logp_from_forward(self._sweep_engine(x).forward_table(x), len(x))
 
     def _log_probability_of_path(self, sequence, path):
         b = self._baked
@@ -246,7 +265,7 @@ class Model(object):
         """(log probability of the ML path, [(state_index, State), ...]) or (-inf, None) (yahmm.pyx:3444-3652)."""
         x = self._seq(sequence)
         offsets = numpy.array([0, len(x)], dtype=numpy.int64)
-        scores, plen, paths = self.engine().viterbi_batch(x, offsets)
+        scores, plen, paths = self._sweep_engine(x).viterbi_batch(x, offsets)
         if plen[0] < 0:
             return (float(scores[0]), None)
         return (float(scores[0]), [(int(k), self.states[k]) for k in paths[:plen[0]]])
@@ -263,7 +282,7 @@ class Model(object):
         """(expected transitions m x m, log emission weights n x silent_start) or (None, None) (yahmm.pyx:3158-3364)."""
         x = self._seq(sequence)
         offsets = numpy.array([0, len(x)], dtype=numpy.int64)
-        logp, edge, _, _, post = self.engine().forward_backward_batch(x, offsets, posteriors=True)
+        logp, edge, _, _, post = self._sweep_engine(x).forward_backward_batch(x, offsets, posteriors=True)
         if logp[0] == NEGINF:
             print("Warning: Sequence is impossible.")
             return (None, None)
@@ -294,7 +313,7 @@ class Model(object):
         """Posterior decoding (yahmm.pyx:3654-3742)."""
         x = self._seq(sequence)
         offsets = numpy.array([0, len(x)], dtype=numpy.int64)
-        logp, _, _, _, post = self.engine().forward_backward_batch(x, offsets, posteriors=True)
+        logp, _, _, _, post = self._sweep_engine(x).forward_backward_batch(x, offsets, posteriors=True)
         if logp[0] == NEGINF:
             print("Warning: Sequence is impossible.")
             return (None, None)
@@ -314,7 +333,7 @@ class Model(object):
     def log_probability_batch(self, sequences, dtype=numpy.float32):
         """log P of many sequences in one GPU call (scaled linear-space sweep, exact re-run where needed)."""
         obs, offsets = self._pack(sequences, dtype)
-        return self.engine().forward_batch(obs, offsets)
+        return self._sweep_engine(obs).forward_batch(obs, offsets)
 
     def viterbi_batch(self, sequences, dtype=numpy.float32, states=True):
         """Viterbi of many sequences in one GPU call.
@@ -322,7 +341,7 @@ class Model(object):
         Returns a list of what `viterbi(seq)` returns per sequence; with `states=False` the path items
         are bare state indices (numpy uint16 arrays) instead of (index, State) tuples."""
         obs, offsets = self._pack(sequences, dtype)
-        scores, plen, paths = self.engine().viterbi_batch(obs, offsets)
+        scores, plen, paths = self._sweep_engine(obs).viterbi_batch(obs, offsets)
         out, pos = [], 0
         for e in range(len(sequences)):
             if plen[e] < 0:
@@ -338,14 +357,14 @@ class Model(object):
         out = []
         for s in sequences:          # per-event dense outputs; statistics for training use baum_welch_statistics
             obs, offsets = self._pack([s], dtype)
-            logp, edge, _, _, post = self.engine().forward_backward_batch(obs, offsets, posteriors=True)
+            logp, edge, _, _, post = self._sweep_engine(obs).forward_backward_batch(obs, offsets, posteriors=True)
             out.append((None, None) if logp[0] == NEGINF else (self._dense_expected(edge), post))
         return out
 
     def baum_welch_statistics(self, sequences, dtype=numpy.float32, accum=None):
         """E-step over many sequences in one GPU call: (logp[n], edge_counts[E], moments[ne,3], minmax[ne,2])."""
         obs, offsets = self._pack(sequences, dtype)
-        logp, edge, mom, mm, _ = self.engine().forward_backward_batch(obs, offsets, accum=accum)
+        logp, edge, mom, mm, _ = self._sweep_engine(obs).forward_backward_batch(obs, offsets, accum=accum)
         return logp, edge, mom, mm
 
     # ---- sampling (yahmm.pyx:2656-2778) ----------------------------------------------------------
@@ -428,7 +447,26 @@ class Model(object):
 
         `allreduce(edge, moments, minmax)` (in place) is where protpore_b200.parallel sums the per-GPU
         statistics over NCCL before every rank runs the identical M-step."""
-        _, edge, mom, mm = self.baum_welch_statistics(sequences, dtype=numpy.float64)
+        kinds = self._device_params()[0]
+        table_states = [k for k, kind in enumerate(kinds) if kind == 2 and not self.states[k].distribution.frozen]
+        if not table_states:
+            _, edge, mom, mm = self.baum_welch_statistics(sequences, dtype=numpy.float64)
+        else:
+            # families without sufficient statistics keep the reference's route (4215-4236): the posterior weights of
+            # every observation go to distribution.summarize(items, weights); tied states pool their weights
+            obs, offsets = self._pack(sequences, numpy.float64)
+            logp, edge, mom, mm, post = self._sweep_engine(obs).forward_backward_batch(obs, offsets, posteriors=True)
+            used = numpy.repeat(numpy.isfinite(logp), numpy.diff(offsets))       # impossible sequences are skipped (4131-4133)
+            b = self._baked
+            seen = set()
+            for k in table_states:
+                dist = self.states[k].distribution
+                if id(dist) in seen:
+                    continue
+                seen.add(id(dist))
+                group = [k] + [int(j) for j in b.tied_idx[b.tied_ptr[k]:b.tied_ptr[k + 1]]]
+                w = numpy.exp(post[:, group][used]).sum(axis=1)
+                dist.summarize(obs[used], w)
         if allreduce is not None:
             allreduce(edge, mom, mm)
         self.apply_m_step(edge, mom, mm, transition_pseudocount, use_pseudocount, edge_inertia, distribution_inertia)
@@ -481,8 +519,11 @@ class Model(object):
             elif hasattr(dist, "summarize_range"):
                 dist.summarize_range(sw, lo, hi)
                 dist.from_summaries(inertia=distribution_inertia)
-            else:
-                raise NotImplementedError("{} cannot be re-estimated from GPU sufficient statistics".format(dist.name))
+            elif not dist.frozen:
+                # a table-state family: _train_once_baum_welch already handed it items and posterior weights
+                # (Distribution.summarize); frozen ones (LambdaDistribution by default) are left alone as in the reference
+                if dist.summaries:
+                    dist.from_summaries()
         self._push_params()
 
     def _train_viterbi(self, sequences, transition_pseudocount, use_pseudocount, edge_inertia, distribution_inertia):
