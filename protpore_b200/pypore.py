@@ -65,3 +65,32 @@ def apply_hmm_batch(events, hmm, algorithm='viterbi'):
     if algorithm == 'forward_backward':
         return hmm.forward_backward_batch(means, dtype=np.float64)
     return [getattr(hmm, algorithm)(x) for x in means]
+
+
+def segment_and_decode(currents, hmm, parser, algorithm='viterbi', device_resident=True):
+    """Raw current -> segments -> HMM, for many events, in two batched GPU calls.
+
+    What peptide_hmm_v0.0.1.py:443-472 does per event -- `event.parse(SpeedyStatSplit(...))`, collect the segment means,
+    `prediction(models, [means], 'viterbi')` -- for a list of 1-D currents.  With `device_resident` the segment offsets
+    and float32 means produced by `pp_statsplit_batch` stay on the GPU and are the `offsets` / `obs` of the batched
+    HMM call (needs torch); otherwise they round-trip through host numpy arrays.
+
+    Returns (seg_offsets, seg_start, seg_mean, result) with `result` = (scores, path_len, paths) for 'viterbi' or the
+    log-probabilities for 'log_probability'."""
+    from . import _engine
+    cur, off = _engine.pack_events([np.asarray(c, dtype=np.float64) for c in currents], dtype=np.float64)
+    if device_resident:
+        import torch
+        dev = torch.device("cuda", parser.device)
+        cur, off = torch.from_numpy(cur).to(dev), torch.from_numpy(off).to(dev)
+    seg_off, seg_start, seg_mean, _, mean32 = parser.segment_means_batch((cur, off), want_std=False, want_f32=True)
+    eng = hmm.engine()
+    if algorithm == 'viterbi':
+        result = eng.viterbi_batch(mean32, seg_off)
+    elif algorithm == 'log_probability':
+        result = eng.forward_batch(mean32, seg_off)
+    else:
+        raise ValueError("algorithm must be 'viterbi' or 'log_probability'")
+    host = lambda a: a.cpu().numpy() if hasattr(a, "cpu") else a
+    result = tuple(host(r) for r in result) if isinstance(result, tuple) else host(result)
+    return host(seg_off), host(seg_start), host(seg_mean), result

@@ -190,3 +190,24 @@ def test_gpu_wide_window_takes_the_tableless_kernel():
     off, start, mean, std, _ = p.segment_means_batch(currents, want_std=True)
     for e, cur in enumerate(currents):
         assert _check_event(cur, kw, p.min_gain, start[off[e]:off[e + 1]], mean[off[e]:off[e + 1]], std[off[e]:off[e + 1]], e)
+
+
+@pytest.mark.gpu
+def test_gpu_segment_and_decode_pipeline():
+    """pypore.segment_and_decode == the reference's per-event loop: parse, segment means, Viterbi (float32 means)."""
+    from protpore_b200 import peptide_hmm, pypore
+    rng = np.random.default_rng(13)
+    currents = [staircase(rng, int(rng.integers(3, 10)), 260, 800) for _ in range(25)]
+    model = peptide_hmm.pro_001_model()
+    parser = parsers.SpeedyStatSplit(**CLI)
+    for resident in (True, False):
+        off, start, mean, (scores, plen, paths) = pypore.segment_and_decode(currents, model, parser, device_resident=resident)
+        assert len(off) == len(currents) + 1
+        poff = np.concatenate([[0], np.cumsum(np.maximum(plen, 0))])
+        for e in (0, 7, 24):
+            segs = parser.parse(currents[e])
+            means32 = np.array([s.mean for s in segs]).astype(np.float32)
+            assert np.array_equal(means32, mean[off[e]:off[e + 1]].astype(np.float32))
+            s, p = model.viterbi(means32.astype(np.float64))
+            assert s == scores[e]
+            assert (p is None and plen[e] < 0) or [k for k, _ in p] == list(paths[poff[e]:poff[e + 1]])
