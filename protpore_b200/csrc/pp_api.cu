@@ -28,12 +28,16 @@ void set_error(const char* fmt, ...) {
 }
 
 void lane_viterbi4_invalidate(const void*);
+void lane_viterbi4g_invalidate(const void*);
+void lane_forwardg_invalidate(const void*);
 void lane_viterbi8_invalidate(const void*);
 void lane_forward_invalidate(const void*);
 void lane_fb_invalidate(const void*);
 void lane_arena_invalidate(const void* owner) {
     lane_fb_invalidate(owner);
     lane_viterbi4_invalidate(owner);
+    lane_viterbi4g_invalidate(owner);
+    lane_forwardg_invalidate(owner);
     lane_viterbi8_invalidate(owner);
     lane_forward_invalidate(owner);
 }
@@ -194,6 +198,8 @@ LaneSched make_sched(const pp_model* M, bool logspace) {
     S.end_slot_off = static_cast<int32_t>((L.end - L.ne) * kSlotBytes);
     S.end_state = L.end; S.finite = L.finite; S.end_final_only = L.end_final_only ? 1 : 0;
     S.n_ptr_words = L.n_ptr_words;
+    S.gcol = nullptr;
+    S.gcol_stride = 0;
     return S;
 }
 
@@ -244,12 +250,47 @@ static int host_offsets(pp_model* M, const int64_t* offsets, int64_t n_events, i
     return PP_OK;
 }
 
+// Column in shared memory, or -- for a model whose column does not fit next to the tables -- in a per-CTA global
+// scratch (k_*_lane<..., CG = true>): same kernels, same results.
+static size_t lane_smem_col(const pp_model* M) {
+    return lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, kLaneWarps);
+}
+static size_t lane_smem_nocol(const pp_model* M) {
+    return lane_smem_bytes2(0, static_cast<int>(M->low.low_src.size()), M->low.ne, kLaneWarps);
+}
+static bool lane_col_global(const pp_model* M) {
+    return M->low.lane_ok && M->low.ptr_bits == 4 && lane_smem_col(M) > M->smem_optin && lane_smem_nocol(M) <= M->smem_optin &&
+           M->arena.size() <= static_cast<size_t>(kArenaDoubles);
+}
+constexpr int kGcolGroups = 1024;         // groups (CTAs) per launch of the global-column kernels: bounds the scratch
+
+template <typename OutT, typename Launch>
+static int launch_gcol(pp_model* M, const LaneSched& S0, const LaneBatchAny& A, const OutT& O, int n_groups, Launch launch,
+                       const char* what) {
+    LaneSched S = S0;
+    const size_t col_bytes = static_cast<size_t>(M->low.n_slots) * kSlotBytes;
+    const int per = std::min(n_groups, kGcolGroups);
+    PP_CUDA(M->d_gcol.reserve(static_cast<size_t>(per) * col_bytes));
+    S.gcol = M->d_gcol.as<unsigned char>();
+    S.gcol_stride = col_bytes;
+    const size_t smem = lane_smem_nocol(M);
+    for (int g0 = 0; g0 < n_groups; g0 += per) {
+        const int ng = std::min(per, n_groups - g0);
+        const LaneBatchAny Ag{A.obs, A.obs_f64, A.offsets, A.order + static_cast<size_t>(g0) * kLanes, A.group_len + g0, A.group_row + g0};
+        const int e = launch(S, Ag, O, ng, smem, M->stream, M->arena.data(), M->arena.size(), M);
+        if (e != 0) { set_error("%s kernel launch failed: %s", what, cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
+        ++M->launches;
+    }
+    return PP_OK;
+}
+
 template <typename ObsT>
 static int launch_viterbi(pp_model* M, const LaneBatch<ObsT>& B, const VitOut& O, int n_groups) {
     int rc = check_lane_model(M);
     if (rc != PP_OK) return rc;
-    const size_t smem = lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, kLaneWarps);
     const LaneBatchAny A{B.obs, sizeof(ObsT) == 8 ? 1 : 0, B.offsets, B.order, B.group_len, B.group_row};
+    if (lane_col_global(M)) return launch_gcol(M, make_sched(M, true), A, O, n_groups, lane_viterbi4g_launch, "Viterbi (global column)");
+    const size_t smem = lane_smem_col(M);
     const int e = (M->low.ptr_bits == 4 ? lane_viterbi4_launch : lane_viterbi8_launch)(
         make_sched(M, true), A, O, n_groups, smem, M->stream, M->arena.data(), M->arena.size(), M);
     if (e != 0) { set_error("Viterbi kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
@@ -261,8 +302,9 @@ template <typename ObsT>
 static int launch_forward(pp_model* M, const LaneBatch<ObsT>& B, const FwdOut& O, int n_groups) {
     int rc = check_lane_model(M);
     if (rc != PP_OK) return rc;
-    const size_t smem = lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, kLaneWarps);
     const LaneBatchAny A{B.obs, sizeof(ObsT) == 8 ? 1 : 0, B.offsets, B.order, B.group_len, B.group_row};
+    if (lane_col_global(M)) return launch_gcol(M, make_sched(M, false), A, O, n_groups, lane_forwardg_launch, "forward (global column)");
+    const size_t smem = lane_smem_col(M);
     const int e = lane_forward_launch(make_sched(M, false), A, O, n_groups, smem, M->stream, M->arena.data(), M->arena.size(), M);
     if (e != 0) { set_error("forward kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
     ++M->launches;
@@ -273,7 +315,8 @@ static int launch_forward(pp_model* M, const LaneBatch<ObsT>& B, const FwdOut& O
 // memory, every in-degree <= 8 and the run records in the constant arena; other models take the
 // state-parallel kernels.
 static bool lane_kernels_fit(const pp_model* M) {
-    const size_t smem = lane_smem_bytes2(M->low.n_slots, static_cast<int>(M->low.low_src.size()), M->low.ne, kLaneWarps);
+    const size_t smem = lane_smem_col(M);
+    if (lane_col_global(M)) return true;
     return M->low.lane_ok && smem <= M->smem_optin && M->arena.size() <= static_cast<size_t>(kArenaDoubles);
 }
 
@@ -370,7 +413,7 @@ void pp_model_destroy(pp_model* M) {
                       &M->d_out_prob, &M->d_alive, &M->d_ws, &M->d_obs, &M->d_offsets, &M->d_order,
                       &M->d_group_len, &M->d_group_row, &M->d_score, &M->d_end_state, &M->d_end_ord, &M->d_path_len,
                       &M->d_path_off, &M->d_path, &M->d_scan_tmp, &M->d_logp, &M->d_bw_wtab, &M->d_acc_map,
-                      &M->d_acc_log2, &M->d_fb_acc, &M->d_fb_scratch, &M->d_fb_ctl, &M->d_fb_minmax, &M->d_etab_own};
+                      &M->d_acc_log2, &M->d_fb_acc, &M->d_fb_scratch, &M->d_fb_ctl, &M->d_fb_minmax, &M->d_etab_own, &M->d_gcol};
     for (DevBuf* b : bufs) b->release();
     release_state_model(M);
     for (int b = 0; b < 2; ++b) {

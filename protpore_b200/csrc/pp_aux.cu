@@ -112,25 +112,28 @@ int rerun_exact_forward(pp_model* M, const void* d_obs_base, int32_t obs_dtype, 
     int64_t maxlen = 0;
     for (int64_t e = 0; e < n_events; ++e) maxlen = std::max(maxlen, h_off[e + 1] - h_off[e]);
     const int grid = static_cast<int>(std::min<int64_t>(n_list, static_cast<int64_t>(M->sm_count) * 4));
-    const int64_t stride = (maxlen + 1) * M->m;
+    // two rolling rows in shared memory are all a score needs; the full-table scratch is the fallback for huge models
+    const bool roll = 2 * static_cast<size_t>(M->m) * sizeof(double) + 16 <= M->smem_optin;
+    const int64_t stride = roll ? 0 : (maxlen + 1) * M->m;
     const size_t need = static_cast<size_t>(grid) * stride * sizeof(double);
-    if (need > M->ws_limit || M->d_tab.reserve(need) != cudaSuccess) {
+    if (!roll && (need > M->ws_limit || M->d_tab.reserve(need) != cudaSuccess)) {
         cudaGetLastError();
         set_error("exact forward re-run needs %zu bytes of workspace", need);
         return PP_ERR_NOMEM;
     }
     PP_CUDA(M->d_xbuf.reserve(static_cast<size_t>(grid) * maxlen * sizeof(double)));
     const int threads = state_threads(M);
-    const size_t smem = static_cast<size_t>(M->ne) * sizeof(double) + 16;
+    const size_t smem = roll ? 2 * static_cast<size_t>(M->m) * sizeof(double) + 16 : static_cast<size_t>(M->ne) * sizeof(double) + 16;
+    double* const d_scratch = roll ? nullptr : M->d_tab.as<double>();
     const StateModel S = make_state_model(M);
     if (obs_dtype == PP_F32) {
         if (set_dyn_smem(k_forward_exact<float>, smem) != PP_OK) return PP_ERR_CUDA;
         k_forward_exact<float><<<grid, threads, smem, M->stream>>>(S, static_cast<const float*>(d_obs_base), d_off,
-            M->d_list.as<int32_t>(), n_list, M->d_tab.as<double>(), stride, M->d_xbuf.as<double>(), maxlen, d_logp);
+            M->d_list.as<int32_t>(), n_list, d_scratch, stride, M->d_xbuf.as<double>(), maxlen, d_logp);
     } else {
         if (set_dyn_smem(k_forward_exact<double>, smem) != PP_OK) return PP_ERR_CUDA;
         k_forward_exact<double><<<grid, threads, smem, M->stream>>>(S, static_cast<const double*>(d_obs_base), d_off,
-            M->d_list.as<int32_t>(), n_list, M->d_tab.as<double>(), stride, M->d_xbuf.as<double>(), maxlen, d_logp);
+            M->d_list.as<int32_t>(), n_list, d_scratch, stride, M->d_xbuf.as<double>(), maxlen, d_logp);
     }
     PP_CUDA(cudaGetLastError());
     ++M->launches;
@@ -158,25 +161,28 @@ int exact_forward_run(pp_model* M, int slot, const void* d_obs_base, int32_t obs
     int64_t maxlen = 0;
     for (int64_t e = 0; e < n_events; ++e) maxlen = std::max(maxlen, h_off[e + 1] - h_off[e]);
     const int grid = static_cast<int>(std::min<int64_t>(n_list, static_cast<int64_t>(M->sm_count) * 4));
-    const int64_t stride = (maxlen + 1) * M->m;
+    // two rolling rows in shared memory are all a score needs; the full-table scratch is the fallback for huge models
+    const bool roll = 2 * static_cast<size_t>(M->m) * sizeof(double) + 16 <= M->smem_optin;
+    const int64_t stride = roll ? 0 : (maxlen + 1) * M->m;
     const size_t need = static_cast<size_t>(grid) * stride * sizeof(double);
-    if (need > M->ws_limit || M->d_tab.reserve(need) != cudaSuccess) {
+    if (!roll && (need > M->ws_limit || M->d_tab.reserve(need) != cudaSuccess)) {
         cudaGetLastError();
         set_error("exact forward re-run needs %zu bytes of workspace", need);
         return PP_ERR_NOMEM;
     }
     PP_CUDA(M->d_xbuf.reserve(static_cast<size_t>(grid) * maxlen * sizeof(double)));
     const int threads = state_threads(M);
-    const size_t smem = static_cast<size_t>(M->ne) * sizeof(double) + 16;
+    const size_t smem = roll ? 2 * static_cast<size_t>(M->m) * sizeof(double) + 16 : static_cast<size_t>(M->ne) * sizeof(double) + 16;
+    double* const d_scratch = roll ? nullptr : M->d_tab.as<double>();
     const StateModel S = make_state_model(M);
     if (obs_dtype == PP_F32) {
         if (set_dyn_smem(k_forward_exact<float>, smem) != PP_OK) return PP_ERR_CUDA;
         k_forward_exact<float><<<grid, threads, smem, M->stream>>>(S, static_cast<const float*>(d_obs_base), d_off,
-            P.list.as<int32_t>(), n_list, M->d_tab.as<double>(), stride, M->d_xbuf.as<double>(), maxlen, d_logp);
+            P.list.as<int32_t>(), n_list, d_scratch, stride, M->d_xbuf.as<double>(), maxlen, d_logp);
     } else {
         if (set_dyn_smem(k_forward_exact<double>, smem) != PP_OK) return PP_ERR_CUDA;
         k_forward_exact<double><<<grid, threads, smem, M->stream>>>(S, static_cast<const double*>(d_obs_base), d_off,
-            P.list.as<int32_t>(), n_list, M->d_tab.as<double>(), stride, M->d_xbuf.as<double>(), maxlen, d_logp);
+            P.list.as<int32_t>(), n_list, d_scratch, stride, M->d_xbuf.as<double>(), maxlen, d_logp);
     }
     PP_CUDA(cudaGetLastError());
     ++M->launches;

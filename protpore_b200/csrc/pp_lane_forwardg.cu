@@ -1,0 +1,24 @@
+// pp_lane_forwardg.cu (global-memory column: models too large for shared memory; see ldcol / stcol) -- derived from pp_lane_forward.cu -- one instantiation of the lane-per-event kernels (pp_lane_kernels.cuh), its own constant arena.
+#include "pp_lane_kernels.cuh"
+
+namespace pp {
+
+static const void* g_owner = nullptr;
+
+int lane_forwardg_launch(const LaneSched& S, const LaneBatchAny& B, const FwdOut& O, int n_groups, size_t smem,
+                     cudaStream_t stream, const double* arena, size_t arena_doubles, const void* owner) {
+    cudaError_t e;
+    if (g_owner != owner) {
+        e = cudaMemcpyToSymbolAsync(c_arena, arena, arena_doubles * sizeof(double), 0, cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        g_owner = owner;
+    }
+    e = cudaFuncSetAttribute(k_forward_lane<kLaneWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    k_forward_lane<kLaneWarps, true><<<n_groups, kLaneWarps * 32, smem, stream>>>(S, B, O);
+    return static_cast<int>(cudaGetLastError());
+}
+
+void lane_forwardg_invalidate(const void* owner) { if (g_owner == owner) g_owner = nullptr; }
+
+}  // namespace pp

@@ -63,6 +63,21 @@ __device__ __forceinline__ void sts64(uint32_t a, double v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 
+// Where the DP column of the CTA's 32 events lives.  CG = false: shared memory (the normal case; `a` is a 32-bit
+// shared address).  CG = true: the column of a model too large for shared memory (n_slots x 256 B > ~220 KB) sits in a
+// per-CTA global scratch that stays L2-resident; `a` is then a byte offset from the warp-uniform base `gcol`, so the
+// load is LDG [R.U32 + UR.64] without address arithmetic.  Weights and emission records are in shared memory either way.
+template <bool CG>
+__device__ __forceinline__ double ldcol(uint32_t a, const unsigned char* gcol) {
+    if (CG) return *reinterpret_cast<const double*>(gcol + a);
+    return lds64(a);
+}
+template <bool CG>
+__device__ __forceinline__ void stcol(uint32_t a, double v, unsigned char* gcol) {
+    if (CG) *reinterpret_cast<double*>(gcol + a) = v;
+    else sts64(a, v);
+}
+
 // induction state of one run: shared-memory addresses and byte strides
 template <int NE>
 struct RunPtrs {
@@ -174,6 +189,7 @@ struct VitCtx {
     int lane;
     bool active;
     double x;
+    unsigned char* gcol; // CG kernels: base of the CTA's column in global memory
 };
 
 // ------------------------------------------------------------------------------------------
@@ -183,7 +199,7 @@ struct VitCtx {
 // item before it.  Candidate j of an item is (v_j + t_j) + e for emitting items, v_j + t_j for silent ones,
 // exactly the reference's operations; the winner is the lowest index attaining the maximum, as the
 // reference's strict '>' scan leaves it (a candidate of -inf never displaces index 0 there either).
-template <int NE, int MODE, int G, int KIND, int BITS>
+template <int NE, int MODE, int G, int KIND, int BITS, bool CG>
 __device__ __forceinline__ void vit_group(RunPtrs<NE>& P, const VitCtx& C, bool start_row0, double& prev) {
     constexpr int NL = (MODE == MODE_CHAIN) ? NE - 1 : NE;          // edges read from the column
     double s[G][NL > 0 ? NL : 1], wl[G], e[G], best[G];
@@ -191,7 +207,7 @@ __device__ __forceinline__ void vit_group(RunPtrs<NE>& P, const VitCtx& C, bool 
 #pragma unroll
     for (int g = 0; g < G; ++g) {
 #pragma unroll
-        for (int j = 0; j < NL; ++j) s[g][j] = lds64(P.sp[j] + g * P.ss[j]);
+        for (int j = 0; j < NL; ++j) s[g][j] = ldcol<CG>(P.sp[j] + g * P.ss[j], C.gcol);
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -230,23 +246,23 @@ __device__ __forceinline__ void vit_group(RunPtrs<NE>& P, const VitCtx& C, bool 
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         if (start_row0) best[g] = 0.0;                // v[0, start] = 0 (3513-3514)
-        sts64(P.dp + g * P.ds, best[g]);
+        stcol<CG>(P.dp + g * P.ds, best[g], C.gcol);
     }
     if (MODE != MODE_CHAIN) prev = best[G - 1];
     store_ordinals<G, BITS>(C.row, P.pbase, C.lane, arg, C.active);
     P.advance(G);
 }
 
-template <int NE, int MODE, int KIND, int BITS>
+template <int NE, int MODE, int KIND, int BITS, bool CG>
 __device__ __forceinline__ void vit_items(RunPtrs<NE>& P, int count, const VitCtx& C, bool start_row0, double& prev) {
     constexpr int G = run_group_size(NE);
     int left = count;
-    for (; left >= G; left -= G) vit_group<NE, MODE, G, KIND, BITS>(P, C, start_row0, prev);
-    if (G > 2 && left >= 2) { vit_group<NE, MODE, 2, KIND, BITS>(P, C, start_row0, prev); left -= 2; }
-    if (left >= 1) vit_group<NE, MODE, 1, KIND, BITS>(P, C, start_row0, prev);
+    for (; left >= G; left -= G) vit_group<NE, MODE, G, KIND, BITS, CG>(P, C, start_row0, prev);
+    if (G > 2 && left >= 2) { vit_group<NE, MODE, 2, KIND, BITS, CG>(P, C, start_row0, prev); left -= 2; }
+    if (left >= 1) vit_group<NE, MODE, 1, KIND, BITS, CG>(P, C, start_row0, prev);
 }
 
-template <int NE, int BITS>
+template <int NE, int BITS, bool CG>
 __device__ __forceinline__ void vit_run_ne(const RunRec& R, int par, bool row0, uint32_t colb, uint32_t wtab,
                                            uint32_t etab, const VitCtx& C) {
     RunPtrs<NE> P;
@@ -255,33 +271,33 @@ __device__ __forceinline__ void vit_run_ne(const RunRec& R, int par, bool row0, 
     const int count = R.count;
     const int kind = R.kind;
     if (kind == EMIS_NORMAL) {
-        vit_items<NE, MODE_EMIT, EMIS_NORMAL, BITS>(P, count, C, false, prev);
+        vit_items<NE, MODE_EMIT, EMIS_NORMAL, BITS, CG>(P, count, C, false, prev);
     } else if (kind == EMIS_POINT) {
-        vit_items<NE, MODE_EMIT, EMIS_POINT, BITS>(P, count, C, false, prev);
+        vit_items<NE, MODE_EMIT, EMIS_POINT, BITS, CG>(P, count, C, false, prev);
     } else if (kind == EMIS_UNIFORM) {
-        vit_items<NE, MODE_EMIT, EMIS_UNIFORM, BITS>(P, count, C, false, prev);
+        vit_items<NE, MODE_EMIT, EMIS_UNIFORM, BITS, CG>(P, count, C, false, prev);
     } else if (NE > 0 && R.fwd) {
-        vit_group<NE, MODE_SILENT, 1, RUN_SILENT, BITS>(P, C, false, prev);       // chain head reads the column
-        vit_items<NE, MODE_CHAIN, RUN_SILENT, BITS>(P, count - 1, C, false, prev);
+        vit_group<NE, MODE_SILENT, 1, RUN_SILENT, BITS, CG>(P, C, false, prev);       // chain head reads the column
+        vit_items<NE, MODE_CHAIN, RUN_SILENT, BITS, CG>(P, count - 1, C, false, prev);
     } else {
-        vit_items<NE, MODE_SILENT, RUN_SILENT, BITS>(P, count, C, row0 && kind == RUN_START, prev);
+        vit_items<NE, MODE_SILENT, RUN_SILENT, BITS, CG>(P, count, C, row0 && kind == RUN_START, prev);
     }
 }
 
-template <int BITS>
+template <int BITS, bool CG>
 __device__ __forceinline__ void vit_run(int r, int par, bool row0, uint32_t colb, uint32_t wtab, uint32_t etab,
                                         const VitCtx& C) {
     const RunRec& R = run_rec(r);
     switch (R.n_edges) {
-        case 0: vit_run_ne<0, BITS>(R, par, row0, colb, wtab, etab, C); break;
-        case 1: vit_run_ne<1, BITS>(R, par, row0, colb, wtab, etab, C); break;
-        case 2: vit_run_ne<2, BITS>(R, par, row0, colb, wtab, etab, C); break;
-        case 3: vit_run_ne<3, BITS>(R, par, row0, colb, wtab, etab, C); break;
-        case 4: vit_run_ne<4, BITS>(R, par, row0, colb, wtab, etab, C); break;
-        case 5: vit_run_ne<5, BITS>(R, par, row0, colb, wtab, etab, C); break;
-        case 6: vit_run_ne<6, BITS>(R, par, row0, colb, wtab, etab, C); break;
-        case 7: vit_run_ne<7, BITS>(R, par, row0, colb, wtab, etab, C); break;
-        default: vit_run_ne<8, BITS>(R, par, row0, colb, wtab, etab, C); break;
+        case 0: vit_run_ne<0, BITS, CG>(R, par, row0, colb, wtab, etab, C); break;
+        case 1: vit_run_ne<1, BITS, CG>(R, par, row0, colb, wtab, etab, C); break;
+        case 2: vit_run_ne<2, BITS, CG>(R, par, row0, colb, wtab, etab, C); break;
+        case 3: vit_run_ne<3, BITS, CG>(R, par, row0, colb, wtab, etab, C); break;
+        case 4: vit_run_ne<4, BITS, CG>(R, par, row0, colb, wtab, etab, C); break;
+        case 5: vit_run_ne<5, BITS, CG>(R, par, row0, colb, wtab, etab, C); break;
+        case 6: vit_run_ne<6, BITS, CG>(R, par, row0, colb, wtab, etab, C); break;
+        case 7: vit_run_ne<7, BITS, CG>(R, par, row0, colb, wtab, etab, C); break;
+        default: vit_run_ne<8, BITS, CG>(R, par, row0, colb, wtab, etab, C); break;
     }
 }
 
@@ -305,9 +321,9 @@ struct LaneSmem {
     double* etab;
     unsigned char* xt;
     int32_t* wmax;
-    __device__ __forceinline__ LaneSmem(unsigned char* smem, const LaneSched& S) {
+    __device__ __forceinline__ LaneSmem(unsigned char* smem, const LaneSched& S, bool col_in_smem = true) {
         col = smem;
-        wtab = reinterpret_cast<double*>(smem + static_cast<size_t>(S.n_slots) * kSlotBytes);
+        wtab = reinterpret_cast<double*>(smem + (col_in_smem ? static_cast<size_t>(S.n_slots) * kSlotBytes : 0));
         etab = wtab + S.n_low;
         xt = reinterpret_cast<unsigned char*>(etab + static_cast<size_t>(S.ne) * 5);
         wmax = reinterpret_cast<int32_t*>(xt + 32 * 33 * 4);
@@ -329,11 +345,11 @@ __device__ __forceinline__ void fill_tile2(double* xt, const void* __restrict__ 
     }
 }
 
-template <int W, int BITS>
+template <int W, int BITS, bool CG = false>
 __global__ void __launch_bounds__(W * 32, 2)
 k_viterbi_lane(const LaneSched S, const LaneBatchAny B, const VitOut O) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const LaneSmem M(smem, S);
+    const LaneSmem M(smem, S, !CG);
     constexpr int TC = kLaneTileCols;
     double* xt = reinterpret_cast<double*>(M.xt);
 
@@ -344,8 +360,9 @@ k_viterbi_lane(const LaneSched S, const LaneBatchAny B, const VitOut O) {
     const int64_t off = ev >= 0 ? B.offsets[ev] : 0;
     const int n = ev >= 0 ? static_cast<int>(B.offsets[ev + 1] - off) : 0;
     const int nmax = B.group_len[g];
-    unsigned char* colp = smem + lane * 8;                       // this lane's column slice
-    const uint32_t colb = static_cast<uint32_t>(__cvta_generic_to_shared(colp));
+    unsigned char* const gcol = CG ? S.gcol + static_cast<size_t>(blockIdx.x) * S.gcol_stride : nullptr;
+    unsigned char* colp = (CG ? gcol : smem) + lane * 8;          // this lane's column slice
+    const uint32_t colb = CG ? static_cast<uint32_t>(lane * 8) : static_cast<uint32_t>(__cvta_generic_to_shared(colp));
     const uint32_t wtab = static_cast<uint32_t>(__cvta_generic_to_shared(M.wtab));
     const uint32_t etab = static_cast<uint32_t>(__cvta_generic_to_shared(M.etab));
     const size_t row_stride = static_cast<size_t>(S.n_ptr_words) * kLanes * 4;                  // bytes per pointer row
@@ -358,7 +375,7 @@ k_viterbi_lane(const LaneSched S, const LaneBatchAny B, const VitOut O) {
     // stage the model: weights and emission records; row 0: v[0, :] = -inf, v[0, start] = 0 (3513-3514)
     for (int i = threadIdx.x; i < S.n_low; i += W * 32) M.wtab[i] = __ldg(S.wtab + i);
     for (int i = threadIdx.x; i < S.ne * S.etab_doubles; i += W * 32) M.etab[i] = __ldg(S.etab + i);
-    double* col = reinterpret_cast<double*>(smem);
+    double* col = reinterpret_cast<double*>(CG ? gcol : smem);
     for (int s = threadIdx.x; s < S.n_slots * kLanes; s += W * 32) col[s] = neg_inf();
     __syncthreads();
 
@@ -377,14 +394,14 @@ k_viterbi_lane(const LaneSched S, const LaneBatchAny B, const VitOut O) {
         PP_CLK(c0);
         uint8_t* pr = prow + static_cast<size_t>(r) * row_stride;
         {
-            const VitCtx C{pr, lane, r == 0 ? ev >= 0 : r <= n, 0.0};
-            for (int u = sb; u < se; ++u) vit_run<BITS>(u, q, r == 0, colb, wtab, etab, C);
+            const VitCtx C{pr, lane, r == 0 ? ev >= 0 : r <= n, 0.0, gcol};
+            for (int u = sb; u < se; ++u) vit_run<BITS, CG>(u, q, r == 0, colb, wtab, etab, C);
         }
         PP_CLK(c1);
         if (r < nmax) {
             x = xt[(r & (TC - 1)) * (kLanes + 1) + lane];       // obs[r] belongs to row r + 1
-            const VitCtx C{pr + row_stride, lane, r + 1 <= n, x};
-            for (int u = xb; u < xe; ++u) vit_run<BITS>(u, q ^ 1, false, colb, wtab, etab, C);
+            const VitCtx C{pr + row_stride, lane, r + 1 <= n, x, gcol};
+            for (int u = xb; u < xe; ++u) vit_run<BITS, CG>(u, q ^ 1, false, colb, wtab, etab, C);
         }
         PP_CLK(c2);
         __syncthreads();
@@ -419,8 +436,8 @@ k_viterbi_lane(const LaneSched S, const LaneBatchAny B, const VitOut O) {
         // ---- phase A of row r + 1: late emitting states (they have a silent source of row r)
         PP_CLK(c4);
         {
-            const VitCtx C{pr + row_stride, lane, r + 1 <= n, x};
-            for (int u = ab; u < ae; ++u) vit_run<BITS>(u, q ^ 1, false, colb, wtab, etab, C);
+            const VitCtx C{pr + row_stride, lane, r + 1 <= n, x, gcol};
+            for (int u = ab; u < ae; ++u) vit_run<BITS, CG>(u, q ^ 1, false, colb, wtab, etab, C);
         }
         PP_CLK(c5);
         __syncthreads();
@@ -439,15 +456,15 @@ k_viterbi_lane(const LaneSched S, const LaneBatchAny B, const VitOut O) {
 // ------------------------------------------------------------------------------------------
 // Forward (scaled linear space)
 // ------------------------------------------------------------------------------------------
-template <int NE, int MODE, int G, int KIND>
+template <int NE, int MODE, int G, int KIND, bool CG>
 __device__ __forceinline__ void fwd_group(RunPtrs<NE>& P, double x, double shiftd, bool start_row0, double& prev,
-                                          int& mx) {
+                                          int& mx, unsigned char* gcol) {
     constexpr int NL = (MODE == MODE_CHAIN) ? NE - 1 : NE;
     double v[G][NL > 0 ? NL : 1], w[G][NE > 0 ? NE : 1], acc[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
 #pragma unroll
-        for (int j = 0; j < NL; ++j) v[g][j] = lds64(P.sp[j] + g * P.ss[j]);
+        for (int j = 0; j < NL; ++j) v[g][j] = ldcol<CG>(P.sp[j] + g * P.ss[j], gcol);
 #pragma unroll
         for (int j = 0; j < NE; ++j) w[g][j] = lds64(P.wp + g * P.ws + j * 8);
     }
@@ -474,66 +491,67 @@ __device__ __forceinline__ void fwd_group(RunPtrs<NE>& P, double x, double shift
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         if (start_row0) acc[g] = 1.0;
-        sts64(P.dp + g * P.ds, acc[g]);
+        stcol<CG>(P.dp + g * P.ds, acc[g], gcol);
         mx = max(mx, __double2hiint(acc[g]));
     }
     if (MODE != MODE_CHAIN) prev = acc[G - 1];
     P.advance(G);
 }
 
-template <int NE, int MODE, int KIND>
+template <int NE, int MODE, int KIND, bool CG>
 __device__ __forceinline__ void fwd_items(RunPtrs<NE>& P, int count, double x, double shiftd, bool start_row0,
-                                          double& prev, int& mx) {
+                                          double& prev, int& mx, unsigned char* gcol) {
     constexpr int G = run_group_size(NE);
     int left = count;
-    for (; left >= G; left -= G) fwd_group<NE, MODE, G, KIND>(P, x, shiftd, start_row0, prev, mx);
-    if (G > 2 && left >= 2) { fwd_group<NE, MODE, 2, KIND>(P, x, shiftd, start_row0, prev, mx); left -= 2; }
-    if (left >= 1) fwd_group<NE, MODE, 1, KIND>(P, x, shiftd, start_row0, prev, mx);
+    for (; left >= G; left -= G) fwd_group<NE, MODE, G, KIND, CG>(P, x, shiftd, start_row0, prev, mx, gcol);
+    if (G > 2 && left >= 2) { fwd_group<NE, MODE, 2, KIND, CG>(P, x, shiftd, start_row0, prev, mx, gcol); left -= 2; }
+    if (left >= 1) fwd_group<NE, MODE, 1, KIND, CG>(P, x, shiftd, start_row0, prev, mx, gcol);
 }
 
-template <int NE>
+template <int NE, bool CG>
 __device__ __forceinline__ void fwd_run_ne(const RunRec& R, int par, bool row0, uint32_t colb, uint32_t wtab,
-                                           uint32_t etab, double x, double shiftd, int& mx) {
+                                           uint32_t etab, double x, double shiftd, int& mx, unsigned char* gcol) {
     RunPtrs<NE> P;
     P.init(R, par, colb, wtab, etab, kFwdEmisBytes);
     double prev = 0.0;
     const int count = R.count;
     const int kind = R.kind;
     if (kind == EMIS_NORMAL) {
-        fwd_items<NE, MODE_EMIT, EMIS_NORMAL>(P, count, x, shiftd, false, prev, mx);
+        fwd_items<NE, MODE_EMIT, EMIS_NORMAL, CG>(P, count, x, shiftd, false, prev, mx, gcol);
     } else if (kind == EMIS_POINT) {
-        fwd_items<NE, MODE_EMIT, EMIS_POINT>(P, count, x, shiftd, false, prev, mx);
+        fwd_items<NE, MODE_EMIT, EMIS_POINT, CG>(P, count, x, shiftd, false, prev, mx, gcol);
     } else if (kind == EMIS_UNIFORM) {
-        fwd_items<NE, MODE_EMIT, EMIS_UNIFORM>(P, count, x, shiftd, false, prev, mx);
+        fwd_items<NE, MODE_EMIT, EMIS_UNIFORM, CG>(P, count, x, shiftd, false, prev, mx, gcol);
     } else if (NE > 0 && R.fwd) {
-        fwd_group<NE, MODE_SILENT, 1, RUN_SILENT>(P, x, shiftd, false, prev, mx);
-        fwd_items<NE, MODE_CHAIN, RUN_SILENT>(P, count - 1, x, shiftd, false, prev, mx);
+        fwd_group<NE, MODE_SILENT, 1, RUN_SILENT, CG>(P, x, shiftd, false, prev, mx, gcol);
+        fwd_items<NE, MODE_CHAIN, RUN_SILENT, CG>(P, count - 1, x, shiftd, false, prev, mx, gcol);
     } else {
-        fwd_items<NE, MODE_SILENT, RUN_SILENT>(P, count, x, shiftd, row0 && kind == RUN_START, prev, mx);
+        fwd_items<NE, MODE_SILENT, RUN_SILENT, CG>(P, count, x, shiftd, row0 && kind == RUN_START, prev, mx, gcol);
     }
 }
 
+template <bool CG = false>
 __device__ __forceinline__ void fwd_run(int r, int par, bool row0, uint32_t colb, uint32_t wtab, uint32_t etab,
-                                        double x, double shiftd, int& mx) {
+                                        double x, double shiftd, int& mx, unsigned char* gcol = nullptr) {
     const RunRec& R = run_rec(r);
     switch (R.n_edges) {
-        case 0: fwd_run_ne<0>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
-        case 1: fwd_run_ne<1>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
-        case 2: fwd_run_ne<2>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
-        case 3: fwd_run_ne<3>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
-        case 4: fwd_run_ne<4>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
-        case 5: fwd_run_ne<5>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
-        case 6: fwd_run_ne<6>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
-        case 7: fwd_run_ne<7>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
-        default: fwd_run_ne<8>(R, par, row0, colb, wtab, etab, x, shiftd, mx); break;
+        case 0: fwd_run_ne<0, CG>(R, par, row0, colb, wtab, etab, x, shiftd, mx, gcol); break;
+        case 1: fwd_run_ne<1, CG>(R, par, row0, colb, wtab, etab, x, shiftd, mx, gcol); break;
+        case 2: fwd_run_ne<2, CG>(R, par, row0, colb, wtab, etab, x, shiftd, mx, gcol); break;
+        case 3: fwd_run_ne<3, CG>(R, par, row0, colb, wtab, etab, x, shiftd, mx, gcol); break;
+        case 4: fwd_run_ne<4, CG>(R, par, row0, colb, wtab, etab, x, shiftd, mx, gcol); break;
+        case 5: fwd_run_ne<5, CG>(R, par, row0, colb, wtab, etab, x, shiftd, mx, gcol); break;
+        case 6: fwd_run_ne<6, CG>(R, par, row0, colb, wtab, etab, x, shiftd, mx, gcol); break;
+        case 7: fwd_run_ne<7, CG>(R, par, row0, colb, wtab, etab, x, shiftd, mx, gcol); break;
+        default: fwd_run_ne<8, CG>(R, par, row0, colb, wtab, etab, x, shiftd, mx, gcol); break;
     }
 }
 
-template <int W>
+template <int W, bool CG = false>
 __global__ void __launch_bounds__(W * 32, 2)
 k_forward_lane(const LaneSched S, const LaneBatchAny B, const FwdOut O) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const LaneSmem M(smem, S);
+    const LaneSmem M(smem, S, !CG);
     constexpr int TC = kLaneTileCols;
     double* xt = reinterpret_cast<double*>(M.xt);
     int32_t* wmax = M.wmax;
@@ -545,8 +563,9 @@ k_forward_lane(const LaneSched S, const LaneBatchAny B, const FwdOut O) {
     const int64_t off = ev >= 0 ? B.offsets[ev] : 0;
     const int n = ev >= 0 ? static_cast<int>(B.offsets[ev + 1] - off) : 0;
     const int nmax = B.group_len[g];
-    unsigned char* colp = smem + lane * 8;
-    const uint32_t colb = static_cast<uint32_t>(__cvta_generic_to_shared(colp));
+    unsigned char* const gcol = CG ? S.gcol + static_cast<size_t>(blockIdx.x) * S.gcol_stride : nullptr;
+    unsigned char* colp = (CG ? gcol : smem) + lane * 8;
+    const uint32_t colb = CG ? static_cast<uint32_t>(lane * 8) : static_cast<uint32_t>(__cvta_generic_to_shared(colp));
     const uint32_t wtab = static_cast<uint32_t>(__cvta_generic_to_shared(M.wtab));
     const uint32_t etab = static_cast<uint32_t>(__cvta_generic_to_shared(M.etab));
 
@@ -556,7 +575,7 @@ k_forward_lane(const LaneSched S, const LaneBatchAny B, const FwdOut O) {
 
     for (int i = threadIdx.x; i < S.n_low; i += W * 32) M.wtab[i] = __ldg(S.wtab + i);
     for (int i = threadIdx.x; i < S.ne * S.etab_doubles; i += W * 32) M.etab[i] = __ldg(S.etab + i);
-    double* col = reinterpret_cast<double*>(smem);
+    double* col = reinterpret_cast<double*>(CG ? gcol : smem);
     for (int s = threadIdx.x; s < S.n_slots * kLanes; s += W * 32) col[s] = 0.0;
     wmax[warp * kLanes + lane] = 0;
     __syncthreads();
@@ -586,11 +605,11 @@ k_forward_lane(const LaneSched S, const LaneBatchAny B, const FwdOut O) {
             }
         }
         int mxs = 0;                              // silent values do not steer the scale
-        for (int u = sb; u < se; ++u) fwd_run(u, q, r == 0, colb, wtab, etab, 0.0, 0.0, mxs);    // silent (2847-2871, 2891-2926)
+        for (int u = sb; u < se; ++u) fwd_run<CG>(u, q, r == 0, colb, wtab, etab, 0.0, 0.0, mxs, gcol);    // silent (2847-2871, 2891-2926)
         mx = 0;
         if (r < nmax) {
             x = xt[(r & (TC - 1)) * (kLanes + 1) + lane];
-            for (int u = xb; u < xe; ++u) fwd_run(u, q ^ 1, false, colb, wtab, etab, x, shiftd, mx);   // early emitting of row r + 1
+            for (int u = xb; u < xe; ++u) fwd_run<CG>(u, q ^ 1, false, colb, wtab, etab, x, shiftd, mx, gcol);   // early emitting of row r + 1
         }
         __syncthreads();
 
@@ -623,7 +642,7 @@ k_forward_lane(const LaneSched S, const LaneBatchAny B, const FwdOut O) {
         }
         if (r == nmax) break;
 
-        for (int u = ab; u < ae; ++u) fwd_run(u, q ^ 1, false, colb, wtab, etab, x, shiftd, mx);       // late emitting (2874-2889)
+        for (int u = ab; u < ae; ++u) fwd_run<CG>(u, q ^ 1, false, colb, wtab, etab, x, shiftd, mx, gcol);       // late emitting (2874-2889)
         wmax[warp * kLanes + lane] = mx;
         __syncthreads();
     }

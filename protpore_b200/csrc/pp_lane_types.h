@@ -23,6 +23,8 @@ struct LaneSched {
     int32_t end_slot_off;            // byte offset of the end state's slot
     int32_t end_state, end_edge_begin, end_n_edges, finite, end_final_only;
     int32_t n_ptr_words, ptr_bits;
+    unsigned char* gcol;             // global-column kernels (models too large for shared memory): per-CTA column scratch
+    uint64_t gcol_stride;            // bytes per CTA
 };
 
 // tile of staged observations: 32 columns for float32, 16 for float64 (same bytes)
@@ -52,6 +54,11 @@ int lane_viterbi8_launch(const LaneSched& S, const LaneBatchAny& B, const VitOut
                          cudaStream_t stream, const double* arena, size_t arena_doubles, const void* owner);
 int lane_forward_launch(const LaneSched& S, const LaneBatchAny& B, const FwdOut& O, int n_groups, size_t smem,
                         cudaStream_t stream, const double* arena, size_t arena_doubles, const void* owner);
+// the same kernels with the column in global memory (S.gcol): pp_lane_gcol.cu
+int lane_viterbi4g_launch(const LaneSched& S, const LaneBatchAny& B, const VitOut& O, int n_groups, size_t smem,
+                          cudaStream_t stream, const double* arena, size_t arena_doubles, const void* owner);
+int lane_forwardg_launch(const LaneSched& S, const LaneBatchAny& B, const FwdOut& O, int n_groups, size_t smem,
+                         cudaStream_t stream, const double* arena, size_t arena_doubles, const void* owner);
 // lane-per-event forward-backward kernel (pp_lane_fb.cuh)
 struct FbSched {
     int32_t run_ranges[kMaxLaneWarps * 6];   // per warp: {begin, end} of its H, silent and emitting runs (arena indices)

@@ -59,6 +59,7 @@ struct pp_model {
     const double* etab = nullptr;
     int64_t etab_rows = 0;
     pp::DevBuf d_etab_own;
+    pp::DevBuf d_gcol;        // per-CTA DP columns of the global-column lane kernels (models too large for shared memory)
     bool has_table_states = false;
 
     // chunk pipeline of the batched host/device calls (pp_api.cu): copy-in and copy-out streams beside the compute

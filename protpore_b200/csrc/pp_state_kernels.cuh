@@ -47,30 +47,54 @@ __device__ __forceinline__ double pair_lse(double x, double y) {       // yahmm.
     return y + log(exp(x - y) + 1);
 }
 
-// One event per CTA.  table: (n+1) x m row-major float64.  e_row: scratch [ne] per CTA.
+// Silent states of one row, level by level of the silent sub-DAG.  A level wider than a warp is spread over the CTA
+// and closed by a CTA barrier; a narrow level (the links of a skip / back-slip chain: one to three states) is done by
+// warp 0 alone behind a warp barrier, so a chain of several hundred links costs several hundred __syncwarp instead of
+// several hundred __syncthreads.  `body(l)` computes and stores state l.  Control flow is CTA-uniform.
+template <typename Body>
+__device__ __forceinline__ void sweep_levels(const int32_t* __restrict__ lev_ptr, const int32_t* __restrict__ lev_states,
+                                             int n_levels, Body body) {
+    const int t = threadIdx.x, nt = blockDim.x;
+    bool pending = false;                         // warp 0 wrote values the rest of the CTA has not synchronised with
+    for (int lev = 0; lev < n_levels; ++lev) {
+        const int b = lev_ptr[lev], e = lev_ptr[lev + 1];
+        if (e - b > 32) {
+            if (pending) { __syncthreads(); pending = false; }
+            for (int j = b + t; j < e; j += nt) body(lev_states[j]);
+            __syncthreads();
+        } else {
+            if (t < 32) {
+                if (b + t < e) body(lev_states[b + t]);
+                __syncwarp();
+            }
+            pending = true;
+        }
+    }
+    if (pending) __syncthreads();
+}
+
+// One event per CTA.  ROLL = false: table (n+1) x m row-major float64 (Model.forward's return value).  ROLL = true: only
+// two rows are kept (row i at f + (i & 1) * m, shared memory) -- all a score needs.  e_row: scratch [ne] per CTA.
+template <bool ROLL>
 __device__ inline void forward_table_event(const StateModel& S, const double* __restrict__ x, int n, double* f,
                                            double* e_row, int64_t row0) {
     const int m = S.m, ne = S.ne;
     const int t = threadIdx.x, nt = blockDim.x;
     for (int l = t; l < m; l += nt) f[l] = (l == S.start) ? 0.0 : neg_inf();
     __syncthreads();
-    for (int lev = 0; lev < S.n_levels; ++lev) {                         // 2847-2871
-        for (int j = S.lev_ptr[lev] + t; j < S.lev_ptr[lev + 1]; j += nt) {
-            const int l = S.lev_states[j];
-            if (l == S.start) continue;
-            double lp = neg_inf();
-            for (int k = S.in_ptr[l]; k < S.in_ptr[l + 1]; ++k) {
-                const int ki = S.in_src[k];
-                if (ki < ne || ki >= l) continue;
-                lp = pair_lse(lp, f[ki] + S.in_logp[k]);
-            }
-            f[l] = lp;
+    sweep_levels(S.lev_ptr, S.lev_states, S.n_levels, [&](int l) {      // 2847-2871
+        if (l == S.start) return;
+        double lp = neg_inf();
+        for (int k = S.in_ptr[l]; k < S.in_ptr[l + 1]; ++k) {
+            const int ki = S.in_src[k];
+            if (ki < ne || ki >= l) continue;
+            lp = pair_lse(lp, f[ki] + S.in_logp[k]);
         }
-        __syncthreads();
-    }
+        f[l] = lp;
+    });
     for (int i = 0; i < n; ++i) {
-        const double* fi = f + static_cast<size_t>(i) * m;
-        double* fn = f + static_cast<size_t>(i + 1) * m;
+        const double* fi = ROLL ? f + static_cast<size_t>(i & 1) * m : f + static_cast<size_t>(i) * m;
+        double* fn = ROLL ? f + static_cast<size_t>((i + 1) & 1) * m : f + static_cast<size_t>(i + 1) * m;
         const double xi = x[i];
         for (int l = t; l < ne; l += nt) {                               // 2874-2889
             double lp = neg_inf();
@@ -78,31 +102,27 @@ __device__ inline void forward_table_event(const StateModel& S, const double* __
             fn[l] = lp + emit_state(S, l, xi, row0 + i);
         }
         __syncthreads();
-        for (int lev = 0; lev < S.n_levels; ++lev) {
-            for (int j = S.lev_ptr[lev] + t; j < S.lev_ptr[lev + 1]; j += nt) {
-                const int l = S.lev_states[j];
-                double lp1 = neg_inf();                                  // 2891-2906
-                for (int k = S.in_ptr[l]; k < S.in_ptr[l + 1]; ++k) {
-                    const int ki = S.in_src[k];
-                    if (ki >= ne) continue;
-                    lp1 = pair_lse(lp1, fn[ki] + S.in_logp[k]);
-                }
-                double lp2 = neg_inf();                                  // 2908-2926
-                for (int k = S.in_ptr[l]; k < S.in_ptr[l + 1]; ++k) {
-                    const int ki = S.in_src[k];
-                    if (ki < ne || ki >= l) continue;
-                    lp2 = pair_lse(lp2, fn[ki] + S.in_logp[k]);
-                }
-                fn[l] = pair_lse(lp1, lp2);
+        sweep_levels(S.lev_ptr, S.lev_states, S.n_levels, [&](int l) {
+            double lp1 = neg_inf();                                      // 2891-2906
+            for (int k = S.in_ptr[l]; k < S.in_ptr[l + 1]; ++k) {
+                const int ki = S.in_src[k];
+                if (ki >= ne) continue;
+                lp1 = pair_lse(lp1, fn[ki] + S.in_logp[k]);
             }
-            __syncthreads();
-        }
+            double lp2 = neg_inf();                                      // 2908-2926
+            for (int k = S.in_ptr[l]; k < S.in_ptr[l + 1]; ++k) {
+                const int ki = S.in_src[k];
+                if (ki < ne || ki >= l) continue;
+                lp2 = pair_lse(lp2, fn[ki] + S.in_logp[k]);
+            }
+            fn[l] = pair_lse(lp1, lp2);
+        });
     }
     (void)e_row;
 }
 
-__device__ inline double logp_from_forward(const StateModel& S, const double* f, int n) {   // 3378-3396
-    const double* fn = f + static_cast<size_t>(n) * S.m;
+__device__ inline double logp_from_forward(const StateModel& S, const double* f, int n, bool roll = false) {   // 3378-3396
+    const double* fn = f + static_cast<size_t>(roll ? (n & 1) : n) * S.m;
     if (S.finite == 1) return fn[S.end];
     double s = neg_inf();
     for (int i = 0; i < S.ne; ++i) s = pair_lse(s, fn[i]);
@@ -202,7 +222,7 @@ __global__ void k_table(const StateModel S, const ObsT* __restrict__ obs, const 
         for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = static_cast<double>(obs[off + i]);
         __syncthreads();
         double* tab = tables + table_off[ev];
-        if (mode == 0) forward_table_event(S, x, n, tab, e_row, off);
+        if (mode == 0) forward_table_event<false>(S, x, n, tab, e_row, off);
         else backward_table_event(S, x, n, tab, e_row, off);
         __syncthreads();
     }
@@ -210,6 +230,8 @@ __global__ void k_table(const StateModel S, const ObsT* __restrict__ obs, const 
 
 // Exact log-space score of selected events (re-run path of the linear-space forward sweep): one
 // CTA per listed event, forward table in per-CTA scratch, only log P is kept.
+// `scratch` == nullptr: two rolling rows in dynamic shared memory (2 * m doubles) -- the normal case; otherwise the full
+// table in per-CTA global scratch (models with more than ~14,000 states).
 template <typename ObsT>
 __global__ void k_forward_exact(const StateModel S, const ObsT* __restrict__ obs, const int64_t* __restrict__ offsets,
                                 const int32_t* __restrict__ list, int n_list, double* __restrict__ scratch,
@@ -223,9 +245,15 @@ __global__ void k_forward_exact(const StateModel S, const ObsT* __restrict__ obs
         double* x = xbuf + static_cast<size_t>(blockIdx.x) * xbuf_stride;
         for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = static_cast<double>(obs[off + i]);
         __syncthreads();
-        double* f = scratch + static_cast<size_t>(blockIdx.x) * scratch_stride;
-        forward_table_event(S, x, n, f, e_row, off);
-        if (threadIdx.x == 0) logp_out[ev] = logp_from_forward(S, f, n);
+        if (scratch == nullptr) {
+            double* f = e_row;                          // [2][m]
+            forward_table_event<true>(S, x, n, f, nullptr, off);
+            if (threadIdx.x == 0) logp_out[ev] = logp_from_forward(S, f, n, true);
+        } else {
+            double* f = scratch + static_cast<size_t>(blockIdx.x) * scratch_stride;
+            forward_table_event<false>(S, x, n, f, e_row, off);
+            if (threadIdx.x == 0) logp_out[ev] = logp_from_forward(S, f, n);
+        }
         __syncthreads();
     }
 }
@@ -279,23 +307,19 @@ __global__ void k_viterbi_state(const StateModel S, const StateVit V, const ObsT
                 }
             }
             __syncthreads();
-            for (int lev = 0; lev < S.n_levels; ++lev) {                             // 3515-3542, 3564-3605
-                for (int i = S.lev_ptr[lev] + t; i < S.lev_ptr[lev + 1]; i += nt) {
-                    const int l = S.lev_states[i];
-                    if (r == 0 && l == S.start) continue;
-                    if (V.end_final_only && l == S.end && r != n) continue;
-                    double best = neg_inf();
-                    int arg = 0;
-                    const int b = V.edge_begin[l];
-                    for (int k = 0; k < V.n_edges[l]; ++k) {
-                        const double s = __dadd_rn(cur[V.low_src[b + k]], V.low_logp[b + k]);
-                        if (s > best) { best = s; arg = k; }
-                    }
-                    cur[l] = best;
-                    tr[l] = static_cast<uint16_t>(arg);
+            sweep_levels(S.lev_ptr, S.lev_states, S.n_levels, [&](int l) {            // 3515-3542, 3564-3605
+                if (r == 0 && l == S.start) return;
+                if (V.end_final_only && l == S.end && r != n) return;
+                double best = neg_inf();
+                int arg = 0;
+                const int b = V.edge_begin[l];
+                for (int k = 0; k < V.n_edges[l]; ++k) {
+                    const double s = __dadd_rn(cur[V.low_src[b + k]], V.low_logp[b + k]);
+                    if (s > best) { best = s; arg = k; }
                 }
-                __syncthreads();
-            }
+                cur[l] = best;
+                tr[l] = static_cast<uint16_t>(arg);
+            });
             double* sw = cur; cur = prv; prv = sw;                                    // prv = the row just finished
         }
         if (t == 0) {                                                                // 3614-3619
@@ -394,7 +418,7 @@ __global__ void k_fb_accumulate(const StateModel S, const ObsT* __restrict__ obs
         __syncthreads();
         double* f = scratch + static_cast<size_t>(blockIdx.x) * scratch_stride;
         double* b = f + static_cast<size_t>(n + 1) * m;
-        forward_table_event(S, x, n, f, e_row, off);
+        forward_table_event<false>(S, x, n, f, e_row, off);
         const double lsp = logp_from_forward(S, f, n);
         if (t == 0) logp_out[ev] = lsp;
         if (lsp == neg_inf() || lsp != lsp) { __syncthreads(); continue; }
