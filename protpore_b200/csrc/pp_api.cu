@@ -30,7 +30,6 @@ void set_error(const char* fmt, ...) {
 void lane_viterbi4_invalidate(const void*);
 void lane_viterbi4g_invalidate(const void*);
 void lane_forwardg_invalidate(const void*);
-void lane_viterbi8_invalidate(const void*);
 void lane_forward_invalidate(const void*);
 void lane_fb_invalidate(const void*);
 void lane_arena_invalidate(const void* owner) {
@@ -38,7 +37,6 @@ void lane_arena_invalidate(const void* owner) {
     lane_viterbi4_invalidate(owner);
     lane_viterbi4g_invalidate(owner);
     lane_forwardg_invalidate(owner);
-    lane_viterbi8_invalidate(owner);
     lane_forward_invalidate(owner);
 }
 
@@ -291,8 +289,9 @@ static int launch_viterbi(pp_model* M, const LaneBatch<ObsT>& B, const VitOut& O
     const LaneBatchAny A{B.obs, sizeof(ObsT) == 8 ? 1 : 0, B.offsets, B.order, B.group_len, B.group_row};
     if (lane_col_global(M)) return launch_gcol(M, make_sched(M, true), A, O, n_groups, lane_viterbi4g_launch, "Viterbi (global column)");
     const size_t smem = lane_smem_col(M);
-    const int e = (M->low.ptr_bits == 4 ? lane_viterbi4_launch : lane_viterbi8_launch)(
-        make_sched(M, true), A, O, n_groups, smem, M->stream, M->arena.data(), M->arena.size(), M);
+    // every item of a lane-lowered model has <= 8 in-edges (kMaxRunEdges), so its ordinals always take 4 bits
+    if (M->low.ptr_bits != 4) { set_error("internal: %d-bit traceback ordinals have no kernel", M->low.ptr_bits); return PP_ERR_UNSUPPORTED; }
+    const int e = lane_viterbi4_launch(make_sched(M, true), A, O, n_groups, smem, M->stream, M->arena.data(), M->arena.size(), M);
     if (e != 0) { set_error("Viterbi kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
     ++M->launches;
     return PP_OK;

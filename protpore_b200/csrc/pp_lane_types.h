@@ -1,6 +1,7 @@
 // pp_lane_types.h -- kernel-parameter structs and launch entry points of the lane-per-event kernels.
 // The kernels themselves (pp_lane_kernels.cuh) are instantiated in three translation units that compile in
-// parallel: pp_lane_viterbi4.cu (4-bit ordinals), pp_lane_viterbi8.cu (8-bit) and pp_lane_forward.cu.
+// parallel: pp_lane_viterbi4.cu (4-bit ordinals), pp_lane_forward.cu, and their global-column twins pp_lane_viterbi4g.cu /
+// pp_lane_forwardg.cu (an 8-bit-ordinal build existed but was unreachable: lane-lowered items have <= 8 in-edges).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -49,8 +50,6 @@ __host__ __device__ inline size_t lane_smem_bytes2(int n_slots, int n_low, int n
 // Launchers.  Each kernel translation unit owns a __constant__ arena holding the run records of ONE model;
 // `arena` / `arena_doubles` / `owner` let it re-upload (stream-ordered) when another handle's image is resident.
 int lane_viterbi4_launch(const LaneSched& S, const LaneBatchAny& B, const VitOut& O, int n_groups, size_t smem,
-                         cudaStream_t stream, const double* arena, size_t arena_doubles, const void* owner);
-int lane_viterbi8_launch(const LaneSched& S, const LaneBatchAny& B, const VitOut& O, int n_groups, size_t smem,
                          cudaStream_t stream, const double* arena, size_t arena_doubles, const void* owner);
 int lane_forward_launch(const LaneSched& S, const LaneBatchAny& B, const FwdOut& O, int n_groups, size_t smem,
                         cudaStream_t stream, const double* arena, size_t arena_doubles, const void* owner);
