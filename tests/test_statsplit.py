@@ -211,3 +211,50 @@ def test_gpu_segment_and_decode_pipeline():
             s, p = model.viterbi(means32.astype(np.float64))
             assert s == scores[e]
             assert (p is None and plen[e] < 0) or [k for k, _ in p] == list(paths[poff[e]:poff[e + 1]])
+
+
+@pytest.mark.gpu
+def test_gpu_random_parameter_sweep():
+    """Seeded sweep over segmenter parameters and signal shapes (staircases, drifts, spikes, constant stretches, a NaN,
+    a 300k-sample event): breakpoints identical to the oracle for every event."""
+    rng = np.random.default_rng(2026)
+
+    def signal(kind, n):
+        if kind == 0:
+            return staircase(rng, max(1, n // 400), 100, 700)[:n] if n >= 700 else rng.normal(30, 1, size=n)
+        if kind == 1:
+            return 40 + np.cumsum(rng.normal(0, 0.05, size=n)) + rng.normal(0, 0.5, size=n)        # drift
+        if kind == 2:
+            x = rng.normal(35, 0.8, size=n)
+            x[rng.integers(0, n, size=max(1, n // 200))] += rng.normal(0, 30, size=max(1, n // 200))   # spikes
+            return x
+        x = rng.normal(35, 1.0, size=n)
+        a = int(rng.integers(0, max(1, n - 50)))
+        x[a:a + 50] = 33.0                                                                         # a constant stretch
+        return x
+
+    checked = 0
+    for trial in range(14):
+        mw = int(rng.integers(1, 300))
+        kw = dict(min_width=mw, max_width=int(mw * rng.integers(1, 30) + rng.integers(0, 50)),
+                  window_width=int(2 * mw + rng.integers(0, 6 * mw + 20)))
+        if trial % 3 == 0:
+            kw["min_gain_per_sample"] = float(rng.uniform(0.001, 0.5))
+        elif trial % 3 == 1:
+            kw.update(prior_segments_per_second=float(rng.uniform(1, 1000)), false_positive_rate=float(rng.uniform(0.1, 100)))
+        p = parsers.FastStatSplit(**kw)
+        currents = [signal(int(rng.integers(0, 4)), int(rng.integers(1, 6000))) for _ in range(24)]
+        if trial == 0:
+            currents.append(staircase(rng, 400, 500, 1000))                   # ~300k samples
+        if trial == 1:
+            x = rng.normal(30, 1, size=3000)
+            x[1234] = np.nan                                                  # NaN poisons the sums from there on
+            currents.append(x)
+        off, start, mean, std, _ = p.segment_means_batch(currents, want_std=False)
+        for e, cur in enumerate(currents):
+            bp, stats = so.parse(cur, kw["min_width"], kw["max_width"], kw["window_width"], gain=p.min_gain, with_stats=True)
+            got = start[off[e]:off[e + 1]]
+            if not np.array_equal(got, np.concatenate([[0], bp])):
+                assert stats[0] < 1e-9, (trial, e, kw, stats[0])
+            checked += 1
+    assert checked >= 14 * 24
