@@ -56,3 +56,22 @@ def test_model_text_roundtrip(tmp_path):
     b = {(again.states[i].name, again.states[j].name): v for (i, j), v in np.ndenumerate(again.dense_transition_matrix())}
     for key, v in a.items():
         assert b[key] == pytest.approx(v, abs=1e-12) or (np.isinf(v) and np.isinf(b[key]))
+
+
+@pytest.mark.reference
+def test_from_matrix_matches_reference():
+    """Model.from_matrix (yahmm.pyx:3884-3936), including its quirk of wiring every `ends` entry to the LAST state."""
+    import numpy as np
+    import protpore_b200.yahmm as ours
+    from oracle import ref_loader
+    ref = ref_loader.load_reference_yahmm()
+    T = np.array([[0.5, 0.3, 0.2], [0.1, 0.6, 0.3], [0.2, 0.2, 0.6]]) * 0.9
+
+    def make(mod):
+        d = [mod.NormalDistribution(0, 1), mod.NormalDistribution(3, 1), mod.UniformDistribution(0, 5)]
+        return mod.Model.from_matrix(T, d, starts=[0.5, 0.25, 0.25], ends=[0.1, 0.1, 0.1], state_names=["a", "b", "c"], name="fm")
+
+    a, b = make(ours), make(ref)
+    assert [s.name for s in a.states] == [s.name for s in b.states]
+    assert np.array_equal(a.dense_transition_matrix(), np.asarray(b.dense_transition_matrix()))
+    assert (a.start_index, a.end_index, a.silent_start) == (b.start_index, b.end_index, b.silent_start)
