@@ -375,6 +375,17 @@ int pp_backward_table(pp_model* M, const double* obs, int64_t n, int32_t mem, do
 // Lane-per-event forward-backward (pp_lane_fb.cuh).  Returns PP_OK and sets *done: 1 = statistics added (events the
 // scaled sweep rejected are listed in d_list / *n_rejects for the exact kernel), 0 = the path does not apply or its
 // checks failed and the caller must run the whole batch on the exact kernel.
+// statistics that left the double range inside k_fb_lane (0 x inf in a row whose scale factors over- / underflow:
+// observations tens of sigmas away from every state) must not reach the caller's accumulators
+static __global__ void k_count_nonfinite(const double* __restrict__ a, size_t n, int32_t* __restrict__ bad) {
+    int local = 0;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const double v = a[i];
+        local += !(fabs(v) <= 1.7976931348623157e308);
+    }
+    if (local) atomicAdd(bad, local);
+}
+
 static int fb_batch_lane(pp_model* M, const void* d_obs, int32_t obs_dtype, const int64_t* d_off, const int64_t* h_off,
                          int64_t n_events, int64_t maxlen, double* d_logp, double* d_edge, double* d_mom, double* d_mm,
                          int* done, int32_t* n_rejects) {
@@ -429,6 +440,13 @@ static int fb_batch_lane(pp_model* M, const void* d_obs, int32_t obs_dtype, cons
     int e = lane_fb_launch(S, F, B, grid, smem, M->stream, M->arena_fb.data(), M->arena_fb.size(), M);
     if (e != 0) { set_error("forward-backward kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
     ++M->launches;
+    {
+        const size_t n_acc = acc_bytes / sizeof(double);
+        k_count_nonfinite<<<static_cast<unsigned>(std::min<size_t>((n_acc + 255) / 256, 1024)), 256, 0, M->stream>>>(
+            F.acc, n_acc, M->d_fb_ctl.as<int32_t>() + 5);
+        PP_CUDA(cudaGetLastError());
+        ++M->launches;
+    }
     int32_t ctl[16] = {0};
     PP_CUDA(cudaMemcpyAsync(ctl, M->d_fb_ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, M->stream));
     PP_CUDA(cudaStreamSynchronize(M->stream));
@@ -437,9 +455,9 @@ static int fb_batch_lane(pp_model* M, const void* d_obs, int32_t obs_dtype, cons
         std::fprintf(stderr, "[pp] k_fb_lane: %d failed events; first: reason %d event %d (n or row %d) values %.17g %.17g %.17g %.17g\n",
                      ctl[1], ctl[2], ctl[3], ctl[4], dv[0], dv[1], dv[2], dv[3]);
     }
-    if (ctl[1] != 0) {                                              // a backward sweep failed its checks: exact path
-        M->fb_info[0] = 2;
-        M->fb_info[2] = ctl[1];
+    if (ctl[1] != 0 || ctl[5] != 0) {                               // a backward sweep failed its checks, or a statistic is
+        M->fb_info[0] = 2;                                          // not finite: the exact kernel redoes the batch
+        M->fb_info[2] = ctl[1] != 0 ? ctl[1] : -ctl[5];
         return PP_OK;
     }
     e = lane_fb_finalize(F.acc, grid, L.n_acc_slots, M->d_acc_map.as<int32_t>(), M->d_acc_log2.as<int32_t>(), M->n_edges,

@@ -191,6 +191,7 @@ std::string lower_model(const pp_model_desc& d, int warps, Lowered* low) {
             if (!describe(states[i], &a)) { ++i; continue; }
             std::vector<Desc> seq{a};
             size_t j = i + 1;
+            bool chain_mode = false;
             while (j < states.size()) {
                 Desc nx;
                 if (!describe(states[j], &nx)) break;
@@ -198,6 +199,23 @@ std::string lower_model(const pp_model_desc& d, int warps, Lowered* low) {
                 if (!silent && seq.size() >= 2 &&
                     states[j] - states[j - 1] != states[j - 1] - states[j - 2]) break;
                 if (!extends(seq.size() >= 2 ? &seq[seq.size() - 2] : nullptr, seq.back(), nx)) break;
+                if (silent) {
+                    // The kernels load ALL sources of a group of items before they store any of them, so the items of
+                    // a run must not read each other -- except for the one pattern they forward in a register: the
+                    // LAST edge of every item reads the item right before it (a chain).  Anything else starts a new run.
+                    bool dep_other = false, dep_chain = false;
+                    for (int k = 0; k < nx.ne; ++k) {
+                        const int src = low->low_src[nx.wbase + k];
+                        for (size_t t = i; t < j; ++t)
+                            if (src == states[t]) {
+                                if (k == nx.ne - 1 && t + 1 == j) dep_chain = true;
+                                else dep_other = true;
+                            }
+                    }
+                    if (dep_other) break;
+                    if (seq.size() == 1) chain_mode = dep_chain;
+                    else if (dep_chain != chain_mode) break;
+                }
                 seq.push_back(nx);
                 ++j;
             }

@@ -36,6 +36,7 @@ void build_runs(const std::vector<BDesc>& seq, bool silent_list, std::vector<Run
     size_t i = 0;
     while (i < seq.size()) {
         size_t j = i + 1;
+        bool chain_mode = false;
         while (j < seq.size()) {
             const BDesc &a = seq[i], &p = seq[j - 1], &n = seq[j];
             if (n.kind != a.kind || n.ne != a.ne) break;
@@ -45,6 +46,20 @@ void build_runs(const std::vector<BDesc>& seq, bool silent_list, std::vector<Run
                           n.state - p.state == p.state - q.state;
                 for (int k = 0; k < n.ne && ok; ++k) ok = n.src[k] - p.src[k] == p.src[k] - q.src[k];
                 if (!ok) break;
+            }
+            if (silent_list) {
+                // as in the forward lowering: the items of a run must not read each other's values (all loads of a
+                // group are issued before its stores), except the chain pattern -- the last edge reads the item before
+                bool dep_other = false, dep_chain = false;
+                for (int k = 0; k < n.ne; ++k)
+                    for (size_t t = i; t < j; ++t)
+                        if (n.src[k] == seq[t].dst) {
+                            if (k == n.ne - 1 && t + 1 == j) dep_chain = true;
+                            else dep_other = true;
+                        }
+                if (dep_other) break;
+                if (j - i == 1) chain_mode = dep_chain;
+                else if (dep_chain != chain_mode) break;
             }
             ++j;
         }
