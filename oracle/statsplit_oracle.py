@@ -51,12 +51,16 @@ def parse(current, min_width=100, max_width=1000000, window_width=10000, gain=No
     x = np.ascontiguousarray(current, dtype=np.float64)
     if gain is None:
         gain = min_gain(window_width=window_width, **kw)
-    cap = max(16, len(x) // max(1, int(min_width)) + 16)
-    out = np.empty(cap, dtype=np.int64)
+    # a forced split (cparsers.pyx:198-201) may cut off a piece shorter than min_width: up to 2 * (n / min_width) segments
+    cap = max(16, 2 * (len(x) // max(1, int(min_width))) + 16)
     stats = np.zeros(3, dtype=np.float64)
-    n = _load().statsplit_parse(x.ctypes.data_as(_f64p), len(x), int(min_width), int(max_width), int(window_width),
-                                float(gain), out.ctypes.data_as(_i64p), cap, stats.ctypes.data_as(_f64p))
-    assert n <= cap, "breakpoint capacity"
+    while True:
+        out = np.empty(cap, dtype=np.int64)
+        n = _load().statsplit_parse(x.ctypes.data_as(_f64p), len(x), int(min_width), int(max_width), int(window_width),
+                                    float(gain), out.ctypes.data_as(_i64p), cap, stats.ctypes.data_as(_f64p))
+        if n <= cap:
+            break
+        cap = int(n)
     bp = out[:n].copy()
     return (bp, stats) if with_stats else bp
 

@@ -435,8 +435,8 @@ def statsplit_batch(current, offsets, min_width, max_width, window_width, min_ga
         return [alloc(cap, "i4"), alloc(cap, "f8"), alloc(cap, "f8") if want_std else None,
                 alloc(cap, "f4") if want_f32 else None]
 
-    if capacity is None:                      # an event of n samples has at most n // min_width + 1 segments
-        lens = (offsets[1:] - offsets[:-1])
+    if capacity is None:                      # usually n // min_width + 1 segments per event (forced splits can double that:
+        lens = (offsets[1:] - offsets[:-1])   # the call is repeated with the exact size if this guess is too small)
         capacity = int((lens // max(1, int(min_width))).sum()) + n_events
     bufs = make(int(capacity))
     rc = call(int(capacity), bufs)

@@ -16,6 +16,7 @@
 //                          operations (no FMA contraction) and a (gain, position) arg-max whose tie rule --
 //                          lowest position among equal gains, gain strictly above the threshold -- is what the
 //                          reference's ascending strict-'>' scan leaves.  Splits go to an unordered per-event list.
+//                 (a forced split may cut off a piece shorter than min_width: at most 2 * (n / min_width) segments)
 //   k_segments    rank-sorts the list (ascending = the reference's in-order concatenation) and reduces every segment to
 //                 mean / std with one warp per segment (Segment.mean / .std, PyPore/core.py:209-214).
 //
@@ -219,7 +220,11 @@ k_statsplit(const SegParams P, const int64_t* __restrict__ offsets, int n_events
         const int n = static_cast<int>(offsets[ev + 1] - off);
         const double* c = cs + off;
         const double* c2 = cs2 + off;
-        int32_t* sl = splits + (off / P.min_width + ev);       // room for n / min_width + 1 entries per event: sum floor(n_j / w) <= floor(off / w)
+        // Split list of this event.  A forced split (198-201) may cut off a piece shorter than min_width, but then its sibling
+        // is exactly min_width long and final, so an event has at most 2 * (n / min_width) segments; the base below is safe
+        // because sum_j floor(n_j / w) <= floor(off / w).  The bound is checked, not trusted.
+        int32_t* sl = splits + (2 * (off / P.min_width) + ev);
+        const int sl_cap = 2 * (n / P.min_width) + 1;
 
         if (tid == 0) { s_stack[0] = make_int2(0, n); s_sp = 1; s_fail = 0; }
         int n_splits = 0;                   // thread 0 only
@@ -251,7 +256,7 @@ k_statsplit(const SegParams P, const int64_t* __restrict__ offsets, int n_events
             if (tid == 0) {
                 int top = sp - 1;
                 if (split_at >= 0) {
-                    if (split_at <= start || split_at >= end || top + 2 > kSegStack) {
+                    if (split_at <= start || split_at >= end || top + 2 > kSegStack || n_splits >= sl_cap) {
                         s_fail = 1;                                  // stack exhausted or a split that cannot terminate
                         top = 0;
                     } else {
@@ -288,7 +293,7 @@ k_segments(const double* __restrict__ current, const int64_t* __restrict__ offse
         const int64_t so = seg_offsets[ev];
         const int n_seg = static_cast<int>(seg_offsets[ev + 1] - so);
         const int k = n_seg - 1;
-        const int32_t* sl = splits + (off / min_width + ev);
+        const int32_t* sl = splits + (2 * (off / min_width) + ev);
         const bool in_smem = k <= kSegSortCap;
         if (in_smem) for (int j = tid; j < k; j += kSegThreads) s_split[j] = sl[j];
         if (tid == 0) seg_start[so] = 0;
@@ -436,7 +441,7 @@ int pp_statsplit_batch(const pp_statsplit_params* prm, int device, const double*
     }
     PP_CUDA(C->d_c.reserve(static_cast<size_t>(total) * 8));
     PP_CUDA(C->d_c2.reserve(static_cast<size_t>(total) * 8));
-    PP_CUDA(C->d_marks.reserve(static_cast<size_t>(total / prm->min_width + ne + 1) * 4));       // split lists
+    PP_CUDA(C->d_marks.reserve(static_cast<size_t>(2 * (total / prm->min_width) + ne + 1) * 4));       // split lists
     PP_CUDA(C->d_count.reserve(static_cast<size_t>(ne) * 4));
     PP_CUDA(C->d_status.reserve(16));
     PP_CUDA(cudaMemsetAsync(C->d_status.p, 0, 16, s));
@@ -479,7 +484,8 @@ int pp_statsplit_batch(const pp_statsplit_params* prm, int device, const double*
     PP_CUDA(cudaMemcpyAsync(&h_status, C->d_status.p, 4, cudaMemcpyDeviceToHost, s));
     PP_CUDA(cudaStreamSynchronize(s));
     if (h_status != 0) {
-        set_error("an event needs more than %d pending intervals (recursion too deep for the shared-memory stack)", kSegStack);
+        set_error("an event needs more than %d pending intervals (recursion too deep for the shared-memory stack) or more "
+                  "splits than 2 * (n / min_width)", kSegStack);
         return PP_ERR_UNSUPPORTED;
     }
     std::vector<int64_t> h_segoff(static_cast<size_t>(ne) + 1);
