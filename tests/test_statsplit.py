@@ -284,8 +284,8 @@ def test_gpu_forced_splits_shorter_than_min_width():
     cur = rng.normal(35, 1.0, size=910)
     kw = dict(min_width=275, max_width=313, window_width=1094, min_gain_per_sample=10.0)       # threshold never met: forced splits only
     p = parsers.FastStatSplit(**kw)
-    batch = [cur, cur[:700], cur[:589], cur]
+    batch = [cur[:400], cur, cur[:500], cur[:330], cur[:400]]        # 400 samples: forced split at min(313, 400 - 275) = 125
     off, start, mean, std, _ = p.segment_means_batch(batch, want_std=True)
     for e, c in enumerate(batch):
         assert _check_event(c, kw, p.min_gain, start[off[e]:off[e + 1]], mean[off[e]:off[e + 1]], std[off[e]:off[e + 1]], e)
-    assert np.diff(start[off[0]:off[1]]).min() < 275
+    assert list(start[off[0]:off[1]]) == [0, 125] and list(start[off[4]:off[5]]) == [0, 125]
