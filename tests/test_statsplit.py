@@ -213,7 +213,7 @@ def test_gpu_segment_and_decode_pipeline():
             assert (p is None and plen[e] < 0) or [k for k, _ in p] == list(paths[poff[e]:poff[e + 1]])
 
 
-def parameter_sweep(n_trials, seed, events_per_trial=24):
+def parameter_sweep(n_trials, seed, events_per_trial=24, mw_max=300, len_max=6000):
     """Seeded sweep over segmenter parameters and signal shapes (staircases, drifts, spikes, constant stretches, a NaN,
     a 300k-sample event).  Returns (events checked, events whose breakpoints differ from the oracle's, smallest oracle
     decision margin among those).  Also used by tools/statsplit_soak.py."""
@@ -235,7 +235,7 @@ def parameter_sweep(n_trials, seed, events_per_trial=24):
 
     checked, differ, worst_margin = 0, 0, np.inf
     for trial in range(n_trials):
-        mw = int(rng.integers(1, 300))
+        mw = int(rng.integers(1, mw_max))
         kw = dict(min_width=mw, max_width=int(mw * rng.integers(1, 30) + rng.integers(0, 50)),
                   window_width=int(2 * mw + rng.integers(0, 6 * mw + 20)))
         if trial % 3 == 0:
@@ -243,7 +243,7 @@ def parameter_sweep(n_trials, seed, events_per_trial=24):
         elif trial % 3 == 1:
             kw.update(prior_segments_per_second=float(rng.uniform(1, 1000)), false_positive_rate=float(rng.uniform(0.1, 100)))
         p = parsers.FastStatSplit(**kw)
-        currents = [signal(int(rng.integers(0, 4)), int(rng.integers(1, 6000))) for _ in range(events_per_trial)]
+        currents = [signal(int(rng.integers(0, 4)), int(rng.integers(1, len_max))) for _ in range(events_per_trial)]
         if trial == 0:
             currents.append(staircase(rng, 400, 500, 1000))                   # ~300k samples
         if trial == 1:
