@@ -70,6 +70,42 @@ def test_oracle_matches_compiled_reference_on_fresh_events():
         assert np.array_equal(so.segment_means(cur, bp), [s.mean for s in segs])
 
 
+@pytest.mark.reference
+def test_oracle_matches_compiled_reference_over_random_parameters():
+    """400 random parameter sets x 8 signals, including the regime where forced splits leave segments shorter than
+    min_width: the C restatement and the compiled reference give the same breakpoints, bit for bit."""
+    if not ref_loader.cparsers_available():
+        pytest.skip("oracle/_ref/cparsers*.so not built")
+    cp = ref_loader.load_reference_cparsers()
+    rng = np.random.default_rng(424242)
+    checked = short = 0
+    for trial in range(400):
+        mw = int(rng.integers(1, 300))
+        kw = dict(min_width=mw, max_width=int(mw * rng.integers(1, 30) + rng.integers(0, 50)),
+                  window_width=int(2 * mw + rng.integers(0, 6 * mw + 20)))
+        if trial % 3 == 0:
+            kw["min_gain_per_sample"] = float(rng.uniform(0.001, 0.5))
+        elif trial % 3 == 1:
+            kw.update(prior_segments_per_second=float(rng.uniform(1, 1000)), false_positive_rate=float(rng.uniform(0.1, 100)))
+        ref = cp.FastStatSplit(**kw)
+        for _ in range(8):
+            n = int(rng.integers(1, 6000))
+            kind = int(rng.integers(0, 3))
+            if kind == 0:
+                cur = staircase(rng, max(1, n // 400), 50, 700)[:max(1, n)]
+            elif kind == 1:
+                cur = 40 + np.cumsum(rng.normal(0, 0.05, size=n)) + rng.normal(0, 0.5, size=n)
+            else:
+                cur = rng.normal(35, 0.8, size=n)
+                cur[rng.integers(0, n, size=max(1, n // 200))] += 30
+            want = [s.start for s in ref.parse(cur)][1:]
+            got = list(so.parse(cur, kw["min_width"], kw["max_width"], kw["window_width"], gain=ref.min_gain))
+            assert got == want, (trial, kw)
+            checked += 1
+            short += int(len(want) > 0 and min(np.diff([0] + want + [len(cur)])) < kw["min_width"])
+    assert checked == 3200 and short > 20
+
+
 def test_segmenter_fails_loudly_without_gpu():
     if _engine.device_count() > 0:
         pytest.skip("a GPU is present")
