@@ -94,6 +94,19 @@ int pp_model_set_emission_table(pp_model *model, const double *table, int64_t n_
  * GPU.  Returns the length of the full text (buf may be NULL to query it), < 0 on error. */
 int64_t pp_schedule_describe(const pp_model_desc *desc, char *buf, int64_t cap);
 
+/*
+ * Kernel family of the batched forward / Viterbi sweeps.  A model whose baked graph is a linear profile -- what
+ * HMM_linear_model builds (peptide_hmm_v0.0.1.py:63-243): match / blip / insert / drop-off / skip / back-slip states per
+ * position, recognised from the CSR alone -- runs on register-resident kernels (pp_profile_kernels.cuh); every other
+ * lane-lowered model on the run-based kernels (pp_lane_kernels.cuh).  Both follow the reference's arithmetic candidate by
+ * candidate and give identical results; `path` 1 pins a handle to the run-based kernels (tests, comparisons), 0 restores
+ * the automatic choice.  The environment variable PP_KERNEL_PATH sets the initial value.
+ * pp_model_kernel_info: out4 = {family: 2 profile, 1 run-based lane kernels, 0 state-parallel; positions of the profile
+ * (0 if none); warps per CTA; bytes of one traceback pointer row (32 events)}.
+ */
+int pp_model_set_kernel_path(pp_model *model, int32_t path);
+int pp_model_kernel_info(const pp_model *model, int32_t *out4);
+
 /* Upper limit for the handle's device workspace in bytes (default: 70% of free memory at creation). */
 int pp_model_set_workspace_limit(pp_model *model, int64_t bytes);
 

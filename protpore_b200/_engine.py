@@ -58,6 +58,8 @@ ABI = [
     ("pp_model_destroy", None, [_vp]),
     ("pp_model_update_params", ctypes.c_int, [_vp, ctypes.POINTER(PPModelDesc)]),
     ("pp_model_set_workspace_limit", ctypes.c_int, [_vp, ctypes.c_int64]),
+    ("pp_model_set_kernel_path", ctypes.c_int, [_vp, ctypes.c_int32]),
+    ("pp_model_kernel_info", ctypes.c_int, [_vp, _vp]),
     ("pp_model_set_emission_table", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32]),
     ("pp_schedule_describe", ctypes.c_int64, [ctypes.POINTER(PPModelDesc), ctypes.c_char_p, ctypes.c_int64]),
     ("pp_viterbi_workspace_bytes", ctypes.c_int64, [_vp, _vp, ctypes.c_int64]),
@@ -233,6 +235,16 @@ class Engine(object):
         self._table_keep = table if dev else None
         self._check(self._lib.pp_model_set_emission_table(self._h, _ptr(table), int(table.shape[0]),
                                                           PP_MEM_DEVICE if dev else PP_MEM_HOST))
+
+    def set_kernel_path(self, path):
+        """0: automatic (register-resident profile kernels where the model is a linear profile); 1: run-based lane kernels."""
+        self._check(self._lib.pp_model_set_kernel_path(self._h, int(path)))
+
+    def kernel_info(self):
+        out = (ctypes.c_int32 * 4)()
+        self._check(self._lib.pp_model_kernel_info(self._h, out))
+        return {"family": {2: "profile", 1: "lane", 0: "state"}[out[0]], "positions": out[1], "warps": out[2],
+                "ptr_row_bytes": out[3]}
 
     def set_workspace_limit(self, nbytes):
         self._check(self._lib.pp_model_set_workspace_limit(self._h, int(nbytes)))

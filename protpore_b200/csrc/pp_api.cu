@@ -8,11 +8,13 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
 #include "pp_lane_types.h"
 #include "pp_model.h"
+#include "pp_profile_sched.h"
 
 namespace pp {
 
@@ -27,6 +29,8 @@ void set_error(const char* fmt, ...) {
     g_err = buf;
 }
 
+int profile_viterbi_launch(const ProfSched& S, const LaneBatchAny& B, const VitOut& O, int n_groups, cudaStream_t stream);
+int profile_forward_launch(const ProfSched& S, const LaneBatchAny& B, const FwdOut& O, int n_groups, cudaStream_t stream);
 void lane_viterbi4_invalidate(const void*);
 void lane_viterbi4g_invalidate(const void*);
 void lane_forwardg_invalidate(const void*);
@@ -134,6 +138,20 @@ int upload_model(pp_model* M) {
     PP_CUDA(upload(&M->d_state_pword, L.state_pword, s));
     PP_CUDA(upload(&M->d_state_pshift, L.state_pshift, s));
     PP_CUDA(upload(&M->d_state_pmul, L.state_pmul, s));
+    PP_CUDA(upload(&M->d_state_pmask, std::vector<int32_t>(static_cast<size_t>(M->m), (1 << L.ptr_bits) - 1), s));
+    if (M->plan.ok) {
+        const ProfilePlan& F = M->plan;
+        PP_CUDA(upload(&M->d_prof_rec_v, F.rec_v, s));
+        PP_CUDA(upload(&M->d_prof_rec_f, F.rec_f, s));
+        PP_CUDA(upload(&M->d_prof_end_v, F.end_v, s));
+        PP_CUDA(upload(&M->d_prof_end_f, F.end_f, s));
+        PP_CUDA(upload(&M->d_prof_unit_off, F.unit_off, s));
+        PP_CUDA(upload(&M->d_prof_unit_bytes, F.unit_bytes, s));
+        PP_CUDA(upload(&M->d_prof_unit_shift, F.unit_shift, s));
+        PP_CUDA(upload(&M->d_prof_unit_mask, F.unit_mask, s));
+        PP_CUDA(upload(&M->d_prof_slot_begin, F.slot_begin, s));
+        PP_CUDA(upload(&M->d_prof_slot_src, F.slot_src, s));
+    }
     PP_CUDA(upload(&M->d_in_ptr, M->in_ptr, s));
     PP_CUDA(upload(&M->d_in_src, M->in_src, s));
     PP_CUDA(upload(&M->d_in_logp, M->in_logp, s));
@@ -198,6 +216,25 @@ LaneSched make_sched(const pp_model* M, bool logspace) {
     S.n_ptr_words = L.n_ptr_words;
     S.gcol = nullptr;
     S.gcol_stride = 0;
+    return S;
+}
+
+// The register-resident kernels of pp_profile_kernels.cuh serve a model whose baked graph is a linear profile.
+static bool use_profile(const pp_model* M) { return M->plan.ok && M->kernel_path == 0; }
+static size_t ptr_row_bytes(const pp_model* M) {
+    return use_profile(M) ? static_cast<size_t>(M->plan.row_bytes) : static_cast<size_t>(M->low.n_ptr_words) * kLanes * sizeof(uint32_t);
+}
+ProfSched make_prof_sched(const pp_model* M, bool logspace) {
+    const ProfilePlan& F = M->plan;
+    ProfSched S;
+    S.rec = (logspace ? M->d_prof_rec_v : M->d_prof_rec_f).as<double>();
+    S.end_list = (logspace ? M->d_prof_end_v : M->d_prof_end_f).as<ProfEndRec>();
+    S.end_n = static_cast<int32_t>(F.end_v.size());
+    S.K = F.K; S.Kp = F.Kp; S.NW = F.NW;
+    S.n_alias = F.n_alias;
+    for (int a = 0; a < kProfMaxAlias; ++a) { S.alias_dst[a] = F.alias_dst[a]; S.alias_src[a] = F.alias_src[a]; }
+    S.row_bytes = F.row_bytes;
+    S.end_state = M->end;
     return S;
 }
 
@@ -287,6 +324,12 @@ static int launch_viterbi(pp_model* M, const LaneBatch<ObsT>& B, const VitOut& O
     int rc = check_lane_model(M);
     if (rc != PP_OK) return rc;
     const LaneBatchAny A{B.obs, sizeof(ObsT) == 8 ? 1 : 0, B.offsets, B.order, B.group_len, B.group_row};
+    if (use_profile(M)) {
+        const int e = profile_viterbi_launch(make_prof_sched(M, true), A, O, n_groups, M->stream);
+        if (e != 0) { set_error("profile Viterbi kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
+        ++M->launches;
+        return PP_OK;
+    }
     if (lane_col_global(M)) return launch_gcol(M, make_sched(M, true), A, O, n_groups, lane_viterbi4g_launch, "Viterbi (global column)");
     const size_t smem = lane_smem_col(M);
     // every item of a lane-lowered model has <= 8 in-edges (kMaxRunEdges), so its ordinals always take 4 bits
@@ -302,6 +345,12 @@ static int launch_forward(pp_model* M, const LaneBatch<ObsT>& B, const FwdOut& O
     int rc = check_lane_model(M);
     if (rc != PP_OK) return rc;
     const LaneBatchAny A{B.obs, sizeof(ObsT) == 8 ? 1 : 0, B.offsets, B.order, B.group_len, B.group_row};
+    if (use_profile(M)) {
+        const int e = profile_forward_launch(make_prof_sched(M, false), A, O, n_groups, M->stream);
+        if (e != 0) { set_error("profile forward kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
+        ++M->launches;
+        return PP_OK;
+    }
     if (lane_col_global(M)) return launch_gcol(M, make_sched(M, false), A, O, n_groups, lane_forwardg_launch, "forward (global column)");
     const size_t smem = lane_smem_col(M);
     const int e = lane_forward_launch(make_sched(M, false), A, O, n_groups, smem, M->stream, M->arena.data(), M->arena.size(), M);
@@ -378,6 +427,8 @@ int pp_model_create(const pp_model_desc* desc, int device, pp_model** out) {
     std::string err = lower_model(*desc, M->warps, &M->low);
     if (!err.empty()) { set_error("cannot lower model: %s", err.c_str()); delete M; return PP_ERR_UNSUPPORTED; }
     copy_desc(M, desc);
+    build_profile_plan(*desc, M->low, kProfPositionsPerWarp, kProfMaxPositionWarps, &M->plan);
+    if (const char* env = std::getenv("PP_KERNEL_PATH")) M->kernel_path = std::atoi(env);
     int rc = PP_OK;
     do {
         if (cudaSetDevice(device) != cudaSuccess) { rc = PP_ERR_CUDA; break; }
@@ -412,7 +463,9 @@ void pp_model_destroy(pp_model* M) {
                       &M->d_out_prob, &M->d_alive, &M->d_ws, &M->d_obs, &M->d_offsets, &M->d_order,
                       &M->d_group_len, &M->d_group_row, &M->d_score, &M->d_end_state, &M->d_end_ord, &M->d_path_len,
                       &M->d_path_off, &M->d_path, &M->d_scan_tmp, &M->d_logp, &M->d_bw_wtab, &M->d_acc_map,
-                      &M->d_acc_log2, &M->d_fb_acc, &M->d_fb_scratch, &M->d_fb_ctl, &M->d_fb_minmax, &M->d_etab_own, &M->d_gcol};
+                      &M->d_acc_log2, &M->d_fb_acc, &M->d_fb_scratch, &M->d_fb_ctl, &M->d_fb_minmax, &M->d_etab_own, &M->d_gcol, &M->d_prof_rec_v, &M->d_prof_rec_f, &M->d_prof_end_v, &M->d_prof_end_f,
+                      &M->d_prof_unit_off, &M->d_prof_unit_bytes, &M->d_prof_unit_shift, &M->d_prof_unit_mask, &M->d_prof_slot_begin,
+                      &M->d_prof_slot_src, &M->d_state_pmask};
     for (DevBuf* b : bufs) b->release();
     release_state_model(M);
     for (int b = 0; b < 2; ++b) {
@@ -437,7 +490,9 @@ int pp_model_update_params(pp_model* M, const pp_model_desc* desc) {
     std::string err = refresh_params(*desc, &M->low);
     if (!err.empty()) { set_error("cannot refresh parameters: %s", err.c_str()); return PP_ERR_ARG; }
     copy_desc(M, desc);
+    build_profile_plan(*desc, M->low, kProfPositionsPerWarp, kProfMaxPositionWarps, &M->plan);
     PP_CUDA(cudaSetDevice(M->device));
+    PP_CUDA(cudaStreamSynchronize(M->stream));
     return upload_model(M);
 }
 
@@ -465,11 +520,39 @@ int64_t pp_schedule_describe(const pp_model_desc* desc, char* buf, int64_t cap) 
     Lowered low;
     std::string err = lower_model(*desc, kLaneWarps, &low);
     if (!err.empty()) { set_error("cannot lower model: %s", err.c_str()); return PP_ERR_UNSUPPORTED; }
-    const std::string text = describe_schedule(low);
+    std::string text = describe_schedule(low);
+    {   // which kernel family takes forward / Viterbi sweeps of this model (pp_profile.h)
+        ProfilePlan plan;
+        build_profile_plan(*desc, low, kProfPositionsPerWarp, kProfMaxPositionWarps, &plan);
+        char line[512];
+        if (plan.ok)
+            std::snprintf(line, sizeof line, "profile ok positions %d position_warps %d positions_per_warp %d ptr_row_bytes %d aliases %d end_edges %zu\n",
+                          plan.K, plan.NW, plan.P, plan.row_bytes, plan.n_alias, plan.end_v.size());
+        else
+            std::snprintf(line, sizeof line, "profile no: %s\n", plan.why.c_str());
+        text += line;
+    }
     if (buf && cap > 0) std::snprintf(buf, static_cast<size_t>(cap), "%s", text.c_str());
     return static_cast<int64_t>(text.size());
 }
 
+
+int pp_model_set_kernel_path(pp_model* M, int32_t path) {
+    if (!M || path < 0 || path > 1) { set_error("bad kernel path"); return PP_ERR_ARG; }
+    PP_CUDA(cudaSetDevice(M->device));
+    PP_CUDA(cudaStreamSynchronize(M->stream));
+    M->kernel_path = path;
+    return PP_OK;
+}
+
+int pp_model_kernel_info(const pp_model* M, int32_t* out4) {
+    if (!M || !out4) { set_error("null argument"); return PP_ERR_ARG; }
+    out4[0] = use_profile(M) ? 2 : (lane_kernels_fit(M) ? 1 : 0);
+    out4[1] = M->plan.ok ? M->plan.K : 0;
+    out4[2] = M->plan.ok ? M->plan.NW + 1 : kLaneWarps;
+    out4[3] = static_cast<int32_t>(ptr_row_bytes(M));
+    return PP_OK;
+}
 
 int pp_model_set_workspace_limit(pp_model* M, int64_t bytes) {
     if (!M || bytes <= 0) { set_error("bad workspace limit"); return PP_ERR_ARG; }
@@ -481,7 +564,7 @@ int64_t pp_viterbi_workspace_bytes(const pp_model* M, const int64_t* offsets_hos
     if (!M || !offsets_host || n_events < 0) return -1;
     Schedule sc;
     build_schedule(offsets_host, 0, n_events, &sc);
-    return sc.total_rows * static_cast<int64_t>(M->low.n_ptr_words) * kLanes * 4;
+    return sc.total_rows * static_cast<int64_t>(ptr_row_bytes(M));
 }
 
 #ifdef PP_PHASE_TIMING
@@ -602,7 +685,7 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     PP_CUDA(M->d_path_off.reserve((n_events + 1) * sizeof(int64_t)));
     PP_CUDA(cudaStreamSynchronize(M->stream));            // offsets are on the device before s_in / kernels use them
 
-    const size_t row_bytes = static_cast<size_t>(M->low.n_ptr_words) * kLanes * sizeof(uint32_t);
+    const size_t row_bytes = ptr_row_bytes(M);
     // two chunks in flight: each gets half the workspace; host batches are cut fine enough for the copies to overlap
     const std::vector<int64_t> cuts = make_chunks(h_off, n_events, row_bytes, M->ws_limit / 2, host ? ob : 0, size_t(96) << 20);
     const int n_chunks = static_cast<int>(cuts.size()) - 1;
@@ -614,11 +697,17 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
 
     auto trace_args = [&](int c) {
         pp_model::PipeSlot& P = M->ps[c & 1];
+        if (use_profile(M))
+            return TraceArgs{P.ws.as<uint32_t>(), P.order.as<int32_t>(), P.group_row.as<int64_t>(), d_off, d_score,
+                             M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), M->d_prof_slot_begin.as<int32_t>(),
+                             M->d_prof_slot_src.as<int32_t>(), M->d_prof_unit_off.as<int32_t>(), M->d_prof_unit_bytes.as<int32_t>(),
+                             M->d_prof_unit_shift.as<int32_t>(), M->d_prof_unit_mask.as<int32_t>(), M->m, M->ne, M->start, 1,
+                             static_cast<int64_t>(row_bytes)};
         return TraceArgs{P.ws.as<uint32_t>(), P.order.as<int32_t>(), P.group_row.as<int64_t>(), d_off, d_score,
                          M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), M->d_state_edge_begin.as<int32_t>(),
                          M->d_low_src.as<int32_t>(), M->d_state_pword.as<int32_t>(), M->d_state_pmul.as<int32_t>(),
-                         M->d_state_pshift.as<int32_t>(), M->m, M->ne, M->start, M->low.end_final_only ? 1 : 0,
-                         M->low.n_ptr_words, (1 << M->low.ptr_bits) - 1};
+                         M->d_state_pshift.as<int32_t>(), M->d_state_pmask.as<int32_t>(), M->m, M->ne, M->start,
+                         M->low.end_final_only ? 1 : 0, static_cast<int64_t>(row_bytes)};
     };
     // phase B of chunk c: the host learns the chunk's path total, then the write pass and the copy out
     auto finish = [&](int c) -> int {

@@ -39,6 +39,25 @@ __host__ __device__ inline size_t lane_smem_bytes(int n_slots, int obs_bytes, in
 
 __device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xFFF0000000000000LL); }
 
+// first maximum of s[lo, hi): a balanced tree of "right replaces left only if strictly greater" steps picks the
+// same index as the reference's left-to-right strict-'>' scan (the lowest index attaining the maximum), with a
+// dependent chain of log2(n) compare+select steps instead of n.
+template <int LO, int HI>
+struct FirstMax {
+    __device__ static __forceinline__ void run(const double* s, double& best, uint32_t& arg) {
+        constexpr int MID = (LO + HI) / 2;
+        double b2;
+        uint32_t a2;
+        FirstMax<LO, MID>::run(s, best, arg);
+        FirstMax<MID, HI>::run(s, b2, a2);
+        if (b2 > best) { best = b2; arg = a2; }
+    }
+};
+template <int LO>
+struct FirstMax<LO, LO + 1> {
+    __device__ static __forceinline__ void run(const double* s, double& best, uint32_t& arg) { best = s[LO]; arg = LO; }
+};
+
 template <typename T>
 __device__ __forceinline__ T ldg_rec(const T* p) {
     // 16-byte vector loads of a warp-uniform record through the read-only path
@@ -134,7 +153,9 @@ struct TraceArgs {
     const int32_t* state_pword;        // [m] byte offset of lane 0's ordinal byte inside a pointer row
     const int32_t* state_pmul;         // [m] bytes per lane of the unit holding it
     const int32_t* state_pshift;       // [m] bit position inside that byte
-    int32_t m, ne, start, end_final_only, n_ptr_words, ptr_mask;
+    const int32_t* state_pmask;        // [m] mask of the ordinal (a field may run into the next byte of its unit)
+    int32_t m, ne, start, end_final_only;
+    int64_t row_bytes;                 // bytes per pointer row (all 32 lanes)
 };
 
 static __global__ void k_traceback(const TraceArgs T, int64_t* __restrict__ path_len, const int64_t* __restrict__ path_off,
@@ -149,7 +170,7 @@ static __global__ void k_traceback(const TraceArgs T, int64_t* __restrict__ path
         return;
     }
     const int n = static_cast<int>(T.offsets[ev + 1] - T.offsets[ev]);
-    const size_t row_stride = static_cast<size_t>(T.n_ptr_words) * kLanes * 4;        // bytes
+    const size_t row_stride = static_cast<size_t>(T.row_bytes);
     const uint8_t* base = reinterpret_cast<const uint8_t*>(T.ptr) + static_cast<size_t>(T.group_row[g]) * row_stride;
     int64_t len = 1;
     int px = n, py = T.end_state[ev];
@@ -164,8 +185,13 @@ static __global__ void k_traceback(const TraceArgs T, int64_t* __restrict__ path
         if (out) out[pos--] = static_cast<uint16_t>(py);
         int ord;
         if (first && T.end_final_only) ord = T.end_ord[ev];
-        else ord = (base[static_cast<size_t>(px) * row_stride + T.state_pword[py] + lane * T.state_pmul[py]] >>
-                    T.state_pshift[py]) & T.ptr_mask;
+        else {
+            const uint8_t* a = base + static_cast<size_t>(px) * row_stride + T.state_pword[py] + lane * T.state_pmul[py];
+            const int sh = T.state_pshift[py], mk = T.state_pmask[py];
+            uint32_t u = a[0];
+            if ((mk << sh) > 0xff) u |= static_cast<uint32_t>(a[1]) << 8;
+            ord = static_cast<int>((u >> sh) & mk);
+        }
         first = false;
         const int src = T.low_src[T.state_edge_begin[py] + ord];
         if (py < T.ne) --px;                             // emitting states point into the previous row

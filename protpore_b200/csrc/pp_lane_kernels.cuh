@@ -165,25 +165,6 @@ __device__ __forceinline__ void store_ordinals(uint8_t* row, int& pbase, int lan
     pbase += UNIT * kLanes;
 }
 
-// first maximum of s[lo, hi): a balanced tree of "right replaces left only if strictly greater" steps picks the
-// same index as the reference's left-to-right strict-'>' scan (the lowest index attaining the maximum), with a
-// dependent chain of log2(n) compare+select steps instead of n.
-template <int LO, int HI>
-struct FirstMax {
-    __device__ static __forceinline__ void run(const double* s, double& best, uint32_t& arg) {
-        constexpr int MID = (LO + HI) / 2;
-        double b2;
-        uint32_t a2;
-        FirstMax<LO, MID>::run(s, best, arg);
-        FirstMax<MID, HI>::run(s, b2, a2);
-        if (b2 > best) { best = b2; arg = a2; }
-    }
-};
-template <int LO>
-struct FirstMax<LO, LO + 1> {
-    __device__ static __forceinline__ void run(const double* s, double& best, uint32_t& arg) { best = s[LO]; arg = LO; }
-};
-
 struct VitCtx {
     uint8_t* row;        // this row's traceback pointer bytes (group base; lane offset applied per unit)
     int lane;

@@ -5,6 +5,7 @@
 
 #include "pp_common.h"
 #include "pp_lowering.h"
+#include "pp_profile.h"
 
 // Kernel-time slots reported by pp_profile_get (milliseconds of the last batched call, summed over
 // its chunks, measured with CUDA events on the model's stream).
@@ -33,6 +34,12 @@ struct pp_model {
     std::vector<double> in_logp, out_logp, emit_p0, emit_p1, emit_logw;
 
     pp::Lowered low;
+    // linear-profile fast path (pp_profile.h): plan.ok says whether the register-resident kernels serve this model;
+    // kernel_path (pp_model_set_kernel_path): 0 = automatic, 1 = run-based lane kernels only
+    pp::ProfilePlan plan;
+    int kernel_path = 0;
+    pp::DevBuf d_prof_rec_v, d_prof_rec_f, d_prof_end_v, d_prof_end_f, d_prof_unit_off, d_prof_unit_bytes, d_prof_unit_shift,
+        d_prof_unit_mask, d_prof_slot_begin, d_prof_slot_src, d_state_pmask;
 
     // device copy of the schedule
     pp::DevBuf d_edges_logp[2], d_edges_prob[2], d_emis, d_warp_run_ranges;

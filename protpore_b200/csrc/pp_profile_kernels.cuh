@@ -1,0 +1,502 @@
+// pp_profile_kernels.cuh -- Viterbi and forward sweeps of a LINEAR PROFILE HMM (pp_profile.h) for sm_100a, register-resident.
+//
+// One CTA = NW position warps + 2 chain warps sweeps 32 events; lane j of every warp works on event j (as in
+// pp_lane_kernels.cuh).  Position warp w owns positions [w P, w P + P): the values of THEIR emitting states -- M_k,
+// I_BLIP_k, I_INS_k -- stay in registers from row to row.  Per row r -> r + 1:
+//   phase A  position warps: every emitting state of row r + 1 from row r (registers), the neighbours' M (read from the
+//            shared-memory exchange while the chains run) and the silent values of row r (shared memory).  They publish
+//            M_k(r + 1) and the pass-1 candidates of the two chain states M_k feeds, M_k + t(M_k -> S_SKIP_{k+1}) and
+//            M_k + t(M_k -> B_BACK_k) (3564-3584), and store 5 bits of ordinals per position (M: 3, insert: 1, blip: 1)
+//            with one coalesced store;
+//   phase B  chain warps, one per chain: S_SKIP ascending, B_BACK descending.  A link is DADD -> DSETP -> FSEL on the
+//            value of the link before it (22.7 cycles on B200, tools/lat_bench.cu); bit i of a 64-bit word per lane
+//            holds the ordinal of link i.  S_DROPOFF_k = M_k + t has a single in-edge and is recomputed where it is read
+//            (same DADD as the reference's, no storage).
+// separated by two barriers.  The end state is evaluated once per event at its last row (a CTA-uniform extra step).
+//
+// Shared memory is laid out per WARP: block w + 1 holds, for the warp's P positions, M | S_SKIP | B_BACK | the two
+// pass-1 candidate arrays, 32 doubles (one per lane) each; blocks 0 and NW + 1 are phantoms that hold the start state and
+// the "nothing beyond the ends" values.  A warp reaches everything it needs -- its own block and the edge slots of its
+// two neighbours -- at COMPILE-TIME offsets from one per-thread base address, so a candidate costs no address arithmetic
+// and no load for its value (registers), and half a load for its weight (16-byte broadcast loads of the position record).
+//
+// Arithmetic is the reference's, candidate by candidate: (v + t) + e for emitting states (yahmm.pyx:3545-3562), v + t for
+// silent ones, pass 1 before pass 2 (3564-3605), strict '>' in the reference's visiting order -- slot order of
+// pp_profile.h; the balanced first-maximum tree picks the same winner as the left-to-right scan.
+//
+// Forward: scaled linear space as in k_forward_lane (exact power-of-two row scaling steered by the largest emitting
+// value of the previous row, collected with one shared-memory atomicMax per warp and row); events whose result is 0 /
+// inf / NaN are re-run by the exact log-space kernel (pp_api.cu).
+#pragma once
+#include "pp_device_common.cuh"
+#include "pp_lane_types.h"
+#include "pp_profile_sched.h"
+
+namespace pp {
+
+#ifndef PP_PROF_MIN_CTAS
+#define PP_PROF_MIN_CTAS 2            // CTAs per SM the register budget is set for
+#endif
+#define PP_PROF_THREADS ((kProfMaxPositionWarps + 2) * 32)
+
+// byte offsets inside a warp block (P slots of 256 bytes per array)
+template <int P>
+struct ProfBlock {
+    static constexpr int SLOT = kSlotBytes;
+    static constexpr int MX = 0;                 // M_k
+    static constexpr int SK = P * SLOT;          // S_SKIP_k
+    static constexpr int BK = 2 * P * SLOT;      // B_BACK_k
+    static constexpr int AS = 3 * P * SLOT;      // M_k + t(M_k -> S_SKIP_{k+1}): pass-1 candidate of S_SKIP_{k+1}
+    static constexpr int AB = 4 * P * SLOT;      // M_k + t(M_k -> B_BACK_k):     pass-1 candidate of B_BACK_k
+    static constexpr int WS = 5 * P * SLOT;      // bytes per block
+};
+
+__host__ __device__ inline size_t prof_smem_bytes(int Kp, int NW, int P) {
+    // records | NW + 2 warp blocks | observation tile | row maxima [2][32]
+    return static_cast<size_t>(Kp) * kProfRecDoubles * 8 + static_cast<size_t>(NW + 2) * 5 * P * kSlotBytes +
+           static_cast<size_t>(kLaneTileCols) * (kLanes + 1) * 8 + 2 * kLanes * 4 + 64;
+}
+
+template <int P>
+struct ProfSmem {
+    double* rec;
+    unsigned char* blocks;                       // block b = w + 1
+    double* xt;
+    int32_t* smax;                               // [2][32]
+    int n_col;                                   // doubles in the blocks
+    __device__ __forceinline__ ProfSmem(unsigned char* smem, int Kp, int NW) {
+        rec = reinterpret_cast<double*>(smem);
+        blocks = smem + static_cast<size_t>(Kp) * kProfRecDoubles * 8;
+        n_col = (NW + 2) * 5 * P * kLanes;
+        xt = reinterpret_cast<double*>(blocks) + n_col;
+        smax = reinterpret_cast<int32_t*>(xt + kLaneTileCols * (kLanes + 1));
+    }
+};
+
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ double ldb(const unsigned char* p, int off) { return *reinterpret_cast<const double*>(p + off); }
+__device__ __forceinline__ void stb(unsigned char* p, int off, double v) { *reinterpret_cast<double*>(p + off) = v; }
+// slot of position k in array `arr` (this lane's slice when `blocks` already carries the lane offset)
+template <int P>
+__device__ __forceinline__ int prof_slot(int k, int arr) { return (k / P + 1) * ProfBlock<P>::WS + arr + (k % P) * kSlotBytes; }
+
+// observation tile with a run-time warp count
+__device__ __forceinline__ void prof_fill_tile(double* xt, const void* __restrict__ obs, bool f64, int64_t off, int n, int i0,
+                                               int warp, int lane, int n_warps) {
+    constexpr int TC = kLaneTileCols;
+    for (int j = warp * (32 / TC) + lane / TC; j < kLanes; j += n_warps * (32 / TC)) {
+        const int64_t oj = __shfl_sync(0xffffffffu, off, j);
+        const int nj = __shfl_sync(0xffffffffu, n, j);
+        const int c = i0 + (lane % TC);
+        double v = 0.0;
+        if (c < nj) v = f64 ? __ldg(static_cast<const double*>(obs) + oj + c)
+                            : static_cast<double>(__ldg(static_cast<const float*>(obs) + oj + c));
+        xt[(lane % TC) * (kLanes + 1) + j] = v;
+    }
+}
+
+// ---- emissions ------------------------------------------------------------------------------------------------
+// exact log-densities (NormalDistribution / UniformDistribution._log_probability, yahmm.pyx:377-390, 257-262)
+__device__ __forceinline__ double prof_log_normal(const double* R, double x) {
+    const double2 a = ld2(R), b = ld2(R + 2);                     // {mu, 2 sigma^2}, {RN(1 / (2 sigma^2)), log peak}
+    const double d = __dsub_rn(x, a.x);
+    const double d2 = __dmul_rn(d, d);
+    const double q0 = __dmul_rn(d2, b.x);
+    const double rem = __fma_rn(-q0, a.y, d2);
+    const double q = __fma_rn(rem, b.x, q0);                      // = RN(d2 / (2 sigma^2)), pp_device_common.cuh
+    return __dsub_rn(b.y, q);
+}
+__device__ __forceinline__ double prof_log_point(const double* R, double x) {
+    return (fabs(__dsub_rn(x, R[0])) < 1E-4) ? 0.0 : neg_inf();
+}
+__device__ __forceinline__ double prof_log_uniform(const double* R, double x) {
+    const double2 a = ld2(R);
+    return (x >= a.x && x <= a.y) ? R[3] : neg_inf();
+}
+// linear-space factors p(x) 2^shift; scale2 = 2^shift as a double
+__device__ __forceinline__ double prof_lin_normal(const double* R, double x, double shiftd) {
+    const double2 a = ld2(R);                                     // {mu, log2(e) / (2 sigma^2)}
+    const double d = x - a.x;
+    return exp2_scaled(fma(-(d * d), a.y, R[2]) + shiftd);
+}
+__device__ __forceinline__ double prof_lin_point(const double* R, double x, double scale2) {
+    return (fabs(x - R[0]) < 1E-4) ? R[3] * scale2 : 0.0;
+}
+__device__ __forceinline__ double prof_lin_uniform(const double* R, double x, double scale2) {
+    const double2 a = ld2(R);
+    return (x >= a.x && x <= a.y) ? R[3] * scale2 : 0.0;
+}
+
+// =================================================================================================================
+// Viterbi
+// =================================================================================================================
+// Phase A of one position warp: rows r -> r + 1 of its P positions.  tb: this lane's slice of the warp's block;
+// left / right: M of the neighbouring positions k0 - 1 and k0 + P in row r (read before the phase started).
+template <int P>
+__device__ __forceinline__ uint32_t prof_vit_emitting(const double* __restrict__ recw, unsigned char* __restrict__ tb,
+                                                      double left, double right, double x, double (&vM)[P], double (&vB)[P],
+                                                      double (&vI)[P]) {
+    using L = ProfBlock<P>;
+    uint32_t ord = 0;
+#pragma unroll
+    for (int p = P - 1; p >= 0; --p) {                            // descending: vM[p - 1] is still row r
+        const double* R = recw + p * kProfRecDoubles;
+        const double2 w01 = ld2(R + PR_WM), w23 = ld2(R + PR_WM + 2), w45 = ld2(R + PR_WM + 4), w67 = ld2(R + PR_WM + 6);
+        const double2 wi = ld2(R + PR_WI), wb = ld2(R + PR_WB);
+        const double2 wdk = ld2(R + PR_WD), wsk = ld2(R + PR_SK);
+        const int kinds = __double2loint(wdk.y);
+        const double mprev = p > 0 ? vM[p > 0 ? p - 1 : 0] : left;
+        // S_SKIP_{k-1} (the start state for k = 0) and B_BACK_{k+1} of row r: own block, or the neighbour's edge slot
+        const double sk = ldb(tb, p > 0 ? L::SK + (p - 1) * L::SLOT : -L::WS + L::SK + (P - 1) * L::SLOT);
+        const double bk = ldb(tb, p < P - 1 ? L::BK + (p + 1) * L::SLOT : L::WS + L::BK);
+        const double eM = prof_log_normal(R + PR_EM, x);
+        const double eB = prof_log_uniform(R + PR_EB, x);
+        const double eI = ((kinds >> 8) & 0xff) == EMIS_POINT ? prof_log_point(R + PR_EI, x) : prof_log_normal(R + PR_EI, x);
+        const double drop = __dadd_rn(vM[p], wdk.x);              // S_DROPOFF_k(r): its one candidate (3564-3584)
+        double s[7];
+        s[0] = __dadd_rn(__dadd_rn(mprev, w01.x), eM);
+        s[1] = __dadd_rn(__dadd_rn(sk, w01.y), eM);
+        s[2] = __dadd_rn(__dadd_rn(vM[p], w23.x), eM);
+        s[3] = __dadd_rn(__dadd_rn(drop, w23.y), eM);
+        s[4] = __dadd_rn(__dadd_rn(vB[p], w45.x), eM);
+        s[5] = __dadd_rn(__dadd_rn(vI[p], w45.y), eM);
+        s[6] = __dadd_rn(__dadd_rn(bk, w67.y), eM);
+        double best;
+        uint32_t arg;
+        FirstMax<0, 7>::run(s, best, arg);
+        if (kinds >> 24) {
+            // a candidate from M_{k+1} sits between the insert's and the back-slip's (bake merged a back-slip state away):
+            // it wins against the earlier ones only if strictly greater, against the back-slip's also on equality.
+            // M_{k+1}(r) is still in the exchange: a warp stores its new M values after its last position.
+            const double mnext = p < P - 1 ? ldb(tb, L::MX + (p + 1) * L::SLOT) : right;
+            const double c = __dadd_rn(__dadd_rn(mnext, w67.x), eM);
+            if (c > best || (c == best && arg == 6)) { best = c; arg = 7; }
+        }
+        const double i0 = __dadd_rn(__dadd_rn(mprev, wi.x), eI), i1 = __dadd_rn(__dadd_rn(vI[p], wi.y), eI);
+        const double b0 = __dadd_rn(__dadd_rn(vM[p], wb.x), eB), b1 = __dadd_rn(__dadd_rn(vB[p], wb.y), eB);
+        const bool pi = i1 > i0, pb = b1 > b0;
+        vM[p] = best;
+        vI[p] = pi ? i1 : i0;
+        vB[p] = pb ? b1 : b0;
+        stb(tb, L::AS + p * L::SLOT, __dadd_rn(best, wsk.x));     // into S_SKIP_{k+1}
+        stb(tb, L::AB + p * L::SLOT, __dadd_rn(best, ld2(R + PR_BK).x));     // into B_BACK_k
+        ord |= (arg | (pi ? 8u : 0u) | (pb ? 16u : 0u)) << (5 * p);
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) stb(tb, L::MX + p * L::SLOT, vM[p]);
+    return ord;
+}
+
+// N consecutive links of a chain.  A[u]: pass-1 candidate, c[u]: weight of the chain edge (pass 2, replaces only if
+// strictly greater, 3586-3605).
+template <int N>
+__device__ __forceinline__ uint32_t prof_vit_links(const double (&A)[N], const double (&c)[N], double (&out)[N], double& v) {
+    uint32_t b = 0;
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        const double t = __dadd_rn(v, c[u]);
+        const bool p = t > A[u];
+        v = p ? t : A[u];
+        out[u] = v;
+        if (p) b |= 1u << u;
+    }
+    return b;
+}
+
+// Phase B, ascending chain: link i = S_SKIP_i.  cb: this lane's slice of block 0 (the phantom before position 0).
+template <int P>
+__device__ __forceinline__ uint64_t prof_vit_chain_up(const double* __restrict__ rec, unsigned char* __restrict__ cb, int K,
+                                                      double startval) {
+    using L = ProfBlock<P>;
+    uint64_t bits = 0;
+    double v = startval;
+    stb(cb, L::SK + (P - 1) * L::SLOT, startval);                 // what M_0 and S_SKIP_0 read through their start edge
+    int k = 0;
+    for (; k + P <= K; k += P) {
+        unsigned char* blk = cb + (k / P + 1) * L::WS;
+        double A[P], c[P], out[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            A[p] = ldb(blk, p > 0 ? L::AS + (p - 1) * L::SLOT : -L::WS + L::AS + (P - 1) * L::SLOT);
+            c[p] = rec[(k + p) * kProfRecDoubles + PR_SK + 1];
+        }
+        bits |= static_cast<uint64_t>(prof_vit_links<P>(A, c, out, v)) << k;
+#pragma unroll
+        for (int p = 0; p < P; ++p) stb(blk, L::SK + p * L::SLOT, out[p]);
+    }
+    for (; k < K; ++k) {
+        double A[1] = {ldb(cb, prof_slot<P>(k - 1 + P, L::AS) - L::WS)}, c[1] = {rec[k * kProfRecDoubles + PR_SK + 1]}, out[1];
+        bits |= static_cast<uint64_t>(prof_vit_links<1>(A, c, out, v)) << k;
+        stb(cb, prof_slot<P>(k, L::SK), out[0]);
+    }
+    return bits;
+}
+// descending chain: link i = B_BACK_{K-1-i}
+template <int P>
+__device__ __forceinline__ uint64_t prof_vit_chain_down(const double* __restrict__ rec, unsigned char* __restrict__ cb, int K) {
+    using L = ProfBlock<P>;
+    uint64_t bits = 0;
+    double v = neg_inf();
+    int k = K - 1, i = 0;
+    for (; (k + 1) % P != 0; --k, ++i) {                           // the partial block at the top
+        double A[1] = {ldb(cb, prof_slot<P>(k, L::AB))}, c[1] = {rec[k * kProfRecDoubles + PR_BK + 1]}, out[1];
+        bits |= static_cast<uint64_t>(prof_vit_links<1>(A, c, out, v)) << i;
+        stb(cb, prof_slot<P>(k, L::BK), out[0]);
+    }
+    for (; k >= 0; k -= P, i += P) {                               // k = last position of a full block
+        unsigned char* blk = cb + (k / P + 1) * L::WS;
+        double A[P], c[P], out[P];
+#pragma unroll
+        for (int u = 0; u < P; ++u) {
+            A[u] = ldb(blk, L::AB + (P - 1 - u) * L::SLOT);
+            c[u] = rec[(k - u) * kProfRecDoubles + PR_BK + 1];
+        }
+        bits |= static_cast<uint64_t>(prof_vit_links<P>(A, c, out, v)) << i;
+#pragma unroll
+        for (int u = 0; u < P; ++u) stb(blk, L::BK + (P - 1 - u) * L::SLOT, out[u]);
+    }
+    return bits;
+}
+
+template <int P>
+__global__ void __launch_bounds__(PP_PROF_THREADS, PP_PROF_MIN_CTAS)
+k_profile_viterbi(const ProfSched S, const LaneBatchAny B, const VitOut O) {
+    using L = ProfBlock<P>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const ProfSmem<P> M(smem, S.Kp, S.NW);
+    constexpr int TC = kLaneTileCols;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    const int n_warps = S.NW + 2;
+    const int g = blockIdx.x;
+    const int ev = B.order[g * kLanes + lane];
+    const int64_t off = ev >= 0 ? B.offsets[ev] : 0;
+    const int n = ev >= 0 ? static_cast<int>(B.offsets[ev + 1] - off) : 0;
+    const int nmax = B.group_len[g];
+    constexpr int UB = 5 * P <= 16 ? 2 : 4;
+    // this warp's unit of row 0 in the pointer table (position warps: emitting ordinals; chain warps: one 64-bit word)
+    uint8_t* prow = reinterpret_cast<uint8_t*>(O.ptr) + static_cast<size_t>(B.group_row[g]) * S.row_bytes +
+                    (warp < S.NW ? warp * UB * kLanes + lane * UB : S.NW * UB * kLanes + (warp - S.NW) * 8 * kLanes + lane * 8);
+
+    for (int i = threadIdx.x; i < S.Kp * kProfRecDoubles; i += n_warps * 32) M.rec[i] = __ldg(S.rec + i);
+    for (int i = threadIdx.x; i < M.n_col; i += n_warps * 32) reinterpret_cast<double*>(M.blocks)[i] = neg_inf();   // v[0, :] = -inf (3513)
+    __syncthreads();
+
+    double vM[P], vB[P], vI[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) vM[p] = vB[p] = vI[p] = neg_inf();
+    unsigned char* const cb = M.blocks + lane * 8;                               // block 0, this lane
+    unsigned char* const tb = cb + (warp + 1) * L::WS;                           // this warp's block (position warps)
+    const double* const recw = M.rec + warp * P * kProfRecDoubles;
+
+    for (int r = 0;; ++r) {
+        if (r < nmax && (r & (TC - 1)) == 0) prof_fill_tile(M.xt, B.obs, B.obs_f64 != 0, off, n, r, warp, lane, n_warps);
+        double left = 0.0, right = 0.0;
+        if (warp == S.NW) {
+            // ---- silent states of row r; v[0, start] = 0 (3514), the start state is -inf in every later row
+            const uint64_t bits = prof_vit_chain_up<P>(M.rec, cb, S.K, r == 0 ? 0.0 : neg_inf());
+            *reinterpret_cast<uint64_t*>(prow) = bits;
+        } else if (warp == S.NW + 1) {
+            const uint64_t bits = prof_vit_chain_down<P>(M.rec, cb, S.K);
+#pragma unroll
+            for (int a = 0; a < kProfMaxAlias; ++a)
+                if (a < S.n_alias) stb(cb, prof_slot<P>(S.alias_dst[a], L::BK), ldb(cb, prof_slot<P>(S.alias_src[a], L::BK)));
+            *reinterpret_cast<uint64_t*>(prow) = bits;
+        } else {
+            left = ldb(tb, -L::WS + L::MX + (P - 1) * L::SLOT);                  // M_{k0-1}(r), M_{k0+P}(r)
+            right = ldb(tb, L::WS + L::MX);
+        }
+        prow += S.row_bytes;
+        __syncthreads();
+        if (r >= 1 && __any_sync(0xffffffffu, r == n)) {
+            // ---- events whose last row this is: the end state (3614-3616).  Every warp holds the same lengths, so the
+            //      branch (and its barrier) is uniform over the CTA.
+            if (warp == S.NW) {
+                double best = neg_inf();
+                int arg = 0;
+                for (int j = 0; j < S.end_n; ++j) {
+                    const ProfEndRec E = ldg_rec(S.end_list + j);
+                    double v;
+                    if (E.cls == PROF_M) v = ldb(cb, prof_slot<P>(E.k, L::MX));
+                    else if (E.cls == PROF_DROP) v = __dadd_rn(ldb(cb, prof_slot<P>(E.k, L::MX)), M.rec[E.k * kProfRecDoubles + PR_WD]);
+                    else if (E.cls == PROF_SKIP) v = ldb(cb, prof_slot<P>(E.k, L::SK));
+                    else v = ldb(cb, prof_slot<P>(E.k, L::BK));
+                    const double s = __dadd_rn(v, E.w);
+                    if (s > best) { best = s; arg = j; }
+                }
+                if (r == n) {
+                    O.score[ev] = best;
+                    O.end_state[ev] = S.end_state;
+                    O.end_ord[ev] = arg;
+                }
+            }
+            __syncthreads();
+        }
+        if (r == nmax) break;
+        if (warp < S.NW) {
+            // ---- emitting states of row r + 1 (3545-3562)
+            const double x = M.xt[(r & (TC - 1)) * (kLanes + 1) + lane];         // obs[r] belongs to row r + 1
+            const uint32_t ord = prof_vit_emitting<P>(recw, tb, left, right, x, vM, vB, vI);
+            if (UB == 2) *reinterpret_cast<uint16_t*>(prow) = static_cast<uint16_t>(ord);
+            else *reinterpret_cast<uint32_t*>(prow) = ord;
+        }
+        __syncthreads();
+    }
+}
+
+// =================================================================================================================
+// Forward (scaled linear space)
+// =================================================================================================================
+template <int P>
+__device__ __forceinline__ int prof_fwd_emitting(const double* __restrict__ recw, unsigned char* __restrict__ tb, double left,
+                                                 double right, double x, double shiftd, double scale2, double (&vM)[P],
+                                                 double (&vB)[P], double (&vI)[P]) {
+    using L = ProfBlock<P>;
+    int mx = 0;
+#pragma unroll
+    for (int p = P - 1; p >= 0; --p) {
+        const double* R = recw + p * kProfRecDoubles;
+        const double2 w01 = ld2(R + PR_WM), w23 = ld2(R + PR_WM + 2), w45 = ld2(R + PR_WM + 4), w67 = ld2(R + PR_WM + 6);
+        const double2 wi = ld2(R + PR_WI), wb = ld2(R + PR_WB);
+        const double2 wdk = ld2(R + PR_WD), wsk = ld2(R + PR_SK);
+        const int kinds = __double2loint(wdk.y);
+        const double mprev = p > 0 ? vM[p > 0 ? p - 1 : 0] : left;
+        const double sk = ldb(tb, p > 0 ? L::SK + (p - 1) * L::SLOT : -L::WS + L::SK + (P - 1) * L::SLOT);
+        const double bk = ldb(tb, p < P - 1 ? L::BK + (p + 1) * L::SLOT : L::WS + L::BK);
+        const double eM = prof_lin_normal(R + PR_EM, x, shiftd);
+        const double eB = prof_lin_uniform(R + PR_EB, x, scale2);
+        const double eI = ((kinds >> 8) & 0xff) == EMIS_POINT ? prof_lin_point(R + PR_EI, x, scale2)
+                                                              : prof_lin_normal(R + PR_EI, x, shiftd);
+        const double drop = vM[p] * wdk.x;
+        double a0 = mprev * w01.x;                                  // two accumulators halve the dependent DFMA chain
+        double a1 = sk * w01.y;
+        a0 = fma(vM[p], w23.x, a0);
+        a1 = fma(drop, w23.y, a1);
+        a0 = fma(vB[p], w45.x, a0);
+        a1 = fma(vI[p], w45.y, a1);
+        if (kinds >> 24) a0 = fma(p < P - 1 ? ldb(tb, L::MX + (p + 1) * L::SLOT) : right, w67.x, a0);
+        a1 = fma(bk, w67.y, a1);
+        const double nM = (a0 + a1) * eM;
+        const double nI = fma(mprev, wi.x, vI[p] * wi.y) * eI;
+        const double nB = fma(vM[p], wb.x, vB[p] * wb.y) * eB;
+        vM[p] = nM;
+        vI[p] = nI;
+        vB[p] = nB;
+        stb(tb, L::AS + p * L::SLOT, nM * wsk.x);
+        stb(tb, L::AB + p * L::SLOT, nM * ld2(R + PR_BK).x);
+        mx = max(mx, max(__double2hiint(nM), max(__double2hiint(nI), __double2hiint(nB))));
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) stb(tb, L::MX + p * L::SLOT, vM[p]);
+    return mx;
+}
+
+template <int P>
+__device__ __forceinline__ void prof_fwd_chain_up(const double* __restrict__ rec, unsigned char* __restrict__ cb, int K,
+                                                  double startval) {
+    using L = ProfBlock<P>;
+    double f = startval;
+    stb(cb, L::SK + (P - 1) * L::SLOT, startval);
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        f = fma(f, rec[k * kProfRecDoubles + PR_SK + 1], ldb(cb, prof_slot<P>(k - 1 + P, L::AS) - L::WS));
+        stb(cb, prof_slot<P>(k, L::SK), f);
+    }
+}
+template <int P>
+__device__ __forceinline__ void prof_fwd_chain_down(const double* __restrict__ rec, unsigned char* __restrict__ cb, int K) {
+    using L = ProfBlock<P>;
+    double f = 0.0;
+#pragma unroll 4
+    for (int k = K - 1; k >= 0; --k) {
+        f = fma(f, rec[k * kProfRecDoubles + PR_BK + 1], ldb(cb, prof_slot<P>(k, L::AB)));
+        stb(cb, prof_slot<P>(k, L::BK), f);
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(PP_PROF_THREADS, PP_PROF_MIN_CTAS)
+k_profile_forward(const ProfSched S, const LaneBatchAny B, const FwdOut O) {
+    using L = ProfBlock<P>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const ProfSmem<P> M(smem, S.Kp, S.NW);
+    constexpr int TC = kLaneTileCols;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    const int n_warps = S.NW + 2;
+    const int g = blockIdx.x;
+    const int ev = B.order[g * kLanes + lane];
+    const int64_t off = ev >= 0 ? B.offsets[ev] : 0;
+    const int n = ev >= 0 ? static_cast<int>(B.offsets[ev + 1] - off) : 0;
+    const int nmax = B.group_len[g];
+
+    for (int i = threadIdx.x; i < S.Kp * kProfRecDoubles; i += n_warps * 32) M.rec[i] = __ldg(S.rec + i);
+    for (int i = threadIdx.x; i < M.n_col; i += n_warps * 32) reinterpret_cast<double*>(M.blocks)[i] = 0.0;
+    if (threadIdx.x < 2 * kLanes) M.smax[threadIdx.x] = 0;
+    __syncthreads();
+
+    double vM[P], vB[P], vI[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) vM[p] = vB[p] = vI[p] = 0.0;
+    unsigned char* const cb = M.blocks + lane * 8;
+    unsigned char* const tb = cb + (warp + 1) * L::WS;
+    const double* const recw = M.rec + warp * P * kProfRecDoubles;
+    long long scale_total = 0;                                      // skip-chain warp: sum of the shifts of rows 1 .. r
+
+    for (int r = 0;; ++r) {
+        const int q = r & 1;
+        if (r < nmax && (r & (TC - 1)) == 0) prof_fill_tile(M.xt, B.obs, B.obs_f64 != 0, off, n, r, warp, lane, n_warps);
+        // the whole of row r + 1 is multiplied by 2^shift, chosen from the largest emitting value of row r
+        const int Mx = M.smax[q * kLanes + lane];
+        const int ex = (Mx >> 20) & 0x7ff;
+        int shift = (ex == 0 || ex == 0x7ff) ? 0 : (kFwdTargetExp + 1023 - ex);
+        shift = max(-900, min(900, shift));
+        double left = 0.0, right = 0.0;
+        if (warp == S.NW) {
+            prof_fwd_chain_up<P>(M.rec, cb, S.K, r == 0 ? 1.0 : 0.0);
+            M.smax[(q ^ 1) * kLanes + lane] = 0;                    // row r + 1 collects its maxima here during phase A
+        } else if (warp == S.NW + 1) {
+            prof_fwd_chain_down<P>(M.rec, cb, S.K);
+#pragma unroll
+            for (int a = 0; a < kProfMaxAlias; ++a)
+                if (a < S.n_alias) stb(cb, prof_slot<P>(S.alias_dst[a], L::BK), ldb(cb, prof_slot<P>(S.alias_src[a], L::BK)));
+        } else {
+            left = ldb(tb, -L::WS + L::MX + (P - 1) * L::SLOT);
+            right = ldb(tb, L::WS + L::MX);
+        }
+        __syncthreads();
+        if (r >= 1 && __any_sync(0xffffffffu, r == n)) {            // log_probability (3378-3396); CTA-uniform branch
+            if (warp == S.NW) {
+                double Pr = 0.0;
+                for (int j = 0; j < S.end_n; ++j) {
+                    const ProfEndRec E = ldg_rec(S.end_list + j);
+                    double v;
+                    if (E.cls == PROF_M) v = ldb(cb, prof_slot<P>(E.k, L::MX));
+                    else if (E.cls == PROF_DROP) v = ldb(cb, prof_slot<P>(E.k, L::MX)) * M.rec[E.k * kProfRecDoubles + PR_WD];
+                    else if (E.cls == PROF_SKIP) v = ldb(cb, prof_slot<P>(E.k, L::SK));
+                    else v = ldb(cb, prof_slot<P>(E.k, L::BK));
+                    Pr = fma(v, E.w, Pr);
+                }
+                if (r == n) {
+                    double lp;
+                    if (Pr == 0.0) lp = neg_inf();
+                    else if (!(Pr < __longlong_as_double(0x7FF0000000000000LL))) lp = __longlong_as_double(0x7FF8000000000000LL);
+                    else lp = log(Pr) - static_cast<double>(scale_total) * 0.693147180559945309417;
+                    O.logp[ev] = lp;
+                }
+            }
+            __syncthreads();
+        }
+        scale_total += shift;
+        if (r == nmax) break;
+        if (warp < S.NW) {
+            const double x = M.xt[(r & (TC - 1)) * (kLanes + 1) + lane];
+            const double scale2 = __hiloint2double((shift + 1023) << 20, 0);
+            const int mx = prof_fwd_emitting<P>(recw, tb, left, right, x, static_cast<double>(shift), scale2, vM, vB, vI);
+            atomicMax(&M.smax[(q ^ 1) * kLanes + lane], mx);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace pp
