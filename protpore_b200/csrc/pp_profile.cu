@@ -19,4 +19,15 @@ int profile_forward_launch(const ProfSched& S, const LaneBatchAny& B, const FwdO
     return static_cast<int>(cudaGetLastError());
 }
 
+#ifdef PP_PHASE_TIMING
+int profile_debug_phase_cycles(unsigned long long* out, int reset) {
+    if (out) cudaMemcpyFromSymbol(out, g_prof_phase, sizeof(unsigned long long) * 2 * 256);
+    if (reset) { static unsigned long long z[512]; cudaMemcpyToSymbol(g_prof_phase, z, sizeof z); }
+    return 0;
+}
+#endif
+
 }  // namespace pp
+#ifdef PP_PHASE_TIMING
+extern "C" int pp_debug_profile_phase_cycles(unsigned long long* out, int reset) { return pp::profile_debug_phase_cycles(out, reset); }
+#endif

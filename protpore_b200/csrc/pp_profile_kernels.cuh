@@ -39,6 +39,16 @@ namespace pp {
 #endif
 #define PP_PROF_THREADS ((kProfMaxPositionWarps + 2) * 32)
 
+// Optional per-warp phase clocks (tools/profile_phase_timing.py builds the library with -DPP_PHASE_TIMING)
+#ifdef PP_PHASE_TIMING
+__device__ unsigned long long g_prof_phase[2][32 * 8];
+#define PPK_CLK(var) const long long var = clock64()
+#define PPK_ACC(slot, a, b) phase_acc[slot] += static_cast<unsigned long long>((b) - (a))
+#else
+#define PPK_CLK(var)
+#define PPK_ACC(slot, a, b)
+#endif
+
 // byte offsets inside a warp block (P slots of 256 bytes per array)
 template <int P>
 struct ProfBlock {
@@ -73,6 +83,14 @@ struct ProfSmem {
     }
 };
 
+// CTA-wide barrier for warp-specialised code: both roles arrive at barrier 1 with the CTA's thread count
+__device__ __forceinline__ void prof_bar(int n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
+// power-of-two shift of the next row from the largest high word among the emitting values of this one
+__device__ __forceinline__ int prof_row_shift(int hi) {
+    const int ex = (hi >> 20) & 0x7ff;
+    const int shift = (ex == 0 || ex == 0x7ff) ? 0 : (kFwdTargetExp + 1023 - ex);
+    return max(-900, min(900, shift));
+}
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ double ldb(const unsigned char* p, int off) { return *reinterpret_cast<const double*>(p + off); }
 __device__ __forceinline__ void stb(unsigned char* p, int off, double v) { *reinterpret_cast<double*>(p + off) = v; }
@@ -130,60 +148,94 @@ __device__ __forceinline__ double prof_lin_uniform(const double* R, double x, do
 // =================================================================================================================
 // Viterbi
 // =================================================================================================================
-// Phase A of one position warp: rows r -> r + 1 of its P positions.  tb: this lane's slice of the warp's block;
-// left / right: M of the neighbouring positions k0 - 1 and k0 + P in row r (read before the phase started).
+// Of the candidates of M_k(r + 1) only two depend on the silent chains of row r: the one from S_SKIP_{k-1} (slot 1) and
+// the one from B_BACK_{k+1} (slot 7).  Everything else -- the emissions, the other five (six) candidates and their
+// first-maximum tree, the insert and blip states, which have no silent source at all -- is computed by the position warps
+// WHILE the chain warps walk the chains of row r (`early`); after the barrier only the two missing candidates are merged
+// in (`late`).  The merge keeps the reference's order: slot 1 beats every later slot on equality and loses to slot 0;
+// slot 7 replaces only if strictly greater.
+//
+// early: rows r -> r + 1 of the warp's P positions.  tb: this lane's slice of the warp's block; left / right: M of the
+// neighbouring positions k0 - 1 and k0 + P in row r.  On return vM[p] holds the PARTIAL maximum of M_k(r + 1), eM[p] its
+// emission, bits 5 p .. 5 p + 4 of the returned word {partial arg (3), insert ordinal, blip ordinal}.
 template <int P>
-__device__ __forceinline__ uint32_t prof_vit_emitting(const double* __restrict__ recw, unsigned char* __restrict__ tb,
-                                                      double left, double right, double x, double (&vM)[P], double (&vB)[P],
-                                                      double (&vI)[P]) {
+__device__ __forceinline__ uint32_t prof_vit_early(const double* __restrict__ recw, const unsigned char* __restrict__ tb,
+                                                   double left, double right, double x, double (&vM)[P], double (&vB)[P],
+                                                   double (&vI)[P], double (&eMv)[P]) {
     using L = ProfBlock<P>;
     uint32_t ord = 0;
 #pragma unroll
     for (int p = P - 1; p >= 0; --p) {                            // descending: vM[p - 1] is still row r
         const double* R = recw + p * kProfRecDoubles;
-        const double2 w01 = ld2(R + PR_WM), w23 = ld2(R + PR_WM + 2), w45 = ld2(R + PR_WM + 4), w67 = ld2(R + PR_WM + 6);
+        const double2 w01 = ld2(R + PR_WM), w23 = ld2(R + PR_WM + 2), w45 = ld2(R + PR_WM + 4);
         const double2 wi = ld2(R + PR_WI), wb = ld2(R + PR_WB);
-        const double2 wdk = ld2(R + PR_WD), wsk = ld2(R + PR_SK);
+        const double2 wdk = ld2(R + PR_WD);
         const int kinds = __double2loint(wdk.y);
         const double mprev = p > 0 ? vM[p > 0 ? p - 1 : 0] : left;
-        // S_SKIP_{k-1} (the start state for k = 0) and B_BACK_{k+1} of row r: own block, or the neighbour's edge slot
-        const double sk = ldb(tb, p > 0 ? L::SK + (p - 1) * L::SLOT : -L::WS + L::SK + (P - 1) * L::SLOT);
-        const double bk = ldb(tb, p < P - 1 ? L::BK + (p + 1) * L::SLOT : L::WS + L::BK);
         const double eM = prof_log_normal(R + PR_EM, x);
         const double eB = prof_log_uniform(R + PR_EB, x);
         const double eI = ((kinds >> 8) & 0xff) == EMIS_POINT ? prof_log_point(R + PR_EI, x) : prof_log_normal(R + PR_EI, x);
         const double drop = __dadd_rn(vM[p], wdk.x);              // S_DROPOFF_k(r): its one candidate (3564-3584)
-        double s[7];
-        s[0] = __dadd_rn(__dadd_rn(mprev, w01.x), eM);
-        s[1] = __dadd_rn(__dadd_rn(sk, w01.y), eM);
-        s[2] = __dadd_rn(__dadd_rn(vM[p], w23.x), eM);
-        s[3] = __dadd_rn(__dadd_rn(drop, w23.y), eM);
-        s[4] = __dadd_rn(__dadd_rn(vB[p], w45.x), eM);
-        s[5] = __dadd_rn(__dadd_rn(vI[p], w45.y), eM);
-        s[6] = __dadd_rn(__dadd_rn(bk, w67.y), eM);
+        double s[5];
+        s[0] = __dadd_rn(__dadd_rn(mprev, w01.x), eM);            // slot 0
+        s[1] = __dadd_rn(__dadd_rn(vM[p], w23.x), eM);            // slots 2 .. 5
+        s[2] = __dadd_rn(__dadd_rn(drop, w23.y), eM);
+        s[3] = __dadd_rn(__dadd_rn(vB[p], w45.x), eM);
+        s[4] = __dadd_rn(__dadd_rn(vI[p], w45.y), eM);
         double best;
         uint32_t arg;
-        FirstMax<0, 7>::run(s, best, arg);
+        FirstMax<0, 5>::run(s, best, arg);
+        arg += arg != 0 ? 1u : 0u;                                // tree index -> slot
         if (kinds >> 24) {
-            // a candidate from M_{k+1} sits between the insert's and the back-slip's (bake merged a back-slip state away):
-            // it wins against the earlier ones only if strictly greater, against the back-slip's also on equality.
-            // M_{k+1}(r) is still in the exchange: a warp stores its new M values after its last position.
+            // a candidate from M_{k+1} sits behind the insert's (bake merged a back-slip state away): strictly greater only.
+            // M_{k+1}(r) is still in the exchange: the warps store their new M values in the late part.
             const double mnext = p < P - 1 ? ldb(tb, L::MX + (p + 1) * L::SLOT) : right;
-            const double c = __dadd_rn(__dadd_rn(mnext, w67.x), eM);
-            if (c > best || (c == best && arg == 6)) { best = c; arg = 7; }
+            const double c = __dadd_rn(__dadd_rn(mnext, ld2(R + PR_WM + 6).x), eM);
+            if (c > best) { best = c; arg = 7; }
         }
         const double i0 = __dadd_rn(__dadd_rn(mprev, wi.x), eI), i1 = __dadd_rn(__dadd_rn(vI[p], wi.y), eI);
         const double b0 = __dadd_rn(__dadd_rn(vM[p], wb.x), eB), b1 = __dadd_rn(__dadd_rn(vB[p], wb.y), eB);
         const bool pi = i1 > i0, pb = b1 > b0;
         vM[p] = best;
+        eMv[p] = eM;
         vI[p] = pi ? i1 : i0;
         vB[p] = pb ? b1 : b0;
-        stb(tb, L::AS + p * L::SLOT, __dadd_rn(best, wsk.x));     // into S_SKIP_{k+1}
-        stb(tb, L::AB + p * L::SLOT, __dadd_rn(best, ld2(R + PR_BK).x));     // into B_BACK_k
         ord |= (arg | (pi ? 8u : 0u) | (pb ? 16u : 0u)) << (5 * p);
     }
+    return ord;
+}
+// late: merges the two chain-dependent candidates, publishes M_k(r + 1) and the pass-1 candidates of the chain states it
+// feeds, M_k + t(M_k -> S_SKIP_{k+1}) and M_k + t(M_k -> B_BACK_k) (3564-3584).
+template <int P>
+__device__ __forceinline__ uint32_t prof_vit_late(const double* __restrict__ recw, unsigned char* __restrict__ tb, uint32_t ord,
+                                                  double (&vM)[P], const double (&eMv)[P]) {
+    using L = ProfBlock<P>;
+    double sk[P], bk[P];
 #pragma unroll
-    for (int p = 0; p < P; ++p) stb(tb, L::MX + p * L::SLOT, vM[p]);
+    for (int p = 0; p < P; ++p) {
+        // S_SKIP_{k-1} (the start state for k = 0) and B_BACK_{k+1} of row r: own block, or the neighbour's edge slot
+        sk[p] = ldb(tb, p > 0 ? L::SK + (p - 1) * L::SLOT : -L::WS + L::SK + (P - 1) * L::SLOT);
+        bk[p] = ldb(tb, p < P - 1 ? L::BK + (p + 1) * L::SLOT : L::WS + L::BK);
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const double* R = recw + p * kProfRecDoubles;
+        const double w1 = R[PR_WM + 1], w7 = R[PR_WM + 7], wa = R[PR_SK], wc = R[PR_BK];
+        const double s1 = __dadd_rn(__dadd_rn(sk[p], w1), eMv[p]);
+        const double s7 = __dadd_rn(__dadd_rn(bk[p], w7), eMv[p]);
+        double m = vM[p];
+        const uint32_t a = (ord >> (5 * p)) & 7u;
+        const bool t1 = s1 > m || (s1 == m && a != 0);
+        m = t1 ? s1 : m;
+        const bool t7 = s7 > m;
+        m = t7 ? s7 : m;
+        const uint32_t na = t7 ? 6u : (t1 ? 1u : a);              // stored ordinal: 6 = back-slip, 7 = M_{k+1}
+        ord = (ord & ~(7u << (5 * p))) | (na << (5 * p));
+        vM[p] = m;
+        stb(tb, L::MX + p * L::SLOT, m);
+        stb(tb, L::AS + p * L::SLOT, __dadd_rn(m, wa));          // into S_SKIP_{k+1}
+        stb(tb, L::AB + p * L::SLOT, __dadd_rn(m, wc));          // into B_BACK_k
+    }
     return ord;
 }
 
@@ -203,7 +255,8 @@ __device__ __forceinline__ uint32_t prof_vit_links(const double (&A)[N], const d
     return b;
 }
 
-// Phase B, ascending chain: link i = S_SKIP_i.  cb: this lane's slice of block 0 (the phantom before position 0).
+// Phase B, ascending chain: link i = S_SKIP_i.  cb: this lane's slice of block 0 (the phantom before position 0).  The
+// operands of the next block are loaded before the links of the current one are walked.
 template <int P>
 __device__ __forceinline__ uint64_t prof_vit_chain_up(const double* __restrict__ rec, unsigned char* __restrict__ cb, int K,
                                                       double startval) {
@@ -211,22 +264,36 @@ __device__ __forceinline__ uint64_t prof_vit_chain_up(const double* __restrict__
     uint64_t bits = 0;
     double v = startval;
     stb(cb, L::SK + (P - 1) * L::SLOT, startval);                 // what M_0 and S_SKIP_0 read through their start edge
-    int k = 0;
-    for (; k + P <= K; k += P) {
-        unsigned char* blk = cb + (k / P + 1) * L::WS;
-        double A[P], c[P], out[P];
+    const int nfull = K / P;
+    double A[P], c[P];
+    if (nfull > 0) {
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            A[p] = ldb(blk, p > 0 ? L::AS + (p - 1) * L::SLOT : -L::WS + L::AS + (P - 1) * L::SLOT);
-            c[p] = rec[(k + p) * kProfRecDoubles + PR_SK + 1];
+            A[p] = ldb(cb, L::WS + (p > 0 ? L::AS + (p - 1) * L::SLOT : -L::WS + L::AS + (P - 1) * L::SLOT));
+            c[p] = rec[p * kProfRecDoubles + PR_SK + 1];
         }
-        bits |= static_cast<uint64_t>(prof_vit_links<P>(A, c, out, v)) << k;
-#pragma unroll
-        for (int p = 0; p < P; ++p) stb(blk, L::SK + p * L::SLOT, out[p]);
     }
-    for (; k < K; ++k) {
-        double A[1] = {ldb(cb, prof_slot<P>(k - 1 + P, L::AS) - L::WS)}, c[1] = {rec[k * kProfRecDoubles + PR_SK + 1]}, out[1];
-        bits |= static_cast<uint64_t>(prof_vit_links<1>(A, c, out, v)) << k;
+    for (int b = 0; b < nfull; ++b) {
+        unsigned char* blk = cb + (b + 1) * L::WS;
+        double An[P], cn[P], out[P];
+        if (b + 1 < nfull) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                An[p] = ldb(blk, L::WS + (p > 0 ? L::AS + (p - 1) * L::SLOT : -L::WS + L::AS + (P - 1) * L::SLOT));
+                cn[p] = rec[((b + 1) * P + p) * kProfRecDoubles + PR_SK + 1];
+            }
+        }
+        bits |= static_cast<uint64_t>(prof_vit_links<P>(A, c, out, v)) << (b * P);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            stb(blk, L::SK + p * L::SLOT, out[p]);
+            A[p] = An[p];
+            c[p] = cn[p];
+        }
+    }
+    for (int k = nfull * P; k < K; ++k) {
+        double A1[1] = {ldb(cb, prof_slot<P>(k - 1 + P, L::AS) - L::WS)}, c1[1] = {rec[k * kProfRecDoubles + PR_SK + 1]}, out[1];
+        bits |= static_cast<uint64_t>(prof_vit_links<1>(A1, c1, out, v)) << k;
         stb(cb, prof_slot<P>(k, L::SK), out[0]);
     }
     return bits;
@@ -238,22 +305,37 @@ __device__ __forceinline__ uint64_t prof_vit_chain_down(const double* __restrict
     uint64_t bits = 0;
     double v = neg_inf();
     int k = K - 1, i = 0;
-    for (; (k + 1) % P != 0; --k, ++i) {                           // the partial block at the top
-        double A[1] = {ldb(cb, prof_slot<P>(k, L::AB))}, c[1] = {rec[k * kProfRecDoubles + PR_BK + 1]}, out[1];
-        bits |= static_cast<uint64_t>(prof_vit_links<1>(A, c, out, v)) << i;
-        stb(cb, prof_slot<P>(k, L::BK), out[0]);
-    }
-    for (; k >= 0; k -= P, i += P) {                               // k = last position of a full block
-        unsigned char* blk = cb + (k / P + 1) * L::WS;
-        double A[P], c[P], out[P];
+    const int nfull = K / P;
+    double A[P], c[P];
+    if (nfull > 0) {                                               // operands of the topmost full block
 #pragma unroll
         for (int u = 0; u < P; ++u) {
-            A[u] = ldb(blk, L::AB + (P - 1 - u) * L::SLOT);
-            c[u] = rec[(k - u) * kProfRecDoubles + PR_BK + 1];
+            A[u] = ldb(cb, nfull * L::WS + L::AB + (P - 1 - u) * L::SLOT);
+            c[u] = rec[(nfull * P - 1 - u) * kProfRecDoubles + PR_BK + 1];
+        }
+    }
+    for (; k >= nfull * P; --k, ++i) {                             // the partial block at the top
+        double A1[1] = {ldb(cb, prof_slot<P>(k, L::AB))}, c1[1] = {rec[k * kProfRecDoubles + PR_BK + 1]}, out[1];
+        bits |= static_cast<uint64_t>(prof_vit_links<1>(A1, c1, out, v)) << i;
+        stb(cb, prof_slot<P>(k, L::BK), out[0]);
+    }
+    for (int b = nfull - 1; b >= 0; --b, i += P) {
+        unsigned char* blk = cb + (b + 1) * L::WS;
+        double An[P], cn[P], out[P];
+        if (b > 0) {
+#pragma unroll
+            for (int u = 0; u < P; ++u) {
+                An[u] = ldb(blk, -L::WS + L::AB + (P - 1 - u) * L::SLOT);
+                cn[u] = rec[(b * P - 1 - u) * kProfRecDoubles + PR_BK + 1];
+            }
         }
         bits |= static_cast<uint64_t>(prof_vit_links<P>(A, c, out, v)) << i;
 #pragma unroll
-        for (int u = 0; u < P; ++u) stb(blk, L::BK + (P - 1 - u) * L::SLOT, out[u]);
+        for (int u = 0; u < P; ++u) {
+            stb(blk, L::BK + (P - 1 - u) * L::SLOT, out[u]);
+            A[u] = An[u];
+            c[u] = cn[u];
+        }
     }
     return bits;
 }
@@ -280,114 +362,167 @@ k_profile_viterbi(const ProfSched S, const LaneBatchAny B, const VitOut O) {
 
     for (int i = threadIdx.x; i < S.Kp * kProfRecDoubles; i += n_warps * 32) M.rec[i] = __ldg(S.rec + i);
     for (int i = threadIdx.x; i < M.n_col; i += n_warps * 32) reinterpret_cast<double*>(M.blocks)[i] = neg_inf();   // v[0, :] = -inf (3513)
+    if (nmax > 0) prof_fill_tile(M.xt, B.obs, B.obs_f64 != 0, off, n, 0, warp, lane, n_warps);
     __syncthreads();
 
-    double vM[P], vB[P], vI[P];
+    unsigned char* const cb = M.blocks + lane * 8;                               // block 0, this lane
+    const int n_threads = n_warps * 32;
+
+    // The two roles run separate loops (separate register allocations) that meet at the same barriers:
+    //   barrier 1 after {chains of row r | early part of row r + 1}, [end state of events ending at row r, + a barrier],
+    //   barrier 2 after the late part of row r + 1.
+    if (warp >= S.NW) {
+        for (int r = 0;; ++r) {
+            // ---- silent states of row r; v[0, start] = 0 (3514), the start state is -inf in every later row
+            uint64_t bits;
+            if (warp == S.NW) {
+                bits = prof_vit_chain_up<P>(M.rec, cb, S.K, r == 0 ? 0.0 : neg_inf());
+            } else {
+                bits = prof_vit_chain_down<P>(M.rec, cb, S.K);
+#pragma unroll
+                for (int a = 0; a < kProfMaxAlias; ++a)
+                    if (a < S.n_alias) stb(cb, prof_slot<P>(S.alias_dst[a], L::BK), ldb(cb, prof_slot<P>(S.alias_src[a], L::BK)));
+            }
+            *reinterpret_cast<uint64_t*>(prow) = bits;
+            prow += S.row_bytes;
+            prof_bar(n_threads);
+            if (r >= 1 && __any_sync(0xffffffffu, r == n)) {
+                // ---- events whose last row this is: the end state (3614-3616).  Every warp holds the same lengths, so
+                //      the branch (and its barrier) is uniform over the CTA.
+                if (warp == S.NW) {
+                    double best = neg_inf();
+                    int arg = 0;
+                    for (int j = 0; j < S.end_n; ++j) {
+                        const ProfEndRec E = ldg_rec(S.end_list + j);
+                        double v;
+                        if (E.cls == PROF_M) v = ldb(cb, prof_slot<P>(E.k, L::MX));
+                        else if (E.cls == PROF_DROP) v = __dadd_rn(ldb(cb, prof_slot<P>(E.k, L::MX)), M.rec[E.k * kProfRecDoubles + PR_WD]);
+                        else if (E.cls == PROF_SKIP) v = ldb(cb, prof_slot<P>(E.k, L::SK));
+                        else v = ldb(cb, prof_slot<P>(E.k, L::BK));
+                        const double s = __dadd_rn(v, E.w);
+                        if (s > best) { best = s; arg = j; }
+                    }
+                    if (r == n) {
+                        O.score[ev] = best;
+                        O.end_state[ev] = S.end_state;
+                        O.end_ord[ev] = arg;
+                    }
+                }
+                prof_bar(n_threads);
+            }
+            if (r == nmax) break;
+            if (r + 1 < nmax && ((r + 1) & (TC - 1)) == 0) prof_fill_tile(M.xt, B.obs, B.obs_f64 != 0, off, n, r + 1, warp, lane, n_warps);
+            prof_bar(n_threads);
+        }
+        return;
+    }
+
+    double vM[P], vB[P], vI[P], eM[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) vM[p] = vB[p] = vI[p] = neg_inf();
-    unsigned char* const cb = M.blocks + lane * 8;                               // block 0, this lane
-    unsigned char* const tb = cb + (warp + 1) * L::WS;                           // this warp's block (position warps)
+    unsigned char* const tb = cb + (warp + 1) * L::WS;                           // this warp's block
     const double* const recw = M.rec + warp * P * kProfRecDoubles;
-
+#ifdef PP_PHASE_TIMING
+    unsigned long long phase_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     for (int r = 0;; ++r) {
-        if (r < nmax && (r & (TC - 1)) == 0) prof_fill_tile(M.xt, B.obs, B.obs_f64 != 0, off, n, r, warp, lane, n_warps);
-        double left = 0.0, right = 0.0;
-        if (warp == S.NW) {
-            // ---- silent states of row r; v[0, start] = 0 (3514), the start state is -inf in every later row
-            const uint64_t bits = prof_vit_chain_up<P>(M.rec, cb, S.K, r == 0 ? 0.0 : neg_inf());
-            *reinterpret_cast<uint64_t*>(prow) = bits;
-        } else if (warp == S.NW + 1) {
-            const uint64_t bits = prof_vit_chain_down<P>(M.rec, cb, S.K);
-#pragma unroll
-            for (int a = 0; a < kProfMaxAlias; ++a)
-                if (a < S.n_alias) stb(cb, prof_slot<P>(S.alias_dst[a], L::BK), ldb(cb, prof_slot<P>(S.alias_src[a], L::BK)));
-            *reinterpret_cast<uint64_t*>(prow) = bits;
-        } else {
-            left = ldb(tb, -L::WS + L::MX + (P - 1) * L::SLOT);                  // M_{k0-1}(r), M_{k0+P}(r)
-            right = ldb(tb, L::WS + L::MX);
+        PPK_CLK(c0);
+        uint32_t ord = 0;
+        if (r < nmax) {
+            // ---- beside the chains of row r: everything of row r + 1 that does not read them (3545-3562)
+            const double left = ldb(tb, -L::WS + L::MX + (P - 1) * L::SLOT);     // M_{k0-1}(r), M_{k0+P}(r)
+            const double right = ldb(tb, L::WS + L::MX);
+            const double x = M.xt[(r & (TC - 1)) * (kLanes + 1) + lane];         // obs[r] belongs to row r + 1
+            ord = prof_vit_early<P>(recw, tb, left, right, x, vM, vB, vI, eM);
         }
         prow += S.row_bytes;
-        __syncthreads();
-        if (r >= 1 && __any_sync(0xffffffffu, r == n)) {
-            // ---- events whose last row this is: the end state (3614-3616).  Every warp holds the same lengths, so the
-            //      branch (and its barrier) is uniform over the CTA.
-            if (warp == S.NW) {
-                double best = neg_inf();
-                int arg = 0;
-                for (int j = 0; j < S.end_n; ++j) {
-                    const ProfEndRec E = ldg_rec(S.end_list + j);
-                    double v;
-                    if (E.cls == PROF_M) v = ldb(cb, prof_slot<P>(E.k, L::MX));
-                    else if (E.cls == PROF_DROP) v = __dadd_rn(ldb(cb, prof_slot<P>(E.k, L::MX)), M.rec[E.k * kProfRecDoubles + PR_WD]);
-                    else if (E.cls == PROF_SKIP) v = ldb(cb, prof_slot<P>(E.k, L::SK));
-                    else v = ldb(cb, prof_slot<P>(E.k, L::BK));
-                    const double s = __dadd_rn(v, E.w);
-                    if (s > best) { best = s; arg = j; }
-                }
-                if (r == n) {
-                    O.score[ev] = best;
-                    O.end_state[ev] = S.end_state;
-                    O.end_ord[ev] = arg;
-                }
-            }
-            __syncthreads();
-        }
+        PPK_CLK(c1);
+        prof_bar(n_threads);
+        PPK_CLK(c2);
+        PPK_ACC(0, c0, c1); PPK_ACC(1, c1, c2);
+        if (r >= 1 && __any_sync(0xffffffffu, r == n)) prof_bar(n_threads);     // the chain warp evaluates the end state
         if (r == nmax) break;
-        if (warp < S.NW) {
-            // ---- emitting states of row r + 1 (3545-3562)
-            const double x = M.xt[(r & (TC - 1)) * (kLanes + 1) + lane];         // obs[r] belongs to row r + 1
-            const uint32_t ord = prof_vit_emitting<P>(recw, tb, left, right, x, vM, vB, vI);
-            if (UB == 2) *reinterpret_cast<uint16_t*>(prow) = static_cast<uint16_t>(ord);
-            else *reinterpret_cast<uint32_t*>(prow) = ord;
-        }
-        __syncthreads();
+        PPK_CLK(c3);
+        // ---- the two candidates that read the chains of row r; publish M(r + 1)
+        ord = prof_vit_late<P>(recw, tb, ord, vM, eM);
+        if (UB == 2) *reinterpret_cast<uint16_t*>(prow) = static_cast<uint16_t>(ord);
+        else *reinterpret_cast<uint32_t*>(prow) = ord;
+        // the observation tile is free now (the early part of this row has read it): stage the next one when due
+        if (r + 1 < nmax && ((r + 1) & (TC - 1)) == 0) prof_fill_tile(M.xt, B.obs, B.obs_f64 != 0, off, n, r + 1, warp, lane, n_warps);
+        PPK_CLK(c4);
+        prof_bar(n_threads);
+        PPK_CLK(c5);
+        PPK_ACC(2, c2, c3); PPK_ACC(3, c3, c4); PPK_ACC(4, c4, c5);
+#ifdef PP_PHASE_TIMING
+        phase_acc[6] += 1;
+#endif
     }
+#ifdef PP_PHASE_TIMING
+    if (lane == 0)
+        for (int k = 0; k < 8; ++k) atomicAdd(&g_prof_phase[0][warp * 8 + k], phase_acc[k]);
+#endif
 }
 
 // =================================================================================================================
 // Forward (scaled linear space)
 // =================================================================================================================
+// Same split: `early` sums every term that does not read the chains of row r and finishes the insert and blip states,
+// `late` adds the two chain terms and applies the emission.  Returns the largest high word among the insert / blip values.
 template <int P>
-__device__ __forceinline__ int prof_fwd_emitting(const double* __restrict__ recw, unsigned char* __restrict__ tb, double left,
-                                                 double right, double x, double shiftd, double scale2, double (&vM)[P],
-                                                 double (&vB)[P], double (&vI)[P]) {
+__device__ __forceinline__ int prof_fwd_early(const double* __restrict__ recw, const unsigned char* __restrict__ tb, double left,
+                                              double right, double x, double shiftd, double scale2, double (&vM)[P],
+                                              double (&vB)[P], double (&vI)[P], double (&eMv)[P]) {
     using L = ProfBlock<P>;
     int mx = 0;
 #pragma unroll
     for (int p = P - 1; p >= 0; --p) {
         const double* R = recw + p * kProfRecDoubles;
-        const double2 w01 = ld2(R + PR_WM), w23 = ld2(R + PR_WM + 2), w45 = ld2(R + PR_WM + 4), w67 = ld2(R + PR_WM + 6);
+        const double2 w01 = ld2(R + PR_WM), w23 = ld2(R + PR_WM + 2), w45 = ld2(R + PR_WM + 4);
         const double2 wi = ld2(R + PR_WI), wb = ld2(R + PR_WB);
-        const double2 wdk = ld2(R + PR_WD), wsk = ld2(R + PR_SK);
+        const double2 wdk = ld2(R + PR_WD);
         const int kinds = __double2loint(wdk.y);
         const double mprev = p > 0 ? vM[p > 0 ? p - 1 : 0] : left;
-        const double sk = ldb(tb, p > 0 ? L::SK + (p - 1) * L::SLOT : -L::WS + L::SK + (P - 1) * L::SLOT);
-        const double bk = ldb(tb, p < P - 1 ? L::BK + (p + 1) * L::SLOT : L::WS + L::BK);
-        const double eM = prof_lin_normal(R + PR_EM, x, shiftd);
+        eMv[p] = prof_lin_normal(R + PR_EM, x, shiftd);
         const double eB = prof_lin_uniform(R + PR_EB, x, scale2);
         const double eI = ((kinds >> 8) & 0xff) == EMIS_POINT ? prof_lin_point(R + PR_EI, x, scale2)
                                                               : prof_lin_normal(R + PR_EI, x, shiftd);
         const double drop = vM[p] * wdk.x;
         double a0 = mprev * w01.x;                                  // two accumulators halve the dependent DFMA chain
-        double a1 = sk * w01.y;
+        double a1 = drop * w23.y;
         a0 = fma(vM[p], w23.x, a0);
-        a1 = fma(drop, w23.y, a1);
-        a0 = fma(vB[p], w45.x, a0);
-        a1 = fma(vI[p], w45.y, a1);
-        if (kinds >> 24) a0 = fma(p < P - 1 ? ldb(tb, L::MX + (p + 1) * L::SLOT) : right, w67.x, a0);
-        a1 = fma(bk, w67.y, a1);
-        const double nM = (a0 + a1) * eM;
+        a1 = fma(vB[p], w45.x, a1);
+        a0 = fma(vI[p], w45.y, a0);
+        if (kinds >> 24) a1 = fma(p < P - 1 ? ldb(tb, L::MX + (p + 1) * L::SLOT) : right, ld2(R + PR_WM + 6).x, a1);
         const double nI = fma(mprev, wi.x, vI[p] * wi.y) * eI;
         const double nB = fma(vM[p], wb.x, vB[p] * wb.y) * eB;
-        vM[p] = nM;
+        vM[p] = a0 + a1;
         vI[p] = nI;
         vB[p] = nB;
-        stb(tb, L::AS + p * L::SLOT, nM * wsk.x);
-        stb(tb, L::AB + p * L::SLOT, nM * ld2(R + PR_BK).x);
-        mx = max(mx, max(__double2hiint(nM), max(__double2hiint(nI), __double2hiint(nB))));
+        mx = max(mx, max(__double2hiint(nI), __double2hiint(nB)));
+    }
+    return mx;
+}
+template <int P>
+__device__ __forceinline__ int prof_fwd_late(const double* __restrict__ recw, unsigned char* __restrict__ tb, int mx,
+                                             double (&vM)[P], const double (&eMv)[P]) {
+    using L = ProfBlock<P>;
+    double sk[P], bk[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        sk[p] = ldb(tb, p > 0 ? L::SK + (p - 1) * L::SLOT : -L::WS + L::SK + (P - 1) * L::SLOT);
+        bk[p] = ldb(tb, p < P - 1 ? L::BK + (p + 1) * L::SLOT : L::WS + L::BK);
     }
 #pragma unroll
-    for (int p = 0; p < P; ++p) stb(tb, L::MX + p * L::SLOT, vM[p]);
+    for (int p = 0; p < P; ++p) {
+        const double* R = recw + p * kProfRecDoubles;
+        const double w1 = R[PR_WM + 1], w7 = R[PR_WM + 7], wa = R[PR_SK], wc = R[PR_BK];
+        const double m = fma(bk[p], w7, fma(sk[p], w1, vM[p])) * eMv[p];
+        vM[p] = m;
+        stb(tb, L::MX + p * L::SLOT, m);
+        stb(tb, L::AS + p * L::SLOT, m * wa);
+        stb(tb, L::AB + p * L::SLOT, m * wc);
+        mx = max(mx, __double2hiint(m));
+    }
     return mx;
 }
 
@@ -397,8 +532,22 @@ __device__ __forceinline__ void prof_fwd_chain_up(const double* __restrict__ rec
     using L = ProfBlock<P>;
     double f = startval;
     stb(cb, L::SK + (P - 1) * L::SLOT, startval);
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
+    const int nfull = K / P;
+    for (int b = 0; b < nfull; ++b) {
+        unsigned char* blk = cb + (b + 1) * L::WS;
+        double A[P], c[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            A[p] = ldb(blk, p > 0 ? L::AS + (p - 1) * L::SLOT : -L::WS + L::AS + (P - 1) * L::SLOT);
+            c[p] = rec[(b * P + p) * kProfRecDoubles + PR_SK + 1];
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            f = fma(f, c[p], A[p]);
+            stb(blk, L::SK + p * L::SLOT, f);
+        }
+    }
+    for (int k = nfull * P; k < K; ++k) {
         f = fma(f, rec[k * kProfRecDoubles + PR_SK + 1], ldb(cb, prof_slot<P>(k - 1 + P, L::AS) - L::WS));
         stb(cb, prof_slot<P>(k, L::SK), f);
     }
@@ -407,10 +556,24 @@ template <int P>
 __device__ __forceinline__ void prof_fwd_chain_down(const double* __restrict__ rec, unsigned char* __restrict__ cb, int K) {
     using L = ProfBlock<P>;
     double f = 0.0;
-#pragma unroll 4
-    for (int k = K - 1; k >= 0; --k) {
+    const int nfull = K / P;
+    for (int k = K - 1; k >= nfull * P; --k) {
         f = fma(f, rec[k * kProfRecDoubles + PR_BK + 1], ldb(cb, prof_slot<P>(k, L::AB)));
         stb(cb, prof_slot<P>(k, L::BK), f);
+    }
+    for (int b = nfull - 1; b >= 0; --b) {
+        unsigned char* blk = cb + (b + 1) * L::WS;
+        double A[P], c[P];
+#pragma unroll
+        for (int u = 0; u < P; ++u) {
+            A[u] = ldb(blk, L::AB + (P - 1 - u) * L::SLOT);
+            c[u] = rec[(b * P + P - 1 - u) * kProfRecDoubles + PR_BK + 1];
+        }
+#pragma unroll
+        for (int u = 0; u < P; ++u) {
+            f = fma(f, c[u], A[u]);
+            stb(blk, L::BK + (P - 1 - u) * L::SLOT, f);
+        }
     }
 }
 
@@ -433,69 +596,81 @@ k_profile_forward(const ProfSched S, const LaneBatchAny B, const FwdOut O) {
     for (int i = threadIdx.x; i < S.Kp * kProfRecDoubles; i += n_warps * 32) M.rec[i] = __ldg(S.rec + i);
     for (int i = threadIdx.x; i < M.n_col; i += n_warps * 32) reinterpret_cast<double*>(M.blocks)[i] = 0.0;
     if (threadIdx.x < 2 * kLanes) M.smax[threadIdx.x] = 0;
+    if (nmax > 0) prof_fill_tile(M.xt, B.obs, B.obs_f64 != 0, off, n, 0, warp, lane, n_warps);
     __syncthreads();
 
-    double vM[P], vB[P], vI[P];
+    unsigned char* const cb = M.blocks + lane * 8;
+    const int n_threads = n_warps * 32;
+    long long scale_total = 0;                                      // sum of the shifts of rows 1 .. r
+
+    if (warp >= S.NW) {
+        for (int r = 0;; ++r) {
+            const int q = r & 1;
+            const int shift = prof_row_shift(M.smax[q * kLanes + lane]);
+            if (warp == S.NW) {
+                prof_fwd_chain_up<P>(M.rec, cb, S.K, r == 0 ? 1.0 : 0.0);
+                M.smax[(q ^ 1) * kLanes + lane] = 0;                // row r + 1 collects its maxima here in the late part
+            } else {
+                prof_fwd_chain_down<P>(M.rec, cb, S.K);
+#pragma unroll
+                for (int a = 0; a < kProfMaxAlias; ++a)
+                    if (a < S.n_alias) stb(cb, prof_slot<P>(S.alias_dst[a], L::BK), ldb(cb, prof_slot<P>(S.alias_src[a], L::BK)));
+            }
+            prof_bar(n_threads);
+            if (r >= 1 && __any_sync(0xffffffffu, r == n)) {        // log_probability (3378-3396); CTA-uniform branch
+                if (warp == S.NW) {
+                    double Pr = 0.0;
+                    for (int j = 0; j < S.end_n; ++j) {
+                        const ProfEndRec E = ldg_rec(S.end_list + j);
+                        double v;
+                        if (E.cls == PROF_M) v = ldb(cb, prof_slot<P>(E.k, L::MX));
+                        else if (E.cls == PROF_DROP) v = ldb(cb, prof_slot<P>(E.k, L::MX)) * M.rec[E.k * kProfRecDoubles + PR_WD];
+                        else if (E.cls == PROF_SKIP) v = ldb(cb, prof_slot<P>(E.k, L::SK));
+                        else v = ldb(cb, prof_slot<P>(E.k, L::BK));
+                        Pr = fma(v, E.w, Pr);
+                    }
+                    if (r == n) {
+                        double lp;
+                        if (Pr == 0.0) lp = neg_inf();
+                        else if (!(Pr < __longlong_as_double(0x7FF0000000000000LL))) lp = __longlong_as_double(0x7FF8000000000000LL);
+                        else lp = log(Pr) - static_cast<double>(scale_total) * 0.693147180559945309417;
+                        O.logp[ev] = lp;
+                    }
+                }
+                prof_bar(n_threads);
+            }
+            scale_total += shift;
+            if (r == nmax) break;
+            if (r + 1 < nmax && ((r + 1) & (TC - 1)) == 0) prof_fill_tile(M.xt, B.obs, B.obs_f64 != 0, off, n, r + 1, warp, lane, n_warps);
+            prof_bar(n_threads);
+        }
+        return;
+    }
+
+    double vM[P], vB[P], vI[P], eM[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) vM[p] = vB[p] = vI[p] = 0.0;
-    unsigned char* const cb = M.blocks + lane * 8;
     unsigned char* const tb = cb + (warp + 1) * L::WS;
     const double* const recw = M.rec + warp * P * kProfRecDoubles;
-    long long scale_total = 0;                                      // skip-chain warp: sum of the shifts of rows 1 .. r
-
     for (int r = 0;; ++r) {
         const int q = r & 1;
-        if (r < nmax && (r & (TC - 1)) == 0) prof_fill_tile(M.xt, B.obs, B.obs_f64 != 0, off, n, r, warp, lane, n_warps);
-        // the whole of row r + 1 is multiplied by 2^shift, chosen from the largest emitting value of row r
-        const int Mx = M.smax[q * kLanes + lane];
-        const int ex = (Mx >> 20) & 0x7ff;
-        int shift = (ex == 0 || ex == 0x7ff) ? 0 : (kFwdTargetExp + 1023 - ex);
-        shift = max(-900, min(900, shift));
-        double left = 0.0, right = 0.0;
-        if (warp == S.NW) {
-            prof_fwd_chain_up<P>(M.rec, cb, S.K, r == 0 ? 1.0 : 0.0);
-            M.smax[(q ^ 1) * kLanes + lane] = 0;                    // row r + 1 collects its maxima here during phase A
-        } else if (warp == S.NW + 1) {
-            prof_fwd_chain_down<P>(M.rec, cb, S.K);
-#pragma unroll
-            for (int a = 0; a < kProfMaxAlias; ++a)
-                if (a < S.n_alias) stb(cb, prof_slot<P>(S.alias_dst[a], L::BK), ldb(cb, prof_slot<P>(S.alias_src[a], L::BK)));
-        } else {
-            left = ldb(tb, -L::WS + L::MX + (P - 1) * L::SLOT);
-            right = ldb(tb, L::WS + L::MX);
-        }
-        __syncthreads();
-        if (r >= 1 && __any_sync(0xffffffffu, r == n)) {            // log_probability (3378-3396); CTA-uniform branch
-            if (warp == S.NW) {
-                double Pr = 0.0;
-                for (int j = 0; j < S.end_n; ++j) {
-                    const ProfEndRec E = ldg_rec(S.end_list + j);
-                    double v;
-                    if (E.cls == PROF_M) v = ldb(cb, prof_slot<P>(E.k, L::MX));
-                    else if (E.cls == PROF_DROP) v = ldb(cb, prof_slot<P>(E.k, L::MX)) * M.rec[E.k * kProfRecDoubles + PR_WD];
-                    else if (E.cls == PROF_SKIP) v = ldb(cb, prof_slot<P>(E.k, L::SK));
-                    else v = ldb(cb, prof_slot<P>(E.k, L::BK));
-                    Pr = fma(v, E.w, Pr);
-                }
-                if (r == n) {
-                    double lp;
-                    if (Pr == 0.0) lp = neg_inf();
-                    else if (!(Pr < __longlong_as_double(0x7FF0000000000000LL))) lp = __longlong_as_double(0x7FF8000000000000LL);
-                    else lp = log(Pr) - static_cast<double>(scale_total) * 0.693147180559945309417;
-                    O.logp[ev] = lp;
-                }
-            }
-            __syncthreads();
-        }
-        scale_total += shift;
-        if (r == nmax) break;
-        if (warp < S.NW) {
+        int mx = 0;
+        if (r < nmax) {
+            // the whole of row r + 1 is multiplied by 2^shift, chosen from the largest emitting value of row r
+            const int shift = prof_row_shift(M.smax[q * kLanes + lane]);
+            const double left = ldb(tb, -L::WS + L::MX + (P - 1) * L::SLOT);
+            const double right = ldb(tb, L::WS + L::MX);
             const double x = M.xt[(r & (TC - 1)) * (kLanes + 1) + lane];
             const double scale2 = __hiloint2double((shift + 1023) << 20, 0);
-            const int mx = prof_fwd_emitting<P>(recw, tb, left, right, x, static_cast<double>(shift), scale2, vM, vB, vI);
-            atomicMax(&M.smax[(q ^ 1) * kLanes + lane], mx);
+            mx = prof_fwd_early<P>(recw, tb, left, right, x, static_cast<double>(shift), scale2, vM, vB, vI, eM);
         }
-        __syncthreads();
+        prof_bar(n_threads);
+        if (r >= 1 && __any_sync(0xffffffffu, r == n)) prof_bar(n_threads);
+        if (r == nmax) break;
+        mx = prof_fwd_late<P>(recw, tb, mx, vM, eM);
+        atomicMax(&M.smax[(q ^ 1) * kLanes + lane], mx);
+        if (r + 1 < nmax && ((r + 1) & (TC - 1)) == 0) prof_fill_tile(M.xt, B.obs, B.obs_f64 != 0, off, n, r + 1, warp, lane, n_warps);
+        prof_bar(n_threads);
     }
 }
 
