@@ -230,9 +230,7 @@ ProfSched make_prof_sched(const pp_model* M, bool logspace) {
     S.rec = (logspace ? M->d_prof_rec_v : M->d_prof_rec_f).as<double>();
     S.end_list = (logspace ? M->d_prof_end_v : M->d_prof_end_f).as<ProfEndRec>();
     S.end_n = static_cast<int32_t>(F.end_v.size());
-    S.K = F.K; S.Kp = F.Kp; S.NW = F.NW;
-    S.n_alias = F.n_alias;
-    for (int a = 0; a < kProfMaxAlias; ++a) { S.alias_dst[a] = F.alias_dst[a]; S.alias_src[a] = F.alias_src[a]; }
+    S.K = F.K; S.Kp = F.Kp; S.Kr = F.Kr; S.NW = F.NW;
     S.row_bytes = F.row_bytes;
     S.end_state = M->end;
     return S;
@@ -549,7 +547,7 @@ int pp_model_kernel_info(const pp_model* M, int32_t* out4) {
     if (!M || !out4) { set_error("null argument"); return PP_ERR_ARG; }
     out4[0] = use_profile(M) ? 2 : (lane_kernels_fit(M) ? 1 : 0);
     out4[1] = M->plan.ok ? M->plan.K : 0;
-    out4[2] = M->plan.ok ? M->plan.NW + 1 : kLaneWarps;
+    out4[2] = use_profile(M) ? M->plan.NW + 1 : kLaneWarps;
     out4[3] = static_cast<int32_t>(ptr_row_bytes(M));
     return PP_OK;
 }

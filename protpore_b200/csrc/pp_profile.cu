@@ -4,18 +4,18 @@
 namespace pp {
 
 int profile_viterbi_launch(const ProfSched& S, const LaneBatchAny& B, const VitOut& O, int n_groups, cudaStream_t stream) {
-    const size_t smem = prof_smem_bytes(S.Kp, S.NW, kProfPositionsPerWarp);
+    const size_t smem = prof_smem_bytes(S.Kr, S.NW, kProfPositionsPerWarp);
     cudaError_t e = cudaFuncSetAttribute(k_profile_viterbi<kProfPositionsPerWarp>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    k_profile_viterbi<kProfPositionsPerWarp><<<n_groups, (S.NW + 2) * 32, smem, stream>>>(S, B, O);
+    k_profile_viterbi<kProfPositionsPerWarp><<<n_groups, (S.NW + 1) * 32, smem, stream>>>(S, B, O);
     return static_cast<int>(cudaGetLastError());
 }
 
 int profile_forward_launch(const ProfSched& S, const LaneBatchAny& B, const FwdOut& O, int n_groups, cudaStream_t stream) {
-    const size_t smem = prof_smem_bytes(S.Kp, S.NW, kProfPositionsPerWarp);
+    const size_t smem = prof_smem_bytes(S.Kr, S.NW, kProfPositionsPerWarp);
     cudaError_t e = cudaFuncSetAttribute(k_profile_forward<kProfPositionsPerWarp>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    k_profile_forward<kProfPositionsPerWarp><<<n_groups, (S.NW + 2) * 32, smem, stream>>>(S, B, O);
+    k_profile_forward<kProfPositionsPerWarp><<<n_groups, (S.NW + 1) * 32, smem, stream>>>(S, B, O);
     return static_cast<int>(cudaGetLastError());
 }
 

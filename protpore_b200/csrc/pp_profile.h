@@ -44,6 +44,10 @@ enum : int {
     PR_EI = 20,     // [4] I_INS_k
     PR_EB = 24,     // [4] I_BLIP_k
     PR_BK = 28,     // [2] B_BACK_k: from M_k, from B_BACK_{k+1}
+    // forward records only, first position of a warp's block: products of the chain weights of the block
+    PR_CUP = 30,    //   prod_j t(S_SKIP_{k0+j-1} -> S_SKIP_{k0+j}), j = 0 .. P-1
+    PR_CDN = 31,    //   prod_j t(B_BACK_{k0+j+1} -> B_BACK_{k0+j})
+    PR_CUT = 19,    //   PR_CUP without j = 0 (the fourth constant of M's emission record is unused in linear space)
 };
 // Emission records.  Viterbi (log domain, exact):   Normal {mu, 2 sigma^2, RN(1 / (2 sigma^2)), log(1/(sigma sqrt(2 pi)))}
 //                                                    Point  {mu, -, -, -}      Uniform {lo, hi, -, log(1/(hi - lo))}
@@ -63,6 +67,7 @@ struct ProfilePlan {
     int P = 3;                                   // positions per warp the tables are padded for
     int NW = 0;                                  // position warps = ceil(K / P);  the CTA has NW + 1 warps
     int Kp = 0;                                  // NW * P (records of padding positions hold -inf / 0 weights)
+    int Kr = 0;                                  // records in rec_v / rec_f: Kp + P
     std::vector<double> rec_v, rec_f;            // [Kp][32]
     std::vector<ProfEndRec> end_v, end_f;        // in-edges of `end` in the reference's visiting order
     int n_alias = 0;                             // B_BACK slots that mirror another one (M_0 reads B_BACK_2 in pro_001)

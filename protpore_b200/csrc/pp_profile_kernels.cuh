@@ -1,32 +1,47 @@
 // pp_profile_kernels.cuh -- Viterbi and forward sweeps of a LINEAR PROFILE HMM (pp_profile.h) for sm_100a, register-resident.
 //
-// One CTA = NW position warps + 2 chain warps sweeps 32 events; lane j of every warp works on event j (as in
-// pp_lane_kernels.cuh).  Position warp w owns positions [w P, w P + P): the values of THEIR emitting states -- M_k,
-// I_BLIP_k, I_INS_k -- stay in registers from row to row.  Per row r -> r + 1:
-//   phase A  position warps: every emitting state of row r + 1 from row r (registers), the neighbours' M (read from the
-//            shared-memory exchange while the chains run) and the silent values of row r (shared memory).  They publish
-//            M_k(r + 1) and the pass-1 candidates of the two chain states M_k feeds, M_k + t(M_k -> S_SKIP_{k+1}) and
-//            M_k + t(M_k -> B_BACK_k) (3564-3584), and store 5 bits of ordinals per position (M: 3, insert: 1, blip: 1)
-//            with one coalesced store;
-//   phase B  chain warps, one per chain: S_SKIP ascending, B_BACK descending.  A link is DADD -> DSETP -> FSEL on the
-//            value of the link before it (22.7 cycles on B200, tools/lat_bench.cu); bit i of a 64-bit word per lane
-//            holds the ordinal of link i.  S_DROPOFF_k = M_k + t has a single in-edge and is recomputed where it is read
-//            (same DADD as the reference's, no storage).
-// separated by two barriers.  The end state is evaluated once per event at its last row (a CTA-uniform extra step).
+// One CTA = NW position warps + 1 chain warp sweeps 32 events; lane j of every warp works on event j (as in
+// pp_lane_kernels.cuh).  Position warp w owns positions [k0, k0 + P), k0 = w P: the values of THEIR emitting states --
+// M_k, I_BLIP_k, I_INS_k -- stay in registers from row to row.
 //
-// Shared memory is laid out per WARP: block w + 1 holds, for the warp's P positions, M | S_SKIP | B_BACK | the two
-// pass-1 candidate arrays, 32 doubles (one per lane) each; blocks 0 and NW + 1 are phantoms that hold the start state and
-// the "nothing beyond the ends" values.  A warp reaches everything it needs -- its own block and the edge slots of its
-// two neighbours -- at COMPILE-TIME offsets from one per-thread base address, so a candidate costs no address arithmetic
-// and no load for its value (registers), and half a load for its weight (16-byte broadcast loads of the position record).
+// What serialises a row is the pair of silent chains: S_SKIP_k = max(A_k, S_SKIP_{k-1} + c_k) ascending and
+// B_BACK_k = max(A'_k, B_BACK_{k+1} + c'_k) descending, with pass-1 candidates A_k = M_{k-1} + a_k, A'_k = M_k + a'_k
+// (yahmm.pyx:3564-3605) -- 43 dependent links of DADD -> DSETP -> FSEL (22.7 cycles each on B200, tools/lat_bench.cu)
+// that a scan cannot re-associate without changing bits.  They are taken off the critical path EXACTLY:
+//   * rounding is monotone, so max(x, y) + c = max(x + c, y + c) bit for bit.  Unrolling the recurrence over the P links
+//     of a block gives  out = max( (((in + c_1) + c_2) ... + c_P),  E ), where E -- the best way INTO the block through
+//     one of its own pass-1 candidates, summed left to right like the reference does -- does not depend on `in`;
+//   * every position warp computes E for its block from its own M values (plus the one entry that comes from its left
+//     neighbour's last M, which that neighbour carries through for it: T);
+//   * the chain warp only propagates the block CARRIES: P dependent DADDs and one maximum per block (~46 cycles instead
+//     of P x 22.7), both chains interleaved, and publishes the value entering every block;
+//   * each position warp then walks ITS P links from that value with the reference's own operations (strict '>', which
+//     also gives the ordinals) -- all warps at once.
+// Per row r -> r + 1, position warps:
+//   early  beside the chain warp's carry sweep of row r: everything of row r + 1 that does not read the chains -- the
+//          emissions, five (six) of M's seven (eight) candidates and their first-maximum tree, the insert and blip states;
+//   fill   after the barrier: the warp's links of row r's chains from the published carries (and their ordinals);
+//   late   the two candidates of M_k(r + 1) that read S_SKIP_{k-1}(r) and B_BACK_{k+1}(r), merged in the reference's order
+//          (slot 1 beats every later slot on equality and loses to slot 0; slot 7 replaces only if strictly greater);
+//          publishes M_k(r + 1), the pass-1 candidates it feeds and the block summaries E, T of row r + 1.
+// S_DROPOFF_k = M_k + t has a single in-edge and is recomputed where it is read (same DADD as the reference's).  The end
+// state is evaluated once per event at its last row (a CTA-uniform extra step).
 //
-// Arithmetic is the reference's, candidate by candidate: (v + t) + e for emitting states (yahmm.pyx:3545-3562), v + t for
-// silent ones, pass 1 before pass 2 (3564-3605), strict '>' in the reference's visiting order -- slot order of
-// pp_profile.h; the balanced first-maximum tree picks the same winner as the left-to-right scan.
+// Shared memory is laid out per WARP: block w + 1 holds, for the warp's P positions, M | the two pass-1 candidate arrays
+// | S_SKIP | B_BACK (kept only for the end state) and the block's E, T, E', carry-in values, 32 doubles (one per lane)
+// each; blocks 0 and NW + 1 are phantoms holding "nothing beyond the ends".  A warp reaches everything it needs -- its
+// own block and the edge slots of its two neighbours -- at COMPILE-TIME offsets from one per-thread base address, so a
+// candidate costs no address arithmetic and no load for its value (registers), and half a load for its weight (16-byte
+// broadcast loads of the position record).
+//
+// Arithmetic is the reference's, candidate by candidate: (v + t) + e for emitting states (3545-3562), v + t for silent
+// ones, pass 1 before pass 2, strict '>' in the reference's visiting order -- slot order of pp_profile.h; the balanced
+// first-maximum tree picks the same winner as the left-to-right scan.
 //
 // Forward: scaled linear space as in k_forward_lane (exact power-of-two row scaling steered by the largest emitting
-// value of the previous row, collected with one shared-memory atomicMax per warp and row); events whose result is 0 /
-// inf / NaN are re-run by the exact log-space kernel (pp_api.cu).
+// value of the previous row, collected with one shared-memory atomicMax per warp and row).  Its chains are linear
+// recurrences, so a block is an affine map out = in * C + E with C the (constant) product of the block's chain weights;
+// events whose result is 0 / inf / NaN are re-run by the exact log-space kernel (pp_api.cu).
 #pragma once
 #include "pp_device_common.cuh"
 #include "pp_lane_types.h"
@@ -37,7 +52,7 @@ namespace pp {
 #ifndef PP_PROF_MIN_CTAS
 #define PP_PROF_MIN_CTAS 2            // CTAs per SM the register budget is set for
 #endif
-#define PP_PROF_THREADS ((kProfMaxPositionWarps + 2) * 32)
+#define PP_PROF_THREADS ((kProfMaxPositionWarps + 1) * 32)
 
 // Optional per-warp phase clocks (tools/profile_phase_timing.py builds the library with -DPP_PHASE_TIMING)
 #ifdef PP_PHASE_TIMING
@@ -49,21 +64,26 @@ __device__ unsigned long long g_prof_phase[2][32 * 8];
 #define PPK_ACC(slot, a, b)
 #endif
 
-// byte offsets inside a warp block (P slots of 256 bytes per array)
+// byte offsets inside a warp block: 5 arrays of P slots and 5 single slots; a slot = 32 doubles, one per lane
 template <int P>
 struct ProfBlock {
     static constexpr int SLOT = kSlotBytes;
     static constexpr int MX = 0;                 // M_k
-    static constexpr int SK = P * SLOT;          // S_SKIP_k
-    static constexpr int BK = 2 * P * SLOT;      // B_BACK_k
-    static constexpr int AS = 3 * P * SLOT;      // M_k + t(M_k -> S_SKIP_{k+1}): pass-1 candidate of S_SKIP_{k+1}
-    static constexpr int AB = 4 * P * SLOT;      // M_k + t(M_k -> B_BACK_k):     pass-1 candidate of B_BACK_k
-    static constexpr int WS = 5 * P * SLOT;      // bytes per block
+    static constexpr int AS = P * SLOT;          // M_k + t(M_k -> S_SKIP_{k+1}): pass-1 candidate of S_SKIP_{k+1}
+    static constexpr int AB = 2 * P * SLOT;      // M_k + t(M_k -> B_BACK_k):     pass-1 candidate of B_BACK_k
+    static constexpr int SK = 3 * P * SLOT;      // S_SKIP_k, B_BACK_k: written only in rows where an event ends
+    static constexpr int BK = 4 * P * SLOT;
+    static constexpr int EO = 5 * P * SLOT;      // E of the ascending chain over the block's own entries
+    static constexpr int TT = EO + SLOT;         // T: the entry from the left neighbour's last M, carried through the block
+    static constexpr int ED = EO + 2 * SLOT;     // E' of the descending chain
+    static constexpr int VIN = EO + 3 * SLOT;    // S_SKIP_{k0-1}: value entering the block from below
+    static constexpr int UIN = EO + 4 * SLOT;    // B_BACK_{k0+P}: value entering the block from above
+    static constexpr int WS = EO + 5 * SLOT;     // bytes per block
 };
 
-__host__ __device__ inline size_t prof_smem_bytes(int Kp, int NW, int P) {
+__host__ __device__ inline size_t prof_smem_bytes(int Kr, int NW, int P) {
     // records | NW + 2 warp blocks | observation tile | row maxima [2][32]
-    return static_cast<size_t>(Kp) * kProfRecDoubles * 8 + static_cast<size_t>(NW + 2) * 5 * P * kSlotBytes +
+    return static_cast<size_t>(Kr) * kProfRecDoubles * 8 + static_cast<size_t>(NW + 2) * (5 * P + 5) * kSlotBytes +
            static_cast<size_t>(kLaneTileCols) * (kLanes + 1) * 8 + 2 * kLanes * 4 + 64;
 }
 
@@ -74,10 +94,10 @@ struct ProfSmem {
     double* xt;
     int32_t* smax;                               // [2][32]
     int n_col;                                   // doubles in the blocks
-    __device__ __forceinline__ ProfSmem(unsigned char* smem, int Kp, int NW) {
+    __device__ __forceinline__ ProfSmem(unsigned char* smem, int Kr, int NW) {
         rec = reinterpret_cast<double*>(smem);
-        blocks = smem + static_cast<size_t>(Kp) * kProfRecDoubles * 8;
-        n_col = (NW + 2) * 5 * P * kLanes;
+        blocks = smem + static_cast<size_t>(Kr) * kProfRecDoubles * 8;
+        n_col = (NW + 2) * (5 * P + 5) * kLanes;
         xt = reinterpret_cast<double*>(blocks) + n_col;
         smax = reinterpret_cast<int32_t*>(xt + kLaneTileCols * (kLanes + 1));
     }
@@ -204,25 +224,54 @@ __device__ __forceinline__ uint32_t prof_vit_early(const double* __restrict__ re
     }
     return ord;
 }
-// late: merges the two chain-dependent candidates, publishes M_k(r + 1) and the pass-1 candidates of the chain states it
-// feeds, M_k + t(M_k -> S_SKIP_{k+1}) and M_k + t(M_k -> B_BACK_k) (3564-3584).
+// fill: the warp's P links of each chain of row r, from the carries the chain warp published.  skin[j] = S_SKIP_{k0+j-1},
+// bkin[j] = B_BACK_{k0+j+1}: what position j reads.  Bit j of the result = ordinal of S_SKIP_{k0+j}, bit P + j of
+// B_BACK_{k0+j} (pass 2 replaces only if strictly greater, 3586-3605).  keep: an event ends at this row, the end state
+// will read the values.
+template <int P>
+__device__ __forceinline__ uint32_t prof_vit_fill(const double* __restrict__ recw, unsigned char* __restrict__ tb, bool keep,
+                                                  double (&skin)[P], double (&bkin)[P]) {
+    using L = ProfBlock<P>;
+    double A[P], D[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        A[j] = ldb(tb, j > 0 ? L::AS + (j - 1) * L::SLOT : -L::WS + L::AS + (P - 1) * L::SLOT);   // M_{k0+j-1} + a
+        D[j] = ldb(tb, L::AB + j * L::SLOT);
+    }
+    double v = ldb(tb, L::VIN), u = ldb(tb, L::UIN);
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int jd = P - 1 - j;
+        skin[j] = v;
+        bkin[jd] = u;
+        const double t = __dadd_rn(v, recw[j * kProfRecDoubles + PR_SK + 1]);
+        const double td = __dadd_rn(u, recw[jd * kProfRecDoubles + PR_BK + 1]);
+        const bool p = t > A[j], pd = td > D[jd];
+        v = p ? t : A[j];
+        u = pd ? td : D[jd];
+        bits |= (p ? 1u : 0u) << j;
+        bits |= (pd ? 1u : 0u) << (P + jd);
+        if (keep) {
+            stb(tb, L::SK + j * L::SLOT, v);
+            stb(tb, L::BK + jd * L::SLOT, u);
+        }
+    }
+    return bits;
+}
+// late: merges the two chain-dependent candidates, publishes M_k(r + 1), the pass-1 candidates of the chain states it
+// feeds (3564-3584) and the block summaries of row r + 1 for the chain warp.
 template <int P>
 __device__ __forceinline__ uint32_t prof_vit_late(const double* __restrict__ recw, unsigned char* __restrict__ tb, uint32_t ord,
-                                                  double (&vM)[P], const double (&eMv)[P]) {
+                                                  double (&vM)[P], const double (&eMv)[P], const double (&skin)[P],
+                                                  const double (&bkin)[P]) {
     using L = ProfBlock<P>;
-    double sk[P], bk[P];
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        // S_SKIP_{k-1} (the start state for k = 0) and B_BACK_{k+1} of row r: own block, or the neighbour's edge slot
-        sk[p] = ldb(tb, p > 0 ? L::SK + (p - 1) * L::SLOT : -L::WS + L::SK + (P - 1) * L::SLOT);
-        bk[p] = ldb(tb, p < P - 1 ? L::BK + (p + 1) * L::SLOT : L::WS + L::BK);
-    }
+    double as[P], ab[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         const double* R = recw + p * kProfRecDoubles;
-        const double w1 = R[PR_WM + 1], w7 = R[PR_WM + 7], wa = R[PR_SK], wc = R[PR_BK];
-        const double s1 = __dadd_rn(__dadd_rn(sk[p], w1), eMv[p]);
-        const double s7 = __dadd_rn(__dadd_rn(bk[p], w7), eMv[p]);
+        const double s1 = __dadd_rn(__dadd_rn(skin[p], R[PR_WM + 1]), eMv[p]);
+        const double s7 = __dadd_rn(__dadd_rn(bkin[p], R[PR_WM + 7]), eMv[p]);
         double m = vM[p];
         const uint32_t a = (ord >> (5 * p)) & 7u;
         const bool t1 = s1 > m || (s1 == m && a != 0);
@@ -232,112 +281,75 @@ __device__ __forceinline__ uint32_t prof_vit_late(const double* __restrict__ rec
         const uint32_t na = t7 ? 6u : (t1 ? 1u : a);              // stored ordinal: 6 = back-slip, 7 = M_{k+1}
         ord = (ord & ~(7u << (5 * p))) | (na << (5 * p));
         vM[p] = m;
+        as[p] = __dadd_rn(m, R[PR_SK]);                           // into S_SKIP_{k+1}
+        ab[p] = __dadd_rn(m, R[PR_BK]);                           // into B_BACK_k
         stb(tb, L::MX + p * L::SLOT, m);
-        stb(tb, L::AS + p * L::SLOT, __dadd_rn(m, wa));          // into S_SKIP_{k+1}
-        stb(tb, L::AB + p * L::SLOT, __dadd_rn(m, wc));          // into B_BACK_k
+        stb(tb, L::AS + p * L::SLOT, as[p]);
+        stb(tb, L::AB + p * L::SLOT, ab[p]);
     }
+    // E: links k0 + 1 .. k0 + P - 1 entered through one of their own pass-1 candidates as[0 .. P - 2]
+    double e = as[0];
+#pragma unroll
+    for (int j = 1; j < P - 1; ++j) {
+        const double t = __dadd_rn(e, recw[(j + 1) * kProfRecDoubles + PR_SK + 1]);
+        e = t > as[j] ? t : as[j];
+    }
+    stb(tb, L::EO, e);
+    // T: as[P - 1] is the first entry of the RIGHT neighbour's block; carried through that block's other links
+    double t = as[P - 1];
+#pragma unroll
+    for (int j = 1; j < P; ++j) t = __dadd_rn(t, recw[(P + j) * kProfRecDoubles + PR_SK + 1]);
+    stb(tb, L::WS + L::TT, t);
+    // E': links k0 + P - 1 .. k0 of the descending chain
+    double ed = ab[P - 1];
+#pragma unroll
+    for (int j = P - 2; j >= 0; --j) {
+        const double td = __dadd_rn(ed, recw[j * kProfRecDoubles + PR_BK + 1]);
+        ed = td > ab[j] ? td : ab[j];
+    }
+    stb(tb, L::ED, ed);
     return ord;
 }
 
-// N consecutive links of a chain.  A[u]: pass-1 candidate, c[u]: weight of the chain edge (pass 2, replaces only if
-// strictly greater, 3586-3605).
-template <int N>
-__device__ __forceinline__ uint32_t prof_vit_links(const double (&A)[N], const double (&c)[N], double (&out)[N], double& v) {
-    uint32_t b = 0;
-#pragma unroll
-    for (int u = 0; u < N; ++u) {
-        const double t = __dadd_rn(v, c[u]);
-        const bool p = t > A[u];
-        v = p ? t : A[u];
-        out[u] = v;
-        if (p) b |= 1u << u;
-    }
-    return b;
-}
-
-// Phase B, ascending chain: link i = S_SKIP_i.  cb: this lane's slice of block 0 (the phantom before position 0).  The
-// operands of the next block are loaded before the links of the current one are walked.
+// The chain warp: block carries of both chains of one row, one block of each per step (two independent dependent
+// sequences).  cb: this lane's slice of block 0.  Publishes the value entering every block.
 template <int P>
-__device__ __forceinline__ uint64_t prof_vit_chain_up(const double* __restrict__ rec, unsigned char* __restrict__ cb, int K,
-                                                      double startval) {
+__device__ __forceinline__ void prof_vit_carries(const double* __restrict__ rec, unsigned char* __restrict__ cb, int NW,
+                                                 double startval) {
     using L = ProfBlock<P>;
-    uint64_t bits = 0;
-    double v = startval;
-    stb(cb, L::SK + (P - 1) * L::SLOT, startval);                 // what M_0 and S_SKIP_0 read through their start edge
-    const int nfull = K / P;
-    double A[P], c[P];
-    if (nfull > 0) {
+    double v = startval, u = neg_inf();
+    double c[P], d[P], ee, ed;
+    auto load = [&](int i, double (&cc)[P], double (&dd)[P], double& e1, double& e2) {
+        const unsigned char* bu = cb + (i + 1) * L::WS;
+        const unsigned char* bd = cb + (NW - i) * L::WS;
+        const double tt = ldb(bu, L::TT), eo = ldb(bu, L::EO);
+        e1 = tt > eo ? tt : eo;
+        e2 = ldb(bd, L::ED);
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            A[p] = ldb(cb, L::WS + (p > 0 ? L::AS + (p - 1) * L::SLOT : -L::WS + L::AS + (P - 1) * L::SLOT));
-            c[p] = rec[p * kProfRecDoubles + PR_SK + 1];
+        for (int j = 0; j < P; ++j) {
+            cc[j] = rec[(i * P + j) * kProfRecDoubles + PR_SK + 1];
+            dd[j] = rec[((NW - 1 - i) * P + (P - 1 - j)) * kProfRecDoubles + PR_BK + 1];
         }
-    }
-    for (int b = 0; b < nfull; ++b) {
-        unsigned char* blk = cb + (b + 1) * L::WS;
-        double An[P], cn[P], out[P];
-        if (b + 1 < nfull) {
+    };
+    load(0, c, d, ee, ed);
+    for (int i = 0; i < NW; ++i) {
+        double cn[P], dn[P], een = 0.0, edn = 0.0;
+        if (i + 1 < NW) load(i + 1, cn, dn, een, edn);
+        stb(cb + (i + 1) * L::WS, L::VIN, v);
+        stb(cb + (NW - i) * L::WS, L::UIN, u);
+        double th = v, td = u;
 #pragma unroll
-            for (int p = 0; p < P; ++p) {
-                An[p] = ldb(blk, L::WS + (p > 0 ? L::AS + (p - 1) * L::SLOT : -L::WS + L::AS + (P - 1) * L::SLOT));
-                cn[p] = rec[((b + 1) * P + p) * kProfRecDoubles + PR_SK + 1];
-            }
+        for (int j = 0; j < P; ++j) {
+            th = __dadd_rn(th, c[j]);
+            td = __dadd_rn(td, d[j]);
         }
-        bits |= static_cast<uint64_t>(prof_vit_links<P>(A, c, out, v)) << (b * P);
+        v = th > ee ? th : ee;
+        u = td > ed ? td : ed;
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            stb(blk, L::SK + p * L::SLOT, out[p]);
-            A[p] = An[p];
-            c[p] = cn[p];
-        }
+        for (int j = 0; j < P; ++j) { c[j] = cn[j]; d[j] = dn[j]; }
+        ee = een;
+        ed = edn;
     }
-    for (int k = nfull * P; k < K; ++k) {
-        double A1[1] = {ldb(cb, prof_slot<P>(k - 1 + P, L::AS) - L::WS)}, c1[1] = {rec[k * kProfRecDoubles + PR_SK + 1]}, out[1];
-        bits |= static_cast<uint64_t>(prof_vit_links<1>(A1, c1, out, v)) << k;
-        stb(cb, prof_slot<P>(k, L::SK), out[0]);
-    }
-    return bits;
-}
-// descending chain: link i = B_BACK_{K-1-i}
-template <int P>
-__device__ __forceinline__ uint64_t prof_vit_chain_down(const double* __restrict__ rec, unsigned char* __restrict__ cb, int K) {
-    using L = ProfBlock<P>;
-    uint64_t bits = 0;
-    double v = neg_inf();
-    int k = K - 1, i = 0;
-    const int nfull = K / P;
-    double A[P], c[P];
-    if (nfull > 0) {                                               // operands of the topmost full block
-#pragma unroll
-        for (int u = 0; u < P; ++u) {
-            A[u] = ldb(cb, nfull * L::WS + L::AB + (P - 1 - u) * L::SLOT);
-            c[u] = rec[(nfull * P - 1 - u) * kProfRecDoubles + PR_BK + 1];
-        }
-    }
-    for (; k >= nfull * P; --k, ++i) {                             // the partial block at the top
-        double A1[1] = {ldb(cb, prof_slot<P>(k, L::AB))}, c1[1] = {rec[k * kProfRecDoubles + PR_BK + 1]}, out[1];
-        bits |= static_cast<uint64_t>(prof_vit_links<1>(A1, c1, out, v)) << i;
-        stb(cb, prof_slot<P>(k, L::BK), out[0]);
-    }
-    for (int b = nfull - 1; b >= 0; --b, i += P) {
-        unsigned char* blk = cb + (b + 1) * L::WS;
-        double An[P], cn[P], out[P];
-        if (b > 0) {
-#pragma unroll
-            for (int u = 0; u < P; ++u) {
-                An[u] = ldb(blk, -L::WS + L::AB + (P - 1 - u) * L::SLOT);
-                cn[u] = rec[(b * P - 1 - u) * kProfRecDoubles + PR_BK + 1];
-            }
-        }
-        bits |= static_cast<uint64_t>(prof_vit_links<P>(A, c, out, v)) << i;
-#pragma unroll
-        for (int u = 0; u < P; ++u) {
-            stb(blk, L::BK + (P - 1 - u) * L::SLOT, out[u]);
-            A[u] = An[u];
-            c[u] = cn[u];
-        }
-    }
-    return bits;
 }
 
 template <int P>
@@ -345,22 +357,19 @@ __global__ void __launch_bounds__(PP_PROF_THREADS, PP_PROF_MIN_CTAS)
 k_profile_viterbi(const ProfSched S, const LaneBatchAny B, const VitOut O) {
     using L = ProfBlock<P>;
     extern __shared__ __align__(16) unsigned char smem[];
-    const ProfSmem<P> M(smem, S.Kp, S.NW);
+    const ProfSmem<P> M(smem, S.Kr, S.NW);
     constexpr int TC = kLaneTileCols;
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
-    const int n_warps = S.NW + 2;
+    const int n_warps = S.NW + 1;
     const int g = blockIdx.x;
     const int ev = B.order[g * kLanes + lane];
     const int64_t off = ev >= 0 ? B.offsets[ev] : 0;
     const int n = ev >= 0 ? static_cast<int>(B.offsets[ev + 1] - off) : 0;
     const int nmax = B.group_len[g];
     constexpr int UB = 5 * P <= 16 ? 2 : 4;
-    // this warp's unit of row 0 in the pointer table (position warps: emitting ordinals; chain warps: one 64-bit word)
-    uint8_t* prow = reinterpret_cast<uint8_t*>(O.ptr) + static_cast<size_t>(B.group_row[g]) * S.row_bytes +
-                    (warp < S.NW ? warp * UB * kLanes + lane * UB : S.NW * UB * kLanes + (warp - S.NW) * 8 * kLanes + lane * 8);
 
-    for (int i = threadIdx.x; i < S.Kp * kProfRecDoubles; i += n_warps * 32) M.rec[i] = __ldg(S.rec + i);
+    for (int i = threadIdx.x; i < S.Kr * kProfRecDoubles; i += n_warps * 32) M.rec[i] = __ldg(S.rec + i);
     for (int i = threadIdx.x; i < M.n_col; i += n_warps * 32) reinterpret_cast<double*>(M.blocks)[i] = neg_inf();   // v[0, :] = -inf (3513)
     if (nmax > 0) prof_fill_tile(M.xt, B.obs, B.obs_f64 != 0, off, n, 0, warp, lane, n_warps);
     __syncthreads();
@@ -369,44 +378,44 @@ k_profile_viterbi(const ProfSched S, const LaneBatchAny B, const VitOut O) {
     const int n_threads = n_warps * 32;
 
     // The two roles run separate loops (separate register allocations) that meet at the same barriers:
-    //   barrier 1 after {chains of row r | early part of row r + 1}, [end state of events ending at row r, + a barrier],
-    //   barrier 2 after the late part of row r + 1.
-    if (warp >= S.NW) {
+    //   barrier 1 after {carries of row r | early part of row r + 1}, [end state of events ending at row r, between two
+    //   more barriers], barrier 2 after the late part of row r + 1.
+    if (warp == 0) {                                                // the chain warp: the oldest warp of the CTA
+#ifdef PP_PHASE_TIMING
+        unsigned long long phase_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
         for (int r = 0;; ++r) {
-            // ---- silent states of row r; v[0, start] = 0 (3514), the start state is -inf in every later row
-            uint64_t bits;
-            if (warp == S.NW) {
-                bits = prof_vit_chain_up<P>(M.rec, cb, S.K, r == 0 ? 0.0 : neg_inf());
-            } else {
-                bits = prof_vit_chain_down<P>(M.rec, cb, S.K);
-#pragma unroll
-                for (int a = 0; a < kProfMaxAlias; ++a)
-                    if (a < S.n_alias) stb(cb, prof_slot<P>(S.alias_dst[a], L::BK), ldb(cb, prof_slot<P>(S.alias_src[a], L::BK)));
-            }
-            *reinterpret_cast<uint64_t*>(prow) = bits;
-            prow += S.row_bytes;
+            // ---- silent chains of row r; v[0, start] = 0 (3514), the start state is -inf in every later row
+            PPK_CLK(c0);
+            prof_vit_carries<P>(M.rec, cb, S.NW, r == 0 ? 0.0 : neg_inf());
+            PPK_CLK(c1);
+            PPK_ACC(0, c0, c1);
+#ifdef PP_PHASE_TIMING
+            phase_acc[6] += 1;
+            if (r == nmax && lane == 0)
+                for (int k = 0; k < 8; ++k) atomicAdd(&g_prof_phase[0][k], phase_acc[k]);
+#endif
             prof_bar(n_threads);
             if (r >= 1 && __any_sync(0xffffffffu, r == n)) {
                 // ---- events whose last row this is: the end state (3614-3616).  Every warp holds the same lengths, so
-                //      the branch (and its barrier) is uniform over the CTA.
-                if (warp == S.NW) {
-                    double best = neg_inf();
-                    int arg = 0;
-                    for (int j = 0; j < S.end_n; ++j) {
-                        const ProfEndRec E = ldg_rec(S.end_list + j);
-                        double v;
-                        if (E.cls == PROF_M) v = ldb(cb, prof_slot<P>(E.k, L::MX));
-                        else if (E.cls == PROF_DROP) v = __dadd_rn(ldb(cb, prof_slot<P>(E.k, L::MX)), M.rec[E.k * kProfRecDoubles + PR_WD]);
-                        else if (E.cls == PROF_SKIP) v = ldb(cb, prof_slot<P>(E.k, L::SK));
-                        else v = ldb(cb, prof_slot<P>(E.k, L::BK));
-                        const double s = __dadd_rn(v, E.w);
-                        if (s > best) { best = s; arg = j; }
-                    }
-                    if (r == n) {
-                        O.score[ev] = best;
-                        O.end_state[ev] = S.end_state;
-                        O.end_ord[ev] = arg;
-                    }
+                //      the branch (and its barriers) is uniform over the CTA.
+                prof_bar(n_threads);                                             // the position warps have filled in row r
+                double best = neg_inf();
+                int arg = 0;
+                for (int j = 0; j < S.end_n; ++j) {
+                    const ProfEndRec E = ldg_rec(S.end_list + j);
+                    double v;
+                    if (E.cls == PROF_M) v = ldb(cb, prof_slot<P>(E.k, L::MX));
+                    else if (E.cls == PROF_DROP) v = __dadd_rn(ldb(cb, prof_slot<P>(E.k, L::MX)), M.rec[E.k * kProfRecDoubles + PR_WD]);
+                    else if (E.cls == PROF_SKIP) v = ldb(cb, prof_slot<P>(E.k, L::SK));
+                    else v = ldb(cb, prof_slot<P>(E.k, L::BK));
+                    const double s = __dadd_rn(v, E.w);
+                    if (s > best) { best = s; arg = j; }
+                }
+                if (r == n) {
+                    O.score[ev] = best;
+                    O.end_state[ev] = S.end_state;
+                    O.end_ord[ev] = arg;
                 }
                 prof_bar(n_threads);
             }
@@ -420,8 +429,12 @@ k_profile_viterbi(const ProfSched S, const LaneBatchAny B, const VitOut O) {
     double vM[P], vB[P], vI[P], eM[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) vM[p] = vB[p] = vI[p] = neg_inf();
-    unsigned char* const tb = cb + (warp + 1) * L::WS;                           // this warp's block
-    const double* const recw = M.rec + warp * P * kProfRecDoubles;
+    const int pw = warp - 1;                                                     // position warp index
+    unsigned char* const tb = cb + (pw + 1) * L::WS;                             // this warp's block
+    const double* const recw = M.rec + pw * P * kProfRecDoubles;
+    // this warp's units of row 0 in the pointer table: emitting ordinals (written with row r + 1), chain ordinals (row r)
+    uint8_t* prow = reinterpret_cast<uint8_t*>(O.ptr) + static_cast<size_t>(B.group_row[g]) * S.row_bytes + pw * UB * kLanes + lane * UB;
+    const int sil_off = S.NW * UB * kLanes + pw * kLanes + lane - (pw * UB * kLanes + lane * UB);
 #ifdef PP_PHASE_TIMING
     unsigned long long phase_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
@@ -429,22 +442,30 @@ k_profile_viterbi(const ProfSched S, const LaneBatchAny B, const VitOut O) {
         PPK_CLK(c0);
         uint32_t ord = 0;
         if (r < nmax) {
-            // ---- beside the chains of row r: everything of row r + 1 that does not read them (3545-3562)
+            // ---- beside the carry sweep of row r: everything of row r + 1 that does not read the chains (3545-3562)
             const double left = ldb(tb, -L::WS + L::MX + (P - 1) * L::SLOT);     // M_{k0-1}(r), M_{k0+P}(r)
             const double right = ldb(tb, L::WS + L::MX);
             const double x = M.xt[(r & (TC - 1)) * (kLanes + 1) + lane];         // obs[r] belongs to row r + 1
             ord = prof_vit_early<P>(recw, tb, left, right, x, vM, vB, vI, eM);
         }
-        prow += S.row_bytes;
         PPK_CLK(c1);
         prof_bar(n_threads);
         PPK_CLK(c2);
         PPK_ACC(0, c0, c1); PPK_ACC(1, c1, c2);
-        if (r >= 1 && __any_sync(0xffffffffu, r == n)) prof_bar(n_threads);     // the chain warp evaluates the end state
+        // ---- the warp's links of row r's chains
+        const bool ends = r >= 1 && __any_sync(0xffffffffu, r == n);
+        double skin[P], bkin[P];
+        const uint32_t sbits = prof_vit_fill<P>(recw, tb, ends, skin, bkin);
+        prow[sil_off] = static_cast<uint8_t>(sbits);
+        prow += S.row_bytes;
+        if (ends) {                                                              // the chain warp evaluates the end state
+            prof_bar(n_threads);
+            prof_bar(n_threads);
+        }
         if (r == nmax) break;
         PPK_CLK(c3);
         // ---- the two candidates that read the chains of row r; publish M(r + 1)
-        ord = prof_vit_late<P>(recw, tb, ord, vM, eM);
+        ord = prof_vit_late<P>(recw, tb, ord, vM, eM, skin, bkin);
         if (UB == 2) *reinterpret_cast<uint16_t*>(prow) = static_cast<uint16_t>(ord);
         else *reinterpret_cast<uint32_t*>(prow) = ord;
         // the observation tile is free now (the early part of this row has read it): stage the next one when due
@@ -502,78 +523,77 @@ __device__ __forceinline__ int prof_fwd_early(const double* __restrict__ recw, c
     }
     return mx;
 }
+// fill (linear): the warp's links of row r's chains from the published carries
+template <int P>
+__device__ __forceinline__ void prof_fwd_fill(const double* __restrict__ recw, unsigned char* __restrict__ tb, bool keep,
+                                              double (&skin)[P], double (&bkin)[P]) {
+    using L = ProfBlock<P>;
+    double A[P], D[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        A[j] = ldb(tb, j > 0 ? L::AS + (j - 1) * L::SLOT : -L::WS + L::AS + (P - 1) * L::SLOT);
+        D[j] = ldb(tb, L::AB + j * L::SLOT);
+    }
+    double v = ldb(tb, L::VIN), u = ldb(tb, L::UIN);
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int jd = P - 1 - j;
+        skin[j] = v;
+        bkin[jd] = u;
+        v = fma(v, recw[j * kProfRecDoubles + PR_SK + 1], A[j]);
+        u = fma(u, recw[jd * kProfRecDoubles + PR_BK + 1], D[jd]);
+        if (keep) {
+            stb(tb, L::SK + j * L::SLOT, v);
+            stb(tb, L::BK + jd * L::SLOT, u);
+        }
+    }
+}
 template <int P>
 __device__ __forceinline__ int prof_fwd_late(const double* __restrict__ recw, unsigned char* __restrict__ tb, int mx,
-                                             double (&vM)[P], const double (&eMv)[P]) {
+                                             double (&vM)[P], const double (&eMv)[P], const double (&skin)[P],
+                                             const double (&bkin)[P]) {
     using L = ProfBlock<P>;
-    double sk[P], bk[P];
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        sk[p] = ldb(tb, p > 0 ? L::SK + (p - 1) * L::SLOT : -L::WS + L::SK + (P - 1) * L::SLOT);
-        bk[p] = ldb(tb, p < P - 1 ? L::BK + (p + 1) * L::SLOT : L::WS + L::BK);
-    }
+    double as[P], ab[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         const double* R = recw + p * kProfRecDoubles;
-        const double w1 = R[PR_WM + 1], w7 = R[PR_WM + 7], wa = R[PR_SK], wc = R[PR_BK];
-        const double m = fma(bk[p], w7, fma(sk[p], w1, vM[p])) * eMv[p];
+        const double m = fma(bkin[p], R[PR_WM + 7], fma(skin[p], R[PR_WM + 1], vM[p])) * eMv[p];
         vM[p] = m;
+        as[p] = m * R[PR_SK];
+        ab[p] = m * R[PR_BK];
         stb(tb, L::MX + p * L::SLOT, m);
-        stb(tb, L::AS + p * L::SLOT, m * wa);
-        stb(tb, L::AB + p * L::SLOT, m * wc);
+        stb(tb, L::AS + p * L::SLOT, as[p]);
+        stb(tb, L::AB + p * L::SLOT, ab[p]);
         mx = max(mx, __double2hiint(m));
     }
+    double e = as[0];
+#pragma unroll
+    for (int j = 1; j < P - 1; ++j) e = fma(e, recw[(j + 1) * kProfRecDoubles + PR_SK + 1], as[j]);
+    stb(tb, L::EO, e);
+    stb(tb, L::WS + L::TT, as[P - 1] * recw[P * kProfRecDoubles + PR_CUT]);
+    double ed = ab[P - 1];
+#pragma unroll
+    for (int j = P - 2; j >= 0; --j) ed = fma(ed, recw[j * kProfRecDoubles + PR_BK + 1], ab[j]);
+    stb(tb, L::ED, ed);
     return mx;
 }
 
+// the chain warp: affine block carries of both chains
 template <int P>
-__device__ __forceinline__ void prof_fwd_chain_up(const double* __restrict__ rec, unsigned char* __restrict__ cb, int K,
-                                                  double startval) {
+__device__ __forceinline__ void prof_fwd_carries(const double* __restrict__ rec, unsigned char* __restrict__ cb, int NW,
+                                                 double startval) {
     using L = ProfBlock<P>;
-    double f = startval;
-    stb(cb, L::SK + (P - 1) * L::SLOT, startval);
-    const int nfull = K / P;
-    for (int b = 0; b < nfull; ++b) {
-        unsigned char* blk = cb + (b + 1) * L::WS;
-        double A[P], c[P];
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            A[p] = ldb(blk, p > 0 ? L::AS + (p - 1) * L::SLOT : -L::WS + L::AS + (P - 1) * L::SLOT);
-            c[p] = rec[(b * P + p) * kProfRecDoubles + PR_SK + 1];
-        }
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            f = fma(f, c[p], A[p]);
-            stb(blk, L::SK + p * L::SLOT, f);
-        }
-    }
-    for (int k = nfull * P; k < K; ++k) {
-        f = fma(f, rec[k * kProfRecDoubles + PR_SK + 1], ldb(cb, prof_slot<P>(k - 1 + P, L::AS) - L::WS));
-        stb(cb, prof_slot<P>(k, L::SK), f);
-    }
-}
-template <int P>
-__device__ __forceinline__ void prof_fwd_chain_down(const double* __restrict__ rec, unsigned char* __restrict__ cb, int K) {
-    using L = ProfBlock<P>;
-    double f = 0.0;
-    const int nfull = K / P;
-    for (int k = K - 1; k >= nfull * P; --k) {
-        f = fma(f, rec[k * kProfRecDoubles + PR_BK + 1], ldb(cb, prof_slot<P>(k, L::AB)));
-        stb(cb, prof_slot<P>(k, L::BK), f);
-    }
-    for (int b = nfull - 1; b >= 0; --b) {
-        unsigned char* blk = cb + (b + 1) * L::WS;
-        double A[P], c[P];
-#pragma unroll
-        for (int u = 0; u < P; ++u) {
-            A[u] = ldb(blk, L::AB + (P - 1 - u) * L::SLOT);
-            c[u] = rec[(b * P + P - 1 - u) * kProfRecDoubles + PR_BK + 1];
-        }
-#pragma unroll
-        for (int u = 0; u < P; ++u) {
-            f = fma(f, c[u], A[u]);
-            stb(blk, L::BK + (P - 1 - u) * L::SLOT, f);
-        }
+    double v = startval, u = 0.0;
+#pragma unroll 2
+    for (int i = 0; i < NW; ++i) {
+        unsigned char* bu = cb + (i + 1) * L::WS;
+        unsigned char* bd = cb + (NW - i) * L::WS;
+        const double ee = ldb(bu, L::TT) + ldb(bu, L::EO), ed = ldb(bd, L::ED);
+        const double cu = rec[i * P * kProfRecDoubles + PR_CUP], cd = rec[(NW - 1 - i) * P * kProfRecDoubles + PR_CDN];
+        stb(bu, L::VIN, v);
+        stb(bd, L::UIN, u);
+        v = fma(v, cu, ee);
+        u = fma(u, cd, ed);
     }
 }
 
@@ -582,18 +602,18 @@ __global__ void __launch_bounds__(PP_PROF_THREADS, PP_PROF_MIN_CTAS)
 k_profile_forward(const ProfSched S, const LaneBatchAny B, const FwdOut O) {
     using L = ProfBlock<P>;
     extern __shared__ __align__(16) unsigned char smem[];
-    const ProfSmem<P> M(smem, S.Kp, S.NW);
+    const ProfSmem<P> M(smem, S.Kr, S.NW);
     constexpr int TC = kLaneTileCols;
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
-    const int n_warps = S.NW + 2;
+    const int n_warps = S.NW + 1;
     const int g = blockIdx.x;
     const int ev = B.order[g * kLanes + lane];
     const int64_t off = ev >= 0 ? B.offsets[ev] : 0;
     const int n = ev >= 0 ? static_cast<int>(B.offsets[ev + 1] - off) : 0;
     const int nmax = B.group_len[g];
 
-    for (int i = threadIdx.x; i < S.Kp * kProfRecDoubles; i += n_warps * 32) M.rec[i] = __ldg(S.rec + i);
+    for (int i = threadIdx.x; i < S.Kr * kProfRecDoubles; i += n_warps * 32) M.rec[i] = __ldg(S.rec + i);
     for (int i = threadIdx.x; i < M.n_col; i += n_warps * 32) reinterpret_cast<double*>(M.blocks)[i] = 0.0;
     if (threadIdx.x < 2 * kLanes) M.smax[threadIdx.x] = 0;
     if (nmax > 0) prof_fill_tile(M.xt, B.obs, B.obs_f64 != 0, off, n, 0, warp, lane, n_warps);
@@ -601,41 +621,33 @@ k_profile_forward(const ProfSched S, const LaneBatchAny B, const FwdOut O) {
 
     unsigned char* const cb = M.blocks + lane * 8;
     const int n_threads = n_warps * 32;
-    long long scale_total = 0;                                      // sum of the shifts of rows 1 .. r
 
-    if (warp >= S.NW) {
+    if (warp == 0) {                                                // the chain warp: the oldest warp of the CTA
+        long long scale_total = 0;                                  // sum of the shifts of rows 1 .. r
         for (int r = 0;; ++r) {
             const int q = r & 1;
             const int shift = prof_row_shift(M.smax[q * kLanes + lane]);
-            if (warp == S.NW) {
-                prof_fwd_chain_up<P>(M.rec, cb, S.K, r == 0 ? 1.0 : 0.0);
-                M.smax[(q ^ 1) * kLanes + lane] = 0;                // row r + 1 collects its maxima here in the late part
-            } else {
-                prof_fwd_chain_down<P>(M.rec, cb, S.K);
-#pragma unroll
-                for (int a = 0; a < kProfMaxAlias; ++a)
-                    if (a < S.n_alias) stb(cb, prof_slot<P>(S.alias_dst[a], L::BK), ldb(cb, prof_slot<P>(S.alias_src[a], L::BK)));
-            }
+            prof_fwd_carries<P>(M.rec, cb, S.NW, r == 0 ? 1.0 : 0.0);
+            M.smax[(q ^ 1) * kLanes + lane] = 0;                    // row r + 1 collects its maxima here in the late part
             prof_bar(n_threads);
             if (r >= 1 && __any_sync(0xffffffffu, r == n)) {        // log_probability (3378-3396); CTA-uniform branch
-                if (warp == S.NW) {
-                    double Pr = 0.0;
-                    for (int j = 0; j < S.end_n; ++j) {
-                        const ProfEndRec E = ldg_rec(S.end_list + j);
-                        double v;
-                        if (E.cls == PROF_M) v = ldb(cb, prof_slot<P>(E.k, L::MX));
-                        else if (E.cls == PROF_DROP) v = ldb(cb, prof_slot<P>(E.k, L::MX)) * M.rec[E.k * kProfRecDoubles + PR_WD];
-                        else if (E.cls == PROF_SKIP) v = ldb(cb, prof_slot<P>(E.k, L::SK));
-                        else v = ldb(cb, prof_slot<P>(E.k, L::BK));
-                        Pr = fma(v, E.w, Pr);
-                    }
-                    if (r == n) {
-                        double lp;
-                        if (Pr == 0.0) lp = neg_inf();
-                        else if (!(Pr < __longlong_as_double(0x7FF0000000000000LL))) lp = __longlong_as_double(0x7FF8000000000000LL);
-                        else lp = log(Pr) - static_cast<double>(scale_total) * 0.693147180559945309417;
-                        O.logp[ev] = lp;
-                    }
+                prof_bar(n_threads);
+                double Pr = 0.0;
+                for (int j = 0; j < S.end_n; ++j) {
+                    const ProfEndRec E = ldg_rec(S.end_list + j);
+                    double v;
+                    if (E.cls == PROF_M) v = ldb(cb, prof_slot<P>(E.k, L::MX));
+                    else if (E.cls == PROF_DROP) v = ldb(cb, prof_slot<P>(E.k, L::MX)) * M.rec[E.k * kProfRecDoubles + PR_WD];
+                    else if (E.cls == PROF_SKIP) v = ldb(cb, prof_slot<P>(E.k, L::SK));
+                    else v = ldb(cb, prof_slot<P>(E.k, L::BK));
+                    Pr = fma(v, E.w, Pr);
+                }
+                if (r == n) {
+                    double lp;
+                    if (Pr == 0.0) lp = neg_inf();
+                    else if (!(Pr < __longlong_as_double(0x7FF0000000000000LL))) lp = __longlong_as_double(0x7FF8000000000000LL);
+                    else lp = log(Pr) - static_cast<double>(scale_total) * 0.693147180559945309417;
+                    O.logp[ev] = lp;
                 }
                 prof_bar(n_threads);
             }
@@ -650,8 +662,9 @@ k_profile_forward(const ProfSched S, const LaneBatchAny B, const FwdOut O) {
     double vM[P], vB[P], vI[P], eM[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) vM[p] = vB[p] = vI[p] = 0.0;
-    unsigned char* const tb = cb + (warp + 1) * L::WS;
-    const double* const recw = M.rec + warp * P * kProfRecDoubles;
+    const int pw = warp - 1;
+    unsigned char* const tb = cb + (pw + 1) * L::WS;
+    const double* const recw = M.rec + pw * P * kProfRecDoubles;
     for (int r = 0;; ++r) {
         const int q = r & 1;
         int mx = 0;
@@ -665,9 +678,15 @@ k_profile_forward(const ProfSched S, const LaneBatchAny B, const FwdOut O) {
             mx = prof_fwd_early<P>(recw, tb, left, right, x, static_cast<double>(shift), scale2, vM, vB, vI, eM);
         }
         prof_bar(n_threads);
-        if (r >= 1 && __any_sync(0xffffffffu, r == n)) prof_bar(n_threads);
+        const bool ends = r >= 1 && __any_sync(0xffffffffu, r == n);
+        double skin[P], bkin[P];
+        prof_fwd_fill<P>(recw, tb, ends, skin, bkin);
+        if (ends) {
+            prof_bar(n_threads);
+            prof_bar(n_threads);
+        }
         if (r == nmax) break;
-        mx = prof_fwd_late<P>(recw, tb, mx, vM, eM);
+        mx = prof_fwd_late<P>(recw, tb, mx, vM, eM, skin, bkin);
         atomicMax(&M.smax[(q ^ 1) * kLanes + lane], mx);
         if (r + 1 < nmax && ((r + 1) & (TC - 1)) == 0) prof_fill_tile(M.xt, B.obs, B.obs_f64 != 0, off, n, r + 1, warp, lane, n_warps);
         prof_bar(n_threads);

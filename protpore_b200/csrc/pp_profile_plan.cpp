@@ -156,14 +156,16 @@ void build_profile_plan(const pp_model_desc& d, const Lowered& low, int P, int m
     // ---- geometry ---------------------------------------------------------------------------------------------
     const int NW = (K + P - 1) / P;
     if (NW > max_warps) { fail("profile has more positions than one CTA's warps can hold in registers"); return; }
-    if (K > 64) { fail("more than 64 positions (chain ordinals are one 64-bit word)"); return; }
+    if (2 * P > 8) { fail("more than 4 positions per warp"); return; }
     const int Kp = NW * P;
     plan->K = K; plan->NW = NW; plan->Kp = Kp;
     const double ninf = -INFINITY;
-    plan->rec_v.assign(static_cast<size_t>(Kp) * kProfRecDoubles, 0.0);
-    plan->rec_f.assign(static_cast<size_t>(Kp) * kProfRecDoubles, 0.0);
+    const int Kr = Kp + P;                                          // records: the positions and one phantom block behind them
+    plan->Kr = Kr;
+    plan->rec_v.assign(static_cast<size_t>(Kr) * kProfRecDoubles, 0.0);
+    plan->rec_f.assign(static_cast<size_t>(Kr) * kProfRecDoubles, 0.0);
     const int n_w = 16;                                             // weights live in [0, 16) except the kinds word
-    for (int k = 0; k < Kp; ++k) {
+    for (int k = 0; k < Kr; ++k) {
         double* v = &plan->rec_v[static_cast<size_t>(k) * kProfRecDoubles];
         for (int j = 0; j < n_w; ++j) if (j != PR_KINDS) v[j] = ninf;
         v[PR_BK] = v[PR_BK + 1] = ninf;
@@ -211,8 +213,8 @@ void build_profile_plan(const pp_model_desc& d, const Lowered& low, int P, int m
         }
         return true;
     };
-    int kinds_word[64];
-    for (int k = 0; k < Kp; ++k) kinds_word[k] = EMIS_POINT | (EMIS_POINT << 8) | (EMIS_POINT << 16);
+    int kinds_word[96];
+    for (int k = 0; k < Kr; ++k) kinds_word[k] = EMIS_POINT | (EMIS_POINT << 8) | (EMIS_POINT << 16);
     for (int k = 0; k < K; ++k) {
         double *v, *f;
         rec(k, &v, &f);
@@ -288,9 +290,30 @@ void build_profile_plan(const pp_model_desc& d, const Lowered& low, int P, int m
             for (int j = 0; j < low.state_n_edges[s]; ++j) { slots[placed[j]] = lowered_src(s, j); set_w(k, PR_BK + placed[j], s, j); }
         }
     }
-    for (int a = 0; a < plan->n_alias; ++a)
-        if (plan->alias_dst[a] > Kp || BACK[plan->alias_src[a]] < 0) { fail("bad back-slip alias"); return; }
-    for (int k = 0; k < Kp; ++k) {
+    // A match state that reads a back-slip state two positions up (bake merged the one between them away): the missing
+    // state becomes a phantom link of the descending chain with weight 0 (1 in linear space) and no pass-1 candidate --
+    // x + 0.0 = x, so it carries its upper neighbour's value unchanged.
+    for (int a = 0; a < plan->n_alias; ++a) {
+        const int dst = plan->alias_dst[a], src = plan->alias_src[a];
+        if (dst >= K || src != dst + 1 || BACK[src] < 0 || BACK[dst] >= 0) { fail("a match state reads a back-slip state that is not adjacent to the missing one"); return; }
+        double *v, *f;
+        rec(dst, &v, &f);
+        v[PR_BK + 1] = 0.0;
+        f[PR_BK + 1] = 1.0;
+    }
+    // forward sweep: products of the chain weights over each warp's block (affine block carries, pp_profile_kernels.cuh)
+    for (int k0 = 0; k0 < Kr; k0 += P) {
+        double up = 1.0, up_tail = 1.0, down = 1.0;
+        for (int j = 0; j < P; ++j) {
+            const double* f = &plan->rec_f[static_cast<size_t>(k0 + j) * kProfRecDoubles];
+            up *= f[PR_SK + 1];
+            if (j > 0) up_tail *= f[PR_SK + 1];
+            down *= f[PR_BK + 1];
+        }
+        double* f0 = &plan->rec_f[static_cast<size_t>(k0) * kProfRecDoubles];
+        f0[PR_CUP] = up; f0[PR_CUT] = up_tail; f0[PR_CDN] = down;
+    }
+    for (int k = 0; k < Kr; ++k) {
         std::memcpy(&plan->rec_v[static_cast<size_t>(k) * kProfRecDoubles + PR_KINDS], &kinds_word[k], sizeof(int32_t));
         std::memcpy(&plan->rec_f[static_cast<size_t>(k) * kProfRecDoubles + PR_KINDS], &kinds_word[k], sizeof(int32_t));
     }
@@ -316,11 +339,12 @@ void build_profile_plan(const pp_model_desc& d, const Lowered& low, int P, int m
     plan->slot_begin[start] = static_cast<int32_t>(plan->slot_src.size());
 
     // ---- where the ordinals sit in a pointer row ----------------------------------------------------------------
-    // position warp w: one unit of UB bytes per lane, 5 bits per position (M: 3, INS: 1, BLIP: 1);
-    // chain warps: one 64-bit word per lane each, bit i = S_SKIP_i / B_BACK_{K-1-i} (the order the links are computed in)
+    // position warp w: one unit of UB bytes per lane with 5 bits per position (M: 3, INS: 1, BLIP: 1), written with row
+    // r + 1's emitting states; behind those a unit of one byte per lane with the ordinals of the warp's chain states
+    // (bit j: S_SKIP_{k0+j}, bit P + j: B_BACK_{k0+j}), written when the warp fills in row r's chain values
     const int UB = 5 * P <= 16 ? 2 : 4;
     const int chain_base = NW * UB * kLanes;
-    plan->row_bytes = chain_base + 2 * 8 * kLanes;
+    plan->row_bytes = chain_base + NW * kLanes;
     plan->unit_off.assign(m, 0); plan->unit_bytes.assign(m, 1); plan->unit_shift.assign(m, 0); plan->unit_mask.assign(m, 0);
     auto place = [&](int s, int unit_off, int stride, int bit, int mask) {
         if (s < 0) return;
@@ -335,8 +359,8 @@ void build_profile_plan(const pp_model_desc& d, const Lowered& low, int P, int m
         place(INS[k], w * UB * kLanes, UB, 5 * p + 3, 1);
         place(BLIP[k], w * UB * kLanes, UB, 5 * p + 4, 1);
         place(DROP[k], 0, 0, 0, 0);                                 // one in-edge: ordinal 0, nothing stored
-        place(SKIP[k], chain_base, 8, k, 1);
-        place(BACK[k], chain_base + 8 * kLanes, 8, K - 1 - k, 1);
+        place(SKIP[k], chain_base + w * kLanes, 1, p, 1);
+        place(BACK[k], chain_base + w * kLanes, 1, P + p, 1);
     }
     plan->ok = true;
 }

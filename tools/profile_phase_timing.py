@@ -39,9 +39,9 @@ buf = np.zeros(512, dtype=np.uint64)
 lib.pp_debug_profile_phase_cycles(buf.ctypes.data, 0)
 buf = buf.reshape(2, 32, 8).astype(np.float64)[0]
 print("warp  phaseB  waitB   end  phaseA  waitA   (cycles per row; %d warp-rows)" % buf[0, 6])
-for w in range(16):
+for w in range(17):
     if buf[w, 6] == 0:
         continue
     c = buf[w] / buf[w, 6]
     print("%4d %7.0f %6.0f %5.0f %7.0f %6.0f" % (w, c[0], c[1], c[2], c[3], c[4]))
-print("row total (warp 0): %.0f cycles" % (buf[0, :5].sum() / buf[0, 6]))
+print("row total (warp 1): %.0f cycles" % (buf[1, :5].sum() / buf[1, 6]))
