@@ -382,8 +382,9 @@ def main():
     m, E = len(model.states), model.edge_count()
     if args.workload == "baum-welch":
         return bench_baum_welch(args, model, rank, world, local)
-    from protpore_b200 import _engine as _eng
-    ptr_bytes_row = int(_eng.describe_schedule(model).split("ptr_row_bytes")[1].split()[0]) / 32.0   # per event-row
+    kinfo = eng.kernel_info()                           # which kernel family serves this model, bytes per pointer row
+    ptr_bytes_row = kinfo["ptr_row_bytes"] / 32.0       # traceback ordinals per event-row
+    vit_kernel = {"profile": "k_profile_viterbi", "lane": "k_viterbi_lane"}.get(kinfo["family"], "k_viterbi_state")
 
     lens = events.uniform_lengths(args.events, args.min_len, args.max_len, seed=args.seed + rank)
     obs_d, off_d = eng.sample_events(lens, seed=args.seed + 1000 + rank, device_out=True)   # synthetic, on the GPU
@@ -391,10 +392,9 @@ def main():
     cells_step = 2.0 * total_obs * m                    # one forward pass + one Viterbi pass
     stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local))
 
-    def step_device():
-        scores, plen, paths = eng.viterbi_batch(obs_d, off_d)
-        logp = eng.forward_batch(obs_d, off_d)
-        return scores, plen, paths, logp
+    def step_device(out=None):
+        # ONE call: one bucketing of the events, Viterbi sweep + forward sweep + traceback (pp_score_batch)
+        return eng.score_batch(obs_d, off_d, out=out)
 
     def barrier():
         torch.cuda.synchronize()
@@ -409,6 +409,11 @@ def main():
     assert bool((plen > 0).all()) and bool(torch.isfinite(logp).all()) and bool((scores <= logp + 1e-6).all())
     path_elems = int(paths.numel())
     del out, scores, plen, paths, logp
+    # a serving loop owns its result buffers: allocated once, reused every step
+    dev = torch.device("cuda", local)
+    bufs = (torch.empty(args.events, dtype=torch.float64, device=dev), torch.empty(args.events, dtype=torch.int64, device=dev),
+            torch.empty(path_elems + 1024, dtype=torch.uint16, device=dev), torch.empty(args.events, dtype=torch.float64, device=dev))
+    step_device(bufs)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -419,15 +424,10 @@ def main():
     t_wall = time.perf_counter()
     prof = {}
     for _ in range(args.steps):
-        scores, plen, paths = eng.viterbi_batch(obs_d, off_d)
+        step_device(bufs)
         pv = eng.profile()
-        logp = eng.forward_batch(obs_d, off_d)
-        pf = eng.profile()
-        for k in ("viterbi_ms", "traceback_ms", "schedule_host_ms"):
+        for k in ("viterbi_ms", "traceback_ms", "schedule_host_ms", "forward_ms"):
             prof[k] = prof.get(k, 0.0) + pv[k]
-        prof["forward_ms"] = prof.get("forward_ms", 0.0) + pf["forward_ms"]
-        prof["schedule_host_ms"] += pf["schedule_host_ms"]
-        del scores, plen, paths, logp
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - t_wall
@@ -450,15 +450,12 @@ def main():
         # a serving loop owns its result buffers: page-locked, allocated once, reused every step
         from protpore_b200._engine import pinned_empty
         outs = (pinned_empty(args.events, np.float64), pinned_empty(args.events, np.int64),
-                pinned_empty(path_elems + 1024, np.uint16))
-        lp_out = pinned_empty(args.events, np.float64)
-        eng.viterbi_batch(obs_h, off_h, out=outs)          # warm the staging buffers
-        eng.forward_batch(obs_h, off_h, out=lp_out)
+                pinned_empty(path_elems + 1024, np.uint16), pinned_empty(args.events, np.float64))
+        eng.score_batch(obs_h, off_h, out=outs)            # warm the staging buffers
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            s_h, l_h, p_h = eng.viterbi_batch(obs_h, off_h, out=outs)
-            lp_h = eng.forward_batch(obs_h, off_h, out=lp_out)
+            s_h, l_h, p_h, lp_h = eng.score_batch(obs_h, off_h, out=outs)
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -466,7 +463,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt[0])
         e2e = {"value": cells_step * world * e2e_steps / dt / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": int(2 * (obs_h.nbytes + off_h.nbytes)),
+               "h2d_bytes_per_step": int(obs_h.nbytes + off_h.nbytes),
                "d2h_bytes_per_step": int(s_h.nbytes + l_h.nbytes + p_h.nbytes + lp_h.nbytes),
                "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps,
                "events_per_s": args.events * world * e2e_steps / dt}
@@ -492,12 +489,12 @@ def main():
     # measured DRAM traffic of one launch (ncu capture of this exact batch, committed under profiles/); null for other batches
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_viterbi_lane"]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[vit_kernel]
         if (tr["events"], tr["min_len"], tr["max_len"], tr["seed"]) == (args.events, args.min_len, args.max_len, args.seed):
             traffic = float(tr["dram_bytes_read"] + tr["dram_bytes_write"])
     except Exception:
         pass
-    roof = {"bound": "hbm", "kernel": "k_viterbi_lane", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+    roof = {"bound": "hbm", "kernel": vit_kernel, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
             "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": traffic,
             "algorithmic_bytes_per_launch": vit_bytes, "launch_ms": vit_ms}
     b = model._baked
@@ -524,7 +521,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "ours",
             "config": {"workload": "pro_001 profile HMM (257 states, 765 edges), {} events/GPU of {}-{} segments sampled "
-                       "from the model, batched forward + Viterbi with traceback".format(args.events, args.min_len, args.max_len),
+                       "from the model, batched forward + Viterbi with traceback in one pp_score_batch call".format(args.events, args.min_len, args.max_len),
                        "events_per_gpu": args.events, "observations_per_gpu": total_obs, "states": m, "edges": E,
                        "cells_per_step_per_gpu": cells_step, "parallelism": "events sharded, dp{}".format(world),
                        "l2_policy": "inputs ({:.2f} GB) and traceback ordinals ({:.1f} GB) per step exceed the 126 MB L2".format(

@@ -14,7 +14,10 @@
  *   - The caller owns every input/output buffer.  `mem` says where ALL data buffers of that call
  *     live: PP_MEM_HOST (library stages H2D/D2H itself; pinned memory recommended) or
  *     PP_MEM_DEVICE (device pointers on the model's GPU; work is enqueued on the model's stream and
- *     the call returns after that stream is synchronised).
+ *     the call returns after that stream is synchronised).  The model's stream is a non-blocking stream of its own
+ *     (pp_model_stream): whatever produced a device input on ANOTHER stream must have completed -- or that stream
+ *     must have been made to precede pp_model_stream with an event -- before the call; the Python layer synchronises
+ *     torch's current stream for every device tensor it passes.
  *   - The library owns only the opaque model handle and its device workspace.  A handle is not
  *     thread-safe; distinct handles are.  One handle per GPU (one process per GPU under torchrun).
  *   - Events are passed CSR-style: `obs` holds the segment means of all events back to back
@@ -139,6 +142,17 @@ int pp_forward_batch(pp_model *model, const void *obs, int32_t obs_dtype, const 
 int pp_viterbi_batch(pp_model *model, const void *obs, int32_t obs_dtype, const int64_t *offsets,
                      int64_t n_events, int32_t mem, double *logp_out, int64_t *path_len_out,
                      uint16_t *path_out, int64_t path_capacity, int64_t *path_total);
+
+/*
+ * The pair the peptide script runs per event -- Model.viterbi to decode, Model.log_probability to score
+ * (peptide_hmm_v0.0.1.py:251-262) -- for a whole batch in ONE call: the observations are uploaded once, the events are
+ * bucketed by length once (on the GPU), then both sweeps and the traceback run back to back on the same buffers.  Outputs as
+ * for pp_viterbi_batch, plus forward_logp_out[e] = log P(event e | model) as for pp_forward_batch.  Results are identical
+ * to the two single calls.
+ */
+int pp_score_batch(pp_model *model, const void *obs, int32_t obs_dtype, const int64_t *offsets, int64_t n_events,
+                   int32_t mem, double *viterbi_logp_out, int64_t *path_len_out, uint16_t *path_out,
+                   int64_t path_capacity, int64_t *path_total, double *forward_logp_out);
 
 /*
  * Full DP tables of ONE event in float64 log space, the reference's return values:

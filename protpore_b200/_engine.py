@@ -66,6 +66,8 @@ ABI = [
     ("pp_forward_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
     ("pp_viterbi_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp,
                                         ctypes.c_int64, _i64p]),
+    ("pp_score_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp,
+                                      ctypes.c_int64, _i64p, _vp]),
     ("pp_forward_table", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
     ("pp_backward_table", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
     ("pp_forward_backward_info", ctypes.c_int, [_vp, _i64p]),
@@ -136,6 +138,16 @@ def _ptr(a):
     if isinstance(a, np.ndarray):
         return a.ctypes.data
     return a.data_ptr()
+
+
+def _torch_inputs_ready(*tensors):
+    """The library enqueues on its own non-blocking stream: work torch still has in flight on ITS current stream (the
+    cast / cat / kernel that produces `obs`) must be complete before a device pointer is handed over."""
+    import torch
+    for t in tensors:
+        if t is not None and hasattr(t, "is_cuda") and t.is_cuda:
+            torch.cuda.current_stream(t.device).synchronize()
+            return
 
 
 def _is_device(a):
@@ -277,6 +289,7 @@ class Engine(object):
             import torch
             out = torch.empty(n, dtype=torch.float64, device=obs.device) if out is None else out
             mem = PP_MEM_DEVICE
+            _torch_inputs_ready(obs)
         else:
             obs = np.ascontiguousarray(obs)
             offsets = np.ascontiguousarray(offsets, dtype=np.int64)
@@ -291,14 +304,32 @@ class Engine(object):
 
         `out` = (scores, path_len, paths) lets a serving loop reuse its own (ideally pinned, see
         `pinned_empty`) host buffers; len(paths) is then the path capacity."""
+        return self._decode(obs, offsets, with_paths, capacity, out, None)
+
+    def score_batch(self, obs, offsets, with_paths=True, capacity=None, out=None):
+        """Viterbi decode AND forward log-probability of every event in one call (pp_score_batch): one upload, one
+        bucketing.  Returns (viterbi scores, path_len, paths, log P); `out` = (scores, path_len, paths, logp)."""
+        n = len(offsets) - 1
+        if out is not None:
+            logp = out[3]
+        elif _is_device(obs):
+            import torch
+            logp = torch.empty(n, dtype=torch.float64, device=obs.device)
+        else:
+            logp = np.empty(n, dtype=np.float64)
+        scores, plen, paths = self._decode(obs, offsets, with_paths, capacity, out, logp)
+        return scores, plen, paths, logp
+
+    def _decode(self, obs, offsets, with_paths, capacity, out, logp):
         n = len(offsets) - 1
         dev = _is_device(obs)
         if dev:
             import torch
             total_obs = int(obs.numel())
             mk = lambda k, dt: torch.empty(k, dtype=dt, device=obs.device)
-            scores, plen = mk(n, torch.float64), mk(n, torch.int64)
+            scores, plen = (out[0], out[1]) if out is not None else (mk(n, torch.float64), mk(n, torch.int64))
             mem = PP_MEM_DEVICE
+            _torch_inputs_ready(obs)
         else:
             obs = np.ascontiguousarray(obs)
             offsets = np.ascontiguousarray(offsets, dtype=np.int64)
@@ -314,12 +345,17 @@ class Engine(object):
                 paths = None
             elif dev:
                 import torch
-                paths = torch.empty(cap, dtype=torch.uint16, device=obs.device)
+                paths = out[2] if (out is not None and len(out[2]) >= cap) else torch.empty(cap, dtype=torch.uint16, device=obs.device)
             else:
                 paths = out[2] if (out is not None and len(out[2]) >= cap) else np.empty(cap, dtype=np.uint16)
-            rc = self._lib.pp_viterbi_batch(self._h, _ptr(obs), self._obs_dtype(obs), _ptr(offsets), n, mem,
-                                            _ptr(scores), _ptr(plen), _ptr(paths), cap if with_paths else 0,
-                                            ctypes.byref(total))
+            if logp is None:
+                rc = self._lib.pp_viterbi_batch(self._h, _ptr(obs), self._obs_dtype(obs), _ptr(offsets), n, mem,
+                                                _ptr(scores), _ptr(plen), _ptr(paths), cap if with_paths else 0,
+                                                ctypes.byref(total))
+            else:
+                rc = self._lib.pp_score_batch(self._h, _ptr(obs), self._obs_dtype(obs), _ptr(offsets), n, mem,
+                                              _ptr(scores), _ptr(plen), _ptr(paths), cap if with_paths else 0,
+                                              ctypes.byref(total), _ptr(logp))
             if rc == PP_ERR_CAPACITY:
                 cap = max(int(total.value), 2 * cap)
                 continue
@@ -392,6 +428,7 @@ class Engine(object):
             dev = torch.device("cuda", self.device)
             d_off = torch.from_numpy(offsets).to(dev)
             obs = torch.empty(int(offsets[-1]), dtype=torch.float32, device=dev)
+            _torch_inputs_ready(d_off)
             self._check(self._lib.pp_sample_events(self._h, _ptr(d_off), len(lengths), int(seed), PP_MEM_DEVICE,
                                                    _ptr(obs)))
             return obs, d_off
@@ -422,6 +459,7 @@ def statsplit_batch(current, offsets, min_width, max_width, window_width, min_ga
         import torch
         dev = current.device
         assert current.dtype == torch.float64 and offsets.dtype == torch.int64 and offsets.is_cuda
+        _torch_inputs_ready(current)
         seg_offsets = torch.empty(n_events + 1, dtype=torch.int64, device=dev)
         mem = PP_MEM_DEVICE
         device = dev.index if dev.index is not None else device

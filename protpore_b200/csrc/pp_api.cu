@@ -2,6 +2,7 @@
 // batched Viterbi + traceback and batched forward over the lane-per-event kernels, event sampler.
 // There is no CPU fallback anywhere in this file: without a CUDA device every entry point that
 // computes returns PP_ERR_CUDA.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/transform_iterator.h>
 
@@ -42,6 +43,112 @@ void lane_arena_invalidate(const void* owner) {
     lane_viterbi4g_invalidate(owner);
     lane_forwardg_invalidate(owner);
     lane_forward_invalidate(owner);
+}
+
+// ---- event bucketing on the device ----------------------------------------------------------------------------
+// The same schedule build_schedule makes on the host -- events sorted by length, longest first, stable; 32 per group;
+// group g owns group_len[g] + 1 rows of the pointer table from group_row[g] -- built with a CUB radix sort and a scan, so
+// a batch of a million events costs ~0.3 ms of GPU time instead of ~8 ms of host time in front of every sweep.
+static __global__ void k_event_lengths(const int64_t* __restrict__ off, int64_t e0, int64_t n, uint32_t* __restrict__ len,
+                                       int32_t* __restrict__ idx, long long* __restrict__ minmax) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    long long lo = 0x7fffffffffffffffLL, hi = -0x7fffffffffffffffLL;
+    if (i < n) {
+        const long long l = off[e0 + i + 1] - off[e0 + i];
+        len[i] = static_cast<uint32_t>(l < 0 ? 0 : (l > 0x7ffffff0LL ? 0x7ffffff0LL : l));
+        idx[i] = static_cast<int32_t>(e0 + i);
+        lo = hi = l;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    if ((threadIdx.x & 31) == 0 && hi >= lo) {
+        atomicMin(&minmax[0], lo);
+        atomicMax(&minmax[1], hi);
+    }
+}
+static __global__ void k_schedule_groups(const uint32_t* __restrict__ len_sorted, const int32_t* __restrict__ idx_sorted, int64_t n,
+                                         int32_t n_groups, int32_t* __restrict__ order, int32_t* __restrict__ group_len,
+                                         int64_t* __restrict__ group_rows) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < static_cast<int64_t>(n_groups) * kLanes) order[i] = i < n ? idx_sorted[i] : -1;
+    if (i < n_groups) {
+        const int32_t l = static_cast<int32_t>(len_sorted[i * kLanes]);
+        group_len[i] = l;
+        group_rows[i] = l + 1;
+    }
+}
+static __global__ void k_schedule_total(const int64_t* __restrict__ group_row, const int32_t* __restrict__ group_len, int32_t n_groups,
+                                        long long* __restrict__ minmax) {
+    minmax[2] = group_row[n_groups - 1] + group_len[n_groups - 1] + 1;
+}
+static __global__ void k_first_bad_event(const int64_t* __restrict__ off, int64_t n, long long* __restrict__ out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const long long l = off[i + 1] - off[i];
+        if (l < 1 || l > 0x7ffffff0LL) atomicMin(out, static_cast<long long>(i));
+    }
+}
+
+struct DevSchedule {
+    int32_t n_groups = 0;
+    cudaEvent_t ready = nullptr;       // the read-back of {min length, max length, total rows} has landed in h_pin
+};
+static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+// Enqueues the bucketing of events [e0, e1) into the buffers of pipeline slot `slot` on `stream`; the three scalars go to
+// h_pin[16 + 4 slot ...].  Nothing is synchronised here.
+static int device_schedule_enqueue(pp_model* M, int slot, const int64_t* d_off, int64_t e0, int64_t e1, cudaStream_t stream,
+                                   DevSchedule* out) {
+    pp_model::PipeSlot& P = M->ps[slot];
+    const int64_t n = e1 - e0;
+    const int32_t ng = static_cast<int32_t>((n + kLanes - 1) / kLanes);
+    out->n_groups = ng;
+    size_t sort_tmp = 0, scan_tmp = 0;
+    PP_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_tmp, static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                                                      static_cast<const int32_t*>(nullptr), static_cast<int32_t*>(nullptr), static_cast<int>(n), 0, 32, stream));
+    PP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, static_cast<const int64_t*>(nullptr), static_cast<int64_t*>(nullptr), ng, stream));
+    const size_t b_len = align256(static_cast<size_t>(n) * 4), b_grp = align256(static_cast<size_t>(ng) * 8), b_tmp = align256(std::max(sort_tmp, scan_tmp));
+    PP_CUDA(P.sched.reserve(4 * b_len + b_grp + b_tmp + 256));
+    unsigned char* base = P.sched.as<unsigned char>();
+    uint32_t* len = reinterpret_cast<uint32_t*>(base);
+    uint32_t* len_sorted = reinterpret_cast<uint32_t*>(base + b_len);
+    int32_t* idx = reinterpret_cast<int32_t*>(base + 2 * b_len);
+    int32_t* idx_sorted = reinterpret_cast<int32_t*>(base + 3 * b_len);
+    int64_t* rows = reinterpret_cast<int64_t*>(base + 4 * b_len);
+    void* tmp = base + 4 * b_len + b_grp;
+    long long* scal = reinterpret_cast<long long*>(base + 4 * b_len + b_grp + b_tmp);
+    PP_CUDA(P.order.reserve(static_cast<size_t>(ng) * kLanes * sizeof(int32_t) + 16));
+    PP_CUDA(P.group_len.reserve(static_cast<size_t>(ng) * sizeof(int32_t) + 16));
+    PP_CUDA(P.group_row.reserve(static_cast<size_t>(ng) * sizeof(int64_t) + 16));
+    const long long init[4] = {0x7fffffffffffffffLL, -0x7fffffffffffffffLL, 0, 0};
+    PP_CUDA(cudaMemcpyAsync(scal, init, sizeof init, cudaMemcpyHostToDevice, stream));
+    const unsigned nb = static_cast<unsigned>((n + 255) / 256);
+    k_event_lengths<<<nb, 256, 0, stream>>>(d_off, e0, n, len, idx, scal);
+    PP_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, sort_tmp, len, len_sorted, idx, idx_sorted, static_cast<int>(n), 0, 32, stream));
+    k_schedule_groups<<<static_cast<unsigned>((static_cast<int64_t>(ng) * kLanes + 255) / 256), 256, 0, stream>>>(
+        len_sorted, idx_sorted, n, ng, P.order.as<int32_t>(), P.group_len.as<int32_t>(), rows);
+    PP_CUDA(cub::DeviceScan::ExclusiveSum(tmp, scan_tmp, rows, P.group_row.as<int64_t>(), ng, stream));
+    k_schedule_total<<<1, 1, 0, stream>>>(P.group_row.as<int64_t>(), P.group_len.as<int32_t>(), ng, scal);
+    PP_CUDA(cudaGetLastError());
+    M->launches += 5;
+    PP_CUDA(cudaMemcpyAsync(M->h_pin + 16 + 4 * slot, scal, 3 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+    return PP_OK;
+}
+static int bad_event_error(pp_model* M, const int64_t* d_off, int64_t n_events, cudaStream_t stream) {
+    long long* d = nullptr;
+    long long first = 0x7fffffffffffffffLL;
+    if (cudaMalloc(&d, sizeof first) == cudaSuccess) {
+        cudaMemcpyAsync(d, &first, sizeof first, cudaMemcpyHostToDevice, stream);
+        k_first_bad_event<<<static_cast<unsigned>((n_events + 255) / 256), 256, 0, stream>>>(d_off, n_events, d);
+        cudaMemcpyAsync(&first, d, sizeof first, cudaMemcpyDeviceToHost, stream);
+        cudaStreamSynchronize(stream);
+        cudaFree(d);
+    }
+    // the reference raises on empty sequences (yahmm.pyx:2836)
+    set_error("event %lld has no observations (or is too long); every event needs at least one", first);
+    return PP_ERR_ARG;
 }
 
 static int check_lane_model(pp_model* M) {
@@ -317,11 +424,9 @@ static int launch_gcol(pp_model* M, const LaneSched& S0, const LaneBatchAny& A, 
     return PP_OK;
 }
 
-template <typename ObsT>
-static int launch_viterbi(pp_model* M, const LaneBatch<ObsT>& B, const VitOut& O, int n_groups) {
+static int launch_viterbi(pp_model* M, const LaneBatchAny& A, const VitOut& O, int n_groups) {
     int rc = check_lane_model(M);
     if (rc != PP_OK) return rc;
-    const LaneBatchAny A{B.obs, sizeof(ObsT) == 8 ? 1 : 0, B.offsets, B.order, B.group_len, B.group_row};
     if (use_profile(M)) {
         const int e = profile_viterbi_launch(make_prof_sched(M, true), A, O, n_groups, M->stream);
         if (e != 0) { set_error("profile Viterbi kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
@@ -338,11 +443,9 @@ static int launch_viterbi(pp_model* M, const LaneBatch<ObsT>& B, const VitOut& O
     return PP_OK;
 }
 
-template <typename ObsT>
-static int launch_forward(pp_model* M, const LaneBatch<ObsT>& B, const FwdOut& O, int n_groups) {
+static int launch_forward(pp_model* M, const LaneBatchAny& A, const FwdOut& O, int n_groups) {
     int rc = check_lane_model(M);
     if (rc != PP_OK) return rc;
-    const LaneBatchAny A{B.obs, sizeof(ObsT) == 8 ? 1 : 0, B.offsets, B.order, B.group_len, B.group_row};
     if (use_profile(M)) {
         const int e = profile_forward_launch(make_prof_sched(M, false), A, O, n_groups, M->stream);
         if (e != 0) { set_error("profile forward kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
@@ -468,9 +571,9 @@ void pp_model_destroy(pp_model* M) {
     release_state_model(M);
     for (int b = 0; b < 2; ++b) {
         pp_model::PipeSlot& P = M->ps[b];
-        DevBuf* pb[] = {&P.obs, &P.ws, &P.path, &P.order, &P.group_len, &P.group_row, &P.list, &P.counter};
+        DevBuf* pb[] = {&P.obs, &P.ws, &P.path, &P.order, &P.group_len, &P.group_row, &P.list, &P.counter, &P.sched};
         for (DevBuf* x : pb) x->release();
-        cudaEvent_t evs[] = {P.in_done, P.a_done, P.tb_done, P.out_done};
+        cudaEvent_t evs[] = {P.in_done, P.a_done, P.tb_done, P.out_done, P.sch_done};
         for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     }
     for (cudaEvent_t e : M->evpool) cudaEventDestroy(e);
@@ -608,8 +711,9 @@ static int pipe_init(pp_model* M) {
         PP_CUDA(cudaEventCreateWithFlags(&M->ps[b].a_done, cudaEventDisableTiming));
         PP_CUDA(cudaEventCreateWithFlags(&M->ps[b].tb_done, cudaEventDisableTiming));
         PP_CUDA(cudaEventCreateWithFlags(&M->ps[b].out_done, cudaEventDisableTiming));
+        PP_CUDA(cudaEventCreateWithFlags(&M->ps[b].sch_done, cudaEventDisableTiming));
     }
-    PP_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&M->h_pin), 16 * sizeof(int64_t), cudaHostAllocDefault));
+    PP_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&M->h_pin), 32 * sizeof(int64_t), cudaHostAllocDefault));
     return PP_OK;
 }
 
@@ -644,53 +748,89 @@ static void spans_collect(pp_model* M) {
     M->evnext = 0;
 }
 
-int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int64_t* offsets, int64_t n_events,
-                     int32_t mem, double* logp_out, int64_t* path_len_out, uint16_t* path_out, int64_t path_capacity,
-                     int64_t* path_total) {
-    if (!M || !obs || !logp_out || !path_len_out) { set_error("null argument"); return PP_ERR_ARG; }
-    if (obs_dtype != PP_F32 && obs_dtype != PP_F64) { set_error("bad obs_dtype"); return PP_ERR_ARG; }
-    if (mem != PP_MEM_HOST && mem != PP_MEM_DEVICE) { set_error("bad mem"); return PP_ERR_ARG; }
-    PP_CUDA(cudaSetDevice(M->device));
-    std::memset(M->prof, 0, sizeof M->prof);
-    if (path_total) *path_total = 0;
-    if (n_events == 0) return PP_OK;
+// One pipeline for the batched Viterbi decode (logp_out / path_* set), the batched forward score (fwd_out set) or both
+// (pp_score_batch): one upload, one bucketing.
+static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const int64_t* offsets, int64_t n_events,
+                          int32_t mem, double* logp_out, int64_t* path_len_out, uint16_t* path_out, int64_t path_capacity,
+                          int64_t* path_total, double* fwd_out) {
+    const bool want_vit = logp_out != nullptr, want_fwd = fwd_out != nullptr;
     const size_t ob = obs_dtype == PP_F32 ? 4 : 8;
-    if (!lane_kernels_fit(M))                         // large model: exact state-parallel kernels
-        return viterbi_batch_state(M, obs, obs_dtype, offsets, n_events, mem, logp_out, path_len_out, path_out,
-                                   path_capacity, path_total);
     int rc = pipe_init(M);
     if (rc != PP_OK) return rc;
     const bool host = mem == PP_MEM_HOST;
 
+    // ---- offsets: on the device for the kernels; on the host only where the host has to cut the batch into chunks
     std::vector<int64_t> store;
-    const int64_t *h_off, *d_off;
-    rc = host_offsets(M, offsets, n_events, mem, &store, &h_off, &d_off);
-    if (rc != PP_OK) return rc;
-
-    double* d_score;
-    int64_t* d_plen;
-    if (!host) {
-        d_score = logp_out;
-        d_plen = path_len_out;
+    const int64_t* h_off = nullptr;
+    const int64_t* d_off = nullptr;
+    if (host) {
+        if (!offsets || n_events < 0) { set_error("null offsets / negative n_events"); return PP_ERR_ARG; }
+        std::vector<int64_t> dummy;
+        rc = host_offsets(M, offsets, n_events, mem, &dummy, &h_off, &d_off);
+        if (rc != PP_OK) return rc;
     } else {
-        PP_CUDA(M->d_score.reserve(n_events * sizeof(double)));
-        PP_CUDA(M->d_path_len.reserve(n_events * sizeof(int64_t)));
-        d_score = M->d_score.as<double>();
-        d_plen = M->d_path_len.as<int64_t>();
+        if (!offsets || n_events < 0) { set_error("null offsets / negative n_events"); return PP_ERR_ARG; }
+        if (n_events > 0x7fffffff - 64) { set_error("more than 2^31 events in one call"); return PP_ERR_ARG; }
+        d_off = offsets;
     }
-    PP_CUDA(M->d_end_state.reserve(n_events * sizeof(int32_t)));
-    PP_CUDA(M->d_end_ord.reserve(n_events * sizeof(int32_t)));
-    PP_CUDA(M->d_path_off.reserve((n_events + 1) * sizeof(int64_t)));
+
+    double* d_score = nullptr;
+    int64_t* d_plen = nullptr;
+    double* d_fwd = fwd_out;
+    if (want_vit) {
+        if (!host) {
+            d_score = logp_out;
+            d_plen = path_len_out;
+        } else {
+            PP_CUDA(M->d_score.reserve(n_events * sizeof(double)));
+            PP_CUDA(M->d_path_len.reserve(n_events * sizeof(int64_t)));
+            d_score = M->d_score.as<double>();
+            d_plen = M->d_path_len.as<int64_t>();
+        }
+        PP_CUDA(M->d_end_state.reserve(n_events * sizeof(int32_t)));
+        PP_CUDA(M->d_end_ord.reserve(n_events * sizeof(int32_t)));
+        PP_CUDA(M->d_path_off.reserve((n_events + 1) * sizeof(int64_t)));
+    }
+    if (want_fwd && host) {
+        PP_CUDA(M->d_logp.reserve(n_events * sizeof(double)));
+        d_fwd = M->d_logp.as<double>();
+    }
     PP_CUDA(cudaStreamSynchronize(M->stream));            // offsets are on the device before s_in / kernels use them
 
-    const size_t row_bytes = ptr_row_bytes(M);
-    // two chunks in flight: each gets half the workspace; host batches are cut fine enough for the copies to overlap
-    const std::vector<int64_t> cuts = make_chunks(h_off, n_events, row_bytes, M->ws_limit / 2, host ? ob : 0, size_t(96) << 20);
+    const size_t row_bytes = want_vit ? ptr_row_bytes(M) : 0;
+    // host wall time this call spends on bucketing: enqueueing it and waiting for its three scalars
+    auto clock_now = [] { return std::chrono::steady_clock::now(); };
+    auto add_host_ms = [&](std::chrono::steady_clock::time_point t0) {
+        M->prof[PP_PROF_SCHEDULE_HOST_MS] += std::chrono::duration<double, std::milli>(clock_now() - t0).count();
+    };
+    std::vector<int64_t> cuts;
+    DevSchedule pre;                                       // device-resident batch: the whole batch is bucketed first
+    bool pre_scheduled = false;
+    if (host) {
+        // two chunks in flight: each gets half the workspace; host batches are cut fine enough for the copies to overlap
+        cuts = make_chunks(h_off, n_events, row_bytes, M->ws_limit / 2, ob, size_t(96) << 20);
+    } else {
+        const auto t0 = clock_now();
+        rc = device_schedule_enqueue(M, 0, d_off, 0, n_events, M->stream, &pre);
+        if (rc != PP_OK) return rc;
+        PP_CUDA(cudaStreamSynchronize(M->stream));
+        add_host_ms(t0);
+        const int64_t minlen = M->h_pin[16], maxlen = M->h_pin[17], rows = M->h_pin[18];
+        if (minlen < 1 || maxlen > 0x7ffffff0LL) return bad_event_error(M, d_off, n_events, M->stream);
+        if (static_cast<size_t>(rows) * row_bytes <= M->ws_limit) {
+            cuts = {0, n_events};
+            pre_scheduled = true;
+        } else {                                           // too large for one pointer table: cut on the host
+            store.resize(static_cast<size_t>(n_events) + 1);
+            PP_CUDA(cudaMemcpy(store.data(), d_off, store.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+            h_off = store.data();
+            cuts = make_chunks(h_off, n_events, row_bytes, M->ws_limit / 2, 0, size_t(96) << 20);
+        }
+    }
     const int n_chunks = static_cast<int>(cuts.size()) - 1;
     int64_t base = 0;
     bool overflow = false;
-    Schedule sc;
-    struct ChunkInfo { int64_t e0, e1; int n_groups; };
+    struct ChunkInfo { int64_t e0, e1; int n_groups; int64_t maxlen; const void* obs_base; };
     std::vector<ChunkInfo> info(n_chunks);
 
     auto trace_args = [&](int c) {
@@ -707,10 +847,19 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
                          M->d_state_pshift.as<int32_t>(), M->d_state_pmask.as<int32_t>(), M->m, M->ne, M->start,
                          M->low.end_final_only ? 1 : 0, static_cast<int64_t>(row_bytes)};
     };
-    // phase B of chunk c: the host learns the chunk's path total, then the write pass and the copy out
+    // phase B of chunk c: the host learns the chunk's path total (and how many events the scaled forward sweep could
+    // not resolve), then the traceback write pass, the exact forward re-run and the copy out
     auto finish = [&](int c) -> int {
         pp_model::PipeSlot& P = M->ps[c & 1];
         PP_CUDA(cudaEventSynchronize(P.a_done));
+        if (want_fwd) {
+            int r = exact_forward_run(M, c & 1, info[c].obs_base, obs_dtype, d_off + info[c].e0, info[c].maxlen, d_fwd + info[c].e0);
+            if (r != PP_OK) return r;
+        }
+        if (!want_vit) {
+            PP_CUDA(cudaEventRecord(P.tb_done, M->stream));
+            return PP_OK;
+        }
         const int64_t last_off = M->h_pin[(c & 1) * 2], last_len = M->h_pin[(c & 1) * 2 + 1];
         const int64_t chunk_total = last_off + (last_len > 0 ? last_len : 0);
         const int nslots = info[c].n_groups * kLanes;
@@ -747,25 +896,16 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     for (int c = 0; c < n_chunks; ++c) {
         pp_model::PipeSlot& P = M->ps[c & 1];
         const int64_t e0 = cuts[c], e1 = cuts[c + 1];
-        auto t0 = std::chrono::steady_clock::now();
-        build_schedule(h_off, e0, e1, &sc);
-        M->prof[PP_PROF_SCHEDULE_HOST_MS] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        info[c] = {e0, e1, sc.n_groups};
-        const size_t ws = static_cast<size_t>(sc.total_rows) * row_bytes;
-        if (ws > M->ws_limit) {
-            set_error("one event needs %zu bytes of traceback workspace (limit %zu)", ws, M->ws_limit);
-            cudaDeviceSynchronize();
-            return PP_ERR_NOMEM;
+        // ---- copy in and bucketing (the slot's buffers were last used by chunk c - 2: its traceback must be through)
+        DevSchedule sc = pre;
+        if (!pre_scheduled) {
+            const auto t0 = clock_now();
+            PP_CUDA(cudaStreamWaitEvent(M->s_in, P.tb_done, 0));
+            rc = device_schedule_enqueue(M, c & 1, d_off, e0, e1, M->s_in, &sc);
+            if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
+            PP_CUDA(cudaEventRecord(P.sch_done, M->s_in));
+            add_host_ms(t0);
         }
-        // ---- copy in (the slot's buffers were last used by chunk c - 2: its traceback must be through)
-        PP_CUDA(cudaStreamWaitEvent(M->s_in, P.tb_done, 0));
-        if (P.ws.cap < ws) {                                  // growing the table frees memory: nothing may be in flight on it
-            PP_CUDA(cudaStreamSynchronize(M->stream));
-            if (P.ws.reserve(ws) != cudaSuccess) { cudaGetLastError(); set_error("cannot allocate %zu bytes of workspace", ws); return PP_ERR_NOMEM; }
-        }
-        PP_CUDA(upload(&P.order, sc.order, M->s_in));
-        PP_CUDA(upload(&P.group_len, sc.group_len, M->s_in));
-        PP_CUDA(upload(&P.group_row, sc.group_row, M->s_in));
         const void* d_obs_base = obs;                        // indexable with the GLOBAL offsets
         if (host) {
             const size_t nob = static_cast<size_t>(h_off[e1] - h_off[e0]) * ob;
@@ -775,23 +915,39 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
             d_obs_base = static_cast<const char*>(P.obs.p) - h_off[e0] * ob;
         }
         PP_CUDA(cudaEventRecord(P.in_done, M->s_in));
-        // ---- phase A: sweep, path lengths, exclusive scan, the chunk's total to pinned memory
+        if (!pre_scheduled) PP_CUDA(cudaEventSynchronize(P.sch_done));
+        const int64_t minlen = M->h_pin[16 + 4 * (c & 1)], maxlen = M->h_pin[17 + 4 * (c & 1)], total_rows = M->h_pin[18 + 4 * (c & 1)];
+        if (minlen < 1 || maxlen > 0x7ffffff0LL) { cudaDeviceSynchronize(); return bad_event_error(M, d_off, n_events, M->stream); }
+        info[c] = {e0, e1, sc.n_groups, maxlen, d_obs_base};
+        const size_t ws = static_cast<size_t>(total_rows) * row_bytes;
+        if (ws > M->ws_limit) {
+            set_error("one event needs %zu bytes of traceback workspace (limit %zu)", ws, M->ws_limit);
+            cudaDeviceSynchronize();
+            return PP_ERR_NOMEM;
+        }
+        if (P.ws.cap < ws) {                                  // growing the table frees memory: nothing may be in flight on it
+            PP_CUDA(cudaStreamSynchronize(M->stream));
+            if (P.ws.reserve(ws) != cudaSuccess) { cudaGetLastError(); set_error("cannot allocate %zu bytes of workspace", ws); return PP_ERR_NOMEM; }
+        }
+        // ---- phase A: sweeps, path lengths, exclusive scan, the chunk's totals to pinned memory
         PP_CUDA(cudaStreamWaitEvent(M->stream, P.in_done, 0));
-        VitOut O{d_score, M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), P.ws.as<uint32_t>()};
-        {
+        const LaneBatchAny A{d_obs_base, obs_dtype == PP_F64 ? 1 : 0, d_off, P.order.as<int32_t>(), P.group_len.as<int32_t>(), P.group_row.as<int64_t>()};
+        if (want_vit) {
+            VitOut O{d_score, M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), P.ws.as<uint32_t>()};
             SpanGuard t(M, PP_PROF_VITERBI, M->stream);
-            if (obs_dtype == PP_F32) {
-                LaneBatch<float> B{static_cast<const float*>(d_obs_base), d_off, P.order.as<int32_t>(),
-                                   P.group_len.as<int32_t>(), P.group_row.as<int64_t>()};
-                rc = launch_viterbi<float>(M, B, O, sc.n_groups);
-            } else {
-                LaneBatch<double> B{static_cast<const double*>(d_obs_base), d_off, P.order.as<int32_t>(),
-                                    P.group_len.as<int32_t>(), P.group_row.as<int64_t>()};
-                rc = launch_viterbi<double>(M, B, O, sc.n_groups);
-            }
+            rc = launch_viterbi(M, A, O, sc.n_groups);
         }
         if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
-        {
+        if (want_fwd) {
+            {
+                SpanGuard t(M, PP_PROF_FORWARD, M->stream);
+                rc = launch_forward(M, A, FwdOut{d_fwd}, sc.n_groups);
+            }
+            if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
+            rc = exact_forward_collect(M, c & 1, d_fwd + e0, e1 - e0);
+            if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
+        }
+        if (want_vit) {
             SpanGuard t(M, PP_PROF_TRACEBACK, M->stream);
             const int nslots = sc.n_groups * kLanes;
             k_traceback<<<(nslots + 127) / 128, 128, 0, M->stream>>>(trace_args(c), d_plen, nullptr, nullptr, nslots);
@@ -818,8 +974,11 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
     if (host) {
         SpanGuard t(M, PP_PROF_D2H, M->stream);
-        PP_CUDA(cudaMemcpyAsync(logp_out, d_score, n_events * sizeof(double), cudaMemcpyDeviceToHost, M->stream));
-        PP_CUDA(cudaMemcpyAsync(path_len_out, d_plen, n_events * sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
+        if (want_vit) {
+            PP_CUDA(cudaMemcpyAsync(logp_out, d_score, n_events * sizeof(double), cudaMemcpyDeviceToHost, M->stream));
+            PP_CUDA(cudaMemcpyAsync(path_len_out, d_plen, n_events * sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
+        }
+        if (want_fwd) PP_CUDA(cudaMemcpyAsync(fwd_out, d_fwd, n_events * sizeof(double), cudaMemcpyDeviceToHost, M->stream));
     }
     PP_CUDA(cudaStreamSynchronize(M->stream));
     PP_CUDA(cudaStreamSynchronize(M->s_out));
@@ -833,6 +992,45 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     return PP_OK;
 }
 
+int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int64_t* offsets, int64_t n_events,
+                     int32_t mem, double* logp_out, int64_t* path_len_out, uint16_t* path_out, int64_t path_capacity,
+                     int64_t* path_total) {
+    if (!M || !obs || !logp_out || !path_len_out) { set_error("null argument"); return PP_ERR_ARG; }
+    if (obs_dtype != PP_F32 && obs_dtype != PP_F64) { set_error("bad obs_dtype"); return PP_ERR_ARG; }
+    if (mem != PP_MEM_HOST && mem != PP_MEM_DEVICE) { set_error("bad mem"); return PP_ERR_ARG; }
+    PP_CUDA(cudaSetDevice(M->device));
+    std::memset(M->prof, 0, sizeof M->prof);
+    if (path_total) *path_total = 0;
+    if (n_events == 0) return PP_OK;
+    if (!lane_kernels_fit(M))                         // large model: exact state-parallel kernels
+        return viterbi_batch_state(M, obs, obs_dtype, offsets, n_events, mem, logp_out, path_len_out, path_out,
+                                   path_capacity, path_total);
+    return score_pipeline(M, obs, obs_dtype, offsets, n_events, mem, logp_out, path_len_out, path_out, path_capacity, path_total, nullptr);
+}
+
+int pp_score_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int64_t* offsets, int64_t n_events, int32_t mem,
+                   double* viterbi_logp_out, int64_t* path_len_out, uint16_t* path_out, int64_t path_capacity,
+                   int64_t* path_total, double* forward_logp_out) {
+    if (!M || !obs || !viterbi_logp_out || !path_len_out || !forward_logp_out) { set_error("null argument"); return PP_ERR_ARG; }
+    if (obs_dtype != PP_F32 && obs_dtype != PP_F64) { set_error("bad obs_dtype"); return PP_ERR_ARG; }
+    if (mem != PP_MEM_HOST && mem != PP_MEM_DEVICE) { set_error("bad mem"); return PP_ERR_ARG; }
+    PP_CUDA(cudaSetDevice(M->device));
+    if (path_total) *path_total = 0;
+    if (n_events == 0) { std::memset(M->prof, 0, sizeof M->prof); return PP_OK; }
+    if (!lane_kernels_fit(M)) {                       // models the lane kernels do not serve: the two single calls
+        int rc = pp_viterbi_batch(M, obs, obs_dtype, offsets, n_events, mem, viterbi_logp_out, path_len_out, path_out, path_capacity, path_total);
+        if (rc != PP_OK) return rc;
+        double keep[PP_PROF_SLOTS];
+        std::memcpy(keep, M->prof, sizeof keep);
+        rc = pp_forward_batch(M, obs, obs_dtype, offsets, n_events, mem, forward_logp_out);
+        for (int i = 0; i < PP_PROF_SLOTS; ++i) M->prof[i] += keep[i];
+        return rc;
+    }
+    std::memset(M->prof, 0, sizeof M->prof);
+    return score_pipeline(M, obs, obs_dtype, offsets, n_events, mem, viterbi_logp_out, path_len_out, path_out, path_capacity,
+                          path_total, forward_logp_out);
+}
+
 // ---------------------------------------------------------------------------------------------
 int pp_forward_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int64_t* offsets, int64_t n_events,
                      int32_t mem, double* logp_out) {
@@ -842,8 +1040,10 @@ int pp_forward_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     PP_CUDA(cudaSetDevice(M->device));
     std::memset(M->prof, 0, sizeof M->prof);
     if (n_events == 0) return PP_OK;
+    if (lane_kernels_fit(M))
+        return score_pipeline(M, obs, obs_dtype, offsets, n_events, mem, nullptr, nullptr, nullptr, 0, nullptr, logp_out);
+    // large model, or emissions from a table: every event takes the exact log-space kernel
     const size_t ob = obs_dtype == PP_F32 ? 4 : 8;
-    const bool lane = lane_kernels_fit(M);
     const bool host = mem == PP_MEM_HOST;
     int rc = pipe_init(M);
     if (rc != PP_OK) return rc;
@@ -861,29 +1061,21 @@ int pp_forward_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     PP_CUDA(cudaStreamSynchronize(M->stream));
     const std::vector<int64_t> cuts = make_chunks(h_off, n_events, 0, 0, host ? ob : 0, size_t(96) << 20);
     const int n_chunks = static_cast<int>(cuts.size()) - 1;
-    Schedule sc;
     std::vector<const void*> obs_base(n_chunks);
-    // phase B of chunk c: events the scaled sweep could not resolve (P == 0, inf, NaN) go through the exact kernel
     auto finish = [&](int c) -> int {
         pp_model::PipeSlot& P = M->ps[c & 1];
         PP_CUDA(cudaEventSynchronize(P.a_done));
         const int64_t e0 = cuts[c], e1 = cuts[c + 1];
-        int r = exact_forward_run(M, c & 1, obs_base[c], obs_dtype, d_off + e0, h_off + e0, e1 - e0, d_logp + e0);
+        int64_t maxlen = 0;
+        for (int64_t e = e0; e < e1; ++e) maxlen = std::max(maxlen, h_off[e + 1] - h_off[e]);
+        int r = exact_forward_run(M, c & 1, obs_base[c], obs_dtype, d_off + e0, maxlen, d_logp + e0);
         PP_CUDA(cudaEventRecord(P.tb_done, M->stream));
         return r;
     };
     for (int c = 0; c < n_chunks; ++c) {
         pp_model::PipeSlot& P = M->ps[c & 1];
         const int64_t e0 = cuts[c], e1 = cuts[c + 1];
-        auto t0 = std::chrono::steady_clock::now();
-        if (lane) build_schedule(h_off, e0, e1, &sc);
-        M->prof[PP_PROF_SCHEDULE_HOST_MS] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         PP_CUDA(cudaStreamWaitEvent(M->s_in, P.tb_done, 0));
-        if (lane) {
-            PP_CUDA(upload(&P.order, sc.order, M->s_in));
-            PP_CUDA(upload(&P.group_len, sc.group_len, M->s_in));
-            PP_CUDA(upload(&P.group_row, sc.group_row, M->s_in));
-        }
         obs_base[c] = obs;
         if (host) {
             const size_t nob = static_cast<size_t>(h_off[e1] - h_off[e0]) * ob;
@@ -894,22 +1086,10 @@ int pp_forward_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
         }
         PP_CUDA(cudaEventRecord(P.in_done, M->s_in));
         PP_CUDA(cudaStreamWaitEvent(M->stream, P.in_done, 0));
-        FwdOut O{d_logp};
         {
             SpanGuard t(M, PP_PROF_FORWARD, M->stream);
-            if (!lane) {                                  // large model: every event takes the exact log-space kernel
-                PP_CUDA(cudaMemsetAsync(d_logp + e0, 0xFF, (e1 - e0) * sizeof(double), M->stream));     // all-ones = NaN
-            } else if (obs_dtype == PP_F32) {
-                LaneBatch<float> B{static_cast<const float*>(obs_base[c]), d_off, P.order.as<int32_t>(),
-                                   P.group_len.as<int32_t>(), P.group_row.as<int64_t>()};
-                rc = launch_forward<float>(M, B, O, sc.n_groups);
-            } else {
-                LaneBatch<double> B{static_cast<const double*>(obs_base[c]), d_off, P.order.as<int32_t>(),
-                                    P.group_len.as<int32_t>(), P.group_row.as<int64_t>()};
-                rc = launch_forward<double>(M, B, O, sc.n_groups);
-            }
+            PP_CUDA(cudaMemsetAsync(d_logp + e0, 0xFF, (e1 - e0) * sizeof(double), M->stream));     // all-ones = NaN: "not resolved"
         }
-        if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
         rc = exact_forward_collect(M, c & 1, d_logp + e0, e1 - e0);
         if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
         PP_CUDA(cudaEventRecord(P.a_done, M->stream));

@@ -154,12 +154,10 @@ int exact_forward_collect(pp_model* M, int slot, const double* d_logp, int64_t n
 }
 
 int exact_forward_run(pp_model* M, int slot, const void* d_obs_base, int32_t obs_dtype, const int64_t* d_off,
-                      const int64_t* h_off, int64_t n_events, double* d_logp) {
+                      int64_t maxlen, double* d_logp) {
     pp_model::PipeSlot& P = M->ps[slot];
     const int32_t n_list = *reinterpret_cast<const int32_t*>(M->h_pin + 8 + slot);
     if (n_list == 0) return PP_OK;
-    int64_t maxlen = 0;
-    for (int64_t e = 0; e < n_events; ++e) maxlen = std::max(maxlen, h_off[e + 1] - h_off[e]);
     const int grid = static_cast<int>(std::min<int64_t>(n_list, static_cast<int64_t>(M->sm_count) * 4));
     // two rolling rows in shared memory are all a score needs; the full-table scratch is the fallback for huge models
     const bool roll = 2 * static_cast<size_t>(M->m) * sizeof(double) + 16 <= M->smem_optin;

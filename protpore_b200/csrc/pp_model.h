@@ -73,10 +73,10 @@ struct pp_model {
     // stream, two slots of per-chunk buffers, pinned scalars the host polls, a pool of timing events
     cudaStream_t s_in = nullptr, s_out = nullptr;
     struct PipeSlot {
-        pp::DevBuf obs, ws, path, order, group_len, group_row, list, counter;
-        cudaEvent_t in_done = nullptr, a_done = nullptr, tb_done = nullptr, out_done = nullptr;
+        pp::DevBuf obs, ws, path, order, group_len, group_row, list, counter, sched;
+        cudaEvent_t in_done = nullptr, a_done = nullptr, tb_done = nullptr, out_done = nullptr, sch_done = nullptr;
     } ps[2];
-    int64_t* h_pin = nullptr;             // [16] pinned
+    int64_t* h_pin = nullptr;             // [32] pinned: path totals, exact-forward counters, schedule read-backs
     struct Span { cudaEvent_t a, b; int slot; };
     std::vector<cudaEvent_t> evpool;
     size_t evnext = 0;
@@ -114,7 +114,7 @@ int rerun_exact_forward(pp_model* M, const void* d_obs_base, int32_t obs_dtype, 
 // slot's a_done event -- run the exact kernel on them.
 int exact_forward_collect(pp_model* M, int slot, const double* d_logp, int64_t n_events);
 int exact_forward_run(pp_model* M, int slot, const void* d_obs_base, int32_t obs_dtype, const int64_t* d_off,
-                      const int64_t* h_off, int64_t n_events, double* d_logp);
+                      int64_t maxlen, double* d_logp);
 
 }  // namespace pp
 

@@ -318,12 +318,13 @@ __device__ __forceinline__ void prof_vit_carries(const double* __restrict__ rec,
                                                  double startval) {
     using L = ProfBlock<P>;
     double v = startval, u = neg_inf();
-    double c[P], d[P], ee, ed;
-    auto load = [&](int i, double (&cc)[P], double (&dd)[P], double& e1, double& e2) {
+    double c[P], d[P], tt, eo, ed;
+    // operands of step i: the ascending chain's block i and the descending chain's block NW - 1 - i
+    auto load = [&](int i, double (&cc)[P], double (&dd)[P], double& t1, double& e1, double& e2) {
         const unsigned char* bu = cb + (i + 1) * L::WS;
         const unsigned char* bd = cb + (NW - i) * L::WS;
-        const double tt = ldb(bu, L::TT), eo = ldb(bu, L::EO);
-        e1 = tt > eo ? tt : eo;
+        t1 = ldb(bu, L::TT);
+        e1 = ldb(bu, L::EO);
         e2 = ldb(bd, L::ED);
 #pragma unroll
         for (int j = 0; j < P; ++j) {
@@ -331,10 +332,12 @@ __device__ __forceinline__ void prof_vit_carries(const double* __restrict__ rec,
             dd[j] = rec[((NW - 1 - i) * P + (P - 1 - j)) * kProfRecDoubles + PR_BK + 1];
         }
     };
-    load(0, c, d, ee, ed);
+    load(0, c, d, tt, eo, ed);
     for (int i = 0; i < NW; ++i) {
-        double cn[P], dn[P], een = 0.0, edn = 0.0;
-        if (i + 1 < NW) load(i + 1, cn, dn, een, edn);
+        // the next step's operands are requested first and touched last: a warp issues in order, and the links below
+        // must not wait behind a load that has nothing to do with them
+        double cn[P], dn[P], ttn = 0.0, eon = 0.0, edn = 0.0;
+        if (i + 1 < NW) load(i + 1, cn, dn, ttn, eon, edn);
         stb(cb + (i + 1) * L::WS, L::VIN, v);
         stb(cb + (NW - i) * L::WS, L::UIN, u);
         double th = v, td = u;
@@ -343,11 +346,13 @@ __device__ __forceinline__ void prof_vit_carries(const double* __restrict__ rec,
             th = __dadd_rn(th, c[j]);
             td = __dadd_rn(td, d[j]);
         }
+        const double ee = tt > eo ? tt : eo;
         v = th > ee ? th : ee;
         u = td > ed ? td : ed;
 #pragma unroll
         for (int j = 0; j < P; ++j) { c[j] = cn[j]; d[j] = dn[j]; }
-        ee = een;
+        tt = ttn;
+        eo = eon;
         ed = edn;
     }
 }

@@ -75,3 +75,17 @@ def test_from_matrix_matches_reference():
     assert [s.name for s in a.states] == [s.name for s in b.states]
     assert np.array_equal(a.dense_transition_matrix(), np.asarray(b.dense_transition_matrix()))
     assert (a.start_index, a.end_index, a.silent_start) == (b.start_index, b.end_index, b.silent_start)
+
+
+def test_profile_plan_recognises_linear_profiles_only():
+    """pp_profile_plan.cpp classifies states from the baked graph alone: the peptide profiles take the register-resident
+    kernels, everything else keeps the run-based ones (the text report needs no GPU)."""
+    from protpore_b200 import _engine
+    for name in ("pro_001_py2", "pro_001_py3", "synth_12"):
+        last = _engine.describe_schedule(util.build_model(name)).splitlines()[-1]
+        assert last.startswith("profile ok"), (name, last)
+    last = _engine.describe_schedule(util.build_model("pro_001_py2")).splitlines()[-1]
+    assert "positions 43 " in last and "end_edges 87" in last and "aliases 1" in last
+    for name in ("toy", "toy_uniform", "toy_infinite"):
+        last = _engine.describe_schedule(util.build_model(name)).splitlines()[-1]
+        assert last.startswith("profile no:"), (name, last)

@@ -555,3 +555,82 @@ def test_kernels_follow_a_changed_emission_kind():
     src = np.repeat(np.arange(len(model.states)), np.diff(b.out_ptr))
     assert np.allclose(edge_s, exp_t[src, b.out_idx], rtol=1e-9, atol=1e-12)
     assert np.allclose(mom_s, mom_o, rtol=1e-9, atol=1e-11)
+
+
+def test_score_batch_equals_the_two_single_calls(models):
+    """pp_score_batch (one upload, one GPU-side bucketing, both sweeps) gives exactly what pp_viterbi_batch and
+    pp_forward_batch give -- host buffers, device buffers, several chunks, and a model the profile kernels do not serve."""
+    import torch
+    for name in ("pro_001_py2", "pro_001_py3", "toy_uniform"):
+        model = models[name]
+        eng = model.engine()
+        lens = events.log_uniform_lengths(1500, 1, 700, seed=11)
+        if name == "toy_uniform":
+            g = util.load_golden(name)
+            obs, offsets = _engine.pack_events([np.asarray(e, dtype=np.float32) for e in util.golden_events(g)], np.float32)
+        else:
+            obs, offsets = eng.sample_events(lens, seed=12)
+        s0, l0, p0 = eng.viterbi_batch(obs, offsets)
+        f0 = eng.forward_batch(obs, offsets)
+        s1, l1, p1, f1 = eng.score_batch(obs, offsets)
+        assert np.array_equal(s0, s1) and np.array_equal(l0, l1) and np.array_equal(p0, p1)
+        assert np.array_equal(f0, f1, equal_nan=True)
+        eng.set_workspace_limit(48 << 20)                    # several chunks
+        try:
+            s2, l2, p2, f2 = eng.score_batch(obs, offsets)
+        finally:
+            eng.set_workspace_limit(32 << 30)
+        assert np.array_equal(s0, s2) and np.array_equal(l0, l2) and np.array_equal(p0, p2) and np.array_equal(f0, f2, equal_nan=True)
+        dev = torch.device("cuda", eng.device)
+        s3, l3, p3, f3 = eng.score_batch(torch.from_numpy(obs).to(dev), torch.from_numpy(offsets).to(dev))
+        assert np.array_equal(s0, s3.cpu().numpy()) and np.array_equal(l0, l3.cpu().numpy())
+        assert np.array_equal(p0, p3.cpu().numpy()) and np.array_equal(f0, f3.cpu().numpy(), equal_nan=True)
+
+
+def test_profile_kernels_equal_run_based_kernels(models):
+    """The register-resident linear-profile kernels and the run-based lane kernels are two implementations of the same
+    arithmetic: bit-identical Viterbi scores, identical paths, forward within 1e-7 relative of each other -- on the
+    untrained profile (point-mass inserts), the Python-3 variant (Normal inserts) and a small synthetic profile."""
+    for name in ("pro_001_py2", "pro_001_py3", "synth_12"):
+        model = models[name]
+        eng = model.engine()
+        assert eng.kernel_info()["family"] == "profile", name
+        lens = events.log_uniform_lengths(2500, 1, 600, seed=21)
+        obs, offsets = eng.sample_events(lens, seed=22)
+        obs[offsets[7]] = 300.0                              # an outlier far from every state
+        s0, l0, p0, f0 = eng.score_batch(obs, offsets)
+        eng.set_kernel_path(1)
+        try:
+            assert eng.kernel_info()["family"] == "lane"
+            s1, l1, p1, f1 = eng.score_batch(obs, offsets)
+        finally:
+            eng.set_kernel_path(0)
+        assert np.array_equal(s0, s1) and np.array_equal(l0, l1) and np.array_equal(p0, p1)
+        fin = np.isfinite(f1)
+        assert np.array_equal(fin, np.isfinite(f0))
+        assert np.max(np.abs(f0[fin] - f1[fin]) / np.maximum(1.0, np.abs(f1[fin]))) < 1e-7   # two MUFU-based sweeps, each < 1e-7 of the reference
+
+
+def test_profile_kernels_after_baum_welch(models):
+    """Training changes every weight and turns the point-mass inserts into Normals (min_std clamp, yahmm.pyx:513): the
+    plan is rebuilt, the profile kernels keep serving the model and keep agreeing with the run-based kernels."""
+    model = util.build_model("pro_001_py2")
+    eng = model.engine()
+    lens = events.uniform_lengths(400, 30, 200, seed=31)
+    obs, offsets = eng.sample_events(lens, seed=32)
+    seqs = [obs[offsets[i]:offsets[i + 1]].astype(np.float64) for i in range(len(lens))]
+    model.train(seqs, max_iterations=1, verbose=False)
+    eng = model.engine()
+    assert eng.kernel_info()["family"] == "profile"
+    s0, l0, p0, f0 = eng.score_batch(obs, offsets)
+    eng.set_kernel_path(1)
+    try:
+        s1, l1, p1, f1 = eng.score_batch(obs, offsets)
+    finally:
+        eng.set_kernel_path(0)
+    assert np.array_equal(s0, s1) and np.array_equal(l0, l1) and np.array_equal(p0, p1)
+    assert np.allclose(f0, f1, rtol=1e-9, atol=1e-9)
+    orc = util.oracle_for(model)
+    for e in range(0, len(lens), 40):
+        s, p, margin = orc.viterbi(seqs[e], with_margin=True)
+        assert s0[e] == s
