@@ -328,16 +328,29 @@ __device__ __forceinline__ void fbb_group(RunPtrs<NE>& P, const unsigned char*& 
     if (ACC) {
 #pragma unroll
         for (int g = 0; g < G; ++g) {
+            // gamma-like terms are products of three factors with independent power-of-two scales: f^ (around 2^480 times
+            // the state's relative forward weight), the backward-scaled term (likewise) and c_r (around 2^-960).  f^ c_r
+            // can leave the double range although the full product does not (a state with a forward weight of 1e-200
+            // and an ordinary backward weight): where that happens for any lane the two large factors are multiplied
+            // first -- they cannot overflow (<= 2^962) -- so a term is lost only if it is not a double at all.  That is the
+            // reference's own limit: exp(f + b - logZ) != 0 (yahmm.pyx:304-326, 4215-4236).
             const double gk = fh[g] * C.c;
+            const bool careful = __any_sync(0xffffffffu, fabs(gk) < 2.3e-308 && fh[g] != 0.0 && C.c != 0.0);
+            if (!careful) {
 #pragma unroll
-            for (int j = 0; j < NE; ++j) t[g * NT1 + j] *= gk;
+                for (int j = 0; j < NE; ++j) t[g * NT1 + j] *= gk;
+            } else {
+#pragma unroll
+                for (int j = 0; j < NE; ++j) t[g * NT1 + j] = (t[g * NT1 + j] * fh[g]) * C.c;
+            }
             if (EMIT) {
-                const double gam = gk * acc[g];
+                const double gam = careful ? (fh[g] * acc[g]) * C.c : gk * acc[g];
                 const double gx = gam * C.xb;
                 t[g * NT1 + NE] = gam;
                 t[g * NT1 + NE + 1] = gx;
                 t[g * NT1 + NE + 2] = gx * C.xb;
-                const uint32_t b = __ballot_sync(0xffffffffu, gam > 0.0);
+                const bool nz = gam > 0.0;                 // "this event gave the state weight"
+                const uint32_t b = __ballot_sync(0xffffffffu, nz);
                 if (A.lane == 0 && b != 0u) {
                     const uint32_t fa = C.flags + static_cast<uint32_t>(st + g * sts) * 4u;
                     uint32_t old;

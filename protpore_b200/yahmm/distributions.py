@@ -135,9 +135,11 @@ class UniformDistribution(Distribution):
         self.summaries.append([items.min(), items.max()])
 
     def summarize_range(self, w_sum, lo, hi):
-        """Batched-path entry (new): one summary from the allreduced statistics of the GPU E-step --
-        total weight of the state and the min / max over every sequence that gave it non-zero weight."""
-        if w_sum == 0 or not (lo <= hi):
+        """Batched-path entry (new): one summary from the allreduced statistics of the GPU E-step -- the min / max over
+        every sequence that gave the state non-zero weight.  The range itself says whether there was such a sequence
+        (the kernels decide that per event, as the reference's `weights.sum() != 0` does, 304-326); the total weight is
+        no substitute: a sum of weights around 1e-300 is not representable next to the scaled sweep's other terms."""
+        if not (lo <= hi):
             return
         self.summaries.append([lo, hi])
 

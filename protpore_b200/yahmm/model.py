@@ -523,7 +523,12 @@ class Model(object):
                 # a table-state family: _train_once_baum_welch already handed it items and posterior weights
                 # (Distribution.summarize); frozen ones (LambdaDistribution by default) are left alone as in the reference
                 if dist.summaries:
-                    dist.from_summaries()
+                    # yahmm.pyx:4326 passes inertia=distribution_inertia to every family; the ones that inherit the base
+                    # from_summaries (the kernel densities, 220) do not take it -- there the reference raises TypeError
+                    try:
+                        dist.from_summaries(inertia=distribution_inertia)
+                    except TypeError:
+                        dist.from_summaries()
         self._push_params()
 
     def _train_viterbi(self, sequences, transition_pseudocount, use_pseudocount, edge_inertia, distribution_inertia):

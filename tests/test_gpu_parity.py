@@ -634,3 +634,28 @@ def test_profile_kernels_after_baum_welch(models):
     for e in range(0, len(lens), 40):
         s, p, margin = orc.viterbi(seqs[e], with_margin=True)
         assert s0[e] == s
+
+
+def test_uniform_range_at_a_tiny_posterior_weight():
+    """UniformDistribution.summarize (yahmm.pyx:304-326) keeps an event's observed range whenever the state's posterior
+    weight is not exactly zero.  Here it is ~1e-203 per row: the compiled reference re-estimates the range from every event
+    (tests/golden/make_golden_tiny_weight.py); the scaled linear-space statistics kernel must decide "non-zero" from the
+    weight itself, not from a product that underflowed on the way."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("mk_tiny", os.path.join(util.GOLDEN, "make_golden_tiny_weight.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    import protpore_b200.yahmm as y
+    g = np.load(os.path.join(util.GOLDEN, "tiny_weight.npz"))
+    model = mod.tiny_weight(y)
+    evs = [g["obs"][g["offsets"][i]:g["offsets"][i + 1]] for i in range(len(g["offsets"]) - 1)]
+    imp = model.train(evs, max_iterations=1, verbose=False)
+    assert model.engine().forward_backward_info()["path"] == "lane"
+    params = np.array([[float(p) for p in s.distribution.parameters[:2]] for s in model.states[:model.silent_start]])
+    assert [s.name for s in model.states[:model.silent_start]] == list(g["names"])
+    iu = list(g["names"]).index("u")
+    assert tuple(params[iu]) == tuple(g["params"][iu]) == (g["obs"].min(), g["obs"].max())
+    assert np.allclose(params, g["params"], rtol=1e-7, atol=1e-9)
+    assert imp == pytest.approx(float(g["improvement"]), rel=1e-7, abs=1e-7)
+    assert np.allclose(model.dense_transition_matrix(), g["dense"], rtol=1e-8, atol=1e-12, equal_nan=True)

@@ -50,6 +50,20 @@ def _worker(rank, world, port, tmp):
         parallel.allreduce_statistics(edge, mom, mm, extra)
         lse = parallel.allreduce_logsumexp(np.array([-5.0 - rank, -7.0, -np.inf]))
         model.apply_m_step(edge, mom, mm)
+        # a trainable family without sufficient statistics cannot be re-estimated from one rank's shard: refused
+        import protpore_b200.yahmm as y
+        kd = y.Model(name="kd")
+        st = y.State(y.GaussianKernelDensity([1.0, 2.0, 3.0], 1.0), name="k")
+        kd.add_state(st)
+        kd.add_transition(kd.start, st, 1.0); kd.add_transition(st, st, 0.5); kd.add_transition(st, kd.end, 0.5)
+        kd.bake()
+        refused = False
+        try:
+            parallel._refuse_unreduced_families(kd)
+        except NotImplementedError:
+            refused = True
+        assert refused
+        parallel._refuse_unreduced_families(model)                      # Normal / Uniform only: fine
         params = np.array([[float(p) for p in s.distribution.parameters[:2]] for s in model.states[:ne]])
         np.savez(os.path.join(tmp, "rank%d.npz" % rank), edge=edge, mom=mom, mm=mm, extra=extra, lse=lse,
                  dense=model.dense_transition_matrix(), params=params, l_edge=local[0], l_mom=local[1], l_mm=local[2],

@@ -63,3 +63,48 @@ def close(a, b, abs_tol=1e-3, rel_tol=1e-6):
     d = np.abs(a[~inf] - b[~inf])
     ok[~inf] = (d <= abs_tol) | (d <= rel_tol * np.abs(b[~inf]))
     return ok
+
+
+def normalise_identities(text):
+    """Model.write output with every state identity (id()-based in the reference, yahmm.pyx:1948) replaced by the ordinal
+    of its first appearance, so that two runs -- or two implementations -- can be compared byte for byte."""
+    lines = text.splitlines()
+    n_states = int(lines[0].split()[-1])
+    ids = {}
+    out = [lines[0]]
+    for ln in lines[1:1 + n_states]:
+        parts = ln.split(" ")
+        ids.setdefault(parts[0], "id%d" % len(ids))
+        out.append(" ".join([ids[parts[0]]] + parts[1:]))
+    for ln in lines[1 + n_states:]:
+        parts = ln.split(" ")
+        out.append(" ".join(parts[:-2] + [ids[parts[-2]], ids[parts[-1]]]))
+    return "\n".join(out) + "\n"
+
+
+def _dist_from_spec(y, spec):
+    t = spec["type"]
+    if t in ("GaussianKernelDensity", "UniformKernelDensity", "TriangleKernelDensity"):
+        return getattr(y, t)(spec["points"], spec["bandwidth"], spec["weights"])
+    if t == "MixtureDistribution":
+        return y.MixtureDistribution([_dist_from_spec(y, p) for p in spec["parts"]], spec["weights"])
+    return getattr(y, t)(*spec["parameters"])
+
+
+def replay_model(log):
+    """Rebuild, on this repository's yahmm, the graph a reference builder constructed (tests/golden/make_golden_pypore.py
+    recorded it node by node and edge by edge in insertion order), and bake it."""
+    import protpore_b200.yahmm as y
+    dists = [_dist_from_spec(y, d) for d in log["dists"]]
+    nodes = log["nodes"]
+    states = [y.State(None if n["dist"] is None else dists[n["dist"]], name=n["name"], weight=n["weight"]) for n in nodes]
+    model = y.Model(name=log["name"], start=states[log["start"]], end=states[log["end"]])
+    from protpore_b200.yahmm import _graph
+    g = _graph.OrderedDiGraph()
+    for s in states:
+        g.add_node(s)
+    for a, b, w, pc, grp in log["edges"]:
+        g.add_edge(states[a], states[b], weight=w, pseudocount=pc, group=grp)
+    model.graph = g
+    model.bake()
+    return model
