@@ -236,6 +236,32 @@ int pp_statsplit_batch(const pp_statsplit_params *prm, int device, const double 
  * since the library was loaded, k_cumsum ms}. */
 int pp_statsplit_profile(int device, double *out4);
 
+/*
+ * ---- Segment alignment ----------------------------------------------------------------------------
+ * Batched cSegmentAligner.align (PyPore/calignment.pyx:20-101; the class SegmentAligner wraps it, PyPore/alignment.py:
+ * 26-47): the Karplus semi-local alignment of a sequence of (mean, std, duration) segments to a model, with a penalty
+ * per unit of model duration skipped or slipped back over.  Model-independent of the HMM handle: takes a device ordinal.
+ *   model            : n >= 2 segments (means, stds, durs) and the two penalties
+ *   seq_*[offsets[e] .. offsets[e+1]) : the segments of sequence e (float64), CSR-style like the HMM calls
+ *   score_out[e]     : score[s-1, n-1] / numpy.sum(seq_durs)   (float64, bit-identical to the reference)
+ *   order_out        : for every segment the model position it is aligned to (the reference's `backtrace` array,
+ *                      which it returns as float64), at the segment's own offset
+ *   status_out[e]    : 0, or a mask of the two cases in which the reference itself is undefined and this library
+ *                      defines the result: bit 0 -- no entry of the last score row exceeds -1, so double_argmax
+ *                      (calignment.pyx:11-18) returns an uninitialised int; defined as the first maximum of the row.
+ *                      bit 1 -- the backtrace stands at model position 0 in a row >= 1, where the reference reads
+ *                      score[i-1, j-1] with an unsigned j = 0 and raises IndexError; defined by skipping that test.
+ */
+typedef struct pp_segment_model {
+    int32_t n;
+    const double *means, *stds, *durs;            /* host pointers, n each */
+    double skip_penalty, backslip_penalty;
+} pp_segment_model;
+
+int pp_segment_align_batch(const pp_segment_model *model, int device, const double *seq_means, const double *seq_stds,
+                           const double *seq_durs, const int64_t *offsets, int64_t n_seqs, int32_t mem,
+                           double *score_out, int32_t *order_out, int32_t *status_out);
+
 /* Number of usable CUDA devices (0 without a driver/GPU; never fails). */
 int pp_device_count(void);
 

@@ -19,6 +19,14 @@ if [ -f "$REF/PyPore/cparsers.pyx" ] && { [ ! -f "$SO2" ] || [ "$REF/PyPore/cpar
       -I"$($PY -c 'import sysconfig;print(sysconfig.get_paths()["include"])')" "$OUT/cparsers.c" -o "$SO2"
   echo "oracle/_ref: built $SO2"
 fi
+# the segment aligner of SURVEY 8f-4 (PyPore/calignment.pyx, cSegmentAligner)
+SO3="$OUT/calignment$EXT"
+if [ -f "$REF/PyPore/calignment.pyx" ] && { [ ! -f "$SO3" ] || [ "$REF/PyPore/calignment.pyx" -nt "$SO3" ] || [ "${1:-}" = "--force" ]; }; then
+  $PY -m cython -2 "$REF/PyPore/calignment.pyx" -o "$OUT/calignment.c"
+  gcc -O2 -fPIC -shared -w -I"$($PY -c 'import numpy;print(numpy.get_include())')" \
+      -I"$($PY -c 'import sysconfig;print(sysconfig.get_paths()["include"])')" "$OUT/calignment.c" -o "$SO3"
+  echo "oracle/_ref: built $SO3"
+fi
 if [ -f "$SO" ] && [ "$SO" -nt "$REF/yahmm/yahmm.pyx" ] && [ "${1:-}" != "--force" ]; then
   echo "oracle/_ref: up to date ($SO)"; exit 0
 fi

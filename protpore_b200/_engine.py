@@ -79,6 +79,7 @@ ABI = [
     ("pp_statsplit_batch", ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp, _vp,
                                           _vp, ctypes.c_int64, _i64p]),
     ("pp_statsplit_profile", ctypes.c_int, [ctypes.c_int, _f64p]),
+    ("pp_segment_align_batch", ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp]),
     ("pp_launch_count", ctypes.c_int64, [_vp]),
     ("pp_model_stream", ctypes.c_uint64, [_vp]),
 ]
@@ -504,3 +505,28 @@ def statsplit_profile(device=0):
     out = (ctypes.c_double * 4)()
     load_library().pp_statsplit_profile(int(device), out)
     return {"statsplit_ms": out[0], "segments_ms": out[1], "launches": int(out[2]), "cumsum_ms": out[3]}
+
+
+class PPSegmentModel(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int32), ("means", _f64p), ("stds", _f64p), ("durs", _f64p),
+                ("skip_penalty", ctypes.c_double), ("backslip_penalty", ctypes.c_double)]
+
+
+def segment_align_batch(model_means, model_stds, model_durs, skip_penalty, backslip_penalty, seq_means, seq_stds, seq_durs,
+                        offsets, device=0):
+    """pp_segment_align_batch on host arrays: (score f64[n], order i32[total], status i32[n])."""
+    lib = load_library()
+    mm, ms, md = (np.ascontiguousarray(a, dtype=np.float64) for a in (model_means, model_stds, model_durs))
+    sm, ss, sd = (np.ascontiguousarray(a, dtype=np.float64) for a in (seq_means, seq_stds, seq_durs))
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    model = PPSegmentModel(len(mm), mm.ctypes.data_as(_f64p), ms.ctypes.data_as(_f64p), md.ctypes.data_as(_f64p),
+                           float(skip_penalty), float(backslip_penalty))
+    score = np.empty(n, dtype=np.float64)
+    order = np.empty(len(sm), dtype=np.int32)
+    status = np.empty(n, dtype=np.int32)
+    rc = lib.pp_segment_align_batch(ctypes.byref(model), int(device), _ptr(sm), _ptr(ss), _ptr(sd), _ptr(offsets), n, PP_MEM_HOST,
+                                    _ptr(score), _ptr(order), _ptr(status))
+    if rc != 0:
+        raise EngineError(rc, lib.pp_last_error().decode())
+    return score, order, status
