@@ -262,6 +262,10 @@ int pp_segment_align_batch(const pp_segment_model *model, int device, const doub
                            const double *seq_durs, const int64_t *offsets, int64_t n_seqs, int32_t mem,
                            double *score_out, int32_t *order_out, int32_t *status_out);
 
+/* Measured float64 issue peaks of `device` (a few milliseconds of independent DADD / DFMA chains): out4 = {float64 adds
+ * per second, float64 FMAs per second, SM count, SM clock in Hz}.  bench.py divides the sweeps' operation rates by these. */
+int pp_device_peaks(int device, double *out4);
+
 /* Number of usable CUDA devices (0 without a driver/GPU; never fails). */
 int pp_device_count(void);
 

@@ -80,6 +80,7 @@ ABI = [
                                           _vp, ctypes.c_int64, _i64p]),
     ("pp_statsplit_profile", ctypes.c_int, [ctypes.c_int, _f64p]),
     ("pp_segment_align_batch", ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp]),
+    ("pp_device_peaks", ctypes.c_int, [ctypes.c_int, _f64p]),
     ("pp_launch_count", ctypes.c_int64, [_vp]),
     ("pp_model_stream", ctypes.c_uint64, [_vp]),
 ]
@@ -126,6 +127,16 @@ def describe_schedule(model):
     if rc < 0:
         raise EngineError(rc, lib.pp_last_error().decode())
     return buf.value.decode()
+
+
+def device_peaks(device=0):
+    """Measured float64 issue peaks: {'dadd_per_s', 'dfma_per_s', 'sms', 'clock_hz'} (pp_device_peaks)."""
+    lib = load_library()
+    out = (ctypes.c_double * 4)()
+    rc = lib.pp_device_peaks(int(device), out)
+    if rc != 0:
+        raise EngineError(rc, lib.pp_last_error().decode())
+    return {"dadd_per_s": out[0], "dfma_per_s": out[1], "sms": int(out[2]), "clock_hz": out[3]}
 
 
 def device_count():

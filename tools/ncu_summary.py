@@ -4,7 +4,8 @@ import csv, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr = rows[0]
+hdr, units = rows[0], rows[1]          # the second row of the raw page carries each metric's unit
+unit_of = dict(zip(hdr, units))
 keys = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "smsp__inst_executed.sum", "sm__inst_executed.avg.per_cycle_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
@@ -18,7 +19,7 @@ for r in rows[2:]:
     print("==", d.get("Kernel Name", "")[:60])
     for k in keys:
         if k in d and d[k] not in ("", "n/a"):
-            print("   %-70s %s" % (k, d[k]))
+            print("   %-70s %s %s" % (k, d[k], unit_of.get(k, "")))
     st = [(h, float(v.replace(",", ""))) for h, v in d.items()
           if "smsp__average_warps_issue_stalled" in h and h.endswith("_per_issue_active.ratio") and v not in ("", "n/a")]
     st.sort(key=lambda t: -t[1])
