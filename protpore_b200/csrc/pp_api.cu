@@ -748,6 +748,18 @@ static void spans_collect(pp_model* M) {
     M->evnext = 0;
 }
 
+// After a failed batched call nothing may be left in flight on the handle's streams (async copies into the caller's
+// buffers, reads of the caller's observations) and the timing spans of the aborted call must not leak into the next one.
+static int settle(pp_model* M, int rc) {
+    if (rc != PP_OK && rc != PP_ERR_CAPACITY) {
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+        M->spans.clear();
+        M->evnext = 0;
+    }
+    return rc;
+}
+
 // One pipeline for the batched Viterbi decode (logp_out / path_* set), the batched forward score (fwd_out set) or both
 // (pp_score_batch): one upload, one bucketing.
 static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const int64_t* offsets, int64_t n_events,
@@ -1005,7 +1017,7 @@ int pp_viterbi_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     if (!lane_kernels_fit(M))                         // large model: exact state-parallel kernels
         return viterbi_batch_state(M, obs, obs_dtype, offsets, n_events, mem, logp_out, path_len_out, path_out,
                                    path_capacity, path_total);
-    return score_pipeline(M, obs, obs_dtype, offsets, n_events, mem, logp_out, path_len_out, path_out, path_capacity, path_total, nullptr);
+    return settle(M, score_pipeline(M, obs, obs_dtype, offsets, n_events, mem, logp_out, path_len_out, path_out, path_capacity, path_total, nullptr));
 }
 
 int pp_score_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int64_t* offsets, int64_t n_events, int32_t mem,
@@ -1027,8 +1039,8 @@ int pp_score_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int64_
         return rc;
     }
     std::memset(M->prof, 0, sizeof M->prof);
-    return score_pipeline(M, obs, obs_dtype, offsets, n_events, mem, viterbi_logp_out, path_len_out, path_out, path_capacity,
-                          path_total, forward_logp_out);
+    return settle(M, score_pipeline(M, obs, obs_dtype, offsets, n_events, mem, viterbi_logp_out, path_len_out, path_out, path_capacity,
+                                    path_total, forward_logp_out));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1041,7 +1053,7 @@ int pp_forward_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     std::memset(M->prof, 0, sizeof M->prof);
     if (n_events == 0) return PP_OK;
     if (lane_kernels_fit(M))
-        return score_pipeline(M, obs, obs_dtype, offsets, n_events, mem, nullptr, nullptr, nullptr, 0, nullptr, logp_out);
+        return settle(M, score_pipeline(M, obs, obs_dtype, offsets, n_events, mem, nullptr, nullptr, nullptr, 0, nullptr, logp_out));
     // large model, or emissions from a table: every event takes the exact log-space kernel
     const size_t ob = obs_dtype == PP_F32 ? 4 : 8;
     const bool host = mem == PP_MEM_HOST;

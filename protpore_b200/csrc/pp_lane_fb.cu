@@ -4,22 +4,21 @@
 
 namespace pp {
 
-static const void* g_owner = nullptr;
+static ArenaOwner g_arena;
 
 size_t lane_fb_smem(int n_slots, int n_w, int ne) { return fb_smem_bytes(n_slots, n_w, ne, kLaneWarps); }
 
 int lane_fb_launch(const LaneSched& S, const FbSched& F, const LaneBatchAny& B, int grid, size_t smem,
                    cudaStream_t stream, const double* arena, size_t arena_doubles, const void* owner) {
-    cudaError_t e;
-    if (g_owner != owner) {
-        e = cudaMemcpyToSymbolAsync(c_arena, arena, arena_doubles * sizeof(double), 0, cudaMemcpyHostToDevice, stream);
-        if (e != cudaSuccess) return static_cast<int>(e);
-        g_owner = owner;
-    }
-    e = cudaFuncSetAttribute(k_fb_lane<kLaneWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return static_cast<int>(e);
-    k_fb_lane<kLaneWarps><<<grid, kLaneWarps * 32, smem, stream>>>(S, F, B);
-    return static_cast<int>(cudaGetLastError());
+    return g_arena.run(
+        owner, stream,
+        [&] { return cudaMemcpyToSymbolAsync(c_arena, arena, arena_doubles * sizeof(double), 0, cudaMemcpyHostToDevice, stream); },
+        [&] {
+            cudaError_t e = cudaFuncSetAttribute(k_fb_lane<kLaneWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) return static_cast<int>(e);
+            k_fb_lane<kLaneWarps><<<grid, kLaneWarps * 32, smem, stream>>>(S, F, B);
+            return static_cast<int>(cudaGetLastError());
+        });
 }
 
 int lane_fb_finalize(const double* acc, int n_ctas, int n_slots, const int32_t* acc_map, const int32_t* acc_log2,
@@ -30,6 +29,6 @@ int lane_fb_finalize(const double* acc, int n_ctas, int n_slots, const int32_t* 
     return static_cast<int>(cudaGetLastError());
 }
 
-void lane_fb_invalidate(const void* owner) { if (g_owner == owner) g_owner = nullptr; }
+void lane_fb_invalidate(const void* owner) { g_arena.invalidate(owner); }
 
 }  // namespace pp

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "pp_device_common.cuh"
 
 namespace pp {
@@ -46,6 +48,39 @@ __host__ __device__ inline size_t lane_smem_bytes2(int n_slots, int n_low, int n
            static_cast<size_t>(32) * 33 * 4 + static_cast<size_t>(warps) * kLanes * sizeof(int32_t) + 64;
 }
 
+
+// One __constant__ arena per kernel translation unit (and device) holds the run records of ONE model at a time.  Handles
+// driven from different host threads take turns: run() serialises "upload the image if another model's is resident, then
+// launch" under a mutex, and orders the upload behind the last launch that read the old image (an event), so a kernel
+// never has its run records replaced under it.
+struct ArenaOwner {
+    static constexpr int kMaxDevices = 64;
+    std::mutex mu;
+    const void* owner[kMaxDevices] = {};
+    cudaEvent_t last[kMaxDevices] = {};
+    template <typename Upload, typename Launch>
+    int run(const void* who, cudaStream_t stream, Upload upload, Launch launch) {
+        std::lock_guard<std::mutex> lock(mu);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev = dev < 0 || dev >= kMaxDevices ? 0 : dev;
+        if (owner[dev] != who) {
+            if (last[dev]) cudaStreamWaitEvent(stream, last[dev], 0);
+            const cudaError_t e = upload();
+            if (e != cudaSuccess) return static_cast<int>(e);
+            owner[dev] = who;
+        }
+        const int rc = launch();
+        if (!last[dev]) cudaEventCreateWithFlags(&last[dev], cudaEventDisableTiming);
+        if (last[dev]) cudaEventRecord(last[dev], stream);
+        return rc;
+    }
+    void invalidate(const void* who) {
+        std::lock_guard<std::mutex> lock(mu);
+        for (int d = 0; d < kMaxDevices; ++d)
+            if (owner[d] == who) owner[d] = nullptr;
+    }
+};
 
 // Launchers.  Each kernel translation unit owns a __constant__ arena holding the run records of ONE model;
 // `arena` / `arena_doubles` / `owner` let it re-upload (stream-ordered) when another handle's image is resident.

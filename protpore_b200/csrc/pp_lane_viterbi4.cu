@@ -3,23 +3,22 @@
 
 namespace pp {
 
-static const void* g_owner = nullptr;
+static ArenaOwner g_arena;
 
 int lane_viterbi4_launch(const LaneSched& S, const LaneBatchAny& B, const VitOut& O, int n_groups, size_t smem,
                      cudaStream_t stream, const double* arena, size_t arena_doubles, const void* owner) {
-    cudaError_t e;
-    if (g_owner != owner) {
-        e = cudaMemcpyToSymbolAsync(c_arena, arena, arena_doubles * sizeof(double), 0, cudaMemcpyHostToDevice, stream);
-        if (e != cudaSuccess) return static_cast<int>(e);
-        g_owner = owner;
-    }
-    e = cudaFuncSetAttribute(k_viterbi_lane<kLaneWarps, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return static_cast<int>(e);
-    k_viterbi_lane<kLaneWarps, 4><<<n_groups, kLaneWarps * 32, smem, stream>>>(S, B, O);
-    return static_cast<int>(cudaGetLastError());
+    return g_arena.run(
+        owner, stream,
+        [&] { return cudaMemcpyToSymbolAsync(c_arena, arena, arena_doubles * sizeof(double), 0, cudaMemcpyHostToDevice, stream); },
+        [&] {
+            cudaError_t e = cudaFuncSetAttribute(k_viterbi_lane<kLaneWarps, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) return static_cast<int>(e);
+            k_viterbi_lane<kLaneWarps, 4><<<n_groups, kLaneWarps * 32, smem, stream>>>(S, B, O);
+            return static_cast<int>(cudaGetLastError());
+        });
 }
 
-void lane_viterbi4_invalidate(const void* owner) { if (g_owner == owner) g_owner = nullptr; }
+void lane_viterbi4_invalidate(const void* owner) { g_arena.invalidate(owner); }
 
 #ifdef PP_PHASE_TIMING
 int lane_debug_phase_cycles(unsigned long long* out, int reset) {

@@ -116,8 +116,8 @@ std::string lower_model(const pp_model_desc& d, int warps, Lowered* low) {
         }
         low->state_n_edges[l] = static_cast<int32_t>(low->low_src.size()) - low->state_edge_begin[l];
         const bool is_final_end = low->end_final_only && l == d.end_index;
-        if (!is_final_end && low->state_n_edges[l] > 255)
-            return "state " + std::to_string(l) + " has more than 255 usable in-edges (8-bit traceback pointers)";
+        // (no limit here: the state-parallel kernels store 16-bit source states; the lane kernels' 4-bit ordinals are
+        //  checked below, where such a model only loses the lane path)
         if (!is_final_end) low->max_item_edges = std::max(low->max_item_edges, low->state_n_edges[l]);
     }
 
@@ -433,10 +433,17 @@ std::string refresh_params(const pp_model_desc& d, Lowered* low) {
             }
         }
     }
+    // a state that switched to / from table emissions changes which kernel family serves the model: lower again
+    // (compared BEFORE the records are refreshed: fill_emissions overwrites the kinds)
+    for (int k = 0; k < d.silent_start; ++k)
+        if ((d.emit_kind[k] == PP_EMIT_TABLE) != (low->emis[k].kind == EMIS_TABLE)) {
+            Lowered fresh;
+            std::string e = lower_model(d, low->warps, &fresh);
+            if (e.empty()) *low = std::move(fresh);
+            return e;
+        }
     std::string err = fill_emissions(d, low);
     if (!err.empty()) return err;
-    for (int k = 0; k < d.silent_start; ++k)                      // a state that switched to / from table emissions: lower again
-        if ((d.emit_kind[k] == PP_EMIT_TABLE) != (low->emis[k].kind == EMIS_TABLE)) return lower_model(d, low->warps, low);
     for (int q = 0; q < 2; ++q)
         for (size_t i = 0; i < low->low_csr.size(); ++i) {
             low->edges_logp[q][i].val = d.in_logp[low->low_csr[i]];

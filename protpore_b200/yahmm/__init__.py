@@ -6,7 +6,8 @@ include/protpore_b200.h; see protpore_b200/yahmm/model.py.
 """
 from .distributions import (Distribution, NormalDistribution, UniformDistribution, LogNormalDistribution,  # noqa: F401
                             ExponentialDistribution, LambdaDistribution, GaussianKernelDensity,
-                            UniformKernelDensity, TriangleKernelDensity, MixtureDistribution)
+                            UniformKernelDensity, TriangleKernelDensity, MixtureDistribution, ExtremeValueDistribution,
+                            GammaDistribution, InverseGammaDistribution, DiscreteDistribution, MultivariateDistribution)
 from .state import State  # noqa: F401
 from .model import Model, log, exp, log_probability  # noqa: F401
 

@@ -430,3 +430,155 @@ class MixtureDistribution(Distribution):
             if w > i:
                 return d.sample()
             i -= w
+
+
+# ---- the remaining families of the reference ---------------------------------------------------
+# Not used by any model builder in the repository.  They evaluate their density exactly as the reference does and reach
+# the GPU sweeps through the emission-table path like every family the kernels do not evaluate themselves
+# (device_params() -> PP_EMIT_TABLE).  Parameter re-estimation is implemented where the reference's is a closed form
+# (Discrete); Gamma / InverseGamma / ExtremeValue keep their parameters under training unless thawed by a user subclass
+# (the reference's Gamma fit is an iterative scheme built on scipy.special, yahmm.pyx:886-1119).
+
+class ExtremeValueDistribution(Distribution):
+    """Generalised extreme value distribution (yahmm.pyx:690-724); frozen by default as in the reference."""
+
+    def __init__(self, mu, sigma, epsilon, frozen=True):
+        self.parameters = [float(mu), float(sigma), float(epsilon)]
+        self.summaries = []
+        self.name = "ExtremeValueDistribution"
+        self.frozen = frozen
+
+    def log_probability(self, symbol):
+        mu, sigma, epsilon = self.parameters
+        t = (float(symbol) - mu) / sigma
+        if epsilon == 0:
+            return -math.log(sigma) - t - math.exp(-t)
+        return -math.log(sigma) + math.log(1 + epsilon * t) * (-1. / epsilon - 1) - (1 + epsilon * t) ** (-1. / epsilon)
+
+
+class GammaDistribution(Distribution):
+    """Gamma distribution, shape / rate parameterisation (yahmm.pyx:844-1119)."""
+
+    def __init__(self, alpha, beta, frozen=False):
+        self.parameters = [alpha, beta]
+        self.summaries = []
+        self.name = "GammaDistribution"
+        self.frozen = frozen
+
+    def log_probability(self, symbol):
+        alpha, beta = self.parameters
+        return _log(beta) * alpha - math.lgamma(alpha) + _log(symbol) * (alpha - 1) - beta * symbol
+
+    def sample(self):
+        return random.gammavariate(self.parameters[0], 1.0 / self.parameters[1])
+
+    def from_sample(self, items, weights=None, inertia=0.0):
+        # the reference fits by an iterative scheme on scipy.special (886-1023); here the method of moments, which is
+        # that scheme's starting point (943-951)
+        if self.frozen or len(items) == 0:
+            return
+        items = numpy.asarray(items, dtype=numpy.float64)
+        weights = numpy.ones_like(items) if weights is None else numpy.asarray(weights, dtype=numpy.float64)
+        if weights.sum() == 0:
+            return
+        mean = numpy.average(items, weights=weights)
+        var = numpy.average((items - mean) ** 2, weights=weights)
+        if var <= 0:
+            return
+        alpha, beta = mean * mean / var, mean / var
+        self.parameters = [self.parameters[0] * inertia + alpha * (1 - inertia), self.parameters[1] * inertia + beta * (1 - inertia)]
+
+
+class InverseGammaDistribution(GammaDistribution):
+    """1 / X ~ Gamma(alpha, beta) (yahmm.pyx:1121-1184)."""
+
+    def __init__(self, alpha, beta, frozen=False):
+        GammaDistribution.__init__(self, alpha, beta, frozen)
+        self.name = "InverseGammaDistribution"
+
+    def log_probability(self, symbol):
+        return GammaDistribution.log_probability(self, 1.0 / symbol)
+
+    def sample(self):
+        return 1.0 / GammaDistribution.sample(self)
+
+    def from_sample(self, items, weights=None, inertia=0.0):
+        GammaDistribution.from_sample(self, 1.0 / numpy.asarray(items, dtype=numpy.float64), weights, inertia)
+
+
+class DiscreteDistribution(Distribution):
+    """Characters (here: the float values an observation can take) and their probabilities (yahmm.pyx:1186-1330)."""
+
+    def __init__(self, characters, frozen=False):
+        self.parameters = [characters]
+        self.summaries = [{}, 0]
+        self.name = "DiscreteDistribution"
+        self.frozen = frozen
+
+    def log_probability(self, symbol):
+        return _log(self.parameters[0].get(symbol, 0))
+
+    def sample(self):
+        rand = random.random()
+        for key, value in self.parameters[0].items():
+            if value >= rand:
+                return key
+            rand -= value
+
+    def from_sample(self, items, weights=None, inertia=0.0):
+        if self.frozen or len(items) == 0:
+            return
+        weights = numpy.ones(len(items)) if weights is None else numpy.asarray(weights, dtype=numpy.float64)
+        if weights.sum() == 0:
+            return
+        counts = {}
+        for x, w in zip(items, weights):
+            counts[x] = counts.get(x, 0.0) + w
+        total = sum(counts.values())
+        prior = self.parameters[0]
+        keys = set(prior) | set(counts)
+        self.parameters = [{k: prior.get(k, 0.0) * inertia + counts.get(k, 0.0) / total * (1 - inertia) for k in keys}]
+
+    def summarize(self, items, weights=None):
+        weights = numpy.ones(len(items)) if weights is None else numpy.asarray(weights, dtype=numpy.float64)
+        for x, w in zip(items, weights):
+            self.summaries[0][x] = self.summaries[0].get(x, 0.0) + w
+        self.summaries[1] += float(weights.sum())
+
+    def from_summaries(self, inertia=0.0):
+        if self.frozen or self.summaries[1] == 0:
+            return
+        counts, total = self.summaries
+        prior = self.parameters[0]
+        keys = set(prior) | set(counts)
+        self.parameters = [{k: prior.get(k, 0.0) * inertia + counts.get(k, 0.0) / total * (1 - inertia) for k in keys}]
+        self.summaries = [{}, 0]
+
+
+class MultivariateDistribution(Distribution):
+    """Independent components over tuple-valued observations (yahmm.pyx:1823-1917).  The batched GPU calls take scalar
+    observations; a model with such a state is served symbol by symbol through `log_probability` on the host."""
+
+    def __init__(self, distributions, weights=None, frozen=False):
+        n = len(distributions)
+        weights = numpy.array(weights) if weights else numpy.ones(n)
+        self.parameters = [distributions, weights]
+        self.summaries = []
+        self.name = "MultivariateDistribution"
+        self.frozen = frozen
+
+    def __str__(self):
+        return "MultivariateDistribution({})".format([str(d) for d in self.parameters[0]]).replace("'", "")
+
+    def log_probability(self, symbol):
+        return sum(d.log_probability(obs) * w for d, obs, w in zip(self.parameters[0], symbol, self.parameters[1]))
+
+    def sample(self):
+        return [d.sample() for d in self.parameters[0]]
+
+    def from_sample(self, items, weights=None, inertia=0.0):
+        if self.frozen:
+            return
+        items = numpy.asarray(items)
+        for i, d in enumerate(self.parameters[0]):
+            d.from_sample(items[:, i], weights=weights, inertia=inertia)
