@@ -246,6 +246,17 @@ int upload_model(pp_model* M) {
     PP_CUDA(upload(&M->d_state_pshift, L.state_pshift, s));
     PP_CUDA(upload(&M->d_state_pmul, L.state_pmul, s));
     PP_CUDA(upload(&M->d_state_pmask, std::vector<int32_t>(static_cast<size_t>(M->m), (1 << L.ptr_bits) - 1), s));
+    {   // traceback lookup of the run-based lane kernels: one record per state + the lowered in-edge sources
+        std::vector<TraceRec> rec(static_cast<size_t>(M->m));
+        for (int k = 0; k < M->m; ++k)
+            rec[k] = TraceRec{static_cast<uint32_t>(L.state_edge_begin[k]), static_cast<uint32_t>(std::max(0, L.state_pword.empty() ? 0 : L.state_pword[k])),
+                              static_cast<uint32_t>(L.state_pmul.empty() ? 1 : L.state_pmul[k]),
+                              static_cast<uint32_t>(((L.state_pshift.empty() ? 0 : L.state_pshift[k]) << 4) | ((1 << L.ptr_bits) - 1 & 15))};
+        std::vector<uint16_t> src(L.low_src.begin(), L.low_src.end());
+        PP_CUDA(upload(&M->d_trace_rec[0], rec, s));
+        PP_CUDA(upload(&M->d_trace_src[0], src, s));
+        M->n_trace_src[0] = static_cast<int32_t>(src.size());
+    }
     if (M->plan.ok) {
         const ProfilePlan& F = M->plan;
         PP_CUDA(upload(&M->d_prof_rec_v, F.rec_v, s));
@@ -258,6 +269,15 @@ int upload_model(pp_model* M) {
         PP_CUDA(upload(&M->d_prof_unit_mask, F.unit_mask, s));
         PP_CUDA(upload(&M->d_prof_slot_begin, F.slot_begin, s));
         PP_CUDA(upload(&M->d_prof_slot_src, F.slot_src, s));
+        std::vector<TraceRec> rec(static_cast<size_t>(M->m));
+        for (int k = 0; k < M->m; ++k)
+            rec[k] = TraceRec{static_cast<uint32_t>(F.slot_begin[k]), static_cast<uint32_t>(F.unit_off[k]), static_cast<uint32_t>(F.unit_bytes[k]),
+                              static_cast<uint32_t>((F.unit_shift[k] << 4) | (F.unit_mask[k] & 15))};
+        std::vector<uint16_t> src(F.slot_src.size());
+        for (size_t i = 0; i < src.size(); ++i) src[i] = static_cast<uint16_t>(F.slot_src[i] < 0 ? 0 : F.slot_src[i]);
+        PP_CUDA(upload(&M->d_trace_rec[1], rec, s));
+        PP_CUDA(upload(&M->d_trace_src[1], src, s));
+        M->n_trace_src[1] = static_cast<int32_t>(src.size());
     }
     PP_CUDA(upload(&M->d_in_ptr, M->in_ptr, s));
     PP_CUDA(upload(&M->d_in_src, M->in_src, s));
@@ -566,12 +586,12 @@ void pp_model_destroy(pp_model* M) {
                       &M->d_path_off, &M->d_path, &M->d_scan_tmp, &M->d_logp, &M->d_bw_wtab, &M->d_acc_map,
                       &M->d_acc_log2, &M->d_fb_acc, &M->d_fb_scratch, &M->d_fb_ctl, &M->d_fb_minmax, &M->d_etab_own, &M->d_gcol, &M->d_prof_rec_v, &M->d_prof_rec_f, &M->d_prof_end_v, &M->d_prof_end_f,
                       &M->d_prof_unit_off, &M->d_prof_unit_bytes, &M->d_prof_unit_shift, &M->d_prof_unit_mask, &M->d_prof_slot_begin,
-                      &M->d_prof_slot_src, &M->d_state_pmask};
+                      &M->d_prof_slot_src, &M->d_state_pmask, &M->d_trace_rec[0], &M->d_trace_rec[1], &M->d_trace_src[0], &M->d_trace_src[1]};
     for (DevBuf* b : bufs) b->release();
     release_state_model(M);
     for (int b = 0; b < 2; ++b) {
         pp_model::PipeSlot& P = M->ps[b];
-        DevBuf* pb[] = {&P.obs, &P.ws, &P.path, &P.order, &P.group_len, &P.group_row, &P.list, &P.counter, &P.sched};
+        DevBuf* pb[] = {&P.obs, &P.ws, &P.path, &P.order, &P.group_len, &P.group_row, &P.list, &P.counter, &P.sched, &P.path_tmp};
         for (DevBuf* x : pb) x->release();
         cudaEvent_t evs[] = {P.in_done, P.a_done, P.tb_done, P.out_done, P.sch_done};
         for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
@@ -818,6 +838,7 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
     std::vector<int64_t> cuts;
     DevSchedule pre;                                       // device-resident batch: the whole batch is bucketed first
     bool pre_scheduled = false;
+    int64_t total_obs_dev = 0;
     if (host) {
         // two chunks in flight: each gets half the workspace; host batches are cut fine enough for the copies to overlap
         cuts = make_chunks(h_off, n_events, row_bytes, M->ws_limit / 2, ob, size_t(96) << 20);
@@ -829,6 +850,10 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
         add_host_ms(t0);
         const int64_t minlen = M->h_pin[16], maxlen = M->h_pin[17], rows = M->h_pin[18];
         if (minlen < 1 || maxlen > 0x7ffffff0LL) return bad_event_error(M, d_off, n_events, M->stream);
+        int64_t ends[2] = {0, 0};
+        PP_CUDA(cudaMemcpy(&ends[0], d_off, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        PP_CUDA(cudaMemcpy(&ends[1], d_off + n_events, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        total_obs_dev = ends[1] - ends[0];
         if (static_cast<size_t>(rows) * row_bytes <= M->ws_limit) {
             cuts = {0, n_events};
             pre_scheduled = true;
@@ -847,17 +872,11 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
 
     auto trace_args = [&](int c) {
         pp_model::PipeSlot& P = M->ps[c & 1];
-        if (use_profile(M))
-            return TraceArgs{P.ws.as<uint32_t>(), P.order.as<int32_t>(), P.group_row.as<int64_t>(), d_off, d_score,
-                             M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), M->d_prof_slot_begin.as<int32_t>(),
-                             M->d_prof_slot_src.as<int32_t>(), M->d_prof_unit_off.as<int32_t>(), M->d_prof_unit_bytes.as<int32_t>(),
-                             M->d_prof_unit_shift.as<int32_t>(), M->d_prof_unit_mask.as<int32_t>(), M->m, M->ne, M->start, 1,
-                             static_cast<int64_t>(row_bytes)};
+        const int f = use_profile(M) ? 1 : 0;
         return TraceArgs{P.ws.as<uint32_t>(), P.order.as<int32_t>(), P.group_row.as<int64_t>(), d_off, d_score,
-                         M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), M->d_state_edge_begin.as<int32_t>(),
-                         M->d_low_src.as<int32_t>(), M->d_state_pword.as<int32_t>(), M->d_state_pmul.as<int32_t>(),
-                         M->d_state_pshift.as<int32_t>(), M->d_state_pmask.as<int32_t>(), M->m, M->ne, M->start,
-                         M->low.end_final_only ? 1 : 0, static_cast<int64_t>(row_bytes)};
+                         M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), M->d_trace_rec[f].as<TraceRec>(),
+                         M->d_trace_src[f].as<uint16_t>(), M->m, M->n_trace_src[f], M->ne, M->start,
+                         (f || M->low.end_final_only) ? 1 : 0, static_cast<int64_t>(row_bytes), cuts[c]};
     };
     // phase B of chunk c: the host learns the chunk's path total (and how many events the scaled forward sweep could
     // not resolve), then the traceback write pass, the exact forward re-run and the copy out
@@ -885,7 +904,11 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
             }
             {
                 SpanGuard t(M, PP_PROF_TRACEBACK, M->stream);
-                k_traceback<<<(nslots + 127) / 128, 128, 0, M->stream>>>(trace_args(c), d_plen, M->d_path_off.as<int64_t>(), dst, nslots);
+                if (M->h_pin[24 + (c & 1)] == 0)      // every path fitted its scratch region: pack them
+                    k_traceback_compact<<<M->sm_count * 16, 256, 0, M->stream>>>(trace_args(c), d_plen, M->d_path_off.as<int64_t>(),
+                                                                                  P.path_tmp.as<uint16_t>(), dst, info[c].e1);
+                else                                  // an unusually long path: walk again, writing in place
+                    k_traceback<<<(nslots + 127) / 128, 128, trace_smem_bytes(M->m, M->n_trace_src[use_profile(M) ? 1 : 0]), M->stream>>>(trace_args(c), d_plen, M->d_path_off.as<int64_t>(), dst, nslots);
             }
             PP_CUDA(cudaGetLastError());
             ++M->launches;
@@ -937,6 +960,15 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
             cudaDeviceSynchronize();
             return PP_ERR_NOMEM;
         }
+        if (want_vit && path_out) {
+            const size_t tmp_elems = 4 * static_cast<size_t>((host || h_off) ? (h_off[e1] - h_off[e0]) : total_obs_dev) + 64 * static_cast<size_t>(e1 - e0);
+            if (P.path_tmp.cap < tmp_elems * sizeof(uint16_t) || P.counter.cap < 16) {
+                PP_CUDA(cudaStreamSynchronize(M->stream));
+                PP_CUDA(P.counter.reserve(16));
+                if (P.path_tmp.reserve(tmp_elems * sizeof(uint16_t)) != cudaSuccess) { cudaGetLastError(); set_error("cannot allocate %zu bytes of traceback scratch", tmp_elems * 2); return PP_ERR_NOMEM; }
+            }
+            M->h_pin[24 + (c & 1)] = 0;
+        }
         if (P.ws.cap < ws) {                                  // growing the table frees memory: nothing may be in flight on it
             PP_CUDA(cudaStreamSynchronize(M->stream));
             if (P.ws.reserve(ws) != cudaSuccess) { cudaGetLastError(); set_error("cannot allocate %zu bytes of workspace", ws); return PP_ERR_NOMEM; }
@@ -962,7 +994,15 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
         if (want_vit) {
             SpanGuard t(M, PP_PROF_TRACEBACK, M->stream);
             const int nslots = sc.n_groups * kLanes;
-            k_traceback<<<(nslots + 127) / 128, 128, 0, M->stream>>>(trace_args(c), d_plen, nullptr, nullptr, nslots);
+            if (path_out) {
+                // one walk: states into per-event scratch regions (4 n + 64 entries each), lengths into d_plen
+                PP_CUDA(cudaMemsetAsync(P.counter.p, 0, 4, M->stream));
+                k_traceback_walk<<<(nslots + 127) / 128, 128, trace_smem_bytes(M->m, M->n_trace_src[use_profile(M) ? 1 : 0]), M->stream>>>(trace_args(c), d_plen, P.path_tmp.as<uint16_t>(),
+                                                                              P.counter.as<int32_t>(), nslots);
+                PP_CUDA(cudaMemcpyAsync(M->h_pin + 24 + (c & 1), P.counter.p, 4, cudaMemcpyDeviceToHost, M->stream));
+            } else {
+                k_traceback<<<(nslots + 127) / 128, 128, trace_smem_bytes(M->m, M->n_trace_src[use_profile(M) ? 1 : 0]), M->stream>>>(trace_args(c), d_plen, nullptr, nullptr, nslots);
+            }
             PP_CUDA(cudaGetLastError());
             ++M->launches;
             const int64_t ne = e1 - e0;                       // exclusive scan of max(len, 0) over the chunk's events

@@ -138,8 +138,21 @@ __device__ __forceinline__ void fill_tile(ObsT* xt, const ObsT* __restrict__ obs
 
 // ------------------------------------------------------------------------------------------
 // Traceback (yahmm.pyx:3632-3646): one thread per event walks the ordinals back from (n, end).
-// Pass 1 (path == nullptr) counts, pass 2 writes the path front-to-back at path_off[ev].
+//   k_traceback        path == nullptr: counts only; else writes the path front-to-back at path_off[ev] (needs the count)
+//   k_traceback_walk   ONE walk: counts and writes the states, back to front, into a per-event scratch region of
+//                      4 n + 64 entries (a path visits ~1.7 states per observation; an event that needs more raises
+//                      *overflow and the caller falls back to the two passes); k_traceback_compact then copies the
+//                      paths to their final, densely packed place with coalesced accesses.
+// The per-state lookup (where the ordinal sits in a pointer row, where the state's in-edge list starts) is one 16-byte
+// record, staged in shared memory together with the in-edge sources when the model is small enough, so a step of the
+// walk costs one global load: the ordinal itself.
 // ------------------------------------------------------------------------------------------
+struct __attribute__((aligned(16))) TraceRec {
+    uint32_t edge_begin;               // first entry of the state's in-edge (slot) list
+    uint32_t byte_off;                 // byte of lane 0's ordinal inside a pointer row
+    uint32_t stride;                   // bytes per lane of the unit holding it
+    uint32_t shift_mask;               // bit position << 4 | mask (ordinals are at most 4 bits wide)
+};
 struct TraceArgs {
     const uint32_t* ptr;
     const int32_t* order;
@@ -148,18 +161,60 @@ struct TraceArgs {
     const double* score;
     const int32_t* end_state;
     const int32_t* end_ord;
-    const int32_t* state_edge_begin;   // [m]
-    const int32_t* low_src;            // [lowered edges]
-    const int32_t* state_pword;        // [m] byte offset of lane 0's ordinal byte inside a pointer row
-    const int32_t* state_pmul;         // [m] bytes per lane of the unit holding it
-    const int32_t* state_pshift;       // [m] bit position inside that byte
-    const int32_t* state_pmask;        // [m] mask of the ordinal (a field may run into the next byte of its unit)
-    int32_t m, ne, start, end_final_only;
+    const TraceRec* rec;               // [m]
+    const uint16_t* src;               // [lowered edges / slots] source state
+    int32_t m, n_src, ne, start, end_final_only;
     int64_t row_bytes;                 // bytes per pointer row (all 32 lanes)
+    int64_t e0;                        // first event of the chunk (scratch regions are laid out from it)
+};
+constexpr int kTraceSmemBytes = 40 * 1024;
+// dynamic shared memory a traceback launch needs: both tables when they fit, else none (they are read through L1)
+inline size_t trace_smem_bytes(int m, int n_src) {
+    const size_t need = static_cast<size_t>(m) * sizeof(TraceRec) + static_cast<size_t>(n_src) * sizeof(uint16_t);
+    return need <= kTraceSmemBytes ? need : 0;
+}
+
+struct TraceTables {
+    const TraceRec* rec;
+    const uint16_t* src;
+    // stage both tables in shared memory when they fit (all threads of the block call this)
+    __device__ __forceinline__ TraceTables(const TraceArgs& T, unsigned char* smem) {
+        const size_t need = static_cast<size_t>(T.m) * sizeof(TraceRec) + static_cast<size_t>(T.n_src) * sizeof(uint16_t);
+        if (need <= kTraceSmemBytes) {
+            TraceRec* r = reinterpret_cast<TraceRec*>(smem);
+            uint16_t* q = reinterpret_cast<uint16_t*>(r + T.m);
+            for (int i = threadIdx.x; i < T.m; i += blockDim.x) r[i] = T.rec[i];
+            for (int i = threadIdx.x; i < T.n_src; i += blockDim.x) q[i] = T.src[i];
+            __syncthreads();
+            rec = r;
+            src = q;
+        } else {
+            rec = T.rec;
+            src = T.src;
+        }
+    }
 };
 
-static __global__ void k_traceback(const TraceArgs T, int64_t* __restrict__ path_len, const int64_t* __restrict__ path_off,
-                            uint16_t* __restrict__ path, int n_slots) {
+// one step back from (px, py): the state the stored ordinal leads to
+__device__ __forceinline__ int trace_step(const TraceArgs& T, const TraceTables& tab, const uint8_t* base, size_t row_stride, int lane,
+                                          int px, int py, bool first, int ev) {
+    const TraceRec R = tab.rec[py];
+    int ord;
+    if (first && T.end_final_only) ord = T.end_ord[ev];
+    else {
+        const uint8_t* a = base + static_cast<size_t>(px) * row_stride + R.byte_off + lane * R.stride;
+        const int sh = R.shift_mask >> 4, mk = R.shift_mask & 15;
+        uint32_t u = a[0];
+        if ((mk << sh) > 0xff) u |= static_cast<uint32_t>(a[1]) << 8;
+        ord = static_cast<int>((u >> sh) & mk);
+    }
+    return tab.src[R.edge_begin + ord];
+}
+
+static __global__ void __launch_bounds__(128) k_traceback(const TraceArgs T, int64_t* __restrict__ path_len,
+                                                          const int64_t* __restrict__ path_off, uint16_t* __restrict__ path, int n_slots) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const TraceTables tab(T, smem);
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_slots) return;
     const int ev = T.order[slot];
@@ -183,23 +238,71 @@ static __global__ void k_traceback(const TraceArgs T, int64_t* __restrict__ path
     bool first = true;
     while (px != 0 || py != T.start) {
         if (out) out[pos--] = static_cast<uint16_t>(py);
-        int ord;
-        if (first && T.end_final_only) ord = T.end_ord[ev];
-        else {
-            const uint8_t* a = base + static_cast<size_t>(px) * row_stride + T.state_pword[py] + lane * T.state_pmul[py];
-            const int sh = T.state_pshift[py], mk = T.state_pmask[py];
-            uint32_t u = a[0];
-            if ((mk << sh) > 0xff) u |= static_cast<uint32_t>(a[1]) << 8;
-            ord = static_cast<int>((u >> sh) & mk);
-        }
+        const int src = trace_step(T, tab, base, row_stride, lane, px, py, first, ev);
         first = false;
-        const int src = T.low_src[T.state_edge_begin[py] + ord];
         if (py < T.ne) --px;                             // emitting states point into the previous row
         py = src;
         ++len;
     }
     if (out) out[pos] = static_cast<uint16_t>(py);
     else path_len[ev] = len;
+}
+
+__device__ __forceinline__ int64_t trace_tmp_base(const TraceArgs& T, int ev) {
+    return 4 * (T.offsets[ev] - T.offsets[T.e0]) + 64 * static_cast<int64_t>(ev - T.e0);
+}
+
+static __global__ void __launch_bounds__(128) k_traceback_walk(const TraceArgs T, int64_t* __restrict__ path_len,
+                                                               uint16_t* __restrict__ tmp, int32_t* __restrict__ overflow, int n_slots) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const TraceTables tab(T, smem);
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const int ev = T.order[slot];
+    if (ev < 0) return;
+    const int g = slot >> 5, lane = slot & 31;
+    if (T.score[ev] == neg_inf()) {
+        path_len[ev] = -1;
+        return;
+    }
+    const int n = static_cast<int>(T.offsets[ev + 1] - T.offsets[ev]);
+    const size_t row_stride = static_cast<size_t>(T.row_bytes);
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(T.ptr) + static_cast<size_t>(T.group_row[g]) * row_stride;
+    const int64_t cap = 4 * static_cast<int64_t>(n) + 64;          // a multiple of 4: the region ends on an 8-byte boundary
+    uint64_t* out = reinterpret_cast<uint64_t*>(tmp + trace_tmp_base(T, ev) + cap);   // filled back to front, 4 states per store
+    int64_t len = 0;
+    int px = n, py = T.end_state[ev];
+    bool first = true;
+    uint64_t word = 0;
+    for (;;) {
+        ++len;
+        word = (word << 16) | static_cast<uint64_t>(py);            // the four latest states, the latest in the low bits:
+        if ((len & 3) == 0 && len <= cap) *--out = word;            // little-endian, so memory reads front to back
+        if (px == 0 && py == T.start) break;
+        const int src = trace_step(T, tab, base, row_stride, lane, px, py, first, ev);
+        first = false;
+        if (py < T.ne) --px;
+        py = src;
+    }
+    if ((len & 3) != 0 && len <= cap) *--out = word << (16 * (4 - (len & 3)));   // the last, partial word: its states in the upper slots
+    if (len > cap) atomicAdd(overflow, 1);
+    path_len[ev] = len;
+}
+
+// one warp per event: scratch region -> the event's place in the packed output
+static __global__ void k_traceback_compact(const TraceArgs T, const int64_t* __restrict__ path_len, const int64_t* __restrict__ path_off,
+                                           const uint16_t* __restrict__ tmp, uint16_t* __restrict__ path, int64_t e1) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t ev = T.e0 + wid; ev < e1; ev += nw) {
+        const int64_t len = path_len[ev];
+        if (len <= 0) continue;
+        const int64_t cap = 4 * (T.offsets[ev + 1] - T.offsets[ev]) + 64;
+        const uint16_t* s = tmp + trace_tmp_base(T, static_cast<int>(ev)) + cap - len;
+        uint16_t* d = path + path_off[ev];
+        for (int64_t i = lane; i < len; i += 32) d[i] = s[i];
+    }
 }
 
 constexpr int kFwdTargetExp = 900;   // a row's largest value is steered to ~2^900

@@ -40,6 +40,9 @@ struct pp_model {
     int kernel_path = 0;
     pp::DevBuf d_prof_rec_v, d_prof_rec_f, d_prof_end_v, d_prof_end_f, d_prof_unit_off, d_prof_unit_bytes, d_prof_unit_shift,
         d_prof_unit_mask, d_prof_slot_begin, d_prof_slot_src, d_state_pmask;
+    // traceback lookup tables (pp_device_common.cuh TraceRec) of the two kernel families; n entries of the source tables
+    pp::DevBuf d_trace_rec[2], d_trace_src[2];
+    int32_t n_trace_src[2] = {0, 0};
 
     // device copy of the schedule
     pp::DevBuf d_edges_logp[2], d_edges_prob[2], d_emis, d_warp_run_ranges;
@@ -73,7 +76,7 @@ struct pp_model {
     // stream, two slots of per-chunk buffers, pinned scalars the host polls, a pool of timing events
     cudaStream_t s_in = nullptr, s_out = nullptr;
     struct PipeSlot {
-        pp::DevBuf obs, ws, path, order, group_len, group_row, list, counter, sched;
+        pp::DevBuf obs, ws, path, order, group_len, group_row, list, counter, sched, path_tmp;
         cudaEvent_t in_done = nullptr, a_done = nullptr, tb_done = nullptr, out_done = nullptr, sch_done = nullptr;
     } ps[2];
     int64_t* h_pin = nullptr;             // [32] pinned: path totals, exact-forward counters, schedule read-backs
