@@ -535,8 +535,10 @@ k_fb_lane(const LaneSched S, const FbSched F, const LaneBatchAny B) {
         __syncthreads();                                         // previous group is done with shared memory
         if (threadIdx.x == 0) s_group = atomicAdd(F.counter, 1);
         __syncthreads();
-        const int g = s_group;
-        if (g >= F.n_groups) break;
+        if (s_group >= F.n_groups) break;
+        // ticket -> group through a stride coprime to the number of groups (1 = sorted by length, the default; see
+        // fb_batch_lane for the measurement behind it)
+        const int g = static_cast<int>((static_cast<long long>(s_group) * F.group_stride) % F.n_groups);
         const int ev = B.order[g * kLanes + lane];
         const int64_t off = ev >= 0 ? B.offsets[ev] : 0;
         const int n = ev >= 0 ? static_cast<int>(B.offsets[ev + 1] - off) : 0;

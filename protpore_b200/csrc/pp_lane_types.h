@@ -102,6 +102,7 @@ struct FbSched {
     int32_t n_acc_slots;
     int32_t row_slots;                       // ns + ne + 1 (the last slot holds S_r)
     int32_t n_groups;
+    int32_t group_stride;                    // coprime to n_groups: ticket t works on group (t * stride) mod n_groups
     unsigned char* scratch;                  // per CTA: (max_len + 1) rows of row_slots * 256 bytes
     size_t scratch_stride;                   // bytes per CTA
     double* acc;                             // per CTA: n_acc_slots * 32 doubles, zeroed by the host
