@@ -589,7 +589,7 @@ void pp_model_destroy(pp_model* M) {
                       &M->d_prof_slot_src, &M->d_state_pmask, &M->d_trace_rec[0], &M->d_trace_rec[1], &M->d_trace_src[0], &M->d_trace_src[1]};
     for (DevBuf* b : bufs) b->release();
     release_state_model(M);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kPipeSlots; ++b) {
         pp_model::PipeSlot& P = M->ps[b];
         DevBuf* pb[] = {&P.obs, &P.ws, &P.path, &P.order, &P.group_len, &P.group_row, &P.list, &P.counter, &P.sched, &P.path_tmp};
         for (DevBuf* x : pb) x->release();
@@ -714,7 +714,7 @@ void pp_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ---------------------------------------------------------------------------------------------
 // Chunk pipeline shared by pp_viterbi_batch and pp_forward_batch.  A batch is cut into chunks of whole events; chunk c
-// uses buffer slot c & 1.  Per chunk, in enqueue order:
+// uses buffer slot c % kPipeSlots.  Per chunk, in enqueue order:
 //   s_in    : upload of the chunk's bucketing arrays and (host buffers) its observations            -> in_done
 //   stream  : phase A = sweep kernel(s) + whatever produces the scalar the host needs (path total,
 //             number of events for the exact re-run), copied to pinned memory                        -> a_done
@@ -726,14 +726,14 @@ static int pipe_init(pp_model* M) {
     if (M->s_in) return PP_OK;
     PP_CUDA(cudaStreamCreateWithFlags(&M->s_in, cudaStreamNonBlocking));
     PP_CUDA(cudaStreamCreateWithFlags(&M->s_out, cudaStreamNonBlocking));
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kPipeSlots; ++b) {
         PP_CUDA(cudaEventCreateWithFlags(&M->ps[b].in_done, cudaEventDisableTiming));
         PP_CUDA(cudaEventCreateWithFlags(&M->ps[b].a_done, cudaEventDisableTiming));
         PP_CUDA(cudaEventCreateWithFlags(&M->ps[b].tb_done, cudaEventDisableTiming));
         PP_CUDA(cudaEventCreateWithFlags(&M->ps[b].out_done, cudaEventDisableTiming));
         PP_CUDA(cudaEventCreateWithFlags(&M->ps[b].sch_done, cudaEventDisableTiming));
     }
-    PP_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&M->h_pin), 32 * sizeof(int64_t), cudaHostAllocDefault));
+    PP_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&M->h_pin), 64 * sizeof(int64_t), cudaHostAllocDefault));
     return PP_OK;
 }
 
@@ -840,8 +840,8 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
     bool pre_scheduled = false;
     int64_t total_obs_dev = 0;
     if (host) {
-        // two chunks in flight: each gets half the workspace; host batches are cut fine enough for the copies to overlap
-        cuts = make_chunks(h_off, n_events, row_bytes, M->ws_limit / 2, ob, size_t(96) << 20);
+        // kPipeSlots chunks in flight share the workspace; host batches are cut fine enough for the copies to overlap
+        cuts = make_chunks(h_off, n_events, row_bytes, M->ws_limit / kPipeSlots, ob, size_t(96) << 20);
     } else {
         const auto t0 = clock_now();
         rc = device_schedule_enqueue(M, 0, d_off, 0, n_events, M->stream, &pre);
@@ -861,7 +861,7 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
             store.resize(static_cast<size_t>(n_events) + 1);
             PP_CUDA(cudaMemcpy(store.data(), d_off, store.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
             h_off = store.data();
-            cuts = make_chunks(h_off, n_events, row_bytes, M->ws_limit / 2, 0, size_t(96) << 20);
+            cuts = make_chunks(h_off, n_events, row_bytes, M->ws_limit / kPipeSlots, 0, size_t(96) << 20);
         }
     }
     const int n_chunks = static_cast<int>(cuts.size()) - 1;
@@ -871,7 +871,7 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
     std::vector<ChunkInfo> info(n_chunks);
 
     auto trace_args = [&](int c) {
-        pp_model::PipeSlot& P = M->ps[c & 1];
+        pp_model::PipeSlot& P = M->ps[c % kPipeSlots];
         const int f = use_profile(M) ? 1 : 0;
         return TraceArgs{P.ws.as<uint32_t>(), P.order.as<int32_t>(), P.group_row.as<int64_t>(), d_off, d_score,
                          M->d_end_state.as<int32_t>(), M->d_end_ord.as<int32_t>(), M->d_trace_rec[f].as<TraceRec>(),
@@ -881,17 +881,17 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
     // phase B of chunk c: the host learns the chunk's path total (and how many events the scaled forward sweep could
     // not resolve), then the traceback write pass, the exact forward re-run and the copy out
     auto finish = [&](int c) -> int {
-        pp_model::PipeSlot& P = M->ps[c & 1];
+        pp_model::PipeSlot& P = M->ps[c % kPipeSlots];
         PP_CUDA(cudaEventSynchronize(P.a_done));
         if (want_fwd) {
-            int r = exact_forward_run(M, c & 1, info[c].obs_base, obs_dtype, d_off + info[c].e0, info[c].maxlen, d_fwd + info[c].e0);
+            int r = exact_forward_run(M, c % kPipeSlots, info[c].obs_base, obs_dtype, d_off + info[c].e0, info[c].maxlen, d_fwd + info[c].e0);
             if (r != PP_OK) return r;
         }
         if (!want_vit) {
             PP_CUDA(cudaEventRecord(P.tb_done, M->stream));
             return PP_OK;
         }
-        const int64_t last_off = M->h_pin[(c & 1) * 2], last_len = M->h_pin[(c & 1) * 2 + 1];
+        const int64_t last_off = M->h_pin[(c % kPipeSlots) * 2], last_len = M->h_pin[(c % kPipeSlots) * 2 + 1];
         const int64_t chunk_total = last_off + (last_len > 0 ? last_len : 0);
         const int nslots = info[c].n_groups * kLanes;
         if (path_out && !overflow && base + chunk_total <= path_capacity) {
@@ -904,7 +904,7 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
             }
             {
                 SpanGuard t(M, PP_PROF_TRACEBACK, M->stream);
-                if (M->h_pin[24 + (c & 1)] == 0)      // every path fitted its scratch region: pack them
+                if (M->h_pin[32 + (c % kPipeSlots)] == 0)      // every path fitted its scratch region: pack them
                     k_traceback_compact<<<M->sm_count * 16, 256, 0, M->stream>>>(trace_args(c), d_plen, M->d_path_off.as<int64_t>(),
                                                                                   P.path_tmp.as<uint16_t>(), dst, info[c].e1);
                 else                                  // an unusually long path: walk again, writing in place
@@ -929,14 +929,14 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
     };
 
     for (int c = 0; c < n_chunks; ++c) {
-        pp_model::PipeSlot& P = M->ps[c & 1];
+        pp_model::PipeSlot& P = M->ps[c % kPipeSlots];
         const int64_t e0 = cuts[c], e1 = cuts[c + 1];
         // ---- copy in and bucketing (the slot's buffers were last used by chunk c - 2: its traceback must be through)
         DevSchedule sc = pre;
         if (!pre_scheduled) {
             const auto t0 = clock_now();
             PP_CUDA(cudaStreamWaitEvent(M->s_in, P.tb_done, 0));
-            rc = device_schedule_enqueue(M, c & 1, d_off, e0, e1, M->s_in, &sc);
+            rc = device_schedule_enqueue(M, c % kPipeSlots, d_off, e0, e1, M->s_in, &sc);
             if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
             PP_CUDA(cudaEventRecord(P.sch_done, M->s_in));
             add_host_ms(t0);
@@ -951,7 +951,7 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
         }
         PP_CUDA(cudaEventRecord(P.in_done, M->s_in));
         if (!pre_scheduled) PP_CUDA(cudaEventSynchronize(P.sch_done));
-        const int64_t minlen = M->h_pin[16 + 4 * (c & 1)], maxlen = M->h_pin[17 + 4 * (c & 1)], total_rows = M->h_pin[18 + 4 * (c & 1)];
+        const int64_t minlen = M->h_pin[16 + 4 * (c % kPipeSlots)], maxlen = M->h_pin[17 + 4 * (c % kPipeSlots)], total_rows = M->h_pin[18 + 4 * (c % kPipeSlots)];
         if (minlen < 1 || maxlen > 0x7ffffff0LL) { cudaDeviceSynchronize(); return bad_event_error(M, d_off, n_events, M->stream); }
         info[c] = {e0, e1, sc.n_groups, maxlen, d_obs_base};
         const size_t ws = static_cast<size_t>(total_rows) * row_bytes;
@@ -967,7 +967,7 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
                 PP_CUDA(P.counter.reserve(16));
                 if (P.path_tmp.reserve(tmp_elems * sizeof(uint16_t)) != cudaSuccess) { cudaGetLastError(); set_error("cannot allocate %zu bytes of traceback scratch", tmp_elems * 2); return PP_ERR_NOMEM; }
             }
-            M->h_pin[24 + (c & 1)] = 0;
+            M->h_pin[32 + (c % kPipeSlots)] = 0;
         }
         if (P.ws.cap < ws) {                                  // growing the table frees memory: nothing may be in flight on it
             PP_CUDA(cudaStreamSynchronize(M->stream));
@@ -988,7 +988,7 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
                 rc = launch_forward(M, A, FwdOut{d_fwd}, sc.n_groups);
             }
             if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
-            rc = exact_forward_collect(M, c & 1, d_fwd + e0, e1 - e0);
+            rc = exact_forward_collect(M, c % kPipeSlots, d_fwd + e0, e1 - e0);
             if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
         }
         if (want_vit) {
@@ -999,7 +999,7 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
                 PP_CUDA(cudaMemsetAsync(P.counter.p, 0, 4, M->stream));
                 k_traceback_walk<<<(nslots + 127) / 128, 128, trace_smem_bytes(M->m, M->n_trace_src[use_profile(M) ? 1 : 0]), M->stream>>>(trace_args(c), d_plen, P.path_tmp.as<uint16_t>(),
                                                                               P.counter.as<int32_t>(), nslots);
-                PP_CUDA(cudaMemcpyAsync(M->h_pin + 24 + (c & 1), P.counter.p, 4, cudaMemcpyDeviceToHost, M->stream));
+                PP_CUDA(cudaMemcpyAsync(M->h_pin + 32 + (c % kPipeSlots), P.counter.p, 4, cudaMemcpyDeviceToHost, M->stream));
             } else {
                 k_traceback<<<(nslots + 127) / 128, 128, trace_smem_bytes(M->m, M->n_trace_src[use_profile(M) ? 1 : 0]), M->stream>>>(trace_args(c), d_plen, nullptr, nullptr, nslots);
             }
@@ -1016,8 +1016,8 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
             }
             PP_CUDA(cub::DeviceScan::ExclusiveSum(M->d_scan_tmp.p, tmp, it, d_poff, static_cast<int>(ne), M->stream));
             ++M->launches;
-            PP_CUDA(cudaMemcpyAsync(M->h_pin + (c & 1) * 2, d_poff + ne - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
-            PP_CUDA(cudaMemcpyAsync(M->h_pin + (c & 1) * 2 + 1, d_plen + e1 - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
+            PP_CUDA(cudaMemcpyAsync(M->h_pin + (c % kPipeSlots) * 2, d_poff + ne - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
+            PP_CUDA(cudaMemcpyAsync(M->h_pin + (c % kPipeSlots) * 2 + 1, d_plen + e1 - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, M->stream));
         }
         PP_CUDA(cudaEventRecord(P.a_done, M->stream));
         if (c >= 1) { rc = finish(c - 1); if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; } }
@@ -1115,17 +1115,17 @@ int pp_forward_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
     const int n_chunks = static_cast<int>(cuts.size()) - 1;
     std::vector<const void*> obs_base(n_chunks);
     auto finish = [&](int c) -> int {
-        pp_model::PipeSlot& P = M->ps[c & 1];
+        pp_model::PipeSlot& P = M->ps[c % kPipeSlots];
         PP_CUDA(cudaEventSynchronize(P.a_done));
         const int64_t e0 = cuts[c], e1 = cuts[c + 1];
         int64_t maxlen = 0;
         for (int64_t e = e0; e < e1; ++e) maxlen = std::max(maxlen, h_off[e + 1] - h_off[e]);
-        int r = exact_forward_run(M, c & 1, obs_base[c], obs_dtype, d_off + e0, maxlen, d_logp + e0);
+        int r = exact_forward_run(M, c % kPipeSlots, obs_base[c], obs_dtype, d_off + e0, maxlen, d_logp + e0);
         PP_CUDA(cudaEventRecord(P.tb_done, M->stream));
         return r;
     };
     for (int c = 0; c < n_chunks; ++c) {
-        pp_model::PipeSlot& P = M->ps[c & 1];
+        pp_model::PipeSlot& P = M->ps[c % kPipeSlots];
         const int64_t e0 = cuts[c], e1 = cuts[c + 1];
         PP_CUDA(cudaStreamWaitEvent(M->s_in, P.tb_done, 0));
         obs_base[c] = obs;
@@ -1142,7 +1142,7 @@ int pp_forward_batch(pp_model* M, const void* obs, int32_t obs_dtype, const int6
             SpanGuard t(M, PP_PROF_FORWARD, M->stream);
             PP_CUDA(cudaMemsetAsync(d_logp + e0, 0xFF, (e1 - e0) * sizeof(double), M->stream));     // all-ones = NaN: "not resolved"
         }
-        rc = exact_forward_collect(M, c & 1, d_logp + e0, e1 - e0);
+        rc = exact_forward_collect(M, c % kPipeSlots, d_logp + e0, e1 - e0);
         if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; }
         PP_CUDA(cudaEventRecord(P.a_done, M->stream));
         if (c >= 1) { rc = finish(c - 1); if (rc != PP_OK) { cudaDeviceSynchronize(); return rc; } }

@@ -21,6 +21,8 @@ enum pp_prof_slot {
     PP_PROF_SLOTS = 8
 };
 
+constexpr int kPipeSlots = 3;   // chunks in flight: copy-in of chunk c overlaps the sweeps of c - 1 and the traceback / copy-out of c - 2
+
 struct pp_model {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -78,8 +80,8 @@ struct pp_model {
     struct PipeSlot {
         pp::DevBuf obs, ws, path, order, group_len, group_row, list, counter, sched, path_tmp;
         cudaEvent_t in_done = nullptr, a_done = nullptr, tb_done = nullptr, out_done = nullptr, sch_done = nullptr;
-    } ps[2];
-    int64_t* h_pin = nullptr;             // [32] pinned: path totals, exact-forward counters, schedule read-backs
+    } ps[3];                              // kPipeSlots
+    int64_t* h_pin = nullptr;             // [64] pinned: per slot s -- path totals [2s, 2s+1], exact-forward counter [8+s], schedule read-back [16+4s ..], scratch overflow [32+s]
     struct Span { cudaEvent_t a, b; int slot; };
     std::vector<cudaEvent_t> evpool;
     size_t evnext = 0;
