@@ -841,7 +841,13 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
     int64_t total_obs_dev = 0;
     if (host) {
         // kPipeSlots chunks in flight share the workspace; host batches are cut fine enough for the copies to overlap
-        cuts = make_chunks(h_off, n_events, row_bytes, M->ws_limit / kPipeSlots, ob, size_t(96) << 20);
+        // ... but a chunk cannot finish before its longest group of 32 events has been swept row by row: keep the
+        // chunk's share of work per resident CTA (2 per SM) at >= 4x that tail, or mixed-length batches (config 5:
+        // 20 .. 20,000 segments) pay the tail once per chunk
+        int64_t longest = 1;
+        for (int64_t e = 0; e < n_events; ++e) longest = std::max(longest, h_off[e + 1] - h_off[e]);
+        const size_t tail_rule = static_cast<size_t>(longest) * kLanes * 2 * M->sm_count * 4 * ob;
+        cuts = make_chunks(h_off, n_events, row_bytes, M->ws_limit / kPipeSlots, ob, std::max(size_t(96) << 20, tail_rule));
     } else {
         const auto t0 = clock_now();
         rc = device_schedule_enqueue(M, 0, d_off, 0, n_events, M->stream, &pre);
