@@ -282,6 +282,15 @@ int pp_profile_get(const pp_model *model, double *out, int32_t n);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t pp_launch_count(const pp_model *model);
 
+/* Guard mode (environment PP_GUARD=1 when the library is loaded): every device buffer of the library carries 4 KiB of a
+ * known pattern in front of and behind its payload.  pp_debug_check_guards synchronises the device and returns the number
+ * of buffers whose guards were overwritten (0 = clean; -1 guard mode off; -2 CUDA error), pp_last_error names the first;
+ * pp_debug_guard_count = buffers currently guarded.  Stands in for compute-sanitizer's memcheck in the GPU test-suite. */
+int pp_debug_check_guards(void);
+int pp_debug_guard_count(void);
+/* Writes one byte behind and eight bytes in front of a scratch buffer and checks that both are reported: PP_OK if so. */
+int pp_debug_guard_selftest(void);
+
 /* CUDA stream the handle enqueues on (a cudaStream_t as an integer), for timing with CUDA events. */
 uint64_t pp_model_stream(const pp_model *model);
 

@@ -82,6 +82,9 @@ ABI = [
     ("pp_segment_align_batch", ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp]),
     ("pp_device_peaks", ctypes.c_int, [ctypes.c_int, _f64p]),
     ("pp_launch_count", ctypes.c_int64, [_vp]),
+    ("pp_debug_check_guards", ctypes.c_int, []),
+    ("pp_debug_guard_count", ctypes.c_int, []),
+    ("pp_debug_guard_selftest", ctypes.c_int, []),
     ("pp_model_stream", ctypes.c_uint64, [_vp]),
 ]
 
@@ -137,6 +140,15 @@ def device_peaks(device=0):
     if rc != 0:
         raise EngineError(rc, lib.pp_last_error().decode())
     return {"dadd_per_s": out[0], "dfma_per_s": out[1], "sms": int(out[2]), "clock_hz": out[3]}
+
+
+def check_guards():
+    """Guard mode (PP_GUARD=1): number of device buffers whose guard bytes were overwritten; raises if any were."""
+    lib = load_library()
+    rc = lib.pp_debug_check_guards()
+    if rc != 0:
+        raise EngineError(rc, lib.pp_last_error().decode())
+    return lib.pp_debug_guard_count()
 
 
 def device_count():

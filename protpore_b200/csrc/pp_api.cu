@@ -694,6 +694,57 @@ int pp_debug_phase_cycles(unsigned long long* out, int reset) { return lane_debu
 #endif
 
 int64_t pp_launch_count(const pp_model* M) { return M ? M->launches : 0; }
+
+int pp_debug_check_guards(void) {
+    if (!GuardRegistry::enabled()) { set_error("guard mode is off (set PP_GUARD=1 before the library allocates)"); return -1; }
+    if (cudaDeviceSynchronize() != cudaSuccess) { set_error("device error before the guard check: %s", cudaGetErrorString(cudaGetLastError())); return -2; }
+    GuardRegistry& G = GuardRegistry::get();
+    std::lock_guard<std::mutex> lk(G.mu);
+    std::vector<unsigned char> h(2 * kGuardBytes + 256);
+    int bad = 0;
+    for (const auto& kv : G.live) {
+        const char* base = static_cast<const char*>(kv.first);
+        const size_t bytes = kv.second, payload = (bytes + 255) / 256 * 256, back = payload - bytes + kGuardBytes;
+        if (cudaMemcpy(h.data(), base, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(h.data() + kGuardBytes, base + kGuardBytes + bytes, back, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error("cannot read the guards of a %zu-byte buffer", bytes);
+            return -2;
+        }
+        for (size_t i = 0; i < kGuardBytes + back; ++i)
+            if (h[i] != kGuardPattern) {
+                if (!bad) set_error("guard of a %zu-byte device buffer overwritten: %s the buffer, byte %zu", bytes,
+                                    i < kGuardBytes ? "in front of" : "behind", i < kGuardBytes ? kGuardBytes - i : i - kGuardBytes);
+                ++bad;
+                break;
+            }
+    }
+    return bad;
+}
+
+int pp_debug_guard_selftest(void) {
+    if (!GuardRegistry::enabled()) { set_error("guard mode is off"); return -1; }
+    const int before = pp_debug_check_guards();
+    if (before != 0) return -3;
+    DevBuf b;
+    PP_CUDA(b.reserve(1000));
+    PP_CUDA(cudaMemset(b.p, 0, 1001));                     // one byte too many
+    const int behind = pp_debug_check_guards();
+    b.release();
+    PP_CUDA(b.reserve(1000));
+    PP_CUDA(cudaMemset(static_cast<char*>(b.p) - 8, 0, 8));  // eight bytes in front
+    const int front = pp_debug_check_guards();
+    b.release();
+    const int after = pp_debug_check_guards();
+    if (behind == 1 && front == 1 && after == 0) return PP_OK;
+    set_error("guard self-test: behind %d, in front %d, after %d (expected 1, 1, 0)", behind, front, after);
+    return -3;
+}
+
+int pp_debug_guard_count(void) {
+    GuardRegistry& G = GuardRegistry::get();
+    std::lock_guard<std::mutex> lk(G.mu);
+    return static_cast<int>(G.live.size());
+}
 uint64_t pp_model_stream(const pp_model* M) { return M ? reinterpret_cast<uint64_t>(M->stream) : 0; }
 
 int pp_profile_get(const pp_model* M, double* out, int32_t n) {

@@ -20,3 +20,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "reference" in item.keywords and not have_ref:
             item.add_marker(skip_ref)
+
+
+@pytest.fixture(autouse=True)
+def _device_buffer_guards(request):
+    """With PP_GUARD=1 (GPU box; compute-sanitizer is closed on the pool) every device buffer of the library carries guard
+    bytes; after each GPU test they are compared, so an out-of-bounds write fails the test that made it."""
+    yield
+    if os.environ.get("PP_GUARD", "0") not in ("", "0") and "gpu" in request.keywords:
+        from protpore_b200 import _engine
+        _engine.check_guards()

@@ -6,6 +6,8 @@ arithmetic is the only documented exception -- the oracle reports it as margin 0
 BIT-identical (same float64 operations in the same order); forward log-probabilities within
 1e-3 nats absolute or 1e-6 relative (util.close) -- in practice ~1e-9 relative.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -659,3 +661,14 @@ def test_uniform_range_at_a_tiny_posterior_weight():
     assert np.allclose(params, g["params"], rtol=1e-7, atol=1e-9)
     assert imp == pytest.approx(float(g["improvement"]), rel=1e-7, abs=1e-7)
     assert np.allclose(model.dense_transition_matrix(), g["dense"], rtol=1e-8, atol=1e-12, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_guard_mode_catches_writes_outside_a_buffer():
+    """PP_GUARD=1 (tests/conftest.py checks the guards after every GPU test): the check must actually see a write one byte
+    behind and a write in front of a buffer.  Without PP_GUARD the entry point says so and the test is skipped."""
+    lib = _engine.load_library()
+    if os.environ.get("PP_GUARD", "0") in ("", "0"):
+        assert lib.pp_debug_check_guards() == -1
+        pytest.skip("guard mode off")
+    assert lib.pp_debug_guard_selftest() == 0, lib.pp_last_error().decode()
