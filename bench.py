@@ -250,7 +250,12 @@ def bench_baum_welch(args, model, rank, world, local):
         # k_fb_lane per column: forward E FMA + ne emissions; backward E x (mul, add, mul) + ne products + 3 ne moment terms,
         # all float64 multiply-add class operations; HBM: the scaled forward column written and read back once + the input
         flops_col = E + ne + 3 * E + ne + 3 * ne
-        bytes_col = 2.0 * (m + 1) * 8 + 4
+        fb_path = eng.forward_backward_info()["path"]
+        if fb_path == "profile":                     # k_profile_fb: 5 values per position (padded to whole warps of 4) + S_r
+            kp = (eng.kernel_info()["positions"] + 3) // 4 * 4
+            fb_kernel, bytes_col = "k_profile_fb", 2.0 * (5 * kp + 1) * 8 + 4
+        else:
+            fb_kernel, bytes_col = "k_fb_lane", 2.0 * (m + 1) * 8 + 4
         achieved = bytes_col * total_obs / (k_ms * 1e-3) / 1e9
         if not args.no_e2e:
             e2e = {"value": cells * world * e2e_steps / dt2 / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(obs_h.nbytes + off_h.nbytes),
@@ -264,13 +269,13 @@ def bench_baum_welch(args, model, rank, world, local):
                           "warmup": warm, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
                           "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "ours",
                           "config": {"workload": "pro_001, {} events/GPU of {}-{} segments, one Baum-Welch iteration on "
-                                     "device-resident events; lane-per-event forward-backward kernel (k_fb_lane)".format(n_ev, args.min_len, args.max_len),
+                                     "device-resident events; lane-per-event forward-backward kernel ({})".format(n_ev, args.min_len, args.max_len, fb_kernel),
                                      "collective": "one all_gather of {} doubles per rank, reduced on the device".format(E + 5 * ne + 2),
                                      "l2_policy": "events ({:.2f} GB) and the forward scratch exceed the 126 MB L2".format(total_obs * 4 / 1e9)},
                           "events_used": used, "sum_loglik": ll, "ranks_hold_identical_model": identical,
                           "e_step_kernel_ms_per_step": k_ms, "non_kernel_ms_per_step": dt / args.steps * 1e3 - k_ms,
                           "e_step_gcups": cells / (k_ms * 1e-3) / 1e9,
-                          "roofline": {"bound": "hbm", "kernel": "k_fb_lane", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                          "roofline": {"bound": "hbm", "kernel": fb_kernel, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                                        "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": None,
                                        "algorithmic_bytes_per_launch": bytes_col * total_obs, "launch_ms": k_ms},
                           "compute_roofline": {"bound": "fp64 FMA issue", "ops_per_s": flops_col * total_obs / (k_ms * 1e-3),

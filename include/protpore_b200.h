@@ -184,7 +184,7 @@ int pp_forward_backward_batch(pp_model *model, const void *obs, int32_t obs_dtyp
 
 /* How the LAST pp_forward_backward_batch call on this handle was served: out[0] = 1 lane-per-event kernel
  * (pp_lane_fb.cuh), 0 exact state-parallel kernel only, 2 lane kernel failed its numeric checks and the batch was
- * redone by the exact kernel; out[1] = events the lane kernel handed to the exact kernel (scaled sweep could not
+ * redone by the exact kernel, 3 linear-profile kernel (pp_profile_fb.cuh), 4 that kernel failed its checks; out[1] = events the lane kernel handed to the exact kernel (scaled sweep could not
  * resolve them); out[2] = events whose backward sweep failed the checks, or -(number of accumulated statistics that
  * were not finite) when that is what sent the batch to the exact kernel. */
 int pp_forward_backward_info(const pp_model *model, int64_t *out3);

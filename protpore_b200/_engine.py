@@ -437,10 +437,11 @@ class Engine(object):
         return logp, edge, mom, mm, post
 
     def forward_backward_info(self):
-        """How the last forward_backward_batch was served: {'path': 'lane' | 'exact' | 'lane-failed', 'rejects', 'failed'}."""
+        """How the last forward_backward_batch was served: {'path': 'profile' | 'lane' | 'exact' | 'lane-failed' |
+        'profile-failed', 'rejects', 'failed'}."""
         out = (ctypes.c_int64 * 3)()
         self._check(self._lib.pp_forward_backward_info(self._h, out))
-        return {"path": ("exact", "lane", "lane-failed")[int(out[0])], "rejects": int(out[1]), "failed": int(out[2])}
+        return {"path": ("exact", "lane", "lane-failed", "profile", "profile-failed")[int(out[0])], "rejects": int(out[1]), "failed": int(out[2])}
 
     def sample_events(self, lengths, seed=0, device_out=False):
         """Length-conditioned synthetic events: (obs float32, offsets int64)."""

@@ -7,9 +7,13 @@
 
 #include "pp_lane_types.h"
 #include "pp_model.h"
+#include "pp_profile_sched.h"
 #include "pp_state_kernels.cuh"
 
 namespace pp {
+
+size_t profile_fb_smem(int Kr, int NW);
+int profile_fb_launch(const ProfFbSched& S, const LaneBatchAny& B, int grid, cudaStream_t stream);
 
 LaneSched make_sched(const pp_model* M, bool logspace);        // pp_api.cu
 
@@ -487,6 +491,102 @@ static int fb_batch_lane(pp_model* M, const void* d_obs, int32_t obs_dtype, cons
     return PP_OK;
 }
 
+// The same E-step on the linear-profile kernel (pp_profile_fb.cuh) for models pp_profile.h recognises; same contract as
+// fb_batch_lane (done = 0: not served here, try the next kernel).
+static int fb_batch_profile(pp_model* M, const void* d_obs, int32_t obs_dtype, const int64_t* d_off, const int64_t* h_off,
+                            int64_t n_events, int64_t maxlen, double* d_logp, double* d_edge, double* d_mom, double* d_mm,
+                            int* done, int32_t* n_rejects) {
+    *done = 0;
+    *n_rejects = 0;
+    const ProfilePlan& F = M->plan;
+    if (!F.ok || !F.fb_ok || M->kernel_path != 0) return PP_OK;
+    const int P = kProfPositionsPerWarp;
+    const size_t smem = profile_fb_smem(F.Kr, F.NW);
+    if (smem > M->smem_optin) return PP_OK;
+    const int row_slots = F.NW * 5 * P + 1;
+    const size_t cta_scratch = static_cast<size_t>(maxlen + 1) * row_slots * kSlotBytes;
+    Schedule sc;
+    build_schedule(h_off, 0, n_events, &sc);
+    int grid = std::min(sc.n_groups, M->sm_count);
+    if (cta_scratch * static_cast<size_t>(grid) > M->ws_limit) grid = static_cast<int>(M->ws_limit / cta_scratch);
+    if (grid < 1) return PP_OK;
+    if (M->d_fb_scratch.reserve(cta_scratch * grid) != cudaSuccess) { cudaGetLastError(); return PP_OK; }
+    const size_t acc_bytes = static_cast<size_t>(grid) * F.fb_slots * kLanes * sizeof(double);
+    PP_CUDA(M->d_fb_acc.reserve(acc_bytes));
+    PP_CUDA(M->d_fb_ctl.reserve(64));
+    PP_CUDA(M->d_fb_minmax.reserve(2 * static_cast<size_t>(M->ne) * sizeof(double)));
+    PP_CUDA(upload(&M->d_order, sc.order, M->stream));
+    PP_CUDA(upload(&M->d_group_len, sc.group_len, M->stream));
+    PP_CUDA(cudaMemsetAsync(M->d_fb_acc.p, 0, acc_bytes, M->stream));
+    PP_CUDA(cudaMemsetAsync(M->d_fb_ctl.p, 0, 64, M->stream));
+    {
+        std::vector<double> mm(2 * static_cast<size_t>(M->ne));
+        for (int k = 0; k < M->ne; ++k) { mm[2 * k] = INFINITY; mm[2 * k + 1] = -INFINITY; }
+        PP_CUDA(cudaMemcpyAsync(M->d_fb_minmax.p, mm.data(), mm.size() * sizeof(double), cudaMemcpyHostToDevice, M->stream));
+        PP_CUDA(cudaStreamSynchronize(M->stream));                 // mm is a stack-lifetime staging buffer
+    }
+    ProfFbSched S;
+    S.rec_f = M->d_prof_rec_f.as<double>();
+    S.rec_b = M->d_prof_rec_b.as<double>();
+    S.end_list = M->d_prof_end_f.as<ProfEndRec>();
+    S.emit_state = M->d_prof_emit_state.as<int32_t>();
+    S.end_n = static_cast<int32_t>(F.end_f.size());
+    S.K = F.K; S.Kp = F.Kp; S.Kr = F.Kr; S.NW = F.NW;
+    S.n_groups = sc.n_groups;
+    S.row_slots = row_slots;
+    S.n_acc_slots = F.fb_slots;
+    S.scratch = M->d_fb_scratch.as<unsigned char>();
+    S.scratch_stride = cta_scratch;
+    S.acc = M->d_fb_acc.as<double>();
+    S.counter = M->d_fb_ctl.as<int32_t>();
+    S.fail = M->d_fb_ctl.as<int32_t>() + 1;
+    S.logp = d_logp;
+    S.minmax = M->d_fb_minmax.as<double>();
+    S.start_wm = F.start_wm;
+    S.start_ws = F.start_ws;
+    const LaneBatchAny B{d_obs, obs_dtype == PP_F64 ? 1 : 0, d_off, M->d_order.as<int32_t>(), M->d_group_len.as<int32_t>(), nullptr};
+    int e = profile_fb_launch(S, B, grid, M->stream);
+    if (e != 0) { set_error("profile forward-backward kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
+    ++M->launches;
+    {
+        const size_t n_acc = acc_bytes / sizeof(double);
+        k_count_nonfinite<<<static_cast<unsigned>(std::min<size_t>((n_acc + 255) / 256, 1024)), 256, 0, M->stream>>>(
+            S.acc, n_acc, M->d_fb_ctl.as<int32_t>() + 5);
+        PP_CUDA(cudaGetLastError());
+        ++M->launches;
+    }
+    int32_t ctl[16] = {0};
+    PP_CUDA(cudaMemcpyAsync(ctl, M->d_fb_ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, M->stream));
+    PP_CUDA(cudaStreamSynchronize(M->stream));
+    if (ctl[1] != 0 && std::getenv("PP_DEBUG_FB")) {
+        const double* dv = reinterpret_cast<const double*>(ctl + 8);
+        std::fprintf(stderr, "[pp] k_profile_fb: %d failed events; first: reason %d event %d (n or row %d) values %.17g %.17g %.17g %.17g\n",
+                     ctl[1], ctl[2], ctl[3], ctl[4], dv[0], dv[1], dv[2], dv[3]);
+    }
+    if (ctl[1] != 0 || ctl[5] != 0) {
+        M->fb_info[0] = 4;
+        M->fb_info[2] = ctl[1] != 0 ? ctl[1] : -ctl[5];
+        return PP_OK;
+    }
+    e = lane_fb_finalize(S.acc, grid, F.fb_slots, M->d_prof_fb_map.as<int32_t>(), M->d_prof_fb_log2.as<int32_t>(), M->n_edges,
+                         M->ne, d_edge, d_mom, S.minmax, d_mm, M->stream);
+    if (e != 0) { set_error("forward-backward finalize failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
+    M->launches += 2;
+    PP_CUDA(M->d_list.reserve(n_events * sizeof(int32_t)));
+    PP_CUDA(M->d_counter.reserve(16));
+    PP_CUDA(cudaMemsetAsync(M->d_counter.p, 0, 4, M->stream));
+    k_collect_flagged<<<static_cast<unsigned>((n_events + 255) / 256), 256, 0, M->stream>>>(
+        d_logp, n_events, M->d_list.as<int32_t>(), M->d_counter.as<int32_t>());
+    PP_CUDA(cudaGetLastError());
+    ++M->launches;
+    PP_CUDA(cudaMemcpyAsync(n_rejects, M->d_counter.p, 4, cudaMemcpyDeviceToHost, M->stream));
+    PP_CUDA(cudaStreamSynchronize(M->stream));
+    *done = 1;
+    M->fb_info[0] = 3;
+    M->fb_info[1] = *n_rejects;
+    return PP_OK;
+}
+
 int pp_forward_backward_info(const pp_model* M, int64_t* out3) {
     if (!M || !out3) { set_error("null argument"); return PP_ERR_ARG; }
     for (int i = 0; i < 3; ++i) out3[i] = M->fb_info[i];
@@ -558,8 +658,12 @@ int pp_forward_backward_batch(pp_model* M, const void* obs, int32_t obs_dtype, c
     int lane_done = 0;
     int32_t n_rej = 0;
     if (!posteriors_out) {
-        int rc = fb_batch_lane(M, d_obs, obs_dtype, d_off, h_off, n_events, maxlen, d_logp, d_edge, d_mom, d_mm, &lane_done, &n_rej);
+        int rc = fb_batch_profile(M, d_obs, obs_dtype, d_off, h_off, n_events, maxlen, d_logp, d_edge, d_mom, d_mm, &lane_done, &n_rej);
         if (rc != PP_OK) return rc;
+        if (!lane_done && M->fb_info[0] == 0) {                    // not a profile (a profile kernel that FAILED goes to the exact kernel)
+            rc = fb_batch_lane(M, d_obs, obs_dtype, d_off, h_off, n_events, maxlen, d_logp, d_edge, d_mom, d_mm, &lane_done, &n_rej);
+            if (rc != PP_OK) return rc;
+        }
     }
     const int64_t n_exact = lane_done ? n_rej : n_events;
     const int32_t* d_evlist = lane_done ? M->d_list.as<int32_t>() : nullptr;

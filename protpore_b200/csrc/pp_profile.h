@@ -59,6 +59,32 @@ struct __attribute__((aligned(16))) ProfEndRec {
     double w;                                    // log p (Viterbi) or p (forward)
 };
 
+// ---- forward-backward (Baum-Welch E-step) on the profile, pp_profile_fb.cuh -------------------------------------------
+// The backward sweep reads the SAME weights by their source: one record per position with everything that leaves it.
+constexpr int kFbRecDoubles = 40;
+enum : int {
+    FR_WM = 0,      // [8] out of M_k: -> M_{k+1}, M_k, I_INS_{k+1}, I_BLIP_k, S_DROPOFF_k, M_{k-1}, S_SKIP_{k+1}, B_BACK_k
+    FR_WE = 8,      // [4] into the end state from M_k, S_DROPOFF_k, S_SKIP_k, B_BACK_k
+    FR_WS = 12,     // [2] out of S_SKIP_k: -> M_{k+1}, S_SKIP_{k+1}
+    FR_WK = 14,     // [2] out of B_BACK_k: -> M_{k-1}, B_BACK_{k-1}
+    FR_WD = 16,     // [2] out of S_DROPOFF_k: -> M_k, (unused)
+    FR_WI = 18,     // [2] out of I_INS_k: -> M_k, I_INS_k
+    FR_WB = 20,     // [2] out of I_BLIP_k: -> M_k, I_BLIP_k
+    FR_EM = 22,     // [4] linear-space emission records (as in the forward records)
+    FR_EI = 26,
+    FR_EB = 30,
+    FR_KINDS = 34,  // int32: kind M | kind INS << 8 | kind BLIP << 16
+    // first position of a warp's block:
+    FR_CDN = 36,    //   prod_j t(S_SKIP_{k0+j} -> S_SKIP_{k0+j+1}): the descending skip chain across the block
+    FR_CUP = 37,    //   prod_j t(B_BACK_{k0+j} -> B_BACK_{k0+j-1}): the ascending back-slip chain
+    FR_TDN = 38,    //   what H[M_{k0}] contributes to the LEFT block's way out: t(S_SKIP_{k0-1} -> M_{k0}) prod_{j<P-1} t(S_SKIP_{k0-P+j} -> ..)
+    FR_TUP = 39,    //   what H[M_{k0+P-1}] contributes to the RIGHT block's: t(B_BACK_{k0+P} -> M_{k0+P-1}) prod_{j>=1} t(B_BACK_{k0+P+j} -> ..)
+};
+// Statistic terms per position: 4 chunks of 8 (pp_profile_fb.cuh lists them); after the in-warp reduction lane L of a
+// chunk holds a partial sum of term L >> 2.
+constexpr int kFbChunks = 4;
+constexpr int kFbTermsPerPosition = 8 * kFbChunks;
+
 constexpr int kProfMaxAlias = 4;
 struct ProfilePlan {
     bool ok = false;
@@ -76,6 +102,15 @@ struct ProfilePlan {
     int32_t row_bytes = 0;                       // bytes of one pointer row (all 32 lanes)
     std::vector<int32_t> unit_off, unit_bytes, unit_shift, unit_mask;   // [m]
     std::vector<int32_t> slot_begin, slot_src;   // [m], [sum of slots]
+    // forward-backward on the profile (fb_ok): backward records, and which statistic every accumulation lane feeds
+    bool fb_ok = false;
+    std::string fb_why;
+    std::vector<double> rec_b;                   // [Kr][kFbRecDoubles]
+    std::vector<int32_t> fb_map;                 // [fb_slots * 32]: out-edge index, n_edges + 3 * state + {0, 1, 2}, or -1
+    std::vector<int32_t> fb_log2;                // [fb_slots]: log2 of the terms per slot (3; the start slot too)
+    int fb_slots = 0;                            // Kp * kFbChunks + 1 (the last one: the two out-edges of the start state)
+    std::vector<int32_t> fb_emit_state;          // [Kp][3]: state index of M_k, I_INS_k, I_BLIP_k or -1
+    double start_wm = 0.0, start_ws = 0.0;       // t(start -> M_0), t(start -> S_SKIP_0)
     // classification (tests, describe)
     std::vector<int32_t> M, BLIP, INS, DROP, SKIP, BACK;               // [K] state index or -1
 };

@@ -363,6 +363,132 @@ void build_profile_plan(const pp_model_desc& d, const Lowered& low, int P, int m
         place(BACK[k], chain_base + w * kLanes, 1, P + p, 1);
     }
     plan->ok = true;
+
+    // ---- forward-backward: the same weights keyed by their SOURCE, and the statistic every term feeds -----------------
+    {
+        auto fb_fail = [&](const std::string& why) { plan->fb_ok = false; plan->fb_why = why; };
+        const int R = kFbRecDoubles;
+        plan->rec_b.assign(static_cast<size_t>(Kr) * R, 0.0);
+        auto F = [&](int k, int field) -> double {
+            return (k >= 0 && k < Kr) ? plan->rec_f[static_cast<size_t>(k) * kProfRecDoubles + field] : 0.0;
+        };
+        for (int k = 0; k < Kr; ++k) {
+            double* b = &plan->rec_b[static_cast<size_t>(k) * R];
+            b[FR_WM + 0] = F(k + 1, PR_WM + 0);
+            b[FR_WM + 1] = F(k, PR_WM + 2);
+            b[FR_WM + 2] = F(k + 1, PR_WI + 0);
+            b[FR_WM + 3] = F(k, PR_WB + 0);
+            b[FR_WM + 4] = F(k, PR_WD);
+            b[FR_WM + 5] = F(k - 1, PR_WM + 6);
+            b[FR_WM + 6] = F(k, PR_SK);
+            b[FR_WM + 7] = F(k, PR_BK);
+            b[FR_WS + 0] = F(k + 1, PR_WM + 1);
+            b[FR_WS + 1] = F(k + 1, PR_SK + 1);
+            b[FR_WK + 0] = F(k - 1, PR_WM + 7);
+            b[FR_WK + 1] = F(k - 1, PR_BK + 1);
+            b[FR_WD] = F(k, PR_WM + 3);
+            b[FR_WI + 0] = F(k, PR_WM + 5);
+            b[FR_WI + 1] = F(k, PR_WI + 1);
+            b[FR_WB + 0] = F(k, PR_WM + 4);
+            b[FR_WB + 1] = F(k, PR_WB + 1);
+            for (int j = 0; j < 4; ++j) {
+                b[FR_EM + j] = F(k, PR_EM + j);
+                b[FR_EI + j] = F(k, PR_EI + j);
+                b[FR_EB + j] = F(k, PR_EB + j);
+            }
+            b[FR_EM + 3] = 0.0;                                     // PR_CUT lives there in the forward records
+            std::memcpy(&b[FR_KINDS], &kinds_word[k], sizeof(int32_t));
+        }
+        for (const ProfEndRec& E : plan->end_f) {
+            const int j = E.cls == PROF_M ? 0 : E.cls == PROF_DROP ? 1 : E.cls == PROF_SKIP ? 2 : 3;
+            plan->rec_b[static_cast<size_t>(E.k) * R + FR_WE + j] = E.w;
+        }
+        auto B = [&](int k, int field) -> double { return (k >= 0 && k < Kr) ? plan->rec_b[static_cast<size_t>(k) * R + field] : 0.0; };
+        for (int k0 = 0; k0 < Kr; k0 += P) {
+            double cdn = 1.0, cup = 1.0, tdn = k0 >= P ? B(k0 - 1, FR_WS + 0) : 0.0, tup = B(k0 + P, FR_WK + 0);
+            for (int j = 0; j < P; ++j) { cdn *= B(k0 + j, FR_WS + 1); cup *= B(k0 + j, FR_WK + 1); }
+            for (int j = 0; j < P - 1; ++j) tdn *= B(k0 - P + j, FR_WS + 1);
+            for (int j = 1; j < P; ++j) tup *= B(k0 + P + j, FR_WK + 1);
+            double* b = &plan->rec_b[static_cast<size_t>(k0) * R];
+            b[FR_CDN] = cdn; b[FR_CUP] = cup; b[FR_TDN] = tdn; b[FR_TUP] = tup;
+        }
+        plan->start_wm = F(0, PR_WM + 1);
+        plan->start_ws = F(0, PR_SK + 1);
+
+        // statistic of every term: the out-edge it counts (or the moment it sums); a phantom back-slip position stands
+        // for the state whose value it carries
+        auto oe = [&](int s, int t) -> int {
+            if (s < 0 || t < 0) return -1;
+            for (int e = out_begin(s); e < out_end(s); ++e) if (d.out_dst[e] == t) return e;
+            return -1;
+        };
+        auto at = [&](const std::vector<int32_t>& v, int k) { return (k >= 0 && k < K) ? v[k] : -1; };
+        auto back_src = [&](int k) {
+            const int s = at(BACK, k);
+            if (s >= 0) return s;
+            for (int a = 0; a < plan->n_alias; ++a) if (plan->alias_dst[a] == k) return at(BACK, plan->alias_src[a]);
+            return -1;
+        };
+        const int E = d.n_edges;
+        plan->fb_slots = Kp * kFbChunks + 1;
+        plan->fb_map.assign(static_cast<size_t>(plan->fb_slots) * kLanes, -1);
+        plan->fb_log2.assign(plan->fb_slots, 3);
+        plan->fb_emit_state.assign(static_cast<size_t>(Kp) * 3, -1);
+        std::vector<int> seen(E, 0);
+        bool weights_ok = true;
+        auto put = [&](int k, int term, int stat, double w) {
+            if (stat < 0) return;
+            if (stat < E) {
+                ++seen[stat];
+                if (w != std::exp(d.out_logp[stat])) weights_ok = false;
+            }
+            const size_t slot = static_cast<size_t>(k) * kFbChunks + term / 8;
+            for (int q = 0; q < 4; ++q) plan->fb_map[slot * kLanes + (term % 8) * 4 + q] = stat;
+        };
+        for (int k = 0; k < K; ++k) {
+            const int mk = M[k], dk = at(DROP, k), sk = at(SKIP, k), bk = back_src(k), ik = at(INS, k), lk = at(BLIP, k);
+            plan->fb_emit_state[k * 3 + 0] = mk;
+            plan->fb_emit_state[k * 3 + 1] = ik;
+            plan->fb_emit_state[k * 3 + 2] = lk;
+            put(k, 0, oe(mk, at(M, k + 1)), B(k, FR_WM + 0));
+            put(k, 1, oe(mk, mk), B(k, FR_WM + 1));
+            put(k, 2, oe(mk, at(INS, k + 1)), B(k, FR_WM + 2));
+            put(k, 3, oe(mk, lk), B(k, FR_WM + 3));
+            put(k, 4, oe(mk, dk), B(k, FR_WM + 4));
+            put(k, 5, oe(mk, at(M, k - 1)), B(k, FR_WM + 5));
+            put(k, 6, oe(mk, end), B(k, FR_WE + 0));
+            put(k, 7, oe(dk, mk), B(k, FR_WD));
+            put(k, 8, oe(dk, end), B(k, FR_WE + 1));
+            put(k, 9, oe(sk, at(M, k + 1)), B(k, FR_WS + 0));
+            put(k, 10, oe(sk, end), B(k, FR_WE + 2));
+            put(k, 11, oe(bk, at(M, k - 1)), B(k, FR_WK + 0));
+            put(k, 12, at(BACK, k) >= 0 ? oe(bk, end) : -1, B(k, FR_WE + 3));
+            put(k, 13, oe(ik, mk), B(k, FR_WI + 0));
+            put(k, 14, oe(ik, ik), B(k, FR_WI + 1));
+            put(k, 15, oe(lk, mk), B(k, FR_WB + 0));
+            put(k, 16, oe(lk, lk), B(k, FR_WB + 1));
+            for (int j = 0; j < 3; ++j) {
+                if (ik >= 0) put(k, 17 + j, E + 3 * ik + j, 0.0);
+                if (lk >= 0) put(k, 20 + j, E + 3 * lk + j, 0.0);
+                put(k, 28 + j, E + 3 * mk + j, 0.0);
+            }
+            put(k, 24, oe(mk, at(SKIP, k + 1)), B(k, FR_WM + 6));
+            put(k, 25, oe(mk, at(BACK, k)), B(k, FR_WM + 7));
+            put(k, 26, oe(sk, at(SKIP, k + 1)), B(k, FR_WS + 1));
+            put(k, 27, at(BACK, k - 1) >= 0 ? oe(bk, at(BACK, k - 1)) : -1, B(k, FR_WK + 1));
+        }
+        {   // the start state: slot Kp * kFbChunks, terms 0 and 1
+            const size_t slot = static_cast<size_t>(Kp) * kFbChunks;
+            const int e0 = oe(start, M[0]), e1 = oe(start, at(SKIP, 0));
+            for (int q = 0; q < 4; ++q) { plan->fb_map[slot * kLanes + q] = e0; plan->fb_map[slot * kLanes + 4 + q] = e1; }
+            if (e0 >= 0) { ++seen[e0]; if (plan->start_wm != std::exp(d.out_logp[e0])) weights_ok = false; }
+            if (e1 >= 0) { ++seen[e1]; if (plan->start_ws != std::exp(d.out_logp[e1])) weights_ok = false; }
+        }
+        plan->fb_ok = weights_ok;
+        if (!weights_ok) fb_fail("a backward weight differs from its out-edge");
+        for (int e = 0; e < E && plan->fb_ok; ++e)
+            if (seen[e] != 1) fb_fail("an out-edge is counted " + std::to_string(seen[e]) + " times by the profile terms");
+    }
 }
 
 }  // namespace pp

@@ -24,4 +24,25 @@ struct ProfSched {
     int32_t end_state;
 };
 
+// forward-backward on the profile (pp_profile_fb.cuh)
+struct ProfFbSched {
+    const double* rec_f;                 // [Kr][32] forward records (probabilities)
+    const double* rec_b;                 // [Kr][40] backward records
+    const ProfEndRec* end_list;          // in-edges of the end state (probabilities)
+    const int32_t* emit_state;           // [Kp][3] state index of M_k, I_INS_k, I_BLIP_k (-1: none)
+    int32_t end_n;
+    int32_t K, Kp, Kr, NW;
+    int32_t n_groups;
+    int32_t row_slots;                   // NW * 5 P + 1 (the last slot holds S_r)
+    int32_t n_acc_slots;                 // Kp * 4 + 1
+    unsigned char* scratch;              // per CTA: (max_len + 1) rows of row_slots * 256 bytes
+    size_t scratch_stride;
+    double* acc;                         // per CTA: n_acc_slots * 32 doubles
+    int32_t* counter;                    // work-stealing group counter (zeroed by the host)
+    int32_t* fail;                       // [0] failed events, [1] reason of the first, [2] its event, [3] row; doubles at +7
+    double* logp;                        // [n_events]
+    double* minmax;                      // [2 * ne]
+    double start_wm, start_ws;           // t(start -> M_0), t(start -> S_SKIP_0)
+};
+
 }  // namespace pp

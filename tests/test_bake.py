@@ -81,10 +81,15 @@ def test_profile_plan_recognises_linear_profiles_only():
     """pp_profile_plan.cpp classifies states from the baked graph alone: the peptide profiles take the register-resident
     kernels, everything else keeps the run-based ones (the text report needs no GPU)."""
     from protpore_b200 import _engine
+    def line(name, prefix):
+        hits = [l for l in _engine.describe_schedule(util.build_model(name)).splitlines() if l.startswith(prefix)]
+        assert len(hits) == 1, (name, prefix, hits)
+        return hits[0]
     for name in ("pro_001_py2", "pro_001_py3", "synth_12"):
-        last = _engine.describe_schedule(util.build_model(name)).splitlines()[-1]
-        assert last.startswith("profile ok"), (name, last)
-    last = _engine.describe_schedule(util.build_model("pro_001_py2")).splitlines()[-1]
+        assert line(name, "profile ").startswith("profile ok"), name
+        # the forward-backward kernel of the profile: every out-edge of the model is counted by exactly one of its terms
+        assert line(name, "profile_fb ").startswith("profile_fb ok"), (name, line(name, "profile_fb "))
+    last = line("pro_001_py2", "profile ")
     assert "positions 43 " in last and "end_edges 87" in last and "aliases 1" in last
     for name in ("toy", "toy_uniform", "toy_infinite"):
         last = _engine.describe_schedule(util.build_model(name)).splitlines()[-1]

@@ -479,7 +479,7 @@ def test_lane_forward_backward_statistics(models):
     obs[offsets[9] + 2] = 119.5                                  # far outlier the scaled sweep still resolves
     logp, edge, mom, mm, _ = eng.forward_backward_batch(obs, offsets)
     info = eng.forward_backward_info()
-    assert info["path"] == "lane" and info["rejects"] >= 1 and info["failed"] == 0
+    assert info["path"] in ("lane", "profile") and info["rejects"] >= 1 and info["failed"] == 0
     # exact kernel: asking for the posteriors keeps the batch on the state-parallel path
     logp_x, edge_x, mom_x, mm_x, _ = eng.forward_backward_batch(obs, offsets, posteriors=True)
     assert eng.forward_backward_info()["path"] == "exact"
@@ -511,7 +511,7 @@ def test_lane_forward_backward_accumulates_and_is_composition_invariant(models):
     lens = events.log_uniform_lengths(500, 1, 700, seed=3)
     obs, offsets = eng.sample_events(lens, seed=5)
     _, edge, mom, mm, _ = eng.forward_backward_batch(obs, offsets)
-    assert eng.forward_backward_info()["path"] == "lane"
+    assert eng.forward_backward_info()["path"] in ("lane", "profile")
     h = 250
     o1, f1 = obs[:offsets[h]], offsets[:h + 1]
     o2, f2 = obs[offsets[h]:], offsets[h:] - offsets[h]
@@ -548,7 +548,7 @@ def test_kernels_follow_a_changed_emission_kind():
         s, p, margin = orc.viterbi(seqs[i], with_margin=True)
         assert vit[i][0] == s and (np.array_equal(vit[i][1], p) or margin == 0.0)
     logp, edge, mom, mm, _ = eng.forward_backward_batch(obs.astype(np.float64), offsets)
-    assert eng.forward_backward_info()["path"] == "lane"
+    assert eng.forward_backward_info()["path"] in ("lane", "profile")
     exp_t, mom_o, mm_o, lz = orc.bw_accumulate(seqs[:60])
     so = np.concatenate(seqs[:60])
     oo = np.concatenate([[0], np.cumsum([len(s) for s in seqs[:60]])])
@@ -613,6 +613,41 @@ def test_profile_kernels_equal_run_based_kernels(models):
         assert np.max(np.abs(f0[fin] - f1[fin]) / np.maximum(1.0, np.abs(f1[fin]))) < 1e-7   # two MUFU-based sweeps, each < 1e-7 of the reference
 
 
+def test_profile_forward_backward_equals_run_based_and_exact_kernels(models):
+    """k_profile_fb (pp_profile_fb.cuh) against k_fb_lane and the exact state-parallel kernel: log-probabilities, expected
+    transition counts, emission moments and observed ranges of the Baum-Welch E-step (yahmm.pyx:4107-4236), with an event
+    the scaled sweep must hand to the exact kernel, a far outlier, and lengths from 1 to 600 in one batch."""
+    for name in ("pro_001_py2", "pro_001_py3", "synth_12"):
+        model = models[name]
+        eng = model.engine()
+        assert "profile_fb ok" in _engine.describe_schedule(model), name
+        lens = events.log_uniform_lengths(700, 1, 600, seed=41)
+        obs, offsets = eng.sample_events(lens, seed=42)
+        obs = obs.astype(np.float64)
+        obs[offsets[5]:offsets[5] + 1] = 250.0
+        obs[offsets[9] + 2] = 119.5
+        lp0, e0, m0, mm0, _ = eng.forward_backward_batch(obs, offsets)
+        info = eng.forward_backward_info()
+        assert info["path"] == "profile" and info["failed"] == 0 and info["rejects"] >= 1, (name, info)
+        eng.set_kernel_path(1)
+        try:
+            lp1, e1, m1, mm1, _ = eng.forward_backward_batch(obs, offsets)
+            # synth_12's batch holds a 2-observation event with log P = -845: k_fb_lane fails its range check on it and the
+            # exact kernel redoes its batch; k_profile_fb hands over that event alone
+            assert eng.forward_backward_info()["path"] in ("lane", "lane-failed")
+        finally:
+            eng.set_kernel_path(0)
+        lpx, ex, mx, mmx, _ = eng.forward_backward_batch(obs, offsets, posteriors=True)
+        assert eng.forward_backward_info()["path"] == "exact"
+        for lp, e, m, mm in ((lp1, e1, m1, mm1), (lpx, ex, mx, mmx)):
+            fin = np.isfinite(lp)
+            assert np.array_equal(fin, np.isfinite(lp0)), name
+            assert np.allclose(lp0[fin], lp[fin], rtol=1e-12, atol=1e-9), name
+            assert np.allclose(e0, e, rtol=1e-9, atol=1e-12), (name, np.max(np.abs(e0 - e)))
+            assert np.allclose(m0, m, rtol=1e-9, atol=1e-11), (name, np.max(np.abs(m0 - m)))
+            assert np.array_equal(mm0, mm), name
+
+
 def test_profile_kernels_after_baum_welch(models):
     """Training changes every weight and turns the point-mass inserts into Normals (min_std clamp, yahmm.pyx:513): the
     plan is rebuilt, the profile kernels keep serving the model and keep agreeing with the run-based kernels."""
@@ -653,7 +688,7 @@ def test_uniform_range_at_a_tiny_posterior_weight():
     model = mod.tiny_weight(y)
     evs = [g["obs"][g["offsets"][i]:g["offsets"][i + 1]] for i in range(len(g["offsets"]) - 1)]
     imp = model.train(evs, max_iterations=1, verbose=False)
-    assert model.engine().forward_backward_info()["path"] == "lane"
+    assert model.engine().forward_backward_info()["path"] in ("lane", "profile")
     params = np.array([[float(p) for p in s.distribution.parameters[:2]] for s in model.states[:model.silent_start]])
     assert [s.name for s in model.states[:model.silent_start]] == list(g["names"])
     iu = list(g["names"]).index("u")
