@@ -251,8 +251,8 @@ def bench_baum_welch(args, model, rank, world, local):
         # all float64 multiply-add class operations; HBM: the scaled forward column written and read back once + the input
         flops_col = E + ne + 3 * E + ne + 3 * ne
         fb_path = eng.forward_backward_info()["path"]
-        if fb_path == "profile":                     # k_profile_fb: 5 values per position (padded to whole warps of 4) + S_r
-            kp = (eng.kernel_info()["positions"] + 3) // 4 * 4
+        if fb_path == "profile":                     # k_profile_fb: 5 values per position (padded to whole warps of 2) + S_r
+            kp = (eng.kernel_info()["positions"] + 1) // 2 * 2
             fb_kernel, bytes_col = "k_profile_fb", 2.0 * (5 * kp + 1) * 8 + 4
         else:
             fb_kernel, bytes_col = "k_fb_lane", 2.0 * (m + 1) * 8 + 4

@@ -269,12 +269,6 @@ int upload_model(pp_model* M) {
         PP_CUDA(upload(&M->d_prof_unit_mask, F.unit_mask, s));
         PP_CUDA(upload(&M->d_prof_slot_begin, F.slot_begin, s));
         PP_CUDA(upload(&M->d_prof_slot_src, F.slot_src, s));
-        if (F.fb_ok) {
-            PP_CUDA(upload(&M->d_prof_rec_b, F.rec_b, s));
-            PP_CUDA(upload(&M->d_prof_fb_map, F.fb_map, s));
-            PP_CUDA(upload(&M->d_prof_fb_log2, F.fb_log2, s));
-            PP_CUDA(upload(&M->d_prof_emit_state, F.fb_emit_state, s));
-        }
         std::vector<TraceRec> rec(static_cast<size_t>(M->m));
         for (int k = 0; k < M->m; ++k)
             rec[k] = TraceRec{static_cast<uint32_t>(F.slot_begin[k]), static_cast<uint32_t>(F.unit_off[k]), static_cast<uint32_t>(F.unit_bytes[k]),
@@ -284,6 +278,15 @@ int upload_model(pp_model* M) {
         PP_CUDA(upload(&M->d_trace_rec[1], rec, s));
         PP_CUDA(upload(&M->d_trace_src[1], src, s));
         M->n_trace_src[1] = static_cast<int32_t>(src.size());
+    }
+    if (M->plan_fb.ok && M->plan_fb.fb_ok) {
+        const ProfilePlan& F = M->plan_fb;
+        PP_CUDA(upload(&M->d_pfb_rec_f, F.rec_f, s));
+        PP_CUDA(upload(&M->d_pfb_end_f, F.end_f, s));
+        PP_CUDA(upload(&M->d_prof_rec_b, F.rec_b, s));
+        PP_CUDA(upload(&M->d_prof_fb_map, F.fb_map, s));
+        PP_CUDA(upload(&M->d_prof_fb_log2, F.fb_log2, s));
+        PP_CUDA(upload(&M->d_prof_emit_state, F.fb_emit_state, s));
     }
     PP_CUDA(upload(&M->d_in_ptr, M->in_ptr, s));
     PP_CUDA(upload(&M->d_in_src, M->in_src, s));
@@ -555,6 +558,7 @@ int pp_model_create(const pp_model_desc* desc, int device, pp_model** out) {
     if (!err.empty()) { set_error("cannot lower model: %s", err.c_str()); delete M; return PP_ERR_UNSUPPORTED; }
     copy_desc(M, desc);
     build_profile_plan(*desc, M->low, kProfPositionsPerWarp, kProfMaxPositionWarps, &M->plan);
+    build_profile_plan(*desc, M->low, kPfbPositionsPerWarp, kPfbMaxPositionWarps, &M->plan_fb);
     if (const char* env = std::getenv("PP_KERNEL_PATH")) M->kernel_path = std::atoi(env);
     int rc = PP_OK;
     do {
@@ -592,7 +596,7 @@ void pp_model_destroy(pp_model* M) {
                       &M->d_path_off, &M->d_path, &M->d_scan_tmp, &M->d_logp, &M->d_bw_wtab, &M->d_acc_map,
                       &M->d_acc_log2, &M->d_fb_acc, &M->d_fb_scratch, &M->d_fb_ctl, &M->d_fb_minmax, &M->d_etab_own, &M->d_gcol, &M->d_prof_rec_v, &M->d_prof_rec_f, &M->d_prof_end_v, &M->d_prof_end_f,
                       &M->d_prof_unit_off, &M->d_prof_unit_bytes, &M->d_prof_unit_shift, &M->d_prof_unit_mask, &M->d_prof_slot_begin,
-                      &M->d_prof_slot_src, &M->d_prof_rec_b, &M->d_prof_fb_map, &M->d_prof_fb_log2, &M->d_prof_emit_state, &M->d_state_pmask, &M->d_trace_rec[0], &M->d_trace_rec[1], &M->d_trace_src[0], &M->d_trace_src[1]};
+                      &M->d_prof_slot_src, &M->d_pfb_rec_f, &M->d_pfb_end_f, &M->d_prof_rec_b, &M->d_prof_fb_map, &M->d_prof_fb_log2, &M->d_prof_emit_state, &M->d_state_pmask, &M->d_trace_rec[0], &M->d_trace_rec[1], &M->d_trace_src[0], &M->d_trace_src[1]};
     for (DevBuf* b : bufs) b->release();
     release_state_model(M);
     for (int b = 0; b < kPipeSlots; ++b) {
@@ -618,6 +622,7 @@ int pp_model_update_params(pp_model* M, const pp_model_desc* desc) {
     if (!err.empty()) { set_error("cannot refresh parameters: %s", err.c_str()); return PP_ERR_ARG; }
     copy_desc(M, desc);
     build_profile_plan(*desc, M->low, kProfPositionsPerWarp, kProfMaxPositionWarps, &M->plan);
+    build_profile_plan(*desc, M->low, kPfbPositionsPerWarp, kPfbMaxPositionWarps, &M->plan_fb);
     PP_CUDA(cudaSetDevice(M->device));
     PP_CUDA(cudaStreamSynchronize(M->stream));
     return upload_model(M);
@@ -659,8 +664,10 @@ int64_t pp_schedule_describe(const pp_model_desc* desc, char* buf, int64_t cap) 
             std::snprintf(line, sizeof line, "profile no: %s\n", plan.why.c_str());
         text += line;
         if (plan.ok) {
-            if (plan.fb_ok) std::snprintf(line, sizeof line, "profile_fb ok slots %d\n", plan.fb_slots);
-            else std::snprintf(line, sizeof line, "profile_fb no: %s\n", plan.fb_why.c_str());
+            ProfilePlan pfb;
+            build_profile_plan(*desc, low, kPfbPositionsPerWarp, kPfbMaxPositionWarps, &pfb);
+            if (pfb.ok && pfb.fb_ok) std::snprintf(line, sizeof line, "profile_fb ok position_warps %d positions_per_warp %d slots %d\n", pfb.NW, pfb.P, pfb.fb_slots);
+            else std::snprintf(line, sizeof line, "profile_fb no: %s\n", (pfb.ok ? pfb.fb_why : pfb.why).c_str());
             text += line;
         }
     }

@@ -498,9 +498,9 @@ static int fb_batch_profile(pp_model* M, const void* d_obs, int32_t obs_dtype, c
                             int* done, int32_t* n_rejects) {
     *done = 0;
     *n_rejects = 0;
-    const ProfilePlan& F = M->plan;
+    const ProfilePlan& F = M->plan_fb;
     if (!F.ok || !F.fb_ok || M->kernel_path != 0) return PP_OK;
-    const int P = kProfPositionsPerWarp;
+    const int P = kPfbPositionsPerWarp;
     const size_t smem = profile_fb_smem(F.Kr, F.NW);
     if (smem > M->smem_optin) return PP_OK;
     const int row_slots = F.NW * 5 * P + 1;
@@ -526,9 +526,9 @@ static int fb_batch_profile(pp_model* M, const void* d_obs, int32_t obs_dtype, c
         PP_CUDA(cudaStreamSynchronize(M->stream));                 // mm is a stack-lifetime staging buffer
     }
     ProfFbSched S;
-    S.rec_f = M->d_prof_rec_f.as<double>();
+    S.rec_f = M->d_pfb_rec_f.as<double>();
     S.rec_b = M->d_prof_rec_b.as<double>();
-    S.end_list = M->d_prof_end_f.as<ProfEndRec>();
+    S.end_list = M->d_pfb_end_f.as<ProfEndRec>();
     S.emit_state = M->d_prof_emit_state.as<int32_t>();
     S.end_n = static_cast<int32_t>(F.end_f.size());
     S.K = F.K; S.Kp = F.Kp; S.Kr = F.Kr; S.NW = F.NW;

@@ -42,7 +42,9 @@ struct pp_model {
     int kernel_path = 0;
     pp::DevBuf d_prof_rec_v, d_prof_rec_f, d_prof_end_v, d_prof_end_f, d_prof_unit_off, d_prof_unit_bytes, d_prof_unit_shift,
         d_prof_unit_mask, d_prof_slot_begin, d_prof_slot_src, d_state_pmask;
-    pp::DevBuf d_prof_rec_b, d_prof_fb_map, d_prof_fb_log2, d_prof_emit_state;    // profile forward-backward (plan.fb_ok)
+    // profile forward-backward (pp_profile_fb.cuh): its own plan -- narrower warp blocks (pp_profile_sched.h)
+    pp::ProfilePlan plan_fb;
+    pp::DevBuf d_pfb_rec_f, d_pfb_end_f, d_prof_rec_b, d_prof_fb_map, d_prof_fb_log2, d_prof_emit_state;
     // traceback lookup tables (pp_device_common.cuh TraceRec) of the two kernel families; n entries of the source tables
     pp::DevBuf d_trace_rec[2], d_trace_src[2];
     int32_t n_trace_src[2] = {0, 0};

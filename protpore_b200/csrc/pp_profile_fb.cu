@@ -3,13 +3,13 @@
 
 namespace pp {
 
-size_t profile_fb_smem(int Kr, int NW) { return pfb_smem_bytes(Kr, NW, kProfPositionsPerWarp); }
+size_t profile_fb_smem(int Kr, int NW) { return pfb_smem_bytes(Kr, NW, kPfbPositionsPerWarp); }
 
 int profile_fb_launch(const ProfFbSched& S, const LaneBatchAny& B, int grid, cudaStream_t stream) {
-    const size_t smem = pfb_smem_bytes(S.Kr, S.NW, kProfPositionsPerWarp);
-    cudaError_t e = cudaFuncSetAttribute(k_profile_fb<kProfPositionsPerWarp>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const size_t smem = pfb_smem_bytes(S.Kr, S.NW, kPfbPositionsPerWarp);
+    cudaError_t e = cudaFuncSetAttribute(k_profile_fb<kPfbPositionsPerWarp, kPfbThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    k_profile_fb<kProfPositionsPerWarp><<<grid, (S.NW + 1) * 32, smem, stream>>>(S, B);
+    k_profile_fb<kPfbPositionsPerWarp, kPfbThreads><<<grid, (S.NW + 1) * 32, smem, stream>>>(S, B);
     return static_cast<int>(cudaGetLastError());
 }
 

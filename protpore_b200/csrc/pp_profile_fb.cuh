@@ -33,7 +33,7 @@ namespace pp {
 constexpr int kPfbTargetExp = 480;       // row maxima of both sweeps are steered to ~2^480 (c_r ~ 2^-960 stays normal)
 constexpr int kPfbT2 = 17;               // 2^(j/16), j = -8 .. 8
 constexpr int kPfbStageRow = 40;         // doubles per staging row: 32 lanes + 8 (rows 16 banks apart: conflict-free 16-byte loads)
-constexpr int kPfbStageDoubles = 2 * 8 * kPfbStageRow;      // per warp: two buffers of 8 terms
+constexpr int kPfbStageDoubles = 8 * kPfbStageRow;          // per warp: one buffer of 8 terms
 
 
 // backward-phase slots of a warp block (phase F uses the ProfBlock layout in the same memory)
@@ -135,8 +135,7 @@ __device__ __forceinline__ void pfb_atomic_max(double* addr, double v) {
 
 // Sum of 8 per-lane terms over the 32 lanes through a shared-memory transpose: lane L returns the sum of term L >> 2
 // over lanes {2q, 2q+1, 2q+8, 2q+9, 2q+16, 2q+17, 2q+24, 2q+25}, q = L & 3 (the four lanes of a term hold its four partial
-// sums).  `stage` = one of the warp's two staging buffers; callers alternate them, the __syncwarp of the next call orders
-// this call's loads before the stores of the call after it.
+// sums).  `stage` = the warp's staging buffer; the leading __syncwarp orders the previous call's loads before these stores.
 __device__ __forceinline__ double pfb_reduce8(const double (&t)[8], double* stage, int lane) {
     __syncwarp();
 #pragma unroll
@@ -259,8 +258,8 @@ __device__ __forceinline__ void pfb_bwd_carries(const double* __restrict__ recb,
     }
 }
 
-template <int P>
-__global__ void __launch_bounds__(PP_PROF_THREADS, 1)
+template <int P, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 k_profile_fb(const ProfFbSched S, const LaneBatchAny B) {
     using L = ProfBlock<P>;
     using Bk = PfbBlock<P>;
@@ -527,7 +526,7 @@ k_profile_fb(const ProfFbSched S, const LaneBatchAny B) {
                 {
                     const double t[8] = {(p8 * fD) * c, (p9 * fS) * c, (p10 * fS) * c, (p11 * fK) * c,
                                          (p12 * fK) * c, (p13 * fI) * c, (p14 * fI) * c, (p15 * fB) * c};
-                    acc[p][1] += pfb_reduce8(t, stage + 8 * kPfbStageRow, lane);
+                    acc[p][1] += pfb_reduce8(t, stage, lane);
                 }
                 {
                     const double gi = (bI[p] * fI) * c, gb = (bB[p] * fB) * c;
@@ -564,7 +563,7 @@ k_profile_fb(const ProfFbSched S, const LaneBatchAny B) {
                 const double gm = (bM[p] * fMv[p]) * c;
                 const double t[8] = {(p24 * fMv[p]) * c, (p25 * fMv[p]) * c, (p26 * fSv[p]) * c, (p27 * fKv[p]) * c,
                                      gm, gm * xb, gm * xx, 0.0};
-                acc[p][3] += pfb_reduce8(t, stage + 8 * kPfbStageRow, lane);
+                acc[p][3] += pfb_reduce8(t, stage, lane);
                 flg[p][0] |= __ballot_sync(0xffffffffu, gm > 0.0);
                 mx = max(mx, __double2hiint(bM[p]));
             }

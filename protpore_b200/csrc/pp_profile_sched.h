@@ -24,7 +24,18 @@ struct ProfSched {
     int32_t end_state;
 };
 
-// forward-backward on the profile (pp_profile_fb.cuh)
+// forward-backward on the profile (pp_profile_fb.cuh): one CTA per SM (the statistics live in registers) with its own plan,
+// so its geometry can differ from the sweeps'.  Measured on B200, 200k events: 4 positions per warp x 11 warps (168
+// registers) 103 ms; 2 x 22 warps (80 registers, 27 % more instructions, the shared-memory pipe saturates) 122 ms.
+#ifndef PP_PFB_P
+#define PP_PFB_P 4
+#endif
+#ifndef PP_PFB_NW
+#define PP_PFB_NW 11
+#endif
+constexpr int kPfbPositionsPerWarp = PP_PFB_P;
+constexpr int kPfbMaxPositionWarps = PP_PFB_NW;
+constexpr int kPfbThreads = (PP_PFB_NW + 1) * 32;
 struct ProfFbSched {
     const double* rec_f;                 // [Kr][32] forward records (probabilities)
     const double* rec_b;                 // [Kr][40] backward records

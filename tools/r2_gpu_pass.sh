@@ -4,6 +4,7 @@ set -x
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_gpu.log 2>&1; tail -3 gpurun_out/r2_pytest_gpu.log
 PP_KERNEL_PATH=1 python -m pytest tests/test_gpu_parity.py -m gpu -q --deselect tests/test_gpu_parity.py::test_profile_kernels_equal_run_based_kernels --deselect tests/test_gpu_parity.py::test_profile_kernels_after_baum_welch --deselect tests/test_gpu_parity.py::test_profile_forward_backward_equals_run_based_and_exact_kernels > gpurun_out/r2_pytest_gpu_lane_family.log 2>&1; tail -2 gpurun_out/r2_pytest_gpu_lane_family.log
+PP_GUARD=1 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_gpu_guarded.log 2>&1; tail -2 gpurun_out/r2_pytest_gpu_guarded.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; tail -2 gpurun_out/r2_smoke.log
 python bench.py --steps 10 --warmup 5 > gpurun_out/r2_bench_config2_1gpu.json 2> gpurun_out/r2_bench_config2.err; tail -c 600 gpurun_out/r2_bench_config2_1gpu.json
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2>&1; tail -c 300 gpurun_out/r2_bench_reference_arm.json
@@ -16,6 +17,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --events 200000 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_l.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_profile" -s 6 -c 2 -o gpurun_out/r2_profile_kernels -f \
     python bench.py --events 30000 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_f.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_profile_fb -c 1 -o gpurun_out/r2_profile_fb -f \
+    python bench.py --workload baum-welch --bw-events 20000 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_pfb.log 2>&1
 # DRAM traffic of ONE Viterbi sweep at the full config-2 size
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_profile_viterbi -s 3 -c 1 --csv \
     --log-file gpurun_out/r2_viterbi_traffic.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_vt.log 2>&1
