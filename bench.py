@@ -592,7 +592,8 @@ def main():
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[vit_kernel]
-        if (tr["events"], tr["min_len"], tr["max_len"], tr["seed"]) == (args.events, args.min_len, args.max_len, args.seed):
+        if args.workload == "score" and args.scaling == "weak" and \
+                (tr["events"], tr["min_len"], tr["max_len"], tr["seed"]) == (args.events, args.min_len, args.max_len, args.seed):
             traffic = float(tr["dram_bytes_read"] + tr["dram_bytes_write"])
     except Exception:
         pass

@@ -102,8 +102,8 @@ int64_t pp_schedule_describe(const pp_model_desc *desc, char *buf, int64_t cap);
  * HMM_linear_model builds (peptide_hmm_v0.0.1.py:63-243): match / blip / insert / drop-off / skip / back-slip states per
  * position, recognised from the CSR alone -- runs on register-resident kernels (pp_profile_kernels.cuh); every other
  * lane-lowered model on the run-based kernels (pp_lane_kernels.cuh).  Both follow the reference's arithmetic candidate by
- * candidate and give identical results; `path` 1 pins a handle to the run-based kernels (tests, comparisons), 0 restores
- * the automatic choice.  The environment variable PP_KERNEL_PATH sets the initial value.
+ * candidate and give identical results; `path` 1 pins a handle to the run-based kernels (tests, comparisons), 2 does the
+ * same and also keeps pp_forward_backward_batch on the exact state-parallel kernel, 0 restores the automatic choice.  The environment variable PP_KERNEL_PATH sets the initial value.
  * pp_model_kernel_info: out4 = {family: 2 profile, 1 run-based lane kernels, 0 state-parallel; positions of the profile
  * (0 if none); warps per CTA; bytes of one traceback pointer row (32 events)}.
  */
@@ -173,10 +173,12 @@ int pp_backward_table(pp_model *model, const double *obs, int64_t n, int32_t mem
  *   posteriors_out         : optional (may be NULL): log emission weights, float64, event e row i
  *                            state k at [(offsets[e] + i) * silent_start + k]  (3304-3321)
  * Accumulators are read-modify-write so a caller can sum shards before an allreduce.
- * Without posteriors_out, models the lane-per-event kernels serve run on k_fb_lane (scaled linear-space forward
- * and backward sweeps, float64, float64-accurate emissions; statistics within ~1e-11 relative of the exact
- * log-space kernel); events it cannot resolve, other models, and calls that ask for posteriors take the exact
- * state-parallel log-space kernel.
+ * Linear profiles run on k_profile_fb (pp_profile_fb.cuh), with or without posteriors_out; other lane-lowered models on
+ * k_fb_lane when no posteriors are asked for (both: scaled linear-space forward and backward sweeps, float64,
+ * float64-accurate emissions; statistics within ~1e-11 relative of the exact log-space kernel).  Events they cannot
+ * resolve, other models, and posteriors of non-profile models take the exact state-parallel log-space kernel.  A
+ * posterior whose linear-space value leaves the double range even after the two large factors are separated (below
+ * ~1e-600) is reported as -inf by k_profile_fb where the reference keeps a finite logarithm.
  */
 int pp_forward_backward_batch(pp_model *model, const void *obs, int32_t obs_dtype, const int64_t *offsets,
                               int64_t n_events, int32_t mem, double *logp_out, double *edge_counts,

@@ -273,7 +273,8 @@ class Engine(object):
                                                           PP_MEM_DEVICE if dev else PP_MEM_HOST))
 
     def set_kernel_path(self, path):
-        """0: automatic (register-resident profile kernels where the model is a linear profile); 1: run-based lane kernels."""
+        """0: automatic (register-resident profile kernels where the model is a linear profile); 1: run-based lane kernels;
+        2: like 1, and forward_backward_batch on the exact state-parallel kernel only."""
         self._check(self._lib.pp_model_set_kernel_path(self._h, int(path)))
 
     def kernel_info(self):

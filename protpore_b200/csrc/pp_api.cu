@@ -677,7 +677,7 @@ int64_t pp_schedule_describe(const pp_model_desc* desc, char* buf, int64_t cap) 
 
 
 int pp_model_set_kernel_path(pp_model* M, int32_t path) {
-    if (!M || path < 0 || path > 1) { set_error("bad kernel path"); return PP_ERR_ARG; }
+    if (!M || path < 0 || path > 2) { set_error("bad kernel path"); return PP_ERR_ARG; }
     PP_CUDA(cudaSetDevice(M->device));
     PP_CUDA(cudaStreamSynchronize(M->stream));
     M->kernel_path = path;

@@ -495,7 +495,7 @@ static int fb_batch_lane(pp_model* M, const void* d_obs, int32_t obs_dtype, cons
 // fb_batch_lane (done = 0: not served here, try the next kernel).
 static int fb_batch_profile(pp_model* M, const void* d_obs, int32_t obs_dtype, const int64_t* d_off, const int64_t* h_off,
                             int64_t n_events, int64_t maxlen, double* d_logp, double* d_edge, double* d_mom, double* d_mm,
-                            int* done, int32_t* n_rejects) {
+                            double* d_post, int* done, int32_t* n_rejects) {
     *done = 0;
     *n_rejects = 0;
     const ProfilePlan& F = M->plan_fb;
@@ -544,6 +544,8 @@ static int fb_batch_profile(pp_model* M, const void* d_obs, int32_t obs_dtype, c
     S.minmax = M->d_fb_minmax.as<double>();
     S.start_wm = F.start_wm;
     S.start_ws = F.start_ws;
+    S.post = d_post;
+    S.ne = M->ne;
     const LaneBatchAny B{d_obs, obs_dtype == PP_F64 ? 1 : 0, d_off, M->d_order.as<int32_t>(), M->d_group_len.as<int32_t>(), nullptr};
     int e = profile_fb_launch(S, B, grid, M->stream);
     if (e != 0) { set_error("profile forward-backward kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return PP_ERR_CUDA; }
@@ -657,10 +659,10 @@ int pp_forward_backward_batch(pp_model* M, const void* obs, int32_t obs_dtype, c
     M->fb_info[0] = M->fb_info[1] = M->fb_info[2] = 0;
     int lane_done = 0;
     int32_t n_rej = 0;
-    if (!posteriors_out) {
-        int rc = fb_batch_profile(M, d_obs, obs_dtype, d_off, h_off, n_events, maxlen, d_logp, d_edge, d_mom, d_mm, &lane_done, &n_rej);
+    if (M->kernel_path != 2) {                                     // 2: the exact state-parallel kernel only
+        int rc = fb_batch_profile(M, d_obs, obs_dtype, d_off, h_off, n_events, maxlen, d_logp, d_edge, d_mom, d_mm, d_post, &lane_done, &n_rej);
         if (rc != PP_OK) return rc;
-        if (!lane_done && M->fb_info[0] == 0) {                    // not a profile (a profile kernel that FAILED goes to the exact kernel)
+        if (!lane_done && M->fb_info[0] == 0 && !posteriors_out) {  // k_fb_lane does not write posteriors                    // not a profile (a profile kernel that FAILED goes to the exact kernel)
             rc = fb_batch_lane(M, d_obs, obs_dtype, d_off, h_off, n_events, maxlen, d_logp, d_edge, d_mom, d_mm, &lane_done, &n_rej);
             if (rc != PP_OK) return rc;
         }

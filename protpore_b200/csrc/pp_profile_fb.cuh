@@ -146,6 +146,14 @@ __device__ __forceinline__ double pfb_reduce8(const double (&t)[8], double* stag
     return ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d.x + d.y));
 }
 
+// log of a posterior (f^ b^) c given log c: the product of the two large factors is formed first; where it is not a normal
+// double although both factors are non-zero the logarithms are added instead
+__device__ __forceinline__ double pfb_log_post(double bf, double b, double f, double lc) {
+    if (bf >= 2.2250738585072014e-308) return log(bf) + lc;
+    if (b > 0.0 && f > 0.0) return (log(b) + log(f)) + lc;
+    return neg_inf();
+}
+
 // ---- phase F ------------------------------------------------------------------------------------------------------
 // prof_fwd_early with float64-accurate exponentials
 template <int P>
@@ -490,6 +498,10 @@ k_profile_fb(const ProfFbSched S, const LaneBatchAny B) {
             const double hiR = ldb(tb, Bk::WS + Bk::HIF + q * Bk::SLOT);
             const double hmL = ldb(tb, -Bk::WS + Bk::HML + q * Bk::SLOT);
             const double xx = xb * xb;
+            // posteriors of row r belong to observation r - 1 (only asked for by forward_backward(): a per-lane scattered store)
+            const bool writes = r >= 1 && r <= n && c > 0.0;
+            const double lc = (S.post != nullptr && writes) ? log(c) : 0.0;
+            const int64_t prow = (off + r - 1) * S.ne;
             double bMp[P], bI[P], bB[P], aS[P], aK[P], fMv[P], fSv[P], fKv[P];
             int mx = 0;
 #pragma unroll
@@ -530,6 +542,11 @@ k_profile_fb(const ProfFbSched S, const LaneBatchAny B) {
                 }
                 {
                     const double gi = (bI[p] * fI) * c, gb = (bB[p] * fB) * c;
+                    if (S.post != nullptr && writes) {
+                        const int sI = __ldg(S.emit_state + (pw * P + p) * 3 + 1), sB = __ldg(S.emit_state + (pw * P + p) * 3 + 2);
+                        if (sI >= 0) S.post[prow + sI] = pfb_log_post(bI[p] * fI, bI[p], fI, lc);
+                        if (sB >= 0) S.post[prow + sB] = pfb_log_post(bB[p] * fB, bB[p], fB, lc);
+                    }
                     const double t[8] = {(p16 * fB) * c, gi, gi * xb, gi * xx, gb, gb * xb, gb * xx, 0.0};
                     acc[p][2] += pfb_reduce8(t, stage, lane);
                     flg[p][1] |= __ballot_sync(0xffffffffu, gi > 0.0);
@@ -561,6 +578,10 @@ k_profile_fb(const ProfFbSched S, const LaneBatchAny B) {
                 const double p26 = R[FR_WS + 1] * sk_up[p], p27 = R[FR_WK + 1] * bk_dn[p];
                 bM[p] = bMp[p] + (p24 + p25);
                 const double gm = (bM[p] * fMv[p]) * c;
+                if (S.post != nullptr && writes) {
+                    const int sM = __ldg(S.emit_state + (pw * P + p) * 3);
+                    if (sM >= 0) S.post[prow + sM] = pfb_log_post(bM[p] * fMv[p], bM[p], fMv[p], lc);
+                }
                 const double t[8] = {(p24 * fMv[p]) * c, (p25 * fMv[p]) * c, (p26 * fSv[p]) * c, (p27 * fKv[p]) * c,
                                      gm, gm * xb, gm * xx, 0.0};
                 acc[p][3] += pfb_reduce8(t, stage, lane);

@@ -54,6 +54,8 @@ struct ProfFbSched {
     double* logp;                        // [n_events]
     double* minmax;                      // [2 * ne]
     double start_wm, start_ws;           // t(start -> M_0), t(start -> S_SKIP_0)
+    double* post;                        // optional: log posteriors, event e row i state k at [(offsets[e] + i) * ne + k] (3304-3321)
+    int32_t ne;
 };
 
 }  // namespace pp

@@ -480,9 +480,13 @@ def test_lane_forward_backward_statistics(models):
     logp, edge, mom, mm, _ = eng.forward_backward_batch(obs, offsets)
     info = eng.forward_backward_info()
     assert info["path"] in ("lane", "profile") and info["rejects"] >= 1 and info["failed"] == 0
-    # exact kernel: asking for the posteriors keeps the batch on the state-parallel path
-    logp_x, edge_x, mom_x, mm_x, _ = eng.forward_backward_batch(obs, offsets, posteriors=True)
-    assert eng.forward_backward_info()["path"] == "exact"
+    # exact kernel: kernel path 2 keeps the batch on the state-parallel path
+    eng.set_kernel_path(2)
+    try:
+        logp_x, edge_x, mom_x, mm_x, _ = eng.forward_backward_batch(obs, offsets, posteriors=True)
+        assert eng.forward_backward_info()["path"] == "exact"
+    finally:
+        eng.set_kernel_path(int(os.environ.get("PP_KERNEL_PATH", "0")))
     assert np.array_equal(np.isfinite(logp), np.isfinite(logp_x))
     fin = np.isfinite(logp)
     assert np.allclose(logp[fin], logp_x[fin], rtol=1e-12, atol=1e-9)
@@ -637,8 +641,25 @@ def test_profile_forward_backward_equals_run_based_and_exact_kernels(models):
             assert eng.forward_backward_info()["path"] in ("lane", "lane-failed")
         finally:
             eng.set_kernel_path(0)
-        lpx, ex, mx, mmx, _ = eng.forward_backward_batch(obs, offsets, posteriors=True)
-        assert eng.forward_backward_info()["path"] == "exact"
+        # posteriors (the emission weights forward_backward() returns, 3304-3321) from the profile kernel ...
+        lpp, ep, mp, mmp, post0 = eng.forward_backward_batch(obs, offsets, posteriors=True)
+        assert eng.forward_backward_info()["path"] == "profile", name
+        assert np.allclose(ep, e0, rtol=1e-12, atol=1e-12) and np.array_equal(mmp, mm0)
+        # ... and from the exact state-parallel kernel
+        eng.set_kernel_path(2)
+        try:
+            lpx, ex, mx, mmx, postx = eng.forward_backward_batch(obs, offsets, posteriors=True)
+            assert eng.forward_backward_info()["path"] == "exact"
+        finally:
+            eng.set_kernel_path(0)
+        rows = np.repeat(np.isfinite(lpx), np.diff(offsets))            # impossible events have no posteriors
+        a, b = post0[rows], postx[rows]
+        both = np.isfinite(a) & np.isfinite(b)
+        assert np.allclose(a[both], b[both], rtol=0, atol=1e-8), (name, np.max(np.abs(a[both] - b[both])))
+        # where only one side is finite the other is a posterior below what the linear-space sweep can hold
+        assert not np.any(np.isfinite(a) & ~np.isfinite(b)), name
+        lost = ~np.isfinite(a) & np.isfinite(b)
+        assert np.all(b[lost] < -1000.0), (name, b[lost].max() if lost.any() else None)
         for lp, e, m, mm in ((lp1, e1, m1, mm1), (lpx, ex, mx, mmx)):
             fin = np.isfinite(lp)
             assert np.array_equal(fin, np.isfinite(lp0)), name
