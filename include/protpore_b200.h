@@ -103,7 +103,8 @@ int64_t pp_schedule_describe(const pp_model_desc *desc, char *buf, int64_t cap);
  * position, recognised from the CSR alone -- runs on register-resident kernels (pp_profile_kernels.cuh); every other
  * lane-lowered model on the run-based kernels (pp_lane_kernels.cuh).  Both follow the reference's arithmetic candidate by
  * candidate and give identical results; `path` 1 pins a handle to the run-based kernels (tests, comparisons), 2 does the
- * same and also keeps pp_forward_backward_batch on the exact state-parallel kernel, 0 restores the automatic choice.  The environment variable PP_KERNEL_PATH sets the initial value.
+ * same and also keeps pp_forward_backward_batch on the exact state-parallel kernel, 3 is 0 plus posteriors from the batched
+ * profile kernel (see pp_forward_backward_batch), 0 restores the automatic choice.  The environment variable PP_KERNEL_PATH sets the initial value.
  * pp_model_kernel_info: out4 = {family: 2 profile, 1 run-based lane kernels, 0 state-parallel; positions of the profile
  * (0 if none); warps per CTA; bytes of one traceback pointer row (32 events)}.
  */
@@ -173,12 +174,13 @@ int pp_backward_table(pp_model *model, const double *obs, int64_t n, int32_t mem
  *   posteriors_out         : optional (may be NULL): log emission weights, float64, event e row i
  *                            state k at [(offsets[e] + i) * silent_start + k]  (3304-3321)
  * Accumulators are read-modify-write so a caller can sum shards before an allreduce.
- * Linear profiles run on k_profile_fb (pp_profile_fb.cuh), with or without posteriors_out; other lane-lowered models on
- * k_fb_lane when no posteriors are asked for (both: scaled linear-space forward and backward sweeps, float64,
- * float64-accurate emissions; statistics within ~1e-11 relative of the exact log-space kernel).  Events they cannot
- * resolve, other models, and posteriors of non-profile models take the exact state-parallel log-space kernel.  A
- * posterior whose linear-space value leaves the double range even after the two large factors are separated (below
- * ~1e-600) is reported as -inf by k_profile_fb where the reference keeps a finite logarithm.
+ * Without posteriors_out linear profiles run on k_profile_fb (pp_profile_fb.cuh), other lane-lowered models on k_fb_lane
+ * (both: scaled linear-space forward and backward sweeps, float64, float64-accurate emissions; statistics within ~1e-11
+ * relative of the exact log-space kernel).  Events they cannot resolve, other models, and calls that ask for posteriors
+ * take the exact state-parallel log-space kernel, which keeps a finite logarithm for posteriors far below the double
+ * range like the reference does.  A handle on kernel path 3 gets the posteriors of a linear profile from k_profile_fb
+ * instead (batched): within 1e-10 of the exact kernel wherever the posterior exceeds e^-300 (a scaled linear-space sweep
+ * spans ~2^1500 below its row maximum); smaller ones lose precision or come out as -inf.  The statistics are not affected.
  */
 int pp_forward_backward_batch(pp_model *model, const void *obs, int32_t obs_dtype, const int64_t *offsets,
                               int64_t n_events, int32_t mem, double *logp_out, double *edge_counts,

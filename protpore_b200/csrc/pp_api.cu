@@ -356,7 +356,7 @@ LaneSched make_sched(const pp_model* M, bool logspace) {
 }
 
 // The register-resident kernels of pp_profile_kernels.cuh serve a model whose baked graph is a linear profile.
-static bool use_profile(const pp_model* M) { return M->plan.ok && M->kernel_path == 0; }
+static bool use_profile(const pp_model* M) { return M->plan.ok && (M->kernel_path == 0 || M->kernel_path == 3); }
 static size_t ptr_row_bytes(const pp_model* M) {
     return use_profile(M) ? static_cast<size_t>(M->plan.row_bytes) : static_cast<size_t>(M->low.n_ptr_words) * kLanes * sizeof(uint32_t);
 }
@@ -677,7 +677,7 @@ int64_t pp_schedule_describe(const pp_model_desc* desc, char* buf, int64_t cap) 
 
 
 int pp_model_set_kernel_path(pp_model* M, int32_t path) {
-    if (!M || path < 0 || path > 2) { set_error("bad kernel path"); return PP_ERR_ARG; }
+    if (!M || path < 0 || path > 3) { set_error("bad kernel path"); return PP_ERR_ARG; }
     PP_CUDA(cudaSetDevice(M->device));
     PP_CUDA(cudaStreamSynchronize(M->stream));
     M->kernel_path = path;

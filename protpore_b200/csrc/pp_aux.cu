@@ -499,7 +499,7 @@ static int fb_batch_profile(pp_model* M, const void* d_obs, int32_t obs_dtype, c
     *done = 0;
     *n_rejects = 0;
     const ProfilePlan& F = M->plan_fb;
-    if (!F.ok || !F.fb_ok || M->kernel_path != 0) return PP_OK;
+    if (!F.ok || !F.fb_ok || (M->kernel_path != 0 && M->kernel_path != 3)) return PP_OK;
     const int P = kPfbPositionsPerWarp;
     const size_t smem = profile_fb_smem(F.Kr, F.NW);
     if (smem > M->smem_optin) return PP_OK;
@@ -659,7 +659,10 @@ int pp_forward_backward_batch(pp_model* M, const void* obs, int32_t obs_dtype, c
     M->fb_info[0] = M->fb_info[1] = M->fb_info[2] = 0;
     int lane_done = 0;
     int32_t n_rej = 0;
-    if (M->kernel_path != 2) {                                     // 2: the exact state-parallel kernel only
+    // posteriors: the exact log-space kernel keeps a finite logarithm for states whose posterior is far below the double
+    // range (e^-750 ... e^-4400 in the narrow-sigma fixtures), the linear-space sweeps only down to ~e^-300; forward_backward() must match
+    // the reference there, so the batched kernel serves posteriors only where the caller opted in (kernel path 3)
+    if (M->kernel_path != 2 && (!posteriors_out || M->kernel_path == 3)) {
         int rc = fb_batch_profile(M, d_obs, obs_dtype, d_off, h_off, n_events, maxlen, d_logp, d_edge, d_mom, d_mm, d_post, &lane_done, &n_rej);
         if (rc != PP_OK) return rc;
         if (!lane_done && M->fb_info[0] == 0 && !posteriors_out) {  // k_fb_lane does not write posteriors                    // not a profile (a profile kernel that FAILED goes to the exact kernel)

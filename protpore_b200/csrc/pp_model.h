@@ -38,7 +38,7 @@ struct pp_model {
     pp::Lowered low;
     // linear-profile fast path (pp_profile.h): plan.ok says whether the register-resident kernels serve this model;
     // kernel_path (pp_model_set_kernel_path): 0 = automatic, 1 = run-based lane kernels only, 2 = like 1 and the exact
-    // state-parallel kernel for forward-backward
+    // state-parallel kernel for forward-backward, 3 = like 0 and posteriors from k_profile_fb too
     pp::ProfilePlan plan;
     int kernel_path = 0;
     pp::DevBuf d_prof_rec_v, d_prof_rec_f, d_prof_end_v, d_prof_end_f, d_prof_unit_off, d_prof_unit_bytes, d_prof_unit_shift,
