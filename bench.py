@@ -148,7 +148,32 @@ class ClockSampler(threading.Thread):
         threading.Thread.__init__(self, daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
 
+    def run_nvml(self):
+        """In-process NVML sampling (nvidia_ml_py): a sample costs microseconds, so short timed regions and 8 ranks
+        sampling at once still get their clocks line; rows have the layout of the nvidia-smi query below."""
+        import pynvml as nv
+        nv.nvmlInit()
+        try:                                           # CUDA ordinal -> NVML handle through the UUID (CUDA_VISIBLE_DEVICES may renumber)
+            import torch
+            h = nv.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(self.index).uuid))
+        except Exception:
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [0x8, 0x40, 0x20, 0x4]                  # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)  # fails here (-> nvidia-smi loop) rather than inside the loop
+        while not self.stop_flag:
+            r = int(reasons(h))
+            self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)] +
+                             ["Active" if r & b else "Not Active" for b in bits])
+            time.sleep(0.02)
+
     def run(self):
+        try:
+            self.run_nvml()
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
