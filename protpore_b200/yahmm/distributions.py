@@ -263,14 +263,39 @@ class LogNormalDistribution(Distribution):
         weights = numpy.ones_like(items) if weights is None else numpy.asarray(weights)
         if weights.sum() == 0:
             return
-        mean = numpy.average(numpy.log(items), weights=weights)               # 595-613
+        logs = numpy.log(items)
+        mean = numpy.average(logs, weights=weights)                            # 595-613
         if len(weights[weights != 0]) > 1:
-            std = math.sqrt(numpy.average((numpy.log(items) - mean) ** 2, weights=weights))
+            variance = numpy.dot(logs ** 2 - mean ** 2, weights) / weights.sum()
+            std = math.sqrt(variance) if variance >= 0 else 0                  # a small negative variance by accident: 0
         else:
-            std = 0
+            std = self.parameters[1]                                           # one data point cannot update the std
         std = max(std, min_std)
         prior_mean, prior_std = self.parameters
         self.parameters = [prior_mean * inertia + mean * (1 - inertia), prior_std * inertia + std * (1 - inertia)]
+
+    def summarize(self, items, weights=None):
+        # (mean of the logs, variance, weight) per call (626-648)
+        items = numpy.asarray(items)
+        weights = numpy.ones_like(items) if weights is None else numpy.asarray(weights)
+        if weights.sum() == 0:
+            return
+        logs = numpy.log(items)
+        mean = numpy.average(logs, weights=weights)
+        variance = numpy.dot(logs ** 2 - mean ** 2, weights) / weights.sum()
+        self.summaries.append([mean, variance, weights.sum()])
+
+    def from_summaries(self, inertia=0.0, min_std=0.01):
+        # merged mean and variance of the summaries (653-688)
+        if len(self.summaries) == 0 or self.frozen:
+            return
+        summaries = numpy.asarray(self.summaries)
+        mean = numpy.average(summaries[:, 0], weights=summaries[:, 2])
+        variance = numpy.sum([(v + m ** 2) * w for m, v, w in summaries]) / summaries[:, 2].sum() - mean ** 2
+        std = max(min_std, math.sqrt(variance) if variance >= 0 else 0)
+        prior_mean, prior_std = self.parameters
+        self.parameters = [prior_mean * inertia + mean * (1 - inertia), prior_std * inertia + std * (1 - inertia)]
+        self.summaries = []
 
 
 class ExponentialDistribution(Distribution):
@@ -300,6 +325,23 @@ class ExponentialDistribution(Distribution):
             return
         rate = 1.0 / numpy.average(items, weights=weights)
         self.parameters[0] = self.parameters[0] * inertia + rate * (1 - inertia)
+
+    def summarize(self, items, weights=None):
+        # (mean, weight) per call (796-815)
+        items = numpy.asarray(items)
+        weights = numpy.ones_like(items) if weights is None else numpy.asarray(weights)
+        if weights.sum() == 0:
+            return
+        self.summaries.append([numpy.average(items, weights=weights), weights.sum()])
+
+    def from_summaries(self, inertia=0.0):
+        # 817-842
+        if len(self.summaries) == 0 or self.frozen:
+            return
+        summaries = numpy.asarray(self.summaries)
+        rate = 1.0 / numpy.average(summaries[:, 0], weights=summaries[:, 1])
+        self.parameters[0] = self.parameters[0] * inertia + rate * (1 - inertia)
+        self.summaries = []
 
 
 class LambdaDistribution(Distribution):

@@ -80,3 +80,4 @@ def test_profile_kernels_use_the_same_density():
     finally:
         eng.set_kernel_path(0)
     assert np.array_equal(s0, s1) and np.array_equal(l0, l1) and np.array_equal(p0, p1)
+
