@@ -13,6 +13,7 @@
 #include <cstring>
 #include <new>
 
+#define PP_WITH_TRACEBACK_KERNELS                   // pp_device_common.cuh: k_traceback* are instantiated here only
 #include "pp_lane_types.h"
 #include "pp_model.h"
 #include "pp_profile_sched.h"

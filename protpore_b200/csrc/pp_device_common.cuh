@@ -211,6 +211,8 @@ __device__ __forceinline__ int trace_step(const TraceArgs& T, const TraceTables&
     return tab.src[R.edge_begin + ord];
 }
 
+// The traceback kernels are launched by pp_api.cu only: other translation units include this header for the helpers above
+#ifdef PP_WITH_TRACEBACK_KERNELS
 static __global__ void __launch_bounds__(128) k_traceback(const TraceArgs T, int64_t* __restrict__ path_len,
                                                           const int64_t* __restrict__ path_off, uint16_t* __restrict__ path, int n_slots) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -304,6 +306,8 @@ static __global__ void k_traceback_compact(const TraceArgs T, const int64_t* __r
         for (int64_t i = lane; i < len; i += 32) d[i] = s[i];
     }
 }
+
+#endif  // PP_WITH_TRACEBACK_KERNELS
 
 constexpr int kFwdTargetExp = 900;   // a row's largest value is steered to ~2^900
 

@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 lib = sys.argv[1] if len(sys.argv) > 1 else "protpore_b200/libprotpore_b200.so"
-want = ("k_profile_viterbi", "k_profile_forward", "k_viterbi_lane", "k_forward_lane", "k_fb_lane", "k_traceback")
+want = ("k_profile_viterbi", "k_profile_forward", "k_profile_fb", "k_viterbi_lane", "k_forward_lane", "k_fb_lane", "k_traceback", "k_statsplit", "k_segment_align")
 text = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 kern, hist = None, {}
 for line in text.splitlines():
