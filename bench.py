@@ -300,6 +300,7 @@ def bench_baum_welch(args, model, rank, world, local):
                           "events_used": used, "sum_loglik": ll, "ranks_hold_identical_model": identical,
                           "e_step_kernel_ms_per_step": k_ms, "non_kernel_ms_per_step": dt / args.steps * 1e3 - k_ms,
                           "e_step_gcups": cells / (k_ms * 1e-3) / 1e9,
+                          "e_step_events_handed_to_exact_kernel": int(eng.forward_backward_info()["rejects"]),
                           "roofline": {"bound": "hbm", "kernel": fb_kernel, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                                        "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": None,
                                        "algorithmic_bytes_per_launch": bytes_col * total_obs, "launch_ms": k_ms},

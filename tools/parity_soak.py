@@ -111,8 +111,8 @@ def main():
         eng = model.engine()
         lens = events.uniform_lengths(n_events, 20, 600, seed=31 + py2)
         obs, off = eng.sample_events(lens, seed=32 + py2)
-        scores, plen, paths = eng.viterbi_batch(obs, off)
-        logp = eng.forward_batch(obs, off)
+        scores, plen, paths, logp = eng.score_batch(obs, off)            # both sweeps in one call (round 2)
+        family = eng.kernel_info()["family"]
         poff = np.concatenate([[0], np.cumsum(np.maximum(plen, 0))])
         xs = [obs[off[e]:off[e + 1]].astype(np.float64) for e in range(n_events)]
         cores = os.cpu_count() or 1
@@ -128,7 +128,36 @@ def main():
                     st["exact_ties" if margin == 0.0 else "path_mismatch"] += 1
                 worst = max(worst, abs(logp[e] - ol) / max(1.0, abs(ol)))
                 st["logp_out_of_tolerance"] += int(not util.close([logp[e]], [ol]).all())
-        print("pro_001 py2_division=%s:" % py2, st, "worst relative logp error %.3g" % worst, "(%.0f s, %d cores)" % (time.time() - t0, cores), flush=True)
+        print("pro_001 py2_division=%s (%s kernels):" % (py2, family), st, "worst relative logp error %.3g" % worst,
+              "(%.0f s, %d cores)" % (time.time() - t0, cores), flush=True)
+        # Baum-Welch E-step (round 2: k_profile_fb): a 30,000-event subset against the exact state-parallel kernel,
+        # 480 of them against the oracle
+        t0 = time.time()
+        n_fb = min(n_events, 30000)
+        o_fb, f_fb = obs[:off[n_fb]].astype(np.float64), off[:n_fb + 1]
+        lp0, e0, m0, mm0, _ = eng.forward_backward_batch(o_fb, f_fb)
+        info = eng.forward_backward_info()
+        eng.set_kernel_path(2)
+        lpx, ex, mx, mmx, _ = eng.forward_backward_batch(o_fb, f_fb)
+        eng.set_kernel_path(0)
+        fin = np.isfinite(lpx)
+        fb = dict(events=n_fb, path=info["path"], rejects=info["rejects"], failed=info["failed"],
+                  logp_ok=bool(np.array_equal(fin, np.isfinite(lp0)) and np.allclose(lp0[fin], lpx[fin], rtol=1e-12, atol=1e-9)),
+                  edge_max_rel=float(np.max(np.abs(e0 - ex) / np.maximum(1e-3, np.abs(ex)))),
+                  moment_max_rel=float(np.max(np.abs(m0 - mx) / np.maximum(1e-3, np.abs(mx)))), ranges_equal=bool(np.array_equal(mm0, mmx)))
+        sub = list(range(0, n_fb, max(1, n_fb // 480)))[:480]
+        seqs = [xs[e] for e in sub]
+        so, oo = np.concatenate(seqs), np.concatenate([[0], np.cumsum([len(x) for x in seqs])])
+        _, e_s, m_s, mm_s, _ = eng.forward_backward_batch(so, oo)
+        from oracle import cpu_oracle
+        orc = cpu_oracle.OracleModel.from_model(model)
+        exp_t, mom_o, mm_o, lz = orc.bw_accumulate(seqs)
+        b = model._baked
+        src = np.repeat(np.arange(len(model.states)), np.diff(b.out_ptr))
+        fb["oracle_edges_ok"] = bool(np.allclose(e_s, exp_t[src, b.out_idx], rtol=1e-9, atol=1e-12))
+        fb["oracle_moments_ok"] = bool(np.allclose(m_s, mom_o, rtol=1e-9, atol=1e-11))
+        fb["oracle_ranges_equal"] = bool(np.array_equal(mm_s, mm_o))
+        print("pro_001 py2_division=%s E-step:" % py2, fb, "(%.0f s)" % (time.time() - t0), flush=True)
 
 
 if __name__ == "__main__":
