@@ -41,10 +41,11 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="score", choices=["score", "config4", "config5", "baum-welch", "segment"],
+    ap.add_argument("--workload", default="score", choices=["score", "config4", "config5", "baum-welch", "segment", "align"],
                     help="score: forward + Viterbi (config 2, the contract line); config4: ~2,000-state synthetic profile on "
                          "10k-segment events; config5: mixed lengths 20-20,000; baum-welch: one distributed BW iteration "
-                         "(config 3); segment: the FastStatSplit segmenter in front of the path (SURVEY 8f-1)")
+                         "(config 3); segment: the FastStatSplit segmenter in front of the path (SURVEY 8f-1); align: the segment aligner "
+                         "behind it (cSegmentAligner, SURVEY 8f-4)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --events per GPU; strong: --events in total, split over the GPUs")
     ap.add_argument("--c4-events", type=int, default=1024, help="events per GPU of config 4 (10,000 segments each)")
@@ -52,6 +53,8 @@ def parse():
     ap.add_argument("--c5-events", type=int, default=200000, help="events per GPU of config 5 (20-20,000 segments, log-uniform)")
     ap.add_argument("--seg-events", type=int, default=20000, help="events per GPU of the segment workload (~18k samples each)")
     ap.add_argument("--bw-events", type=int, default=20000, help="events per GPU of the baum-welch workload")
+    ap.add_argument("--align-seqs", type=int, default=200000, help="sequences per GPU of the align workload (20-200 segments each)")
+    ap.add_argument("--align-model", type=int, default=64, help="model segments of the align workload")
     return ap.parse_args()
 
 
@@ -446,6 +449,156 @@ def bench_segment(args, rank, world, local):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------
+# align workload: cSegmentAligner.align of many segment sequences against one model
+# ---------------------------------------------------------------------------------------------
+ALIGN_METRIC = "segment aligner (cSegmentAligner.align): sequence segments x model positions per second"
+ALIGN_PENALTIES = (0.3, 1.1)
+
+
+def align_data(n_seqs, m, seed):
+    """A model of m (mean, std, duration) segments and n_seqs noisy walks along it (mostly +1 steps, some stays, skips and
+    back-slips), 20-200 segments each: what PyPore/alignment.py feeds the aligner."""
+    rs = np.random.RandomState(seed)
+    mm, ms, md = np.sort(rs.uniform(20, 70, m)), rs.uniform(0.5, 2.0, m), rs.uniform(0.001, 0.05, m)
+    lens = rs.randint(20, 201, size=n_seqs).astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    total = int(off[-1])
+    steps = rs.choice(np.array([1, 0, 2, -1]), size=total, p=[0.8, 0.1, 0.05, 0.05])
+    walk = np.cumsum(steps)
+    start = rs.randint(0, m // 2, size=n_seqs)
+    pos = walk - np.repeat(walk[off[:-1]], lens) + np.repeat(start, lens)
+    pos = np.clip(pos, 0, m - 1)
+    sm = mm[pos] + rs.normal(0.0, 0.5, size=total) * ms[pos]
+    ss = rs.uniform(0.5, 2.0, size=total)
+    sd = rs.uniform(0.0005, 0.01, size=total)
+    return (mm, ms, md), (sm, ss, sd), off
+
+
+def _align_cpu_worker(args):
+    kind, model, shard, reps = args
+    t0 = time.perf_counter()
+    from oracle import segalign_oracle
+    if kind == "reference":
+        al = segalign_oracle.load_reference().cSegmentAligner(model[0], model[1], model[2], *ALIGN_PENALTIES)
+    for _ in range(reps):
+        for sm, ss, sd in shard:
+            if kind == "reference":
+                try:
+                    al.align(sm, ss, sd)
+                except Exception:             # the reference raises where its backtrace is undefined (DESIGN 3.12)
+                    pass
+            else:
+                segalign_oracle.align(model[0], model[1], model[2], ALIGN_PENALTIES[0], ALIGN_PENALTIES[1], sm, ss, sd)
+    return time.perf_counter() - t0
+
+
+def align_cpu(m, seed, per_worker=150, reps=120):
+    """The compiled reference aligner (oracle/_ref/calignment) on every host core over a bounded sample."""
+    import multiprocessing as mp
+    from oracle import segalign_oracle
+    kind = "reference" if segalign_oracle.reference_available() else "port"
+    if kind == "port":
+        segalign_oracle.build()
+    cores = os.cpu_count() or 1
+    model, (sm, ss, sd), off = align_data(cores * per_worker, m, seed + 7)
+    seqs = [(sm[off[i]:off[i + 1]].copy(), ss[off[i]:off[i + 1]].copy(), sd[off[i]:off[i + 1]].copy()) for i in range(len(off) - 1)]
+    cells = float(off[-1]) * m * reps
+    shards = [(kind, model, seqs[w::cores], reps) for w in range(cores)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_align_cpu_worker, [(kind, model, s[2][:2], 1) for s in shards])      # warm-up: import + first call
+        t0 = time.perf_counter()
+        pool.map(_align_cpu_worker, shards)
+        dt = time.perf_counter() - t0
+    return dict(value=cells / dt / 1e9, unit=UNIT, cores=cores, kind=kind, seconds=dt,
+                sample="{} sequences of 20-200 segments x {} passes against a model of {} ({:.3g} cells), cSegmentAligner.align per "
+                       "sequence, {} worker processes".format(len(seqs), reps, m, cells, cores)), dt
+
+
+def bench_align(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    from protpore_b200 import _engine
+    n_seqs = args.align_seqs if args.scaling == "weak" else max(1, args.align_seqs // world)
+    m = args.align_model
+    model, (sm, ss, sd), off = align_data(n_seqs, m, args.seed + rank)
+    cells = float(off[-1]) * m
+    dev = torch.device("cuda", local)
+    d = [torch.from_numpy(a).to(dev) for a in (sm, ss, sd, off)]
+    call = lambda a: _engine.segment_align_batch(model[0], model[1], model[2], ALIGN_PENALTIES[0], ALIGN_PENALTIES[1], a[0], a[1], a[2], a[3], local)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    warm = max(3, args.warmup)
+    for _ in range(warm):
+        out = call(d)
+    # check a sample against the CPU oracle (bit-identical scores, identical orders and status words)
+    from oracle import segalign_oracle
+    segalign_oracle.build()
+    sc, od, st = (t.cpu().numpy() for t in out)
+    for i in range(0, n_seqs, max(1, n_seqs // 64)):
+        s_o, o_o, st_o = segalign_oracle.align(model[0], model[1], model[2], ALIGN_PENALTIES[0], ALIGN_PENALTIES[1],
+                                               sm[off[i]:off[i + 1]], ss[off[i]:off[i + 1]], sd[off[i]:off[i + 1]])
+        assert sc[i] == s_o and np.array_equal(od[off[i]:off[i + 1]], o_o.astype(np.int32)) and st[i] == st_o, i
+    sampler = ClockSampler(local)
+    sampler.start()
+    sync()
+    t0 = time.perf_counter()
+    k_ms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        call(d)
+        pr = _engine.segment_align_profile()
+        k_ms += pr["kernel_ms"]
+        launches += pr["launches"]
+    sync()
+    dt = time.perf_counter() - t0
+    clocks = sampler.summary()
+    h = [torch.from_numpy(a).pin_memory().numpy() for a in (sm, ss, sd)] + [off]
+    call(h)
+    e2e_steps = max(1, min(args.steps, 3))
+    sync()
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        oh = call(h)
+    sync()
+    dt2 = time.perf_counter() - t1
+    t = torch.tensor([dt, dt2], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt, dt2 = float(t[0]), float(t[1])
+    if rank == 0:
+        hbm_peak, peak_src, fp, _ = measured_peaks(local)
+        ms = k_ms / args.steps
+        alg = 24.0 * cells + 24.0 * float(off[-1])          # the three float64 tables written once; the sequences read once
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu, _ = align_cpu(m, args.seed)
+        print(json.dumps({
+            "metric": ALIGN_METRIC, "value": cells * world * args.steps / dt / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "ours",
+            "config": {"workload": "{} sequences/GPU of 20-200 (mean, std, duration) segments against a model of {} segments, skip / "
+                                   "back-slip penalties {} / {}, device-resident float64 inputs; results checked against the C oracle "
+                                   "on 64 sequences".format(n_seqs, m, *ALIGN_PENALTIES),
+                       "cells_per_step_per_gpu": cells, "parallelism": "sequences sharded, dp{}".format(world),
+                       "l2_policy": "the three DP tables ({:.1f} GB per step) exceed the 126 MB L2".format(24.0 * cells / 1e9)},
+            "kernel_ms_per_step": {"k_segment_align": ms},
+            "roofline": {"bound": "hbm", "kernel": "k_segment_align", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg * args.steps / max(1, launches), "launch_ms": k_ms / max(1, launches)},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cells * world * e2e_steps / dt2 / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(sum(a.nbytes for a in h)),
+                    "d2h_bytes_per_step": int(sum(a.nbytes for a in oh)), "ms_per_step": dt2 / e2e_steps * 1e3},
+            "gpu_launches": int(launches), "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -462,6 +615,15 @@ def main():
                           "config": {"workload": "synthetic events of ~18k samples; bounded CPU sample"}, "cpu_baseline": cpu,
                           "e2e": {"value": cpu["value"], "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "gpu_launches": 0}))
+        return 0
+    if args.impl == "reference" and args.workload == "align":
+        if rank != 0:
+            return 0
+        cpu, dt = align_cpu(args.align_model, args.seed)
+        print(json.dumps({"metric": ALIGN_METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 1,
+                          "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "impl": "reference", "config": {"workload": cpu["sample"]}, "cpu_baseline": cpu,
+                          "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
         return 0
     if args.impl == "reference":
         if rank != 0:
@@ -488,6 +650,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.workload == "segment":
         return bench_segment(args, rank, world, local)
+    if args.workload == "align":
+        return bench_align(args, rank, world, local)
     import protpore_b200.yahmm as y
     y.Model.device = local
     which = "synth334" if args.workload == "config4" else "pro_001"

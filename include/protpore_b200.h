@@ -266,6 +266,13 @@ int pp_segment_align_batch(const pp_segment_model *model, int device, const doub
                            const double *seq_durs, const int64_t *offsets, int64_t n_seqs, int32_t mem,
                            double *score_out, int32_t *order_out, int32_t *status_out);
 
+/* The LAST pp_segment_align_batch call of this process: out4 = {device time of its kernel launches in ms (CUDA events),
+ * launches, bytes of table workspace, groups of 32 sequences}. */
+int pp_segment_align_profile(double *out4);
+/* pp_segment_align_batch keeps its device buffers (the three DP tables above all) between calls, per device; this frees
+ * them.  PP_SEGALIGN_CACHE=0 in the environment makes every call free them itself. */
+int pp_segment_align_trim(int device);
+
 /* Measured float64 issue peaks of `device` (a few milliseconds of independent DADD / DFMA chains): out4 = {float64 adds
  * per second, float64 FMAs per second, SM count, SM clock in Hz}.  bench.py divides the sweeps' operation rates by these. */
 int pp_device_peaks(int device, double *out4);

@@ -82,6 +82,8 @@ ABI = [
     ("pp_segment_align_batch", ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp]),
     ("pp_device_peaks", ctypes.c_int, [ctypes.c_int, _f64p]),
     ("pp_launch_count", ctypes.c_int64, [_vp]),
+    ("pp_segment_align_profile", ctypes.c_int, [_f64p]),
+    ("pp_segment_align_trim", ctypes.c_int, [ctypes.c_int]),
     ("pp_debug_check_guards", ctypes.c_int, []),
     ("pp_debug_guard_count", ctypes.c_int, []),
     ("pp_debug_guard_selftest", ctypes.c_int, []),
@@ -538,11 +540,40 @@ class PPSegmentModel(ctypes.Structure):
                 ("skip_penalty", ctypes.c_double), ("backslip_penalty", ctypes.c_double)]
 
 
+def segment_align_trim(device=0):
+    """Frees the device buffers pp_segment_align_batch keeps between calls."""
+    load_library().pp_segment_align_trim(int(device))
+
+
+def segment_align_profile():
+    """{'kernel_ms', 'launches', 'workspace_bytes', 'groups'} of the last segment_align_batch call."""
+    out = (ctypes.c_double * 4)()
+    load_library().pp_segment_align_profile(out)
+    return {"kernel_ms": out[0], "launches": int(out[1]), "workspace_bytes": out[2], "groups": int(out[3])}
+
+
 def segment_align_batch(model_means, model_stds, model_durs, skip_penalty, backslip_penalty, seq_means, seq_stds, seq_durs,
                         offsets, device=0):
-    """pp_segment_align_batch on host arrays: (score f64[n], order i32[total], status i32[n])."""
+    """pp_segment_align_batch: (score f64[n], order i32[total], status i32[n]).  Host numpy arrays, or float64 / int64 torch
+    tensors resident on the device (results are then device tensors too)."""
     lib = load_library()
     mm, ms, md = (np.ascontiguousarray(a, dtype=np.float64) for a in (model_means, model_stds, model_durs))
+    if hasattr(seq_means, "is_cuda") and seq_means.is_cuda:
+        import torch
+        _torch_inputs_ready(seq_means, seq_stds, seq_durs, offsets)
+        n = int(offsets.numel()) - 1
+        model = PPSegmentModel(len(mm), mm.ctypes.data_as(_f64p), ms.ctypes.data_as(_f64p), md.ctypes.data_as(_f64p),
+                               float(skip_penalty), float(backslip_penalty))
+        dev = seq_means.device
+        score = torch.empty(n, dtype=torch.float64, device=dev)
+        order = torch.empty(int(seq_means.numel()), dtype=torch.int32, device=dev)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        rc = lib.pp_segment_align_batch(ctypes.byref(model), int(dev.index or 0), vp(seq_means), vp(seq_stds), vp(seq_durs), vp(offsets), n,
+                                        PP_MEM_DEVICE, vp(score), vp(order), vp(status))
+        if rc != 0:
+            raise EngineError(rc, lib.pp_last_error().decode())
+        return score, order, status
     sm, ss, sd = (np.ascontiguousarray(a, dtype=np.float64) for a in (seq_means, seq_stds, seq_durs))
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     n = len(offsets) - 1

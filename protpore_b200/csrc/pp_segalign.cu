@@ -14,7 +14,9 @@
 // Two places where the reference is undefined are DEFINED here and reported per sequence (status bits, see
 // protpore_b200.h); the CPU restatement oracle/segalign_oracle.c defines them identically.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <vector>
 
@@ -23,6 +25,21 @@
 namespace pp {
 
 constexpr double kSegNegInf = -99999999.0;            // calignment.pyx:38
+
+static double g_seg_profile[4] = {0, 0, 0, 0};        // last call: kernel ms, launches, workspace bytes, groups
+
+struct SegCache {
+    std::mutex mu;
+    DevBuf b[12];
+    bool keep = true;                                 // PP_SEGALIGN_CACHE=0 frees everything at the end of a call
+};
+static SegCache& seg_cache(int device) {
+    static SegCache caches[64];
+    static const bool keep = [] { const char* e = std::getenv("PP_SEGALIGN_CACHE"); return !(e && std::atoi(e) == 0); }();
+    SegCache& c = caches[device < 0 || device >= 64 ? 0 : device];
+    c.keep = keep;
+    return c;
+}
 
 struct SegAlignArgs {
     const double* model;          // [4][m]: means, stds, durs, cumulative durs
@@ -71,6 +88,9 @@ __global__ void __launch_bounds__(128) k_segment_align(const SegAlignArgs A) {
     __syncthreads();
     const double *mean = s_model, *stdv = s_model + m, *dur = s_model + 2 * m, *cdur = s_model + 3 * m;
     const int lane = threadIdx.x & 31;
+    // the previous score row of the warp's 32 sequences stays in shared memory ([position][lane]): the chains read it at
+    // shared-memory latency instead of waiting for DRAM (the rows of all resident warps exceed the L2)
+    double* const prow = s_model + 4 * m + static_cast<size_t>(threadIdx.x >> 5) * m * 32 + lane;
     const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= A.n_groups) return;
     const int sq = A.order[g * 32 + lane];
@@ -91,31 +111,53 @@ __global__ void __launch_bounds__(128) k_segment_align(const SegAlignArgs A) {
     };
     {
         const double d0 = xd[0];
-        for (int j = 0; j < m; ++j) S_(0, j) = __dsub_rn(__dmul_rn(match(0, j), d0), __dmul_rn(sp, __dsub_rn(cdur[j], dur[j])));   // 50
+        for (int j = 0; j < m; ++j) {
+            const double v = __dsub_rn(__dmul_rn(match(0, j), d0), __dmul_rn(sp, __dsub_rn(cdur[j], dur[j])));   // 50
+            S_(0, j) = v;
+            prow[j * 32] = v;
+        }
     }
     for (int i = 1; i < s; ++i) {
-        const double di = xd[i];
+        const double di = xd[i], xmi = xm[i], xsi = xs[i];
+        // disjoint rows: the compiler may hoist loads above the stores of row i (through one base pointer every link of the
+        // chains waited for a memory round trip)
+        double* __restrict__ Sc = &S_(i, 0);
+        double* __restrict__ Kc = &K_(i, 0);
+        double* __restrict__ Bc = &B_(i, 0);
         double c = kSegNegInf;
-        K_(i, 0) = c;
-        for (int j = 1; j < m; ++j) {                          // 55: the skip chain
-            c = __dsub_rn(seg_max(c, S_(i - 1, j - 1)), __dmul_rn(dur[j], sp));
-            K_(i, j) = c;
-        }
-        c = kSegNegInf;
-        B_(i, m - 1) = c;
+        Bc[static_cast<size_t>(m - 1) * 32] = c;
+#pragma unroll 8
         for (int j = m - 2; j >= 0; --j) {                     // 58-59: the back-slip chain
-            c = __dsub_rn(seg_max(c, S_(i - 1, j + 1)), __dmul_rn(dur[j + 1], bp));
-            B_(i, j) = c;
+            c = __dsub_rn(seg_max(c, prow[(j + 1) * 32]), __dmul_rn(dur[j + 1], bp));
+            Bc[static_cast<size_t>(j) * 32] = c;
         }
-        for (int j = 0; j < m; ++j) {                          // 61-67
-            double prev = S_(i - 1, j);
-            if (j > 0) {
-                const double dg = S_(i - 1, j - 1), sk = K_(i, j - 1);
-                if (dg > prev) prev = dg;
-                if (sk > prev) prev = sk;
-            }
-            if (j < m - 1) prev = seg_max(prev, B_(i, j));
-            S_(i, j) = __dadd_rn(prev, __dmul_rn(match(i, j), di));
+        // 55 and 61-67 in one ascending sweep: K(i, j - 1) and S(i - 1, j - 1) are carried in registers
+        auto match_i = [&](int j) {
+            const double d = __dsub_rn(xmi, mean[j]);
+            return __ddiv_rn(-__dmul_rn(d, d), __dmul_rn(xsi, stdv[j]));
+        };
+        double kc = kSegNegInf, sjm1 = prow[0];
+        Kc[0] = kc;
+        {
+            double prev = sjm1;
+            if (0 < m - 1) prev = seg_max(prev, Bc[0]);
+            const double v = __dadd_rn(prev, __dmul_rn(match_i(0), di));
+            Sc[0] = v;
+            prow[0] = v;
+        }
+#pragma unroll 4
+        for (int j = 1; j < m; ++j) {
+            const double sj = prow[j * 32];
+            double prev = sj;
+            if (sjm1 > prev) prev = sjm1;
+            if (kc > prev) prev = kc;
+            if (j < m - 1) prev = seg_max(prev, Bc[static_cast<size_t>(j) * 32]);
+            const double v = __dadd_rn(prev, __dmul_rn(match_i(j), di));
+            Sc[static_cast<size_t>(j) * 32] = v;
+            prow[j * 32] = v;                                                   // row i replaces row i - 1 in place (sjm1 keeps the old value)
+            kc = __dsub_rn(seg_max(kc, sjm1), __dmul_rn(dur[j], sp));           // the skip chain: K(i, j)
+            Kc[static_cast<size_t>(j) * 32] = kc;
+            sjm1 = sj;
         }
     }
     int status = 0;
@@ -210,15 +252,31 @@ extern "C" int pp_segment_align_batch(const pp_segment_model* model, int device,
     }
     // sequences by length, longest first, 32 per warp
     std::vector<int32_t> idx(static_cast<size_t>(n_seqs));
-    std::iota(idx.begin(), idx.end(), 0);
-    std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return h_off[a + 1] - h_off[a] > h_off[b + 1] - h_off[b]; });
+    {   // stable, descending by length: a counting sort when the lengths are small numbers (they are: segments per event)
+        int64_t longest = 0;
+        for (int64_t e = 0; e < n_seqs; ++e) longest = std::max(longest, h_off[e + 1] - h_off[e]);
+        if (longest <= (int64_t(1) << 22)) {
+            std::vector<int64_t> first(static_cast<size_t>(longest) + 2, 0);
+            for (int64_t e = 0; e < n_seqs; ++e) ++first[static_cast<size_t>(longest - (h_off[e + 1] - h_off[e])) + 1];
+            for (size_t k = 1; k < first.size(); ++k) first[k] += first[k - 1];
+            for (int64_t e = 0; e < n_seqs; ++e) idx[static_cast<size_t>(first[static_cast<size_t>(longest - (h_off[e + 1] - h_off[e]))]++)] = static_cast<int32_t>(e);
+        } else {
+            std::iota(idx.begin(), idx.end(), 0);
+            std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return h_off[a + 1] - h_off[a] > h_off[b + 1] - h_off[b]; });
+        }
+    }
     const int32_t ng = static_cast<int32_t>((n_seqs + 31) / 32);
     std::vector<int32_t> order(static_cast<size_t>(ng) * 32, -1), glen(ng);
     std::copy(idx.begin(), idx.end(), order.begin());
     for (int32_t g = 0; g < ng; ++g) glen[g] = static_cast<int32_t>(h_off[idx[static_cast<size_t>(g) * 32] + 1] - h_off[idx[static_cast<size_t>(g) * 32]]);
 
-    DevBuf d_model, d_means, d_stds, d_durs, d_off, d_order, d_gws, d_glen, d_ws, d_score, d_ord, d_status;
-    auto release = [&] { for (DevBuf* b : {&d_model, &d_means, &d_stds, &d_durs, &d_off, &d_order, &d_gws, &d_glen, &d_ws, &d_score, &d_ord, &d_status}) b->release(); };
+    // device buffers live in a per-device cache between calls (the aligner has no handle: PyPore builds one per call);
+    // cudaMalloc / cudaFree of the 30 GB of tables cost more than the kernel.  Calls on one device take turns.
+    SegCache& C = seg_cache(device);
+    std::lock_guard<std::mutex> cache_lock(C.mu);
+    DevBuf &d_model = C.b[0], &d_means = C.b[1], &d_stds = C.b[2], &d_durs = C.b[3], &d_off = C.b[4], &d_order = C.b[5], &d_gws = C.b[6],
+           &d_glen = C.b[7], &d_ws = C.b[8], &d_score = C.b[9], &d_ord = C.b[10], &d_status = C.b[11];
+    auto release = [&] { if (!C.keep) for (DevBuf& b : C.b) b.release(); };
 #define SEG_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error("%s failed: %s", #x, cudaGetErrorString(e_)); release(); return PP_ERR_CUDA; } } while (0)
     SEG_CUDA(upload(&d_model, hm, nullptr));
     SEG_CUDA(upload(&d_order, order, nullptr));
@@ -242,10 +300,27 @@ extern "C" int pp_segment_align_batch(const pp_segment_model* model, int device,
     // the three tables of a group take 3 x rows x m x 32 doubles: launch as many groups as fit the workspace
     size_t fr = 0, tot = 0;
     SEG_CUDA(cudaMemGetInfo(&fr, &tot));
-    const size_t limit = std::max<size_t>(size_t(256) << 20, static_cast<size_t>(fr * 0.6)) / sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(k_segment_align, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(4 * m * sizeof(double)));
+    const size_t limit = std::max<size_t>(size_t(256) << 20, static_cast<size_t>((fr + d_ws.cap) * 0.6)) / sizeof(double);   // the cached tables count as free
+    // shared memory: the model and one score row (m x 32 doubles) per warp; as many warps per block (<= 4) as fit
+    struct { size_t sharedMemPerBlockOptin; } prop;
+    {
+        int optin = 0;
+        SEG_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        prop.sharedMemPerBlockOptin = static_cast<size_t>(optin);
+    }
+    const size_t row_bytes = static_cast<size_t>(m) * 32 * sizeof(double), model_bytes = 4 * static_cast<size_t>(m) * sizeof(double);
+    if (model_bytes + row_bytes > prop.sharedMemPerBlockOptin) { set_error("model of %d segments does not fit shared memory", m); release(); return PP_ERR_UNSUPPORTED; }
+    // blocks of one warp pack an SM best (16 KB each for m = 64); four warps share one copy of the model when rows are small
+    const int wpb = row_bytes >= 8192 ? 1 : static_cast<int>(std::min<size_t>(4, (prop.sharedMemPerBlockOptin - model_bytes) / row_bytes));
+    const size_t smem = model_bytes + wpb * row_bytes;
+    cudaError_t e = cudaFuncSetAttribute(k_segment_align, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) { set_error("model of %d segments does not fit shared memory", m); release(); return PP_ERR_UNSUPPORTED; }
     std::vector<int64_t> gws(ng);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    double kernel_ms = 0.0, ws_bytes = 0.0;
+    int launches = 0;
     for (int32_t g0 = 0; g0 < ng;) {
         size_t used = 0;
         int32_t g1 = g0;
@@ -262,11 +337,20 @@ extern "C" int pp_segment_align_batch(const pp_segment_model* model, int device,
         SegAlignArgs A{d_model.as<double>(), m, model->skip_penalty, model->backslip_penalty, p_means, p_stds, p_durs, p_off,
                        d_order.as<int32_t>() + static_cast<size_t>(g0) * 32, d_gws.as<int64_t>() + g0, d_glen.as<int32_t>() + g0,
                        d_ws.as<double>(), p_score, p_ord, p_status, g1 - g0};
-        k_segment_align<<<(g1 - g0 + 3) / 4, 128, 4 * m * sizeof(double)>>>(A);
+        if (ev0) cudaEventRecord(ev0, 0);
+        k_segment_align<<<(g1 - g0 + wpb - 1) / wpb, wpb * 32, smem>>>(A);
+        if (ev1) cudaEventRecord(ev1, 0);
         SEG_CUDA(cudaGetLastError());
         SEG_CUDA(cudaDeviceSynchronize());
+        float ms = 0.f;
+        if (ev0 && ev1 && cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) kernel_ms += ms;
+        ++launches;
+        ws_bytes = std::max(ws_bytes, static_cast<double>(used) * sizeof(double));
         g0 = g1;
     }
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    g_seg_profile[0] = kernel_ms; g_seg_profile[1] = launches; g_seg_profile[2] = ws_bytes; g_seg_profile[3] = ng;
     if (host) {
         SEG_CUDA(cudaMemcpy(score_out, d_score.p, n_seqs * sizeof(double), cudaMemcpyDeviceToHost));
         SEG_CUDA(cudaMemcpy(status_out, d_status.p, n_seqs * sizeof(int32_t), cudaMemcpyDeviceToHost));
@@ -275,4 +359,18 @@ extern "C" int pp_segment_align_batch(const pp_segment_model* model, int device,
     release();
     return PP_OK;
 #undef SEG_CUDA
+}
+
+extern "C" int pp_segment_align_profile(double* out4) {
+    if (!out4) { pp::set_error("null argument"); return PP_ERR_ARG; }
+    for (int i = 0; i < 4; ++i) out4[i] = pp::g_seg_profile[i];
+    return PP_OK;
+}
+
+extern "C" int pp_segment_align_trim(int device) {
+    pp::SegCache& C = pp::seg_cache(device);
+    std::lock_guard<std::mutex> lock(C.mu);
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); pp::set_error("bad device"); return PP_ERR_ARG; }
+    for (pp::DevBuf& b : C.b) b.release();
+    return PP_OK;
 }
