@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(128) k_segment_align(const SegAlignArgs A) {
     const int lane = threadIdx.x & 31;
     // the previous score row of the warp's 32 sequences stays in shared memory ([position][lane]): the chains read it at
     // shared-memory latency instead of waiting for DRAM (the rows of all resident warps exceed the L2)
-    double* const prow = s_model + 4 * m + static_cast<size_t>(threadIdx.x >> 5) * m * 32 + lane;
+    double* const prow = s_model + 4 * m + static_cast<size_t>(threadIdx.x >> 5) * 2 * m * 32 + lane;
+    double* const brow = prow + m * 32;                       // the back-slip chain of the current row, read back by the ascending sweep
     const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= A.n_groups) return;
     const int sq = A.order[g * 32 + lane];
@@ -126,10 +127,12 @@ __global__ void __launch_bounds__(128) k_segment_align(const SegAlignArgs A) {
         double* __restrict__ Bc = &B_(i, 0);
         double c = kSegNegInf;
         Bc[static_cast<size_t>(m - 1) * 32] = c;
+        brow[(m - 1) * 32] = c;
 #pragma unroll 8
         for (int j = m - 2; j >= 0; --j) {                     // 58-59: the back-slip chain
             c = __dsub_rn(seg_max(c, prow[(j + 1) * 32]), __dmul_rn(dur[j + 1], bp));
             Bc[static_cast<size_t>(j) * 32] = c;
+            brow[j * 32] = c;
         }
         // 55 and 61-67 in one ascending sweep: K(i, j - 1) and S(i - 1, j - 1) are carried in registers
         auto match_i = [&](int j) {
@@ -140,18 +143,18 @@ __global__ void __launch_bounds__(128) k_segment_align(const SegAlignArgs A) {
         Kc[0] = kc;
         {
             double prev = sjm1;
-            if (0 < m - 1) prev = seg_max(prev, Bc[0]);
+            if (0 < m - 1) prev = seg_max(prev, brow[0]);
             const double v = __dadd_rn(prev, __dmul_rn(match_i(0), di));
             Sc[0] = v;
             prow[0] = v;
         }
-#pragma unroll 4
+#pragma unroll 8
         for (int j = 1; j < m; ++j) {
             const double sj = prow[j * 32];
             double prev = sj;
             if (sjm1 > prev) prev = sjm1;
             if (kc > prev) prev = kc;
-            if (j < m - 1) prev = seg_max(prev, Bc[static_cast<size_t>(j) * 32]);
+            if (j < m - 1) prev = seg_max(prev, brow[j * 32]);
             const double v = __dadd_rn(prev, __dmul_rn(match_i(j), di));
             Sc[static_cast<size_t>(j) * 32] = v;
             prow[j * 32] = v;                                                   // row i replaces row i - 1 in place (sjm1 keeps the old value)
@@ -308,10 +311,10 @@ extern "C" int pp_segment_align_batch(const pp_segment_model* model, int device,
         SEG_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         prop.sharedMemPerBlockOptin = static_cast<size_t>(optin);
     }
-    const size_t row_bytes = static_cast<size_t>(m) * 32 * sizeof(double), model_bytes = 4 * static_cast<size_t>(m) * sizeof(double);
+    const size_t row_bytes = 2 * static_cast<size_t>(m) * 32 * sizeof(double), model_bytes = 4 * static_cast<size_t>(m) * sizeof(double);
     if (model_bytes + row_bytes > prop.sharedMemPerBlockOptin) { set_error("model of %d segments does not fit shared memory", m); release(); return PP_ERR_UNSUPPORTED; }
     // blocks of one warp pack an SM best (16 KB each for m = 64); four warps share one copy of the model when rows are small
-    const int wpb = row_bytes >= 8192 ? 1 : static_cast<int>(std::min<size_t>(4, (prop.sharedMemPerBlockOptin - model_bytes) / row_bytes));
+    const int wpb = row_bytes >= 4096 ? 1 : static_cast<int>(std::min<size_t>(4, (prop.sharedMemPerBlockOptin - model_bytes) / row_bytes));
     const size_t smem = model_bytes + wpb * row_bytes;
     cudaError_t e = cudaFuncSetAttribute(k_segment_align, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) { set_error("model of %d segments does not fit shared memory", m); release(); return PP_ERR_UNSUPPORTED; }
