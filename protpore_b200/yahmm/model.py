@@ -476,43 +476,62 @@ class Model(object):
         """M-step from E-step sufficient statistics (yahmm.pyx:4253-4327, 489-523, 328-348)."""
         b = self._baked
         m = len(self.states)
-        src = numpy.repeat(numpy.arange(m), numpy.diff(b.out_ptr))
-        expected = {}
-        for e in range(len(b.out_idx)):
-            expected[(int(src[e]), int(b.out_idx[e]))] = float(edge_counts[e])
+        # plain Python lists: the arithmetic below is the reference's, operation by operation and in its order (the sums
+        # that normalise a state's out-edges are sequential), and numpy scalar indexing would cost more than the arithmetic
+        out_ptr, out_idx, in_ptr, in_idx = b.out_ptr.tolist(), b.out_idx.tolist(), b.in_ptr.tolist(), b.in_idx.tolist()
+        out_pseudo, in_pseudo = b.out_pseudo.tolist(), b.in_pseudo.tolist()
+        out_logp, in_logp = b.out_logp.tolist(), b.in_logp.tolist()
+        cache = self.__dict__.get("_mstep_edge_of")            # (source, destination) -> out-edge index, per bake
+        if cache is None or cache[0] is not b:
+            edge_of = {}
+            for k in range(m):
+                for l in range(out_ptr[k], out_ptr[k + 1]):
+                    edge_of[(k, out_idx[l])] = l
+            self.__dict__["_mstep_edge_of"] = (b, edge_of)
+        else:
+            edge_of = cache[1]
+        expected = [float(v) for v in edge_counts]
         # tied edge groups pool their counts (4253-4266)
         sizes = b.tied_edge_group_size
         for g in range(len(sizes) - 1):
-            members = [(int(b.tied_edges_starts[l]), int(b.tied_edges_ends[l])) for l in range(sizes[g], sizes[g + 1])]
-            total = sum(expected[k] for k in members)
-            for k in members:
-                expected[k] = total
-        norm = numpy.zeros(m)
+            members = [edge_of[(int(b.tied_edges_starts[l]), int(b.tied_edges_ends[l]))] for l in range(sizes[g], sizes[g + 1])]
+            total = sum(expected[e] for e in members)
+            for e in members:
+                expected[e] = total
+        norm = [0.0] * m
         for k in range(m):
-            for l in range(b.out_ptr[k], b.out_ptr[k + 1]):
-                norm[k] += expected[(k, int(b.out_idx[l]))] + transition_pseudocount + b.out_pseudo[l] * use_pseudocount
+            acc = 0.0
+            for l in range(out_ptr[k], out_ptr[k + 1]):
+                acc += expected[l] + transition_pseudocount + out_pseudo[l] * use_pseudocount
+            norm[k] = acc
+        keep = 1 - edge_inertia
         for k in range(m):
             if norm[k] > 0:
-                for l in range(b.out_ptr[k], b.out_ptr[k + 1]):
-                    p = (expected[(k, int(b.out_idx[l]))] + transition_pseudocount +
-                         b.out_pseudo[l] * use_pseudocount) / norm[k]
-                    b.out_logp[l] = log(math.exp(b.out_logp[l]) * edge_inertia + p * (1 - edge_inertia))
-            for l in range(b.in_ptr[k], b.in_ptr[k + 1]):
-                li = int(b.in_idx[l])
+                for l in range(out_ptr[k], out_ptr[k + 1]):
+                    p = (expected[l] + transition_pseudocount + out_pseudo[l] * use_pseudocount) / norm[k]
+                    out_logp[l] = log(math.exp(out_logp[l]) * edge_inertia + p * keep)
+            for l in range(in_ptr[k], in_ptr[k + 1]):
+                li = in_idx[l]
                 if norm[li] > 0:
-                    p = (expected[(li, k)] + transition_pseudocount + b.in_pseudo[l] * use_pseudocount) / norm[li]
-                    b.in_logp[l] = log(math.exp(b.in_logp[l]) * edge_inertia + p * (1 - edge_inertia))
+                    p = (expected[edge_of[(li, k)]] + transition_pseudocount + in_pseudo[l] * use_pseudocount) / norm[li]
+                    in_logp[l] = log(math.exp(in_logp[l]) * edge_inertia + p * keep)
+        b.out_logp[:] = out_logp
+        b.in_logp[:] = in_logp
         # emission distributions, once per tied group, members' statistics pooled (4215-4236, 4304-4327)
         visited = numpy.zeros(self.silent_start, dtype=bool)
         for k in range(self.silent_start):
             if visited[k]:
                 continue
             visited[k] = True
-            group = [k] + [int(j) for j in b.tied_idx[b.tied_ptr[k]:b.tied_ptr[k + 1]]]
-            visited[group] = True
             dist = self.states[k].distribution
-            sw, swx, swxx = moments[group, 0].sum(), moments[group, 1].sum(), moments[group, 2].sum()
-            lo, hi = minmax[group, 0].min(), minmax[group, 1].max()
+            if b.tied_ptr[k] == b.tied_ptr[k + 1]:             # not tied (the common case): no pooling, no numpy reductions
+                sw, swx, swxx = moments[k]
+                lo, hi = minmax[k]
+            else:
+                group = [k] + [int(j) for j in b.tied_idx[b.tied_ptr[k]:b.tied_ptr[k + 1]]]
+                visited[group] = True
+                sw, swx, swxx = moments[group, 0].sum(), moments[group, 1].sum(), moments[group, 2].sum()
+                lo, hi = minmax[group, 0].min(), minmax[group, 1].max()
             if hasattr(dist, "summarize_moments"):
                 dist.summarize_moments(sw, swx, swxx)
                 dist.from_summaries(inertia=distribution_inertia)
