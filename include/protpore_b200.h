@@ -179,7 +179,7 @@ int pp_backward_table(pp_model *model, const double *obs, int64_t n, int32_t mem
  * relative of the exact log-space kernel).  Events they cannot resolve, other models, and calls that ask for posteriors
  * take the exact state-parallel log-space kernel, which keeps a finite logarithm for posteriors far below the double
  * range like the reference does.  A handle on kernel path 3 gets the posteriors of a linear profile from k_profile_fb
- * instead (batched): within 1e-10 of the exact kernel wherever the posterior exceeds e^-300 (a scaled linear-space sweep
+ * instead (batched): within 1e-10 of the exact kernel wherever the posterior exceeds e^-250 (a scaled linear-space sweep
  * spans ~2^1500 below its row maximum); smaller ones lose precision or come out as -inf.  The statistics are not affected.
  */
 int pp_forward_backward_batch(pp_model *model, const void *obs, int32_t obs_dtype, const int64_t *offsets,

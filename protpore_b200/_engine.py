@@ -277,7 +277,7 @@ class Engine(object):
     def set_kernel_path(self, path):
         """0: automatic (register-resident profile kernels where the model is a linear profile); 1: run-based lane kernels;
         2: like 1, and forward_backward_batch on the exact state-parallel kernel only; 3: like 0, and posteriors from the
-        batched profile kernel (within 1e-10 above e^-300, imprecise or -inf below; the default keeps them on the exact kernel)."""
+        batched profile kernel (within 1e-10 above e^-250, imprecise or -inf below; the default keeps them on the exact kernel)."""
         self._check(self._lib.pp_model_set_kernel_path(self._h, int(path)))
 
     def kernel_info(self):

@@ -660,7 +660,7 @@ int pp_forward_backward_batch(pp_model* M, const void* obs, int32_t obs_dtype, c
     int lane_done = 0;
     int32_t n_rej = 0;
     // posteriors: the exact log-space kernel keeps a finite logarithm for states whose posterior is far below the double
-    // range (e^-750 ... e^-4400 in the narrow-sigma fixtures), the linear-space sweeps only down to ~e^-300; forward_backward() must match
+    // range (e^-750 ... e^-4400 in the narrow-sigma fixtures), the linear-space sweeps only down to ~e^-250; forward_backward() must match
     // the reference there, so the batched kernel serves posteriors only where the caller opted in (kernel path 3)
     if (M->kernel_path != 2 && (!posteriors_out || M->kernel_path == 3)) {
         int rc = fb_batch_profile(M, d_obs, obs_dtype, d_off, h_off, n_events, maxlen, d_logp, d_edge, d_mom, d_mm, d_post, &lane_done, &n_rej);

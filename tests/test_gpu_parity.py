@@ -658,9 +658,9 @@ def test_profile_forward_backward_equals_run_based_and_exact_kernels(models):
             eng.set_kernel_path(0)
         rows = np.repeat(np.isfinite(lpx), np.diff(offsets))            # impossible events have no posteriors
         a, b = post0[rows], postx[rows]
-        # every posterior above e^-300 within 1e-8 (measured: 2e-11); below that a scaled linear-space sweep -- each spans
+        # every posterior above e^-250 within 1e-8 (measured: 2e-11; the largest posterior a soak found lost: e^-296); below that a scaled linear-space sweep -- each spans
         # ~2^1500 under its row maximum -- loses precision or flushes to -inf where the log-space kernel stays finite
-        big = np.isfinite(b) & (b > -300.0)
+        big = np.isfinite(b) & (b > -250.0)
         assert np.all(np.isfinite(a[big])), name
         assert np.max(np.abs(a[big] - b[big])) < 1e-8, (name, np.max(np.abs(a[big] - b[big])))
         assert not np.any(np.isfinite(a) & ~np.isfinite(b)), name
