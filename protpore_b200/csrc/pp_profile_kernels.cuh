@@ -357,8 +357,47 @@ __device__ __forceinline__ void prof_vit_carries(const double* __restrict__ rec,
     }
 }
 
-template <int P>
-__global__ void __launch_bounds__(PP_PROF_THREADS, PP_PROF_MIN_CTAS)
+// One chain per warp (two chain warps): half the instructions on the row's critical path
+template <int P, bool UP>
+__device__ __forceinline__ void prof_vit_carry_one(const double* __restrict__ rec, unsigned char* __restrict__ cb, int NW,
+                                                   double startval) {
+    using L = ProfBlock<P>;
+    double v = startval;
+    double c[P], tt = neg_inf(), eo;
+    auto load = [&](int i, double (&cc)[P], double& t1, double& e1) {
+        if (UP) {
+            const unsigned char* bu = cb + (i + 1) * L::WS;
+            t1 = ldb(bu, L::TT);
+            e1 = ldb(bu, L::EO);
+#pragma unroll
+            for (int j = 0; j < P; ++j) cc[j] = rec[(i * P + j) * kProfRecDoubles + PR_SK + 1];
+        } else {
+            const unsigned char* bd = cb + (NW - i) * L::WS;
+            e1 = ldb(bd, L::ED);
+#pragma unroll
+            for (int j = 0; j < P; ++j) cc[j] = rec[((NW - 1 - i) * P + (P - 1 - j)) * kProfRecDoubles + PR_BK + 1];
+        }
+    };
+    load(0, c, tt, eo);
+    for (int i = 0; i < NW; ++i) {
+        double cn[P], ttn = neg_inf(), eon = 0.0;
+        if (i + 1 < NW) load(i + 1, cn, ttn, eon);
+        if (UP) stb(cb + (i + 1) * L::WS, L::VIN, v);
+        else stb(cb + (NW - i) * L::WS, L::UIN, v);
+        double th = v;
+#pragma unroll
+        for (int j = 0; j < P; ++j) th = __dadd_rn(th, c[j]);
+        const double ee = UP ? (tt > eo ? tt : eo) : eo;
+        v = th > ee ? th : ee;
+#pragma unroll
+        for (int j = 0; j < P; ++j) c[j] = cn[j];
+        tt = ttn;
+        eo = eon;
+    }
+}
+
+template <int P, int NC>
+__global__ void __launch_bounds__(PP_PROF_THREADS + (NC - 1) * 32, PP_PROF_MIN_CTAS)
 k_profile_viterbi(const ProfSched S, const LaneBatchAny B, const VitOut O) {
     using L = ProfBlock<P>;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -366,7 +405,7 @@ k_profile_viterbi(const ProfSched S, const LaneBatchAny B, const VitOut O) {
     constexpr int TC = kLaneTileCols;
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
-    const int n_warps = S.NW + 1;
+    const int n_warps = S.NW + NC;
     const int g = blockIdx.x;
     const int ev = B.order[g * kLanes + lane];
     const int64_t off = ev >= 0 ? B.offsets[ev] : 0;
@@ -392,7 +431,8 @@ k_profile_viterbi(const ProfSched S, const LaneBatchAny B, const VitOut O) {
         for (int r = 0;; ++r) {
             // ---- silent chains of row r; v[0, start] = 0 (3514), the start state is -inf in every later row
             PPK_CLK(c0);
-            prof_vit_carries<P>(M.rec, cb, S.NW, r == 0 ? 0.0 : neg_inf());
+            if (NC == 1) prof_vit_carries<P>(M.rec, cb, S.NW, r == 0 ? 0.0 : neg_inf());
+            else prof_vit_carry_one<P, true>(M.rec, cb, S.NW, r == 0 ? 0.0 : neg_inf());
             PPK_CLK(c1);
             PPK_ACC(0, c0, c1);
 #ifdef PP_PHASE_TIMING
@@ -431,10 +471,25 @@ k_profile_viterbi(const ProfSched S, const LaneBatchAny B, const VitOut O) {
         return;
     }
 
+    if (NC == 2 && warp == 1) {                                     // the second chain warp: the descending chain
+        for (int r = 0;; ++r) {
+            prof_vit_carry_one<P, false>(M.rec, cb, S.NW, neg_inf());
+            prof_bar(n_threads);
+            if (r >= 1 && __any_sync(0xffffffffu, r == n)) {
+                prof_bar(n_threads);
+                prof_bar(n_threads);
+            }
+            if (r == nmax) break;
+            if (r + 1 < nmax && ((r + 1) & (TC - 1)) == 0) prof_fill_tile(M.xt, B.obs, B.obs_f64 != 0, off, n, r + 1, warp, lane, n_warps);
+            prof_bar(n_threads);
+        }
+        return;
+    }
+
     double vM[P], vB[P], vI[P], eM[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) vM[p] = vB[p] = vI[p] = neg_inf();
-    const int pw = warp - 1;                                                     // position warp index
+    const int pw = warp - NC;                                                    // position warp index
     unsigned char* const tb = cb + (pw + 1) * L::WS;                             // this warp's block
     const double* const recw = M.rec + pw * P * kProfRecDoubles;
     // this warp's units of row 0 in the pointer table: emitting ordinals (written with row r + 1), chain ordinals (row r)
