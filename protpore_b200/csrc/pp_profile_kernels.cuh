@@ -494,7 +494,8 @@ k_profile_viterbi(const ProfSched S, const LaneBatchAny B, const VitOut O) {
     const double* const recw = M.rec + pw * P * kProfRecDoubles;
     // this warp's units of row 0 in the pointer table: emitting ordinals (written with row r + 1), chain ordinals (row r)
     uint8_t* prow = reinterpret_cast<uint8_t*>(O.ptr) + static_cast<size_t>(B.group_row[g]) * S.row_bytes + pw * UB * kLanes + lane * UB;
-    const int sil_off = S.NW * UB * kLanes + pw * kLanes + lane - (pw * UB * kLanes + lane * UB);
+    constexpr int CB = 2 * P <= 8 ? 1 : 2;                                       // bytes per lane of the chain ordinals
+    const int sil_off = S.NW * UB * kLanes + pw * CB * kLanes + lane * CB - (pw * UB * kLanes + lane * UB);
 #ifdef PP_PHASE_TIMING
     unsigned long long phase_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
@@ -516,7 +517,8 @@ k_profile_viterbi(const ProfSched S, const LaneBatchAny B, const VitOut O) {
         const bool ends = r >= 1 && __any_sync(0xffffffffu, r == n);
         double skin[P], bkin[P];
         const uint32_t sbits = prof_vit_fill<P>(recw, tb, ends, skin, bkin);
-        prow[sil_off] = static_cast<uint8_t>(sbits);
+        if (CB == 1) prow[sil_off] = static_cast<uint8_t>(sbits);
+        else *reinterpret_cast<uint16_t*>(prow + sil_off) = static_cast<uint16_t>(sbits);
         prow += S.row_bytes;
         if (ends) {                                                              // the chain warp evaluates the end state
             prof_bar(n_threads);

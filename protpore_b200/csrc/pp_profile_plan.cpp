@@ -156,7 +156,7 @@ void build_profile_plan(const pp_model_desc& d, const Lowered& low, int P, int m
     // ---- geometry ---------------------------------------------------------------------------------------------
     const int NW = (K + P - 1) / P;
     if (NW > max_warps) { fail("profile has more positions than one CTA's warps can hold in registers"); return; }
-    if (2 * P > 8) { fail("more than 4 positions per warp"); return; }
+    if (5 * P > 32) { fail("more than 6 positions per warp"); return; }
     const int Kp = NW * P;
     plan->K = K; plan->NW = NW; plan->Kp = Kp;
     const double ninf = -INFINITY;
@@ -343,8 +343,9 @@ void build_profile_plan(const pp_model_desc& d, const Lowered& low, int P, int m
     // r + 1's emitting states; behind those a unit of one byte per lane with the ordinals of the warp's chain states
     // (bit j: S_SKIP_{k0+j}, bit P + j: B_BACK_{k0+j}), written when the warp fills in row r's chain values
     const int UB = 5 * P <= 16 ? 2 : 4;
+    const int CB = 2 * P <= 8 ? 1 : 2;                              // bytes per lane of a warp's chain ordinals (2 P bits)
     const int chain_base = NW * UB * kLanes;
-    plan->row_bytes = chain_base + NW * kLanes;
+    plan->row_bytes = chain_base + NW * CB * kLanes;
     plan->unit_off.assign(m, 0); plan->unit_bytes.assign(m, 1); plan->unit_shift.assign(m, 0); plan->unit_mask.assign(m, 0);
     auto place = [&](int s, int unit_off, int stride, int bit, int mask) {
         if (s < 0) return;
@@ -359,8 +360,8 @@ void build_profile_plan(const pp_model_desc& d, const Lowered& low, int P, int m
         place(INS[k], w * UB * kLanes, UB, 5 * p + 3, 1);
         place(BLIP[k], w * UB * kLanes, UB, 5 * p + 4, 1);
         place(DROP[k], 0, 0, 0, 0);                                 // one in-edge: ordinal 0, nothing stored
-        place(SKIP[k], chain_base + w * kLanes, 1, p, 1);
-        place(BACK[k], chain_base + w * kLanes, 1, P + p, 1);
+        place(SKIP[k], chain_base + w * CB * kLanes, CB, p, 1);
+        place(BACK[k], chain_base + w * CB * kLanes, CB, P + p, 1);
     }
     plan->ok = true;
 
