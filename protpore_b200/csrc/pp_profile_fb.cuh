@@ -69,9 +69,11 @@ __device__ __forceinline__ int pfb_row_shift(int hi) {
 // Backward sweep: H(r - 1) is made from b^_r while only the maxima of b^_{r+1} are known (those of b^_r are being collected),
 // so the shift allows for the one already applied in between: b^_r ~ b^_{r+1} 2^prev.  (Steering by the stale maximum
 // alone applies every correction twice and oscillates between 2^0 and 2^960.)
-__device__ __forceinline__ int pfb_row_shift_lagged(int hi, int prev) {
+// `first`: row r is the event's last row (b^_n is the end weights, ~2^-4, and nothing is known yet): the first shift lifts
+// H(n - 1) to the target at once -- an outlier in the last observation (2^-1200) would otherwise flush the whole sweep.
+__device__ __forceinline__ int pfb_row_shift_lagged(int hi, int prev, bool first) {
     const int ex = (hi >> 20) & 0x7ff;
-    const int shift = (ex == 0 || ex == 0x7ff) ? 0 : (kPfbTargetExp + 1023 - ex - prev);
+    const int shift = (ex == 0 || ex == 0x7ff) ? (first ? kPfbTargetExp : 0) : (kPfbTargetExp + 1023 - ex - prev);
     return max(-900, min(900, shift));
 }
 
@@ -353,10 +355,13 @@ k_profile_fb(const ProfFbSched S, const LaneBatchAny B) {
                         Pr = fma(v, E.w, Pr);
                     }
                     if (r == n) {
-                        // P^ far below the level the rows are steered to (an outlier in the last rows of a short event):
-                        // 2^(S_n - S_r - T_r) / P^ would leave the double range in the backward sweep.  Such an event is
-                        // flagged (NaN) like one with P^ = inf and goes to the exact kernel, alone
-                        const bool usable = Pr > 7.52316384526264e-37 && Pr < __longlong_as_double(0x7FF0000000000000LL);   // 2^-120
+                        // P^ hundreds of orders below the level the rows are steered to (outliers in the last rows): 1 / P^
+                        // must stay a double with room for the row factors.  Such an event is flagged (NaN) like one with
+                        // P^ = inf and goes to the exact kernel, alone
+                        // (2^-900; when posteriors are asked for, 2^-120: in such an event the supports of the two sweeps are
+                        // nearly disjoint in the last rows and posteriors far above e^-250 would be lost)
+                        const double floor_p = S.post != nullptr ? 7.52316384526264e-37 : 1.1832913578315177e-271;
+                        const bool usable = Pr > floor_p && Pr < __longlong_as_double(0x7FF0000000000000LL);
                         double lp;
                         if (Pr == 0.0) lp = neg_inf();
                         else if (!usable) lp = __longlong_as_double(0x7FF8000000000000LL);
@@ -457,7 +462,7 @@ k_profile_fb(const ProfFbSched S, const LaneBatchAny B) {
                 prof_bar(n_threads);                             // A: the summaries of row r are published
                 pfb_bwd_carries<P>(s_recb, cb, S.NW);
                 if (r > 0) {
-                    sh_prev = pfb_row_shift_lagged(smax[(q ^ 1) * kLanes + lane], sh_prev);   // shift of H(r - 1): from the maxima of b^_{r+1}
+                    sh_prev = pfb_row_shift_lagged(smax[(q ^ 1) * kLanes + lane], sh_prev, r == n);   // shift of H(r - 1): from the maxima of b^_{r+1}
                     T += static_cast<double>(sh_prev);
                     s_cr[(q ^ 1) * kLanes + lane] = c_of(r - 1, T);
                 }
@@ -592,7 +597,7 @@ k_profile_fb(const ProfFbSched S, const LaneBatchAny B) {
             if (r == 0) break;
             // H(r - 1) = p(obs[r - 1]) 2^shift b^_r, shift from the maxima of b^_{r+1}
             {
-                const int shift = pfb_row_shift_lagged(smax[(q ^ 1) * kLanes + lane], sh_prev);
+                const int shift = pfb_row_shift_lagged(smax[(q ^ 1) * kLanes + lane], sh_prev, r == n);
                 sh_prev = shift;
                 const double shiftd = static_cast<double>(shift);
                 const double scale2 = __hiloint2double((shift + 1023) << 20, 0);
