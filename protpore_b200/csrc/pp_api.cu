@@ -917,7 +917,8 @@ static int score_pipeline(pp_model* M, const void* obs, int32_t obs_dtype, const
         int64_t longest = 1;
         for (int64_t e = 0; e < n_events; ++e) longest = std::max(longest, h_off[e + 1] - h_off[e]);
         const size_t tail_rule = static_cast<size_t>(longest) * kLanes * 2 * M->sm_count * 4 * ob;
-        cuts = make_chunks(h_off, n_events, row_bytes, M->ws_limit / kPipeSlots, ob, std::max(size_t(96) << 20, tail_rule));
+        static const size_t chunk_bytes = [] { const char* e = std::getenv("PP_CHUNK_MB"); return (e && std::atoi(e) > 0 ? static_cast<size_t>(std::atoi(e)) : size_t(96)) << 20; }();
+        cuts = make_chunks(h_off, n_events, row_bytes, M->ws_limit / kPipeSlots, ob, std::max(chunk_bytes, tail_rule));
     } else {
         const auto t0 = clock_now();
         rc = device_schedule_enqueue(M, 0, d_off, 0, n_events, M->stream, &pre);
