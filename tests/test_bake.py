@@ -94,3 +94,19 @@ def test_profile_plan_recognises_linear_profiles_only():
     for name in ("toy", "toy_uniform", "toy_infinite"):
         last = _engine.describe_schedule(util.build_model(name)).splitlines()[-1]
         assert last.startswith("profile no:"), (name, last)
+
+
+def test_profile_plans_over_profile_lengths():
+    """Every profile length the kernels serve (1 warp ... 11 warps, lengths that do and do not fill the last warp), both division
+    variants: the plan is recognised, and the forward-backward plan counts every out-edge exactly once (CPU: text report)."""
+    from protpore_b200 import _engine, peptide_hmm
+    import protpore_b200.yahmm as y
+    for K in (2, 3, 4, 5, 8, 9, 17, 31, 40, 43, 44):
+        for py2 in (True, False):
+            model = peptide_hmm.model_maker(peptide_hmm.synthetic_profile(K, seed=K), "plan_%d" % K, y, py2)
+            text = _engine.describe_schedule(model)
+            assert "profile ok positions %d " % K in text, (K, py2, text.splitlines()[-2:])
+            assert "profile_fb ok" in text, (K, py2, text.splitlines()[-2:])
+    # one position more than the kernels hold in registers: the run-based kernels keep the model
+    text = _engine.describe_schedule(peptide_hmm.model_maker(peptide_hmm.synthetic_profile(45, seed=1), "plan_45", y, True))
+    assert "profile no:" in text
