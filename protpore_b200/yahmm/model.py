@@ -61,6 +61,11 @@ def log_probability(model, samples):
     return reduce(_pair_lse, map(model.log_probability, samples))
 
 
+class _PackedSequences(list):
+    """A list of sequences that remembers its packed form (observations back to back, offsets) for `Model._pack`."""
+    packed = None
+
+
 class Model(object):
     """Hidden Markov Model: states in a graph, lowered by `bake`, swept on the GPU."""
 
@@ -212,6 +217,9 @@ class Model(object):
     @staticmethod
     def _pack(sequences, dtype):
         from .._engine import pack_events
+        packed = getattr(sequences, "packed", None)             # _PackedSequences: packed once per training run
+        if packed is not None and packed[0].dtype == numpy.dtype(dtype):
+            return packed
         for s in sequences:
             if len(s) == 0:
                 raise ValueError("Invalid shape in axis 0: 0.")
@@ -428,6 +436,9 @@ class Model(object):
     def _train_baum_welch(self, sequences, stop_threshold, min_iterations, max_iterations, verbose,
                           transition_pseudocount, use_pseudocount, edge_inertia, distribution_inertia):
         iteration, improvement = 0, float("+inf")
+        # every iteration sweeps the same observations twice (E-step, then log_probability): copy them back to back ONCE
+        sequences = _PackedSequences(sequences)
+        sequences.packed = self._pack(list(sequences), numpy.float64)
         last = log_probability(self, sequences)
         while improvement > stop_threshold or iteration < min_iterations:
             if max_iterations and iteration >= max_iterations:
