@@ -829,6 +829,15 @@ struct SpanGuard {
     ~SpanGuard() { cudaEventRecord(b, s); }
 };
 static void spans_collect(pp_model* M) {
+    if (!M->spans.empty() && std::getenv("PP_TRACE_SPANS")) {       // debugging aid: the call's timeline, ms from its first span
+        static const char* names[] = {"viterbi", "traceback", "forward", "backward", "sample", "h2d", "d2h", "host"};
+        for (const pp_model::Span& sp : M->spans) {
+            float a = 0, b = 0;
+            if (cudaEventElapsedTime(&a, M->spans.front().a, sp.a) == cudaSuccess && cudaEventElapsedTime(&b, M->spans.front().a, sp.b) == cudaSuccess)
+                std::fprintf(stderr, "[pp span] %-9s %9.3f .. %9.3f ms\n", sp.slot >= 0 && sp.slot < 8 ? names[sp.slot] : "?", a, b);
+        }
+        cudaGetLastError();
+    }
     for (const pp_model::Span& sp : M->spans) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) M->prof[sp.slot] += ms;
